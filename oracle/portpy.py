@@ -1,0 +1,89 @@
+"""ctypes binding of oracle/libtbvh_oracle.so (the plain-C restatement, oracle/tbvh_oracle.c).
+
+TEST INFRASTRUCTURE ONLY: imported by tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+--impl reference arms.  The product package (tinybvh_b200/) never imports this module.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+PORT_SO = os.path.join(_HERE, "libtbvh_oracle.so")
+_lib = None
+
+NODE32 = np.dtype([("aabbMin", "3f4"), ("leftFirst", "u4"), ("aabbMax", "3f4"), ("triCount", "u4")])
+NODE64 = np.dtype([("lmin", "3f4"), ("left", "u4"), ("lmax", "3f4"), ("right", "u4"),
+                   ("rmin", "3f4"), ("triCount", "u4"), ("rmax", "3f4"), ("firstTri", "u4")])
+
+
+def build_lib(force: bool = False):
+    src = os.path.join(_HERE, "tbvh_oracle.c")
+    if force or not os.path.isfile(PORT_SO) or os.path.getmtime(PORT_SO) < os.path.getmtime(src):
+        subprocess.check_call(["make", "-C", _HERE, "port"], stdout=subprocess.DEVNULL)
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build_lib()
+        L = C.CDLL(PORT_SO)
+        vp, u32, u64, i32, f32 = C.c_void_p, C.c_uint32, C.c_uint64, C.c_int, C.c_float
+        L.orc_build.restype, L.orc_build.argtypes = u32, [vp, u32, vp, vp, f32, f32]
+        L.orc_intersect.restype, L.orc_intersect.argtypes = None, [vp, vp, vp, vp, u64, i32]
+        L.orc_occluded.restype, L.orc_occluded.argtypes = None, [vp, vp, vp, vp, u64, vp, i32]
+        L.orc_tri_test.restype, L.orc_tri_test.argtypes = i32, [vp] * 5 + [f32] + [vp] * 3
+        L.orc_to_bvh_gpu.restype, L.orc_to_bvh_gpu.argtypes = u32, [vp, vp]
+        L.orc_sah_cost.restype, L.orc_sah_cost.argtypes = f32, [vp, u32, f32, f32]
+        _lib = L
+    return _lib
+
+
+def _ptr(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+class PortBVH:
+    """orc_build + orc_intersect / orc_occluded: restatement of BVH::Build + Intersect / IsOccluded."""
+
+    def __init__(self, verts=None, c_trav: float = 1.0, c_int: float = 1.0, nodes=None, prim_idx=None):
+        self.verts = np.ascontiguousarray(verts, np.float32).reshape(-1, 4)
+        n = self.verts.shape[0] // 3
+        if nodes is not None:
+            self.nodes = np.ascontiguousarray(nodes).view(NODE32).reshape(-1)
+            self.prim_idx = np.ascontiguousarray(prim_idx, np.uint32)
+            return
+        nodes = np.zeros(max(2 * n, 2), NODE32)
+        self.prim_idx = np.zeros(n, np.uint32)
+        used = lib().orc_build(_ptr(self.verts), n, _ptr(nodes), _ptr(self.prim_idx), c_trav, c_int)
+        self.nodes = nodes[:used].copy()
+
+    used_nodes = property(lambda s: s.nodes.shape[0])
+
+    def intersect(self, rays, threads: int = 0):
+        assert rays.dtype.itemsize == 128 and rays.flags.c_contiguous
+        lib().orc_intersect(_ptr(self.nodes), _ptr(self.prim_idx), _ptr(self.verts), _ptr(rays), rays.shape[0], threads)
+        return rays
+
+    def occluded(self, rays, threads: int = 0):
+        assert rays.dtype.itemsize == 128 and rays.flags.c_contiguous
+        bits = np.zeros((rays.shape[0] + 31) // 32, np.uint32)
+        lib().orc_occluded(_ptr(self.nodes), _ptr(self.prim_idx), _ptr(self.verts), _ptr(rays), rays.shape[0], _ptr(bits), threads)
+        return bits
+
+    def to_bvh_gpu(self):
+        out = np.zeros(self.nodes.shape[0], NODE64)
+        used = lib().orc_to_bvh_gpu(_ptr(self.nodes), _ptr(out))
+        return out[:used].copy()
+
+    def sah_cost(self, c_trav=1.0, c_int=1.0):
+        return float(lib().orc_sah_cost(_ptr(self.nodes), 0, c_trav, c_int))
+
+
+def tri_test(O, D, v0, v1, v2, tmax):
+    a = [np.ascontiguousarray(x, np.float32) for x in (O, D, v0, v1, v2)]
+    t, u, v = (np.zeros(1, np.float32) for _ in range(3))
+    ok = lib().orc_tri_test(*[_ptr(x) for x in a], float(tmax), _ptr(t), _ptr(u), _ptr(v))
+    return bool(ok), float(t[0]), float(u[0]), float(v[0])

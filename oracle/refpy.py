@@ -1,0 +1,184 @@
+"""ctypes binding of oracle/_ref/libtinybvh_ref.so (the unmodified reference behind oracle/ref_wrap.cpp).
+
+TEST INFRASTRUCTURE ONLY: imported by tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+--impl reference arms.  The product package (tinybvh_b200/) never imports this module.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+REF_SO = os.path.join(_HERE, "_ref", "libtinybvh_ref.so")
+_lib = None
+
+NODE32 = np.dtype([("aabbMin", "3f4"), ("leftFirst", "u4"), ("aabbMax", "3f4"), ("triCount", "u4")])
+NODE64 = np.dtype([("lmin", "3f4"), ("left", "u4"), ("lmax", "3f4"), ("right", "u4"),
+                   ("rmin", "3f4"), ("triCount", "u4"), ("rmax", "3f4"), ("firstTri", "u4")])
+
+
+def available() -> bool:
+    return os.path.isfile(REF_SO)
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not available():
+            raise FileNotFoundError(f"{REF_SO} missing: run `make -C oracle ref` where /root/reference exists")
+        L = C.CDLL(REF_SO)
+        vp, u32, u64, i32 = C.c_void_p, C.c_uint32, C.c_uint64, C.c_int
+        sig = {
+            "ref_hardware_threads": (i32, []),
+            "ref_bvh_build": (vp, [vp, u32, i32, i32]),
+            "ref_bvh_destroy": (None, [vp]),
+            "ref_bvh_used_nodes": (u32, [vp]), "ref_bvh_idx_count": (u32, [vp]), "ref_bvh_tri_count": (u32, [vp]),
+            "ref_bvh_nodes": (vp, [vp]), "ref_bvh_prim_idx": (vp, [vp]),
+            "ref_bvh_sah_cost": (C.c_float, [vp]),
+            "ref_bvh_compact": (None, [vp]), "ref_bvh_split_leafs": (None, [vp, u32]),
+            "ref_bvh_from_arrays": (vp, [vp, u32, vp, u32, vp, u32]),
+            "ref_bvh_intersect": (None, [vp, vp, u64, i32]),
+            "ref_bvh_occluded": (None, [vp, vp, u64, vp, i32]),
+            "ref_bvhgpu_from_bvh": (vp, [vp, i32]), "ref_bvhgpu_destroy": (None, [vp]),
+            "ref_bvhgpu_used_nodes": (u32, [vp]), "ref_bvhgpu_nodes": (vp, [vp]),
+            "ref_bvhgpu_intersect": (None, [vp, vp, u64, i32]),
+            "ref_cwbvh_build": (vp, [vp, u32, i32, i32]), "ref_cwbvh_destroy": (None, [vp]),
+            "ref_cwbvh_used_blocks": (u32, [vp]), "ref_cwbvh_idx_count": (u32, [vp]), "ref_cwbvh_tri_count": (u32, [vp]),
+            "ref_cwbvh_nodes": (vp, [vp]), "ref_cwbvh_tris": (vp, [vp]), "ref_cwbvh_source_bvh": (vp, [vp]),
+            "ref_cwbvh_intersect": (None, [vp, vp, u64, i32]),
+            "ref_bvh8cpu_build": (vp, [vp, u32, i32]), "ref_bvh8cpu_destroy": (None, [vp]),
+            "ref_bvh8cpu_intersect": (None, [vp, vp, u64, i32]),
+            "ref_bvh8cpu_occluded": (None, [vp, vp, u64, vp, i32]),
+        }
+        for name, (res, args) in sig.items():
+            fn = getattr(L, name)
+            fn.restype, fn.argtypes = res, args
+        _lib = L
+    return _lib
+
+
+def _ptr(a: np.ndarray):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def _view(addr, dtype, count):
+    buf = (C.c_char * (np.dtype(dtype).itemsize * count)).from_address(addr)
+    return np.frombuffer(buf, dtype=dtype, count=count)
+
+
+class _Traceable:
+    _intersect = _occluded = None
+
+    def intersect(self, rays: np.ndarray, threads: int = 0) -> np.ndarray:
+        assert rays.dtype.itemsize == 128 and rays.flags.c_contiguous
+        getattr(lib(), self._intersect)(self.h, _ptr(rays), rays.shape[0], threads)
+        return rays
+
+    def occluded(self, rays: np.ndarray, threads: int = 0) -> np.ndarray:
+        assert rays.dtype.itemsize == 128 and rays.flags.c_contiguous
+        bits = np.zeros((rays.shape[0] + 31) // 32, np.uint32)
+        getattr(lib(), self._occluded)(self.h, _ptr(rays), rays.shape[0], _ptr(bits), threads)
+        return bits
+
+
+class RefBVH(_Traceable):
+    """BVH::Build / BuildAVX / BuildHQ + BVH::Intersect / IsOccluded - THE parity oracle (mode 0)."""
+    _intersect, _occluded = "ref_bvh_intersect", "ref_bvh_occluded"
+
+    def __init__(self, verts: np.ndarray = None, mode: int = 0, threaded: bool = False, _handle=None, _owner=None):
+        self._owner = _owner
+        if _handle is not None:
+            self.h, self._own = _handle, False
+            return
+        self.verts = np.ascontiguousarray(verts, np.float32).reshape(-1, 4)
+        self.h = lib().ref_bvh_build(_ptr(self.verts), self.verts.shape[0] // 3, mode, int(threaded))
+        self._own = True
+
+    @classmethod
+    def from_arrays(cls, nodes, prim_idx, verts):
+        self = cls.__new__(cls)
+        self._owner = None
+        self.verts = np.ascontiguousarray(verts, np.float32).reshape(-1, 4)
+        nodes = np.ascontiguousarray(nodes)
+        prim_idx = np.ascontiguousarray(prim_idx, np.uint32)
+        self.h = lib().ref_bvh_from_arrays(_ptr(nodes), nodes.shape[0], _ptr(prim_idx), prim_idx.shape[0],
+                                           _ptr(self.verts), self.verts.shape[0] // 3)
+        self._own = True
+        return self
+
+    def __del__(self):
+        if getattr(self, "_own", False) and self.h:
+            lib().ref_bvh_destroy(self.h)
+            self.h = None
+
+    used_nodes = property(lambda s: lib().ref_bvh_used_nodes(s.h))
+    idx_count = property(lambda s: lib().ref_bvh_idx_count(s.h))
+    tri_count = property(lambda s: lib().ref_bvh_tri_count(s.h))
+    nodes = property(lambda s: _view(lib().ref_bvh_nodes(s.h), NODE32, s.used_nodes))
+    prim_idx = property(lambda s: _view(lib().ref_bvh_prim_idx(s.h), np.uint32, s.idx_count))
+
+    def sah_cost(self):
+        return float(lib().ref_bvh_sah_cost(self.h))
+
+    def compact(self):
+        lib().ref_bvh_compact(self.h)
+
+    def split_leafs(self, n):
+        lib().ref_bvh_split_leafs(self.h, n)
+
+
+class RefBVHGPU(_Traceable):
+    _intersect = "ref_bvhgpu_intersect"
+
+    def __init__(self, bvh: RefBVH, compact: bool = True):
+        self.src = bvh
+        self.h = lib().ref_bvhgpu_from_bvh(bvh.h, int(compact))
+
+    def __del__(self):
+        if self.h:
+            lib().ref_bvhgpu_destroy(self.h)
+            self.h = None
+
+    used_nodes = property(lambda s: lib().ref_bvhgpu_used_nodes(s.h))
+    nodes = property(lambda s: _view(lib().ref_bvhgpu_nodes(s.h), NODE64, s.used_nodes))
+
+
+class RefCWBVH(_Traceable):
+    """mode 0 Build, 1 BuildHQ, 2 = the Build conversion chain over the scalar BVH::Build tree."""
+    _intersect = "ref_cwbvh_intersect"
+
+    def __init__(self, verts: np.ndarray, mode: int = 2, threaded: bool = False):
+        self.verts = np.ascontiguousarray(verts, np.float32).reshape(-1, 4)
+        self.h = lib().ref_cwbvh_build(_ptr(self.verts), self.verts.shape[0] // 3, mode, int(threaded))
+
+    def __del__(self):
+        if self.h:
+            lib().ref_cwbvh_destroy(self.h)
+            self.h = None
+
+    used_blocks = property(lambda s: lib().ref_cwbvh_used_blocks(s.h))
+    idx_count = property(lambda s: lib().ref_cwbvh_idx_count(s.h))
+    nodes = property(lambda s: _view(lib().ref_cwbvh_nodes(s.h), np.float32, s.used_blocks * 4).reshape(-1, 4))
+    tris = property(lambda s: _view(lib().ref_cwbvh_tris(s.h), np.float32, s.idx_count * 12).reshape(-1, 4))
+
+    def source_bvh(self) -> RefBVH:
+        return RefBVH(_handle=lib().ref_cwbvh_source_bvh(self.h), _owner=self)
+
+
+class RefBVH8CPU(_Traceable):
+    """BVH8_CPU (AVX2) - the CPU performance baseline; NOT a parity oracle."""
+    _intersect, _occluded = "ref_bvh8cpu_intersect", "ref_bvh8cpu_occluded"
+
+    def __init__(self, verts: np.ndarray, hq: bool = False):
+        self.verts = np.ascontiguousarray(verts, np.float32).reshape(-1, 4)
+        self.h = lib().ref_bvh8cpu_build(_ptr(self.verts), self.verts.shape[0] // 3, int(hq))
+
+    def __del__(self):
+        if self.h:
+            lib().ref_bvh8cpu_destroy(self.h)
+            self.h = None
+
+
+def hardware_threads() -> int:
+    return lib().ref_hardware_threads()

@@ -1,0 +1,336 @@
+/* oracle/tbvh_oracle.c - plain-C CPU restatement of the tinybvh hot path.  See tbvh_oracle.h.
+ *
+ * TEST INFRASTRUCTURE ONLY - never linked or loaded by the product.
+ *
+ * Floating point.  The reference is built with gcc -O3 (CMakeLists.txt:49) and gcc's default
+ * -ffp-contract=fast, so gcc fuses multiply-add pairs ("expect fma", tiny_bvh.h:3203).  Which pairs it
+ * fuses is a compiler decision, so this file is compiled with -ffp-contract=off and spells every fused
+ * operation as an explicit fmaf(), in the pairing read off the disassembly of the frozen oracle build
+ * (g++ 13.3 -O3 -mavx2 -mfma, oracle/Makefile) and confirmed bit-for-bit by tests/test_oracle_pin.py:
+ *   slab term           t = fmaf( bound, rD, -(O*rD) )                     (vfmsub, :3203-3214)
+ *   h = cross(D,e2)     h.x = fmaf( D.y, e2.z, -(D.z*e2.y) )  (first product fused, second rounded)
+ *   q = cross(s,e1)     q.x = fmaf( -s.z, e1.y, s.y*e1.z )    (second product fused, first rounded)
+ *   a = dot(e1,h), dot(s,h), dot(e2,q)  = fmaf( z, z', fmaf( x, x', y*y' ) )
+ *   dot(D,q)                            = fmaf( z, z', fmaf( y, y', x*x' ) )
+ *   half area / SA      fmaf( ez, ex, fmaf( ey, ex, ey*ez ) )              (:460, :8477)
+ *   bin index           trunc( fmaf( bmin+bmax, 0.5, -nmin ) * rpd )       (:2362, :2418)
+ *   split cost          fmaf( c_int*rSAV, splitCost, c_trav )              (:2406)
+ * The CUDA kernels use the same pairing through __fmaf_rn / __fmul_rn.
+ */
+#include "tbvh_oracle.h"
+#include <math.h>
+#include <string.h>
+#include <stdlib.h>
+#include <stdio.h>
+#include <pthread.h>
+#include <unistd.h>
+
+#define BVH_FAR 1e30f
+#define BVHBINS 8
+
+static inline float fminf_( float a, float b ) { return a < b ? a : b; }   /* tinybvh_min :445 */
+static inline float fmaxf_( float a, float b ) { return a > b ? a : b; }   /* tinybvh_max :446 */
+
+/* BVHBase::SA :8477 / tinybvh_half_area :460 (without its v.x < -BVH_FAR guard) */
+static inline float half_area( float ex, float ey, float ez ) { return fmaf( ez, ex, fmaf( ey, ex, ey * ez ) ); }
+
+/* ------------------------------------------------------------------------------------------------ build */
+
+typedef struct { float bmin[3]; uint32_t primIdx; float bmax[3]; uint32_t clipped; } orc_fragment; /* BVHBase::Fragment :796-806 */
+
+static inline int bin_of( float bmin, float bmax, float nmin, float rpd )
+{
+	/* :2362 - (int)(((bmin+bmax)*0.5f - nmin) * rpd); x86 cvttss2si semantics for NaN/overflow (-> INT_MIN) */
+	float f = fmaf( bmin + bmax, 0.5f, -nmin ) * rpd;
+	int bi = (f != f || f >= 2147483648.0f || f < -2147483648.0f) ? (int)0x80000000 : (int)f;
+	return bi > 0 ? (bi < BVHBINS - 1 ? bi : BVHBINS - 1) : 0;  /* tinybvh_clamp :458 */
+}
+
+uint32_t orc_build( const float* verts, uint32_t primCount, orc_node* nodes, uint32_t* primIdx, float c_trav, float c_int )
+{
+	orc_fragment* fragment = (orc_fragment*)malloc( (size_t)primCount * sizeof( orc_fragment ) );
+	memset( &nodes[1], 0, sizeof( orc_node ) ); /* node 1 unused, :2285 */
+	orc_node* root = &nodes[0];
+	root->leftFirst = 0, root->triCount = primCount;
+	float rmin[3] = { BVH_FAR, BVH_FAR, BVH_FAR }, rmax[3] = { -BVH_FAR, -BVH_FAR, -BVH_FAR };
+	for (uint32_t i = 0; i < primCount; i++) /* PrepareBuild :2300-2308 */
+	{
+		const float* v0 = verts + (size_t)i * 12, * v1 = v0 + 4, * v2 = v0 + 8;
+		for (int a = 0; a < 3; a++)
+		{
+			fragment[i].bmin[a] = fminf_( v0[a], fminf_( v1[a], v2[a] ) );
+			fragment[i].bmax[a] = fmaxf_( v0[a], fmaxf_( v1[a], v2[a] ) );
+			rmin[a] = fminf_( rmin[a], fragment[i].bmin[a] ), rmax[a] = fmaxf_( rmax[a], fragment[i].bmax[a] );
+		}
+		fragment[i].primIdx = i, fragment[i].clipped = 0, primIdx[i] = i;
+	}
+	root->minx = rmin[0], root->miny = rmin[1], root->minz = rmin[2];
+	root->maxx = rmax[0], root->maxy = rmax[1], root->maxz = rmax[2];
+	uint32_t newNodePtr = 2;
+	/* Build(nodeIdx, depth) :2332-2461, non-threaded numbering */
+	uint32_t task[256], taskCount = 0, nodeIdx = 0;
+	float minDim[3] = { (rmax[0] - rmin[0]) * 1e-20f, (rmax[1] - rmin[1]) * 1e-20f, (rmax[2] - rmin[2]) * 1e-20f };
+	float bestLMin[3] = { 0 }, bestLMax[3] = { 0 }, bestRMin[3] = { 0 }, bestRMax[3] = { 0 };
+	while (1)
+	{
+		while (1)
+		{
+			orc_node* node = &nodes[nodeIdx];
+			const float nmin3[3] = { node->minx, node->miny, node->minz }, nmax3[3] = { node->maxx, node->maxy, node->maxz };
+			float binMin[3][BVHBINS][3], binMax[3][BVHBINS][3];
+			uint32_t count[3][BVHBINS];
+			for (int a = 0; a < 3; a++) for (int i = 0; i < BVHBINS; i++) for (int k = 0; k < 3; k++)
+				binMin[a][i][k] = BVH_FAR, binMax[a][i][k] = -BVH_FAR;
+			memset( count, 0, sizeof( count ) );
+			float rpd3[3];
+			for (int a = 0; a < 3; a++) rpd3[a] = (float)BVHBINS / (nmax3[a] - nmin3[a]);
+			for (uint32_t i = 0; i < node->triCount; i++) /* binning :2357-2376 */
+			{
+				const orc_fragment* f = &fragment[primIdx[node->leftFirst + i]];
+				for (int a = 0; a < 3; a++)
+				{
+					const int bi = bin_of( f->bmin[a], f->bmax[a], nmin3[a], rpd3[a] );
+					for (int k = 0; k < 3; k++)
+						binMin[a][bi][k] = fminf_( binMin[a][bi][k], f->bmin[k] ),
+						binMax[a][bi][k] = fmaxf_( binMax[a][bi][k], f->bmax[k] );
+					count[a][bi]++;
+				}
+			}
+			/* sweep :2380-2405 */
+			float splitCost = BVH_FAR;
+			const float rSAV = 1.0f / half_area( nmax3[0] - nmin3[0], nmax3[1] - nmin3[1], nmax3[2] - nmin3[2] );
+			uint32_t bestAxis = 0, bestPos = 0;
+			for (int a = 0; a < 3; a++) if ((nmax3[a] - nmin3[a]) > minDim[a])
+			{
+				float lBMin[BVHBINS - 1][3], rBMin[BVHBINS - 1][3], lBMax[BVHBINS - 1][3], rBMax[BVHBINS - 1][3];
+				float l1[3] = { BVH_FAR, BVH_FAR, BVH_FAR }, l2[3] = { -BVH_FAR, -BVH_FAR, -BVH_FAR };
+				float r1[3] = { BVH_FAR, BVH_FAR, BVH_FAR }, r2[3] = { -BVH_FAR, -BVH_FAR, -BVH_FAR };
+				float ANL[BVHBINS - 1], ANR[BVHBINS - 1];
+				uint32_t lN = 0, rN = 0;
+				for (int i = 0; i < BVHBINS - 1; i++)
+				{
+					for (int k = 0; k < 3; k++)
+					{
+						lBMin[i][k] = l1[k] = fminf_( l1[k], binMin[a][i][k] );
+						rBMin[BVHBINS - 2 - i][k] = r1[k] = fminf_( r1[k], binMin[a][BVHBINS - 1 - i][k] );
+						lBMax[i][k] = l2[k] = fmaxf_( l2[k], binMax[a][i][k] );
+						rBMax[BVHBINS - 2 - i][k] = r2[k] = fmaxf_( r2[k], binMax[a][BVHBINS - 1 - i][k] );
+					}
+					lN += count[a][i], rN += count[a][BVHBINS - 1 - i];
+					/* tinybvh_half_area :460 returns 0 when v.x < -BVH_FAR (cannot happen once lN > 0) */
+					{
+						const float ex = l2[0] - l1[0], ey = l2[1] - l1[1], ez = l2[2] - l1[2];
+						ANL[i] = lN == 0 ? BVH_FAR : ((ex < -BVH_FAR ? 0 : half_area( ex, ey, ez )) * (float)lN);
+					}
+					{
+						const float ex = r2[0] - r1[0], ey = r2[1] - r1[1], ez = r2[2] - r1[2];
+						ANR[BVHBINS - 2 - i] = rN == 0 ? BVH_FAR : ((ex < -BVH_FAR ? 0 : half_area( ex, ey, ez )) * (float)rN);
+					}
+				}
+				for (int i = 0; i < BVHBINS - 1; i++)
+				{
+					const float C = ANL[i] + ANR[i];
+					if (C < splitCost)
+					{
+						splitCost = C, bestAxis = a, bestPos = i;
+						for (int k = 0; k < 3; k++)
+							bestLMin[k] = lBMin[i][k], bestRMin[k] = rBMin[i][k], bestLMax[k] = lBMax[i][k], bestRMax[k] = rBMax[i][k];
+					}
+				}
+			}
+			splitCost = fmaf( c_int * rSAV, splitCost, c_trav ); /* :2406 */
+			const float noSplitCost = (float)node->triCount * c_int;
+			if (splitCost >= noSplitCost) break;
+			/* in-place partition :2414-2422 */
+			uint32_t j = node->leftFirst + node->triCount, src = node->leftFirst;
+			const float rpd = rpd3[bestAxis], nmin = nmin3[bestAxis];
+			for (uint32_t i = 0; i < node->triCount; i++)
+			{
+				const orc_fragment* f = &fragment[primIdx[src]];
+				const int bi = bin_of( f->bmin[bestAxis], f->bmax[bestAxis], nmin, rpd );
+				if ((uint32_t)bi <= bestPos) src++;
+				else { uint32_t t = primIdx[src]; primIdx[src] = primIdx[--j], primIdx[j] = t; }
+			}
+			const uint32_t leftCount = src - node->leftFirst, rightCount = node->triCount - leftCount;
+			if (leftCount == 0 || rightCount == 0 || taskCount == 256) break;
+			const uint32_t n = newNodePtr;
+			newNodePtr += 2;
+			nodes[n].minx = bestLMin[0], nodes[n].miny = bestLMin[1], nodes[n].minz = bestLMin[2];
+			nodes[n].maxx = bestLMax[0], nodes[n].maxy = bestLMax[1], nodes[n].maxz = bestLMax[2];
+			nodes[n].leftFirst = node->leftFirst, nodes[n].triCount = leftCount;
+			nodes[n + 1].minx = bestRMin[0], nodes[n + 1].miny = bestRMin[1], nodes[n + 1].minz = bestRMin[2];
+			nodes[n + 1].maxx = bestRMax[0], nodes[n + 1].maxy = bestRMax[1], nodes[n + 1].maxz = bestRMax[2];
+			nodes[n + 1].leftFirst = j, nodes[n + 1].triCount = rightCount;
+			node->leftFirst = n, node->triCount = 0;
+			task[taskCount++] = n + 1, nodeIdx = n;
+		}
+		if (taskCount == 0) break; else nodeIdx = task[--taskCount];
+	}
+	free( fragment );
+	return newNodePtr;
+}
+
+/* -------------------------------------------------------------------------------------------- traversal */
+
+typedef struct { float O[3]; uint32_t mask; float D[3]; uint32_t instIdx; float rD[3]; uint32_t pad; float t, u, v; uint32_t prim; uint8_t aux[64]; } orc_ray; /* Ray :688-709 */
+
+/* MOLLER_TRUMBORE_TEST :1644-1656, IntersectTri :8508-8511 */
+int orc_tri_test( const float* O, const float* D, const float* v0, const float* v1, const float* v2, float tmax, float* to, float* uo, float* vo )
+{
+	const float e1x = v1[0] - v0[0], e1y = v1[1] - v0[1], e1z = v1[2] - v0[2];
+	const float e2x = v2[0] - v0[0], e2y = v2[1] - v0[1], e2z = v2[2] - v0[2];
+	const float hx = fmaf( D[1], e2z, -(D[2] * e2y) );
+	const float hy = fmaf( D[2], e2x, -(D[0] * e2z) );
+	const float hz = fmaf( D[0], e2y, -(D[1] * e2x) );
+	const float a = fmaf( e1z, hz, fmaf( e1x, hx, e1y * hy ) );
+	if (fabsf( a ) < 0.000001f) return 0;
+	const float f = 1 / a;
+	const float sx = O[0] - v0[0], sy = O[1] - v0[1], sz = O[2] - v0[2];
+	const float u = f * fmaf( hz, sz, fmaf( hx, sx, hy * sy ) );
+	const float qx = fmaf( -e1y, sz, e1z * sy );
+	const float qy = fmaf( -e1z, sx, e1x * sz );
+	const float qz = fmaf( -e1x, sy, e1y * sx );
+	const float v = f * fmaf( D[2], qz, fmaf( D[1], qy, D[0] * qx ) );
+	if (u < 0 || v < 0 || u + v > 1) return 0;
+	const float t = f * fmaf( e2z, qz, fmaf( e2x, qx, e2y * qy ) );
+	if (t < 0 || t > tmax) return 0;
+	*to = t, *uo = u, *vo = v;
+	return 1;
+}
+
+/* SLAB_TEST_TWO_NODES :3202-3220 for one child; returns tmin or BVH_FAR */
+static inline float slab( const orc_node* c, const float* rD, const float* ro, const int* pos, float tmax )
+{
+	const float* lo = &c->minx, * hi = &c->maxx;
+	const float tx1 = fmaf( pos[0] ? lo[0] : hi[0], rD[0], -ro[0] ), tx2 = fmaf( pos[0] ? hi[0] : lo[0], rD[0], -ro[0] );
+	const float ty1 = fmaf( pos[1] ? lo[1] : hi[1], rD[1], -ro[1] ), ty2 = fmaf( pos[1] ? hi[1] : lo[1], rD[1], -ro[1] );
+	const float tz1 = fmaf( pos[2] ? lo[2] : hi[2], rD[2], -ro[2] ), tz2 = fmaf( pos[2] ? hi[2] : lo[2], rD[2], -ro[2] );
+	const float tmin = fmaxf_( fmaxf_( tx1, ty1 ), fmaxf_( tz1, 0.0f ) );
+	const float tmx = fminf_( fminf_( tx2, ty2 ), fminf_( tz2, tmax ) );
+	return tmx >= tmin ? tmin : BVH_FAR;
+}
+
+static int intersect1( const orc_node* nodes, const uint32_t* primIdx, const float* verts, orc_ray* ray, int anyhit )
+{
+	const orc_node* node = &nodes[0], * stack[256];
+	uint32_t stackPtr = 0;
+	const int pos[3] = { ray->D[0] >= 0, ray->D[1] >= 0, ray->D[2] >= 0 };
+	const float ro[3] = { ray->O[0] * ray->rD[0], ray->O[1] * ray->rD[1], ray->O[2] * ray->rD[2] };
+	while (1)
+	{
+		if (node->triCount > 0)
+		{
+			for (uint32_t i = 0; i < node->triCount; i++)
+			{
+				const uint32_t pi = primIdx[node->leftFirst + i];
+				const float* v0 = verts + (size_t)pi * 12;
+				float t, u, v;
+				if (orc_tri_test( ray->O, ray->D, v0, v0 + 4, v0 + 8, ray->t, &t, &u, &v ))
+				{
+					if (anyhit) return 1;
+					ray->t = t, ray->u = u, ray->v = v, ray->prim = pi;
+				}
+			}
+			if (stackPtr == 0) break; else node = stack[--stackPtr];
+			continue;
+		}
+		const orc_node* child1 = &nodes[node->leftFirst], * child2 = &nodes[node->leftFirst + 1];
+		float dist1 = slab( child1, ray->rD, ro, pos, ray->t ), dist2 = slab( child2, ray->rD, ro, pos, ray->t );
+		if (dist1 > dist2) { float t = dist1; dist1 = dist2, dist2 = t; const orc_node* c = child1; child1 = child2, child2 = c; }
+		if (dist1 == BVH_FAR) { if (stackPtr == 0) break; else node = stack[--stackPtr]; }
+		else { node = child1; if (dist2 != BVH_FAR) stack[stackPtr++] = child2; }
+	}
+	return 0;
+}
+
+/* worker pool: chunks of 4096 rays (a multiple of 32, so occlusion words never straddle) off an atomic counter */
+typedef struct { const orc_node* nodes; const uint32_t* primIdx; const float* verts; orc_ray* rays; uint64_t n; uint32_t* bits; uint64_t next; } orc_job;
+#define ORC_CHUNK 4096
+static void* orc_worker( void* arg )
+{
+	orc_job* j = (orc_job*)arg;
+	for (;;)
+	{
+		const uint64_t s = __atomic_fetch_add( &j->next, ORC_CHUNK, __ATOMIC_RELAXED );
+		if (s >= j->n) break;
+		const uint64_t e = s + ORC_CHUNK < j->n ? s + ORC_CHUNK : j->n;
+		if (!j->bits) for (uint64_t i = s; i < e; i++) intersect1( j->nodes, j->primIdx, j->verts, &j->rays[i], 0 );
+		else for (uint64_t w = s / 32; w * 32 < e; w++)
+		{
+			uint32_t m = 0;
+			for (int b = 0; b < 32 && w * 32 + b < e; b++)
+			{
+				orc_ray tmp = j->rays[w * 32 + b];
+				if (intersect1( j->nodes, j->primIdx, j->verts, &tmp, 1 )) m |= 1u << b;
+			}
+			j->bits[w] = m;
+		}
+	}
+	return 0;
+}
+static void orc_run( orc_job* j, int threads )
+{
+	if (threads <= 0) threads = (int)sysconf( _SC_NPROCESSORS_ONLN );
+	if (threads > 512) threads = 512;
+	if (threads <= 1 || j->n <= ORC_CHUNK) { orc_worker( j ); return; }
+	pthread_t tid[512];
+	for (int t = 0; t < threads; t++) pthread_create( &tid[t], 0, orc_worker, j );
+	for (int t = 0; t < threads; t++) pthread_join( tid[t], 0 );
+}
+
+void orc_intersect( const orc_node* nodes, const uint32_t* primIdx, const float* verts, void* rays, uint64_t n, int threads )
+{
+	orc_job j = { nodes, primIdx, verts, (orc_ray*)rays, n, 0, 0 };
+	orc_run( &j, threads );
+}
+
+void orc_occluded( const orc_node* nodes, const uint32_t* primIdx, const float* verts, const void* rays, uint64_t n, uint32_t* bits, int threads )
+{
+	orc_job j = { nodes, primIdx, verts, (orc_ray*)rays, n, bits, 0 };
+	orc_run( &j, threads );
+}
+
+/* BVH_GPU::ConvertFrom :4612-4655 */
+uint32_t orc_to_bvh_gpu( const orc_node* nodes, orc_node_gpu* out )
+{
+	uint32_t newNodePtr = 0, nodeIdx = 0, stack[512], stackPtr = 0;
+	while (1)
+	{
+		const orc_node* orig = &nodes[nodeIdx];
+		const uint32_t idx = newNodePtr++;
+		memset( &out[idx], 0, sizeof( orc_node_gpu ) );
+		if (orig->triCount > 0)
+		{
+			out[idx].triCount = orig->triCount, out[idx].firstTri = orig->leftFirst;
+			if (!stackPtr) break;
+			nodeIdx = stack[--stackPtr];
+			const uint32_t parent = stack[--stackPtr];
+			out[parent].right = newNodePtr;
+		}
+		else
+		{
+			const orc_node* l = &nodes[orig->leftFirst], * r = &nodes[orig->leftFirst + 1];
+			memcpy( out[idx].lmin, &l->minx, 12 ), memcpy( out[idx].lmax, &l->maxx, 12 );
+			memcpy( out[idx].rmin, &r->minx, 12 ), memcpy( out[idx].rmax, &r->maxx, 12 );
+			out[idx].left = newNodePtr;
+			stack[stackPtr++] = idx, stack[stackPtr++] = orig->leftFirst + 1;
+			nodeIdx = orig->leftFirst;
+		}
+	}
+	return newNodePtr;
+}
+
+/* BVH::SAHCost :1889-1898 (quality metric; recursion as the reference) */
+static float sah_rec( const orc_node* nodes, uint32_t i, float c_trav, float c_int )
+{
+	const orc_node* n = &nodes[i];
+	const float sa = half_area( n->maxx - n->minx, n->maxy - n->miny, n->maxz - n->minz );
+	if (n->triCount > 0) return c_int * sa * n->triCount;
+	return c_trav * sa + sah_rec( nodes, n->leftFirst, c_trav, c_int ) + sah_rec( nodes, n->leftFirst + 1, c_trav, c_int );
+}
+float orc_sah_cost( const orc_node* nodes, uint32_t nodeIdx, float c_trav, float c_int )
+{
+	const orc_node* n = &nodes[nodeIdx];
+	const float cost = sah_rec( nodes, nodeIdx, c_trav, c_int );
+	return nodeIdx == 0 ? cost / half_area( n->maxx - n->minx, n->maxy - n->miny, n->maxz - n->minz ) : cost;
+}

@@ -1,0 +1,45 @@
+/* oracle/tbvh_oracle.h - plain-C CPU restatement of the tinybvh hot path (the "port" oracle).
+ *
+ * TEST INFRASTRUCTURE ONLY.  Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+ * --impl reference arms may load this library; the product (tinybvh_b200/) never does.
+ *
+ * Parity status: PINNED - tests/test_oracle_pin.py checks every function here bit-for-bit against the
+ * unmodified reference compiled into oracle/_ref (oracle/ref_wrap.cpp) and against the committed golden
+ * vectors under tests/golden/ that were produced by that build (tools/make_golden.py).
+ *
+ * All file:line citations are /root/reference/tiny_bvh.h.
+ */
+#ifndef TBVH_ORACLE_H
+#define TBVH_ORACLE_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct { float minx, miny, minz; uint32_t leftFirst; float maxx, maxy, maxz; uint32_t triCount; } orc_node;   /* BVH::BVHNode :861-869 */
+typedef struct { float lmin[3]; uint32_t left; float lmax[3]; uint32_t right; float rmin[3]; uint32_t triCount; float rmax[3]; uint32_t firstTri; } orc_node_gpu; /* BVH_GPU::BVHNode :1095-1105 */
+
+/* BVH::PrepareBuild (:2261) + BVH::Build(nodeIdx,depth) (:2332), single-threaded numbering.
+ * verts: primCount*3 float4; nodes: room for 2*primCount; primIdx: room for primCount. Returns usedNodes. */
+uint32_t orc_build( const float* verts, uint32_t primCount, orc_node* nodes, uint32_t* primIdx, float c_trav, float c_int );
+
+/* BVH::Intersect (:3222,:3247) / BVH::IsOccluded (:3382,:3407) over 128-byte host Ray records, in place.
+ * threads<=0 -> all cores (OpenMP). */
+void orc_intersect( const orc_node* nodes, const uint32_t* primIdx, const float* verts, void* rays, uint64_t n, int threads );
+void orc_occluded( const orc_node* nodes, const uint32_t* primIdx, const float* verts, const void* rays, uint64_t n, uint32_t* bits, int threads );
+
+/* One Moeller-Trumbore test in the oracle's arithmetic (MOLLER_TRUMBORE_TEST :1644-1656).
+ * Returns 1 and writes t,u,v when the triangle is accepted for a ray with the given tmax. */
+int orc_tri_test( const float* O, const float* D, const float* v0, const float* v1, const float* v2, float tmax, float* t, float* u, float* v );
+
+/* BVH_GPU::ConvertFrom (:4612): DFS re-layout into 64-byte Aila-Laine nodes. Returns usedNodes. */
+uint32_t orc_to_bvh_gpu( const orc_node* nodes, orc_node_gpu* out );
+
+/* BVH::SAHCost (:1889) */
+float orc_sah_cost( const orc_node* nodes, uint32_t nodeIdx, float c_trav, float c_int );
+
+#ifdef __cplusplus
+}
+#endif
+#endif
