@@ -1,0 +1,124 @@
+/* include/tinybvh_b200.h - the drop-in boundary: a C-ABI over the B200 (sm_100a) engine.
+ *
+ * Plain pointers and sizes only; no torch / C++ types.  Each entry point names the reference interface it
+ * replaces (file:line under the jbikker/tinybvh checkout, v1.6.7).  The C++ shim that keeps tinybvh's class
+ * and method names on top of this ABI is include/tinybvh_b200.hpp; the reference-side binding a maintainer
+ * would add is shown in INTEGRATION.md.
+ *
+ * Conventions
+ *  - every function returns TBVH_OK (0) or a negative TBVH_E_* code; tbvh_last_error() gives the message
+ *    (the reference has no error codes: BVH_FATAL_ERROR prints and exit(1)s, tiny_bvh.h:1617-1620 - the
+ *    shim maps non-zero to that behaviour).
+ *  - there is NO CPU fallback: without a CUDA device every call that touches data fails with TBVH_E_CUDA.
+ *  - `space` says where a caller pointer lives: TBVH_HOST or TBVH_DEVICE (device pointers are plain
+ *    CUdeviceptr values of the context's device, e.g. torch tensor data_ptr()).
+ *  - ray records are the reference's `Ray` (tiny_bvh.h:688-709): O at byte 0, D at 16, rD at 32, hit
+ *    (t,u,v,prim) at 48..63; `stride` is 128 for the host struct, 64 for the packed GPU record
+ *    (traverse.cl:11-17).  hit.t on entry is the ray's maximum distance.
+ */
+#ifndef TINYBVH_B200_H
+#define TINYBVH_B200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TBVH_OK 0
+#define TBVH_E_CUDA -1      /* CUDA runtime / driver error, or no device */
+#define TBVH_E_ARG -2       /* invalid argument */
+#define TBVH_E_STATE -3     /* handle does not hold the requested layout */
+#define TBVH_E_LIMIT -4     /* tree exceeds a device limit (e.g. depth > traversal stack) */
+#define TBVH_E_UNSUPPORTED -5
+
+#define TBVH_HOST 0
+#define TBVH_DEVICE 1
+
+/* layouts a handle can hold (values follow BVHBase::BVHType, tiny_bvh.h:773-793) */
+#define TBVH_LAYOUT_BVH 1      /* Wald 32-byte nodes, BVH::BVHNode tiny_bvh.h:861-869 */
+#define TBVH_LAYOUT_BVH_GPU 5  /* Aila-Laine 64-byte nodes, BVH_GPU::BVHNode tiny_bvh.h:1095-1105 */
+#define TBVH_LAYOUT_CWBVH 10   /* 80-byte compressed wide nodes + 48-byte triangles, tiny_bvh.h:1356-1359 */
+
+typedef struct tbvh_ctx_t* tbvh_ctx;   /* one per CUDA device */
+typedef struct tbvh_bvh_t* tbvh_bvh;   /* one acceleration structure (any subset of the layouts) */
+
+typedef struct tbvh_info
+{
+	uint32_t prim_count;     /* BVHBase::triCount */
+	uint32_t idx_count;      /* BVHBase::idxCount */
+	uint32_t used_nodes;     /* BVH::usedNodes (32-byte nodes, node 1 unused) */
+	uint32_t used_nodes_gpu; /* BVH_GPU::usedNodes (64-byte nodes) */
+	uint32_t used_blocks;    /* BVH8_CWBVH::usedBlocks (16-byte blocks; nodes = used_blocks/5) */
+	uint32_t cwbvh_tri_count;/* BVH8_CWBVH triangle records (48 bytes each) */
+	uint32_t max_depth;      /* depth of the BVH2 (root = 0) */
+	uint32_t layouts;        /* bit (1<<TBVH_LAYOUT_*) per resident layout */
+	float aabb_min[3], aabb_max[3]; /* BVHBase::aabbMin / aabbMax */
+	double build_ms;         /* device time of the last tbvh_build on this handle */
+} tbvh_info;
+
+/* ---- context ---------------------------------------------------------------------------------------- */
+int tbvh_ctx_create( int device, tbvh_ctx* out );
+int tbvh_ctx_destroy( tbvh_ctx ctx );
+const char* tbvh_last_error( void );
+int tbvh_device_count( void );
+/* pinned host memory for ray buffers (replaces tinybvh::malloc64 / BVHContext::malloc for rays, tiny_bvh.h:261-292, 763-768) */
+int tbvh_host_alloc( size_t bytes, void** out );
+int tbvh_host_free( void* p );
+int tbvh_host_register( void* p, size_t bytes );
+int tbvh_host_unregister( void* p );
+
+/* ---- acceleration structure --------------------------------------------------------------------------- */
+int tbvh_bvh_create( tbvh_ctx ctx, tbvh_bvh* out );
+int tbvh_bvh_destroy( tbvh_bvh bvh );
+int tbvh_bvh_info( tbvh_bvh bvh, tbvh_info* out );
+
+/* BVH::Build( const bvhvec4*, primCount ) tiny_bvh.h:2124 / Build( bvhvec4slice ) :2131 - binned SAH on the GPU.
+ * verts: prim_count*3 vertices, `stride` bytes apart (16 for bvhvec4), xyz used.  The engine copies them
+ * (the reference keeps a pointer: "we're not copying this data").  c_trav / c_int = BVHBase::c_trav, c_int. */
+int tbvh_build( tbvh_bvh bvh, const void* verts, uint32_t stride, uint32_t prim_count, int space, float c_trav, float c_int );
+
+/* consume a tree built elsewhere, in the reference's own layouts (the public members bvhNode / primIdx /
+ * verts of tiny_bvh.h:952-964, BVH_GPU::bvhNode :1124, BVH8_CWBVH::bvh8Data / bvh8Tris :1356-1357) */
+int tbvh_upload_bvh( tbvh_bvh bvh, const void* nodes32, uint32_t used_nodes, const uint32_t* prim_idx, uint32_t idx_count,
+	const void* verts, uint32_t stride, uint32_t prim_count, int space );
+int tbvh_upload_bvh_gpu( tbvh_bvh bvh, const void* nodes64, uint32_t used_nodes, const uint32_t* prim_idx, uint32_t idx_count,
+	const void* verts, uint32_t stride, uint32_t prim_count, int space );
+int tbvh_upload_cwbvh( tbvh_bvh bvh, const void* bvh8_data, uint32_t used_blocks, const void* bvh8_tris, uint32_t tri_count, int space );
+
+/* layout conversion on the device: BVH_GPU::ConvertFrom tiny_bvh.h:4612; BVH8_CWBVH::Build's chain
+ * Compact :3733 + SplitLeafs(3) :1988 + MBVH<8>::ConvertFrom :4975 + BVH8_CWBVH::ConvertFrom :5884 */
+int tbvh_convert( tbvh_bvh bvh, int to_layout );
+
+/* read a layout back in the reference's format so SAHCost / Save / ConvertFrom / the CPU traversals can use a
+ * GPU-built tree.  Buffers are sized from tbvh_bvh_info. */
+int tbvh_download_bvh( tbvh_bvh bvh, void* nodes32, uint32_t* prim_idx, int space );
+int tbvh_download_bvh_gpu( tbvh_bvh bvh, void* nodes64, int space );
+int tbvh_download_cwbvh( tbvh_bvh bvh, void* bvh8_data, void* bvh8_tris, int space );
+
+/* ---- traversal ------------------------------------------------------------------------------------------ */
+/* BVH::Intersect( Ray& ) tiny_bvh.h:3222 / BVH_GPU::Intersect :4657 / BVH8_CWBVH::Intersect :7046 and the OpenCL
+ * batch kernels batch_ailalaine (traverse_bvh2.cl:209) / batch_cwbvh (traverse_cwbvh.cl:554) for a whole batch:
+ * host records, in place - copies bytes 0..63 in, writes t,u,v,prim back to bytes 48..63 of every record. */
+int tbvh_intersect( tbvh_bvh bvh, int layout, void* rays, uint32_t stride, uint64_t n );
+/* BVH::IsOccluded( const Ray& ) tiny_bvh.h:3382 / isoccluded_cwbvh (traverse_cwbvh.cl:343) for a batch:
+ * bits[i>>5] bit (i&31) = occluded; (n+31)/32 words are written. */
+int tbvh_occluded( tbvh_bvh bvh, int layout, const void* rays, uint32_t stride, uint64_t n, uint32_t* bits );
+
+/* the same with everything already resident in HBM, asynchronous on `stream` (a cudaStream_t, 0 = default).
+ * hits == NULL writes t,u,v,prim into bytes 48..63 of each record; otherwise 16-byte records to hits[]. */
+int tbvh_intersect_device( tbvh_bvh bvh, int layout, void* d_rays, uint32_t stride, void* d_hits, uint64_t n, void* stream );
+int tbvh_occluded_device( tbvh_bvh bvh, int layout, const void* d_rays, uint32_t stride, uint32_t* d_bits, uint64_t n, void* stream );
+
+/* counters of the last device traversal on this handle when statistics are enabled (debug aid; the reference
+ * returns the per-ray cost from Intersect, tiny_bvh.h:3303): steps = nodes visited, tris = triangle tests. */
+int tbvh_set_stats( tbvh_bvh bvh, int enable );
+int tbvh_get_stats( tbvh_bvh bvh, uint64_t* steps, uint64_t* tris );
+
+/* number of kernels this library has launched since load (bench.py reports it as gpu_launches) */
+uint64_t tbvh_launch_count( void );
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,45 @@
+"""CPU-side checks of the drop-in boundary: the shared library loads and exports every symbol the header declares;
+a data call without a CUDA device fails loudly (no CPU fallback)."""
+import ctypes
+import os
+import re
+
+import pytest
+
+from tinybvh_b200 import _lib, build
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_builds_and_loads():
+    so = build.build()
+    assert os.path.isfile(so)
+    L = ctypes.CDLL(so)
+    assert L is not None
+
+
+def test_every_declared_symbol_is_exported():
+    hdr = open(os.path.join(REPO, "include", "tinybvh_b200.h")).read()
+    declared = set(re.findall(r"\b(tbvh_[a-z0-9_]+)\s*\(", hdr))
+    declared -= {"tbvh_ctx_t", "tbvh_bvh_t"}
+    assert len(declared) >= 20
+    L = ctypes.CDLL(build.build())
+    missing = [s for s in sorted(declared) if not hasattr(L, s)]
+    assert not missing, f"header declares symbols the library does not export: {missing}"
+    # and the Python binding table covers exactly the header
+    assert set(_lib.SYMBOLS) == declared
+
+
+def test_header_cites_reference_lines():
+    hdr = open(os.path.join(REPO, "include", "tinybvh_b200.h")).read()
+    assert hdr.count("tiny_bvh.h:") >= 10
+
+
+def test_no_cpu_fallback_without_device():
+    L = _lib.lib()
+    if L.tbvh_device_count() > 0:
+        pytest.skip("a CUDA device is present")
+    h = ctypes.c_void_p()
+    rc = L.tbvh_ctx_create(0, ctypes.byref(h))
+    assert rc != 0
+    assert b"no CPU fallback" in L.tbvh_last_error() or b"cuda" in L.tbvh_last_error().lower()

@@ -1,0 +1,233 @@
+"""Python mirror of the reference's operator interface for the hot path, over the C-ABI.
+
+Names, argument meaning and error behaviour follow tiny_bvh.h: `BVH.Build(verts, primCount)` (:2124),
+`BVH.Intersect` (:3222) / `IsOccluded` (:3382) - here over whole `Ray` batches (the reference has per-ray calls only;
+its GPU "batch" is a kernel launch, tiny_bvh_speedtest.cpp:1092-1241) -, `BVH_GPU.ConvertFrom` (:4612),
+`BVH8_CWBVH.ConvertFrom` (:5884).  Rays are numpy arrays of the 128-byte host record (rays.RAY_DTYPE) or torch CUDA
+tensors of 64-/128-byte records.  Errors raise TbvhError (the reference prints and exit(1)s, :1617-1620).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import numpy as np
+
+from . import _lib
+from ._lib import LAYOUT_BVH, LAYOUT_BVH_GPU, LAYOUT_CWBVH, HOST, DEVICE, TbvhError, check
+
+NODE32 = np.dtype([("aabbMin", "3f4"), ("leftFirst", "u4"), ("aabbMax", "3f4"), ("triCount", "u4")])
+NODE64 = np.dtype([("lmin", "3f4"), ("left", "u4"), ("lmax", "3f4"), ("right", "u4"),
+                   ("rmin", "3f4"), ("triCount", "u4"), ("rmax", "3f4"), ("firstTri", "u4")])
+
+_contexts = {}
+
+
+def context(device: int = 0):
+    """One engine context per CUDA device (lazily created)."""
+    if device not in _contexts:
+        h = C.c_void_p()
+        check(_lib.lib().tbvh_ctx_create(device, C.byref(h)))
+        _contexts[device] = h
+    return _contexts[device]
+
+
+def device_count() -> int:
+    return _lib.lib().tbvh_device_count()
+
+
+def launch_count() -> int:
+    return int(_lib.lib().tbvh_launch_count())
+
+
+def _np_ptr(a: np.ndarray):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def _is_torch(x) -> bool:
+    return type(x).__module__.startswith("torch")
+
+
+def _verts_arg(verts):
+    """-> (pointer, stride, vertex count, space, keepalive)"""
+    if _is_torch(verts):
+        assert verts.is_cuda and verts.is_contiguous() and verts.dtype.is_floating_point and verts.element_size() == 4
+        v = verts.reshape(-1, 4)
+        return C.c_void_p(v.data_ptr()), 16, v.shape[0], DEVICE, v
+    v = np.ascontiguousarray(verts, np.float32).reshape(-1, 4)
+    return _np_ptr(v), 16, v.shape[0], HOST, v
+
+
+class _Base:
+    layout = LAYOUT_BVH
+
+    def __init__(self, device: int = 0):
+        self.device = device
+        self.ctx = context(device)
+        self.h = C.c_void_p()
+        check(_lib.lib().tbvh_bvh_create(self.ctx, C.byref(self.h)))
+        self.c_trav, self.c_int = 1.0, 1.0  # BVHBase::c_trav / c_int (:819-820)
+
+    def __del__(self):
+        try:
+            if getattr(self, "h", None) and self.h.value:
+                _lib.lib().tbvh_bvh_destroy(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+    # -- info (the reference's public members usedNodes / idxCount / triCount / aabbMin / aabbMax)
+    def info(self) -> _lib.Info:
+        i = _lib.Info()
+        check(_lib.lib().tbvh_bvh_info(self.h, C.byref(i)))
+        return i
+
+    usedNodes = property(lambda s: s.info().used_nodes)
+    idxCount = property(lambda s: s.info().idx_count)
+    triCount = property(lambda s: s.info().prim_count)
+
+    # -- traversal over batches
+    def Intersect(self, rays, hits=None, stream=None):
+        """Closest hit for every ray, in place (t,u,v,prim at bytes 48..63).  numpy -> host path (copies inside);
+        torch CUDA tensor -> device path, asynchronous on `stream` (default: torch's current stream)."""
+        L = _lib.lib()
+        if _is_torch(rays):
+            import torch
+            assert rays.is_cuda and rays.is_contiguous()
+            stride = rays.stride(0) * rays.element_size() if rays.dim() > 1 else None
+            assert stride in (64, 128), "ray tensor must be [n, 64|128 bytes]"
+            st = stream if stream is not None else torch.cuda.current_stream(rays.device).cuda_stream
+            hp = C.c_void_p(hits.data_ptr()) if hits is not None else None
+            check(L.tbvh_intersect_device(self.h, self.layout, C.c_void_p(rays.data_ptr()), stride, hp, rays.shape[0], C.c_void_p(st)))
+            return rays if hits is None else hits
+        assert rays.dtype.itemsize in (64, 128) and rays.flags.c_contiguous
+        check(L.tbvh_intersect(self.h, self.layout, _np_ptr(rays), rays.dtype.itemsize, rays.shape[0]))
+        return rays
+
+    def IsOccluded(self, rays, bits=None, stream=None):
+        """Any hit within [0, ray.hit.t] per ray -> uint32 bit mask, bit (i&31) of word i>>5."""
+        L = _lib.lib()
+        if _is_torch(rays):
+            import torch
+            assert rays.is_cuda and rays.is_contiguous()
+            stride = rays.stride(0) * rays.element_size()
+            n = rays.shape[0]
+            if bits is None:
+                bits = torch.empty((n + 31) // 32, dtype=torch.int32, device=rays.device)
+            st = stream if stream is not None else torch.cuda.current_stream(rays.device).cuda_stream
+            check(L.tbvh_occluded_device(self.h, self.layout, C.c_void_p(rays.data_ptr()), stride, C.c_void_p(bits.data_ptr()), n, C.c_void_p(st)))
+            return bits
+        assert rays.dtype.itemsize in (64, 128) and rays.flags.c_contiguous
+        n = rays.shape[0]
+        if bits is None:
+            bits = np.zeros((n + 31) // 32, np.uint32)
+        check(L.tbvh_occluded(self.h, self.layout, _np_ptr(rays), rays.dtype.itemsize, n, _np_ptr(bits)))
+        return bits
+
+    def set_stats(self, enable: bool):
+        check(_lib.lib().tbvh_set_stats(self.h, int(enable)))
+
+    def get_stats(self):
+        a, b = C.c_uint64(), C.c_uint64()
+        check(_lib.lib().tbvh_get_stats(self.h, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+
+class BVH(_Base):
+    """tinybvh::BVH (tiny_bvh.h:846-985): Wald 32-byte nodes; binned-SAH Build on the GPU."""
+    layout = LAYOUT_BVH
+
+    def Build(self, vertices, primCount: int = 0):
+        p, stride, nv, space, keep = _verts_arg(vertices)
+        n = primCount or nv // 3
+        check(_lib.lib().tbvh_build(self.h, p, stride, n, space, self.c_trav, self.c_int))
+        return self
+
+    def BuildHQ(self, vertices, primCount: int = 0):
+        raise TbvhError("BVH::BuildHQ (SBVH, tiny_bvh.h:2623) is not implemented on the GPU yet; no CPU fallback")
+
+    def upload(self, nodes, primIdx, vertices):
+        """Consume a tree built elsewhere in the reference's BVH layout (bvhNode / primIdx / verts, :952-964)."""
+        p, stride, nv, space, keep = _verts_arg(vertices)
+        nodes = np.ascontiguousarray(nodes)
+        primIdx = np.ascontiguousarray(primIdx, np.uint32)
+        assert nodes.dtype.itemsize == 32
+        check(_lib.lib().tbvh_upload_bvh(self.h, _np_ptr(nodes), nodes.shape[0], _np_ptr(primIdx), primIdx.shape[0], p, stride, nv // 3, space))
+        return self
+
+    def download(self):
+        """-> (bvhNode[usedNodes] as NODE32, primIdx[idxCount]) in the reference layout."""
+        i = self.info()
+        nodes = np.zeros(i.used_nodes, NODE32)
+        idx = np.zeros(i.idx_count, np.uint32)
+        check(_lib.lib().tbvh_download_bvh(self.h, _np_ptr(nodes), _np_ptr(idx), HOST))
+        return nodes, idx
+
+
+class BVH_GPU(_Base):
+    """tinybvh::BVH_GPU (tiny_bvh.h:1092-1127): Aila-Laine 64-byte nodes."""
+    layout = LAYOUT_BVH_GPU
+
+    def Build(self, vertices, primCount: int = 0):
+        p, stride, nv, space, keep = _verts_arg(vertices)
+        check(_lib.lib().tbvh_build(self.h, p, stride, primCount or nv // 3, space, self.c_trav, self.c_int))
+        check(_lib.lib().tbvh_convert(self.h, LAYOUT_BVH_GPU))
+        return self
+
+    def upload(self, nodes, primIdx, vertices):
+        p, stride, nv, space, keep = _verts_arg(vertices)
+        nodes = np.ascontiguousarray(nodes)
+        primIdx = np.ascontiguousarray(primIdx, np.uint32)
+        assert nodes.dtype.itemsize == 64
+        check(_lib.lib().tbvh_upload_bvh_gpu(self.h, _np_ptr(nodes), nodes.shape[0], _np_ptr(primIdx), primIdx.shape[0], p, stride, nv // 3, space))
+        return self
+
+    def download(self):
+        i = self.info()
+        nodes = np.zeros(i.used_nodes_gpu, NODE64)
+        check(_lib.lib().tbvh_download_bvh_gpu(self.h, _np_ptr(nodes), HOST))
+        return nodes
+
+
+class BVH8_CWBVH(_Base):
+    """tinybvh::BVH8_CWBVH (tiny_bvh.h:1334-1362): 80-byte compressed wide nodes + 48-byte triangles."""
+    layout = LAYOUT_CWBVH
+
+    def Build(self, vertices, primCount: int = 0):
+        p, stride, nv, space, keep = _verts_arg(vertices)
+        check(_lib.lib().tbvh_build(self.h, p, stride, primCount or nv // 3, space, self.c_trav, self.c_int))
+        check(_lib.lib().tbvh_convert(self.h, LAYOUT_CWBVH))
+        return self
+
+    def upload(self, bvh8Data, bvh8Tris):
+        """bvh8Data: float32 [usedBlocks,4]; bvh8Tris: float32 [3*triCount,4] (public members :1356-1357)."""
+        d = np.ascontiguousarray(bvh8Data, np.float32).reshape(-1, 4)
+        t = np.ascontiguousarray(bvh8Tris, np.float32).reshape(-1, 4)
+        check(_lib.lib().tbvh_upload_cwbvh(self.h, _np_ptr(d), d.shape[0], _np_ptr(t), t.shape[0] // 3, HOST))
+        return self
+
+    def download(self):
+        i = self.info()
+        d = np.zeros((i.used_blocks, 4), np.float32)
+        t = np.zeros((i.cwbvh_tri_count * 3, 4), np.float32)
+        check(_lib.lib().tbvh_download_cwbvh(self.h, _np_ptr(d), _np_ptr(t), HOST))
+        return d, t
+
+
+def pinned_empty(n: int, dtype) -> np.ndarray:
+    """numpy array in page-locked host memory (tbvh_host_alloc): full-speed DMA for the host path."""
+    dtype = np.dtype(dtype)
+    p = C.c_void_p()
+    check(_lib.lib().tbvh_host_alloc(n * dtype.itemsize, C.byref(p)))
+    buf = (C.c_char * (n * dtype.itemsize)).from_address(p.value)
+    a = np.frombuffer(buf, dtype=dtype, count=n)
+    a.flags.writeable = True
+    _pinned[a.ctypes.data] = p
+    return a
+
+
+_pinned = {}
+
+
+def pinned_free(a: np.ndarray):
+    p = _pinned.pop(a.ctypes.data, None)
+    if p is not None:
+        check(_lib.lib().tbvh_host_free(p))

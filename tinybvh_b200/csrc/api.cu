@@ -1,0 +1,393 @@
+// tinybvh_b200/csrc/api.cu - C-ABI entry points (include/tinybvh_b200.h): contexts, handles, uploads, the host-buffer
+// traversal pipeline.  Kernels live in trace_bvh2.cu / trace_cwbvh.cu / build_sah.cu / convert.cu.
+#include "common.cuh"
+#include <stdarg.h>
+#include <string.h>
+#include <vector>
+#include <new>
+
+static thread_local char g_err[512] = "";
+unsigned long long g_tbvh_launches = 0;
+
+void tbvh_set_error( const char* fmt, ... )
+{
+	va_list ap;
+	va_start( ap, fmt );
+	vsnprintf( g_err, sizeof( g_err ), fmt, ap );
+	va_end( ap );
+}
+
+#define ARG_CHECK( c, msg ) do { if (!(c)) { tbvh_set_error( "%s: %s", __func__, msg ); return TBVH_E_ARG; } } while (0)
+#define TRY( x ) do { int r_ = (x); if (r_ != TBVH_OK) return r_; } while (0)
+
+static const size_t STAGE_RAYS = 1u << 20; // rays per host-path chunk (64 MiB of device records)
+
+extern "C" {
+
+const char* tbvh_last_error( void ) { return g_err; }
+uint64_t tbvh_launch_count( void ) { return g_tbvh_launches; }
+
+int tbvh_device_count( void )
+{
+	int n = 0;
+	if (cudaGetDeviceCount( &n ) != cudaSuccess) { cudaGetLastError(); return 0; }
+	return n;
+}
+
+int tbvh_ctx_create( int device, tbvh_ctx* out )
+{
+	ARG_CHECK( out, "out == NULL" );
+	int n = 0;
+	CUDA_TRY( cudaGetDeviceCount( &n ) );
+	if (device < 0 || device >= n) { tbvh_set_error( "tbvh_ctx_create: device %d of %d - no CUDA device, and there is no CPU fallback", device, n ); return TBVH_E_CUDA; }
+	CUDA_TRY( cudaSetDevice( device ) );
+	tbvh_ctx c = new (std::nothrow) tbvh_ctx_t();
+	ARG_CHECK( c, "out of host memory" );
+	c->device = device;
+	cudaDeviceProp prop;
+	CUDA_TRY( cudaGetDeviceProperties( &prop, device ) );
+	c->sm_count = prop.multiProcessorCount;
+	CUDA_TRY( cudaStreamCreateWithFlags( &c->stream, cudaStreamNonBlocking ) );
+	for (int i = 0; i < 3; i++) CUDA_TRY( cudaStreamCreateWithFlags( &c->copy_streams[i], cudaStreamNonBlocking ) );
+	*out = c;
+	return TBVH_OK;
+}
+
+int tbvh_ctx_destroy( tbvh_ctx c )
+{
+	if (!c) return TBVH_OK;
+	cudaSetDevice( c->device );
+	for (int i = 0; i < 3; i++) { if (c->d_stage[i]) cudaFree( c->d_stage[i] ); if (c->d_stage_bits[i]) cudaFree( c->d_stage_bits[i] ); cudaStreamDestroy( c->copy_streams[i] ); }
+	cudaStreamDestroy( c->stream );
+	delete c;
+	return TBVH_OK;
+}
+
+int tbvh_host_alloc( size_t bytes, void** out ) { ARG_CHECK( out, "out == NULL" ); CUDA_TRY( cudaHostAlloc( out, bytes, cudaHostAllocDefault ) ); return TBVH_OK; }
+int tbvh_host_free( void* p ) { if (p) CUDA_TRY( cudaFreeHost( p ) ); return TBVH_OK; }
+int tbvh_host_register( void* p, size_t bytes ) { CUDA_TRY( cudaHostRegister( p, bytes, cudaHostRegisterDefault ) ); return TBVH_OK; }
+int tbvh_host_unregister( void* p ) { CUDA_TRY( cudaHostUnregister( p ) ); return TBVH_OK; }
+
+int tbvh_bvh_create( tbvh_ctx ctx, tbvh_bvh* out )
+{
+	ARG_CHECK( ctx && out, "NULL argument" );
+	tbvh_bvh b = new (std::nothrow) tbvh_bvh_t();
+	ARG_CHECK( b, "out of host memory" );
+	b->ctx = ctx;
+	CUDA_TRY( cudaSetDevice( ctx->device ) );
+	CUDA_TRY( cudaMalloc( &b->d_stats, 16 ) );
+	CUDA_TRY( cudaMemset( b->d_stats, 0, 16 ) );
+	*out = b;
+	return TBVH_OK;
+}
+
+static void free_layouts( tbvh_bvh b )
+{
+	if (b->d_trav && b->d_trav != b->d_nodes) cudaFree( b->d_trav );
+	void* p[] = { b->d_verts, b->d_nodes, b->d_prim_idx, b->d_leaf_tris, b->d_nodes_gpu, b->d_cw_nodes, b->d_cw_tris };
+	for (void* q : p) if (q) cudaFree( q );
+	b->d_verts = 0, b->d_nodes = 0, b->d_prim_idx = 0, b->d_leaf_tris = 0, b->d_nodes_gpu = 0, b->d_cw_nodes = 0, b->d_cw_tris = 0, b->d_trav = 0;
+	memset( &b->info, 0, sizeof( b->info ) );
+}
+
+int tbvh_bvh_destroy( tbvh_bvh b )
+{
+	if (!b) return TBVH_OK;
+	cudaSetDevice( b->ctx->device );
+	free_layouts( b );
+	if (b->d_stats) cudaFree( b->d_stats );
+	delete b;
+	return TBVH_OK;
+}
+
+int tbvh_bvh_info( tbvh_bvh b, tbvh_info* out ) { ARG_CHECK( b && out, "NULL argument" ); *out = b->info; return TBVH_OK; }
+int tbvh_set_stats( tbvh_bvh b, int enable ) { ARG_CHECK( b, "NULL handle" ); b->stats = enable; return TBVH_OK; }
+int tbvh_get_stats( tbvh_bvh b, uint64_t* steps, uint64_t* tris )
+{
+	ARG_CHECK( b, "NULL handle" );
+	unsigned long long h[2];
+	CUDA_TRY( cudaSetDevice( b->ctx->device ) );
+	CUDA_TRY( cudaDeviceSynchronize() );
+	CUDA_TRY( cudaMemcpy( h, b->d_stats, 16, cudaMemcpyDeviceToHost ) );
+	if (steps) *steps = h[0];
+	if (tris) *tris = h[1];
+	return TBVH_OK;
+}
+
+} // extern "C"
+
+// ---- uploads ------------------------------------------------------------------------------------------------
+
+// vertices -> engine-owned float4 array (xyz of each vertex, w copied when the stride holds it)
+static int upload_verts( tbvh_bvh b, const void* verts, uint32_t stride, uint32_t prim_count, int space, cudaStream_t s )
+{
+	ARG_CHECK( verts && stride >= 12 && (stride & 3) == 0 && prim_count > 0, "bad vertex slice" );
+	const size_t nv = (size_t)prim_count * 3;
+	CUDA_TRY( cudaMalloc( &b->d_verts, nv * 16 ) );
+	const cudaMemcpyKind kind = space == TBVH_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+	if (stride == 16) CUDA_TRY( cudaMemcpyAsync( b->d_verts, verts, nv * 16, kind, s ) );
+	else
+	{
+		CUDA_TRY( cudaMemsetAsync( b->d_verts, 0, nv * 16, s ) );
+		CUDA_TRY( cudaMemcpy2DAsync( b->d_verts, 16, verts, stride, stride < 16 ? stride : 16, nv, kind, s ) );
+	}
+	b->info.prim_count = prim_count;
+	return TBVH_OK;
+}
+
+static uint32_t depth_of_bvh( const uint32_t* nodes /* 8 words per node */, uint32_t used_nodes )
+{
+	// iterative DFS over Wald nodes; returns the depth of the deepest node (root = 0)
+	std::vector<uint2> st;
+	st.push_back( make_uint2( 0, 0 ) );
+	uint32_t maxd = 0;
+	while (!st.empty())
+	{
+		const uint2 e = st.back();
+		st.pop_back();
+		if (e.y > maxd) maxd = e.y;
+		const uint32_t* n = nodes + (size_t)e.x * 8;
+		if (n[7] == 0 && n[3] + 1 < used_nodes) { st.push_back( make_uint2( n[3], e.y + 1 ) ); st.push_back( make_uint2( n[3] + 1, e.y + 1 ) ); }
+	}
+	return maxd;
+}
+
+static uint32_t depth_of_bvh_gpu( const uint32_t* nodes /* 16 words per node */, uint32_t used_nodes )
+{
+	std::vector<uint2> st;
+	st.push_back( make_uint2( 0, 0 ) );
+	uint32_t maxd = 0;
+	while (!st.empty())
+	{
+		const uint2 e = st.back();
+		st.pop_back();
+		if (e.y > maxd) maxd = e.y;
+		const uint32_t* n = nodes + (size_t)e.x * 16;
+		if (n[11] == 0 && n[3] < used_nodes && n[7] < used_nodes) { st.push_back( make_uint2( n[3], e.y + 1 ) ); st.push_back( make_uint2( n[7], e.y + 1 ) ); }
+	}
+	return maxd;
+}
+
+extern "C" {
+
+int tbvh_upload_bvh( tbvh_bvh b, const void* nodes32, uint32_t used_nodes, const uint32_t* prim_idx, uint32_t idx_count,
+	const void* verts, uint32_t stride, uint32_t prim_count, int space )
+{
+	ARG_CHECK( b && nodes32 && prim_idx && used_nodes >= 1 && idx_count >= 1, "bad tree arrays" );
+	CUDA_TRY( cudaSetDevice( b->ctx->device ) );
+	cudaStream_t s = b->ctx->stream;
+	free_layouts( b );
+	TRY( upload_verts( b, verts, stride, prim_count, space, s ) );
+	const cudaMemcpyKind kind = space == TBVH_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+	CUDA_TRY( cudaMalloc( &b->d_nodes, (size_t)(used_nodes < 2 ? 2 : used_nodes) * 32 ) );
+	CUDA_TRY( cudaMemcpyAsync( b->d_nodes, nodes32, (size_t)used_nodes * 32, kind, s ) );
+	CUDA_TRY( cudaMalloc( &b->d_prim_idx, (size_t)idx_count * 4 ) );
+	CUDA_TRY( cudaMemcpyAsync( b->d_prim_idx, prim_idx, (size_t)idx_count * 4, kind, s ) );
+	// root record + depth from a host copy of the nodes
+	std::vector<uint32_t> host;
+	const uint32_t* hn = (const uint32_t*)nodes32;
+	if (space == TBVH_DEVICE)
+	{
+		host.resize( (size_t)used_nodes * 8 );
+		CUDA_TRY( cudaMemcpyAsync( host.data(), nodes32, (size_t)used_nodes * 32, cudaMemcpyDeviceToHost, s ) );
+		CUDA_TRY( cudaStreamSynchronize( s ) );
+		hn = host.data();
+	}
+	b->root_ref = hn[3], b->root_count = hn[7];
+	b->info.used_nodes = used_nodes, b->info.idx_count = idx_count;
+	b->info.max_depth = depth_of_bvh( hn, used_nodes );
+	memcpy( b->info.aabb_min, hn, 12 ), memcpy( b->info.aabb_max, hn + 4, 12 );
+	b->d_trav = b->d_nodes;
+	TRY( make_leaf_tris( b, s ) );
+	CUDA_TRY( cudaStreamSynchronize( s ) );
+	b->info.layouts = 1u << TBVH_LAYOUT_BVH;
+	return TBVH_OK;
+}
+
+int tbvh_upload_bvh_gpu( tbvh_bvh b, const void* nodes64, uint32_t used_nodes, const uint32_t* prim_idx, uint32_t idx_count,
+	const void* verts, uint32_t stride, uint32_t prim_count, int space )
+{
+	ARG_CHECK( b && nodes64 && prim_idx && used_nodes >= 1 && idx_count >= 1, "bad tree arrays" );
+	CUDA_TRY( cudaSetDevice( b->ctx->device ) );
+	cudaStream_t s = b->ctx->stream;
+	free_layouts( b );
+	TRY( upload_verts( b, verts, stride, prim_count, space, s ) );
+	const cudaMemcpyKind kind = space == TBVH_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+	CUDA_TRY( cudaMalloc( &b->d_nodes_gpu, (size_t)used_nodes * 64 ) );
+	CUDA_TRY( cudaMemcpyAsync( b->d_nodes_gpu, nodes64, (size_t)used_nodes * 64, kind, s ) );
+	CUDA_TRY( cudaMalloc( &b->d_prim_idx, (size_t)idx_count * 4 ) );
+	CUDA_TRY( cudaMemcpyAsync( b->d_prim_idx, prim_idx, (size_t)idx_count * 4, kind, s ) );
+	std::vector<uint32_t> host;
+	const uint32_t* hn = (const uint32_t*)nodes64;
+	if (space == TBVH_DEVICE)
+	{
+		host.resize( (size_t)used_nodes * 16 );
+		CUDA_TRY( cudaMemcpyAsync( host.data(), nodes64, (size_t)used_nodes * 64, cudaMemcpyDeviceToHost, s ) );
+		CUDA_TRY( cudaStreamSynchronize( s ) );
+		hn = host.data();
+	}
+	b->info.used_nodes_gpu = used_nodes, b->info.idx_count = idx_count;
+	b->info.max_depth = depth_of_bvh_gpu( hn, used_nodes );
+	// root as a child record: a leaf root keeps (firstTri, triCount); an interior root is pair 0 (pairs are indexed by 2*node)
+	if (hn[11] > 0) b->root_ref = hn[15], b->root_count = hn[11]; else b->root_ref = 0, b->root_count = 0;
+	TRY( bvh_gpu_to_bvh( b, used_nodes, s ) );
+	TRY( make_leaf_tris( b, s ) );
+	CUDA_TRY( cudaStreamSynchronize( s ) );
+	b->info.layouts = 1u << TBVH_LAYOUT_BVH_GPU;
+	return TBVH_OK;
+}
+
+int tbvh_upload_cwbvh( tbvh_bvh b, const void* bvh8_data, uint32_t used_blocks, const void* bvh8_tris, uint32_t tri_count, int space )
+{
+	ARG_CHECK( b && bvh8_data && bvh8_tris && used_blocks >= 5 && tri_count >= 1, "bad CWBVH arrays" );
+	CUDA_TRY( cudaSetDevice( b->ctx->device ) );
+	cudaStream_t s = b->ctx->stream;
+	const cudaMemcpyKind kind = space == TBVH_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+	if (b->d_cw_nodes) cudaFree( b->d_cw_nodes );
+	if (b->d_cw_tris) cudaFree( b->d_cw_tris );
+	b->d_cw_nodes = 0, b->d_cw_tris = 0;
+	CUDA_TRY( cudaMalloc( &b->d_cw_nodes, (size_t)used_blocks * 16 ) );
+	CUDA_TRY( cudaMalloc( &b->d_cw_tris, (size_t)tri_count * 48 ) );
+	CUDA_TRY( cudaMemcpyAsync( b->d_cw_nodes, bvh8_data, (size_t)used_blocks * 16, kind, s ) );
+	CUDA_TRY( cudaMemcpyAsync( b->d_cw_tris, bvh8_tris, (size_t)tri_count * 48, kind, s ) );
+	CUDA_TRY( cudaStreamSynchronize( s ) );
+	b->info.used_blocks = used_blocks, b->info.cwbvh_tri_count = tri_count;
+	b->info.layouts |= 1u << TBVH_LAYOUT_CWBVH;
+	return TBVH_OK;
+}
+
+int tbvh_build( tbvh_bvh b, const void* verts, uint32_t stride, uint32_t prim_count, int space, float c_trav, float c_int )
+{
+	ARG_CHECK( b, "NULL handle" );
+	CUDA_TRY( cudaSetDevice( b->ctx->device ) );
+	free_layouts( b );
+	TRY( upload_verts( b, verts, stride, prim_count, space, b->ctx->stream ) );
+	TRY( build_sah_launch( b, c_trav, c_int ) );
+	b->info.layouts = 1u << TBVH_LAYOUT_BVH;
+	return TBVH_OK;
+}
+
+int tbvh_convert( tbvh_bvh b, int to_layout )
+{
+	ARG_CHECK( b, "NULL handle" );
+	CUDA_TRY( cudaSetDevice( b->ctx->device ) );
+	if (!(b->info.layouts & (1u << TBVH_LAYOUT_BVH))) { tbvh_set_error( "tbvh_convert: source layout BVH not resident" ); return TBVH_E_STATE; }
+	if (to_layout == TBVH_LAYOUT_BVH_GPU) { TRY( bvh_to_bvh_gpu( b, b->ctx->stream ) ); b->info.layouts |= 1u << TBVH_LAYOUT_BVH_GPU; return TBVH_OK; }
+	if (to_layout == TBVH_LAYOUT_CWBVH) { TRY( bvh_to_cwbvh( b, b->ctx->stream ) ); b->info.layouts |= 1u << TBVH_LAYOUT_CWBVH; return TBVH_OK; }
+	tbvh_set_error( "tbvh_convert: unsupported target layout %d", to_layout );
+	return TBVH_E_UNSUPPORTED;
+}
+
+static cudaMemcpyKind out_kind( int space ) { return space == TBVH_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost; }
+
+int tbvh_download_bvh( tbvh_bvh b, void* nodes32, uint32_t* prim_idx, int space )
+{
+	ARG_CHECK( b, "NULL handle" );
+	if (!(b->info.layouts & (1u << TBVH_LAYOUT_BVH))) { tbvh_set_error( "layout BVH not resident" ); return TBVH_E_STATE; }
+	CUDA_TRY( cudaSetDevice( b->ctx->device ) );
+	if (nodes32) CUDA_TRY( cudaMemcpy( nodes32, b->d_nodes, (size_t)b->info.used_nodes * 32, out_kind( space ) ) );
+	if (prim_idx) CUDA_TRY( cudaMemcpy( prim_idx, b->d_prim_idx, (size_t)b->info.idx_count * 4, out_kind( space ) ) );
+	return TBVH_OK;
+}
+
+int tbvh_download_bvh_gpu( tbvh_bvh b, void* nodes64, int space )
+{
+	ARG_CHECK( b && nodes64, "NULL argument" );
+	if (!(b->info.layouts & (1u << TBVH_LAYOUT_BVH_GPU)) || !b->d_nodes_gpu) { tbvh_set_error( "layout BVH_GPU not resident" ); return TBVH_E_STATE; }
+	CUDA_TRY( cudaSetDevice( b->ctx->device ) );
+	CUDA_TRY( cudaMemcpy( nodes64, b->d_nodes_gpu, (size_t)b->info.used_nodes_gpu * 64, out_kind( space ) ) );
+	return TBVH_OK;
+}
+
+int tbvh_download_cwbvh( tbvh_bvh b, void* bvh8_data, void* bvh8_tris, int space )
+{
+	ARG_CHECK( b, "NULL handle" );
+	if (!(b->info.layouts & (1u << TBVH_LAYOUT_CWBVH))) { tbvh_set_error( "layout CWBVH not resident" ); return TBVH_E_STATE; }
+	CUDA_TRY( cudaSetDevice( b->ctx->device ) );
+	if (bvh8_data) CUDA_TRY( cudaMemcpy( bvh8_data, b->d_cw_nodes, (size_t)b->info.used_blocks * 16, out_kind( space ) ) );
+	if (bvh8_tris) CUDA_TRY( cudaMemcpy( bvh8_tris, b->d_cw_tris, (size_t)b->info.cwbvh_tri_count * 48, out_kind( space ) ) );
+	return TBVH_OK;
+}
+
+// ---- traversal ------------------------------------------------------------------------------------------------
+
+static int trace_dispatch( tbvh_bvh b, int layout, const void* d_rays, uint32_t stride, void* d_hits, uint32_t hit_stride,
+	uint32_t* d_bits, uint64_t n, bool anyhit, cudaStream_t s )
+{
+	if (layout == TBVH_LAYOUT_BVH || layout == TBVH_LAYOUT_BVH_GPU) return bvh2_trace_launch( b, d_rays, stride, d_hits, hit_stride, d_bits, n, anyhit, s );
+	if (layout == TBVH_LAYOUT_CWBVH) return cwbvh_trace_launch( b, d_rays, stride, d_hits, hit_stride, d_bits, n, anyhit, s );
+	tbvh_set_error( "unknown layout %d", layout );
+	return TBVH_E_ARG;
+}
+
+int tbvh_intersect_device( tbvh_bvh b, int layout, void* d_rays, uint32_t stride, void* d_hits, uint64_t n, void* stream )
+{
+	ARG_CHECK( b && d_rays && stride >= 64 && (stride & 15) == 0, "bad ray buffer" );
+	CUDA_TRY( cudaSetDevice( b->ctx->device ) );
+	if (d_hits) return trace_dispatch( b, layout, d_rays, stride, d_hits, 16, 0, n, false, (cudaStream_t)stream );
+	return trace_dispatch( b, layout, d_rays, stride, (char*)d_rays + 48, stride, 0, n, false, (cudaStream_t)stream );
+}
+
+int tbvh_occluded_device( tbvh_bvh b, int layout, const void* d_rays, uint32_t stride, uint32_t* d_bits, uint64_t n, void* stream )
+{
+	ARG_CHECK( b && d_rays && d_bits && stride >= 64 && (stride & 15) == 0, "bad ray buffer" );
+	CUDA_TRY( cudaSetDevice( b->ctx->device ) );
+	return trace_dispatch( b, layout, d_rays, stride, 0, 0, d_bits, n, true, (cudaStream_t)stream );
+}
+
+static int ensure_stage( tbvh_ctx c )
+{
+	if (c->stage_rays) return TBVH_OK;
+	for (int i = 0; i < 3; i++)
+	{
+		CUDA_TRY( cudaMalloc( &c->d_stage[i], STAGE_RAYS * 64 ) );
+		CUDA_TRY( cudaMalloc( &c->d_stage_bits[i], STAGE_RAYS / 8 ) );
+	}
+	c->stage_rays = STAGE_RAYS;
+	return TBVH_OK;
+}
+
+// Host-buffer path: chunks of 2^20 rays round-robin over three streams so the H2D copy of chunk k+1, the kernel of
+// chunk k and the D2H copy of chunk k-1 overlap.  Only bytes 0..63 of each record cross PCIe inbound and only the
+// 16-byte hit (or 1 bit) outbound.
+int tbvh_intersect( tbvh_bvh b, int layout, void* rays, uint32_t stride, uint64_t n )
+{
+	ARG_CHECK( b && rays && stride >= 64, "bad ray buffer" );
+	CUDA_TRY( cudaSetDevice( b->ctx->device ) );
+	tbvh_ctx c = b->ctx;
+	TRY( ensure_stage( c ) );
+	int k = 0;
+	for (uint64_t off = 0; off < n; off += c->stage_rays, k = (k + 1) % 3)
+	{
+		const uint64_t cnt = n - off < c->stage_rays ? n - off : c->stage_rays;
+		cudaStream_t s = c->copy_streams[k];
+		char* h = (char*)rays + off * stride;
+		CUDA_TRY( cudaMemcpy2DAsync( c->d_stage[k], 64, h, stride, 64, cnt, cudaMemcpyHostToDevice, s ) );
+		TRY( trace_dispatch( b, layout, c->d_stage[k], 64, (char*)c->d_stage[k] + 48, 64, 0, cnt, false, s ) );
+		CUDA_TRY( cudaMemcpy2DAsync( h + 48, stride, (char*)c->d_stage[k] + 48, 64, 16, cnt, cudaMemcpyDeviceToHost, s ) );
+	}
+	for (int i = 0; i < 3; i++) CUDA_TRY( cudaStreamSynchronize( c->copy_streams[i] ) );
+	return TBVH_OK;
+}
+
+int tbvh_occluded( tbvh_bvh b, int layout, const void* rays, uint32_t stride, uint64_t n, uint32_t* bits )
+{
+	ARG_CHECK( b && rays && bits && stride >= 64, "bad ray buffer" );
+	CUDA_TRY( cudaSetDevice( b->ctx->device ) );
+	tbvh_ctx c = b->ctx;
+	TRY( ensure_stage( c ) );
+	int k = 0;
+	for (uint64_t off = 0; off < n; off += c->stage_rays, k = (k + 1) % 3)
+	{
+		const uint64_t cnt = n - off < c->stage_rays ? n - off : c->stage_rays;
+		cudaStream_t s = c->copy_streams[k];
+		const char* h = (const char*)rays + off * stride;
+		CUDA_TRY( cudaMemcpy2DAsync( c->d_stage[k], 64, h, stride, 64, cnt, cudaMemcpyHostToDevice, s ) );
+		TRY( trace_dispatch( b, layout, c->d_stage[k], 64, 0, 0, (uint32_t*)c->d_stage_bits[k], cnt, true, s ) );
+		CUDA_TRY( cudaMemcpyAsync( bits + off / 32, c->d_stage_bits[k], ((cnt + 31) / 32) * 4, cudaMemcpyDeviceToHost, s ) );
+	}
+	for (int i = 0; i < 3; i++) CUDA_TRY( cudaStreamSynchronize( c->copy_streams[i] ) );
+	return TBVH_OK;
+}
+
+} // extern "C"

@@ -1,0 +1,61 @@
+#!/usr/bin/env python
+"""Generate tests/golden/*.npz from the UNMODIFIED reference compiled in oracle/_ref (needs /root/reference at build
+time; run in the build container).  Each file holds a small triangle soup, ray sets, and what the reference's
+BVH::Build + BVH::Intersect / IsOccluded produce for them: the node array, primIdx, per-ray (t,u,v,prim) and
+occlusion bits.  The restatement (oracle/tbvh_oracle.c) and the CUDA engine are both tested against these."""
+import os
+import sys
+
+import numpy as np
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, REPO)
+from tinybvh_b200 import rays as R, scenes  # noqa: E402
+from oracle import refpy  # noqa: E402
+
+OUT = os.path.join(REPO, "tests", "golden")
+
+
+def ray_core(r):
+    return {"O": r["O"].copy(), "D": r["D"].copy(), "rD": r["rD"].copy(), "tmax": r["t"].copy()}
+
+
+def make(name, verts, res):
+    ref = refpy.RefBVH(verts, mode=0, threaded=False)
+    lo, hi = scenes.scene_bounds(verts)
+    prim = np.concatenate([R.primary_rays(*R.bounds_camera(lo, hi, k), res, res, 4) for k in ("outside", "inside")])
+    d = {"verts": verts, "nodes": ref.nodes.copy().view(np.uint32).reshape(-1, 8), "prim_idx": ref.prim_idx.copy()}
+    for k, v in ray_core(prim).items():
+        d["primary_" + k] = v
+    ref.intersect(prim, threads=1)
+    d["primary_hit"] = np.stack([prim["t"].view(np.uint32), prim["u"].view(np.uint32), prim["v"].view(np.uint32), prim["prim"]], 1)
+    eps = float((hi - lo).max() * 5e-7)
+    light = (lo + hi) * 0.5 + np.array([0, (hi - lo)[1] * 0.45, 0], np.float32)
+    sh = R.shadow_rays(prim, light, eps)
+    for k, v in ray_core(sh).items():
+        d["shadow_" + k] = v
+    d["shadow_bits"] = ref.occluded(sh, threads=1)
+    df = R.diffuse_rays(prim, verts)
+    for k, v in ray_core(df).items():
+        d["diffuse_" + k] = v
+    ref.intersect(df, threads=1)
+    d["diffuse_hit"] = np.stack([df["t"].view(np.uint32), df["u"].view(np.uint32), df["v"].view(np.uint32), df["prim"]], 1)
+    g = refpy.RefBVHGPU(ref)
+    d["nodes_gpu"] = g.nodes.copy().view(np.uint32).reshape(-1, 16)
+    os.makedirs(OUT, exist_ok=True)
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **d)
+    print(name, "tris", verts.shape[0] // 3, "nodes", ref.used_nodes, "rays", prim.shape[0],
+          "hits", int((prim["t"] < 1e30).sum()), "occluded", int(np.unpackbits(d["shadow_bits"].view(np.uint8)).sum()))
+
+
+if __name__ == "__main__":
+    make("atrium_3k", scenes.procedural_scene(3000, seed=11), 32)
+    # degenerate inputs: coincident triangles (exact t ties), a flat (zero-extent axis) soup, a single triangle
+    rng = np.random.default_rng(5)
+    base = scenes.procedural_scene(400, seed=3)
+    dup = np.concatenate([base, base[: 150 * 3], base[: 60 * 3]])
+    make("coincident_610", dup, 24)
+    flat = scenes.procedural_scene(500, seed=9)
+    flat[:, 1] = 2.0
+    make("flat_500", flat, 24)
+    make("single_tri", np.array([[0, 0, 0, 0], [1, 0, 0, 0], [0, 1, 0, 0]], np.float32), 16)
