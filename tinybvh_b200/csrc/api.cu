@@ -347,24 +347,67 @@ static int ensure_stage( tbvh_ctx c )
 	return TBVH_OK;
 }
 
-// Host-buffer path: chunks of 2^20 rays round-robin over three streams so the H2D copy of chunk k+1, the kernel of
-// chunk k and the D2H copy of chunk k-1 overlap.  Only bytes 0..63 of each record cross PCIe inbound and only the
-// 16-byte hit (or 1 bit) outbound.
+// Host-buffer path: chunks of 2^20 rays round-robin over three streams so the inbound copy of chunk k+1, the kernel of
+// chunk k and the outbound copy of chunk k-1 overlap.  Only bytes 0..63 of each record cross PCIe inbound and only the
+// 16-byte hit (or 1 bit) outbound.  Page-locked buffers (tbvh_host_alloc / tbvh_host_register) are read and written by
+// copy kernels straight through their device mapping (64 B per ray = one coalesced request per 4 lanes), which beats
+// the copy engine's 2D mode on 64-byte rows; pageable buffers fall back to cudaMemcpy2DAsync.
+__global__ void __launch_bounds__( 256 ) k_gather_rays( const float4* __restrict__ src, const uint32_t stride_f4, float4* __restrict__ dst, const uint64_t n )
+{
+	const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x, r = t >> 2;
+	if (r < n) dst[t] = src[r * stride_f4 + (t & 3)];
+}
+
+__global__ void __launch_bounds__( 256 ) k_scatter_hits( const float4* __restrict__ src, float4* __restrict__ dst, const uint32_t stride_f4, const uint64_t n )
+{
+	const uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (r < n) dst[r * stride_f4 + 3] = src[r * 4 + 3];
+}
+
+// device alias of a page-locked host pointer, or NULL when the memory is pageable
+static void* mapped_alias( const void* host )
+{
+	cudaPointerAttributes a;
+	if (cudaPointerGetAttributes( &a, host ) != cudaSuccess) { cudaGetLastError(); return 0; }
+	if (a.type != cudaMemoryTypeHost || !a.devicePointer) return 0;
+	return a.devicePointer;
+}
+
+static int stage_in( tbvh_ctx c, int k, const char* h, const char* h_dev, uint32_t stride, uint64_t cnt, cudaStream_t s )
+{
+	if (h_dev && (stride & 15) == 0)
+	{
+		const uint64_t threads = cnt * 4;
+		k_gather_rays<<<(uint32_t)((threads + 255) / 256), 256, 0, s>>>( (const float4*)h_dev, stride / 16, (float4*)c->d_stage[k], cnt );
+		LAUNCHED();
+		return TBVH_OK;
+	}
+	CUDA_TRY( cudaMemcpy2DAsync( c->d_stage[k], 64, h, stride, 64, cnt, cudaMemcpyHostToDevice, s ) );
+	return TBVH_OK;
+}
+
 int tbvh_intersect( tbvh_bvh b, int layout, void* rays, uint32_t stride, uint64_t n )
 {
 	ARG_CHECK( b && rays && stride >= 64, "bad ray buffer" );
 	CUDA_TRY( cudaSetDevice( b->ctx->device ) );
 	tbvh_ctx c = b->ctx;
 	TRY( ensure_stage( c ) );
+	char* dev_alias = (char*)mapped_alias( rays );
 	int k = 0;
 	for (uint64_t off = 0; off < n; off += c->stage_rays, k = (k + 1) % 3)
 	{
 		const uint64_t cnt = n - off < c->stage_rays ? n - off : c->stage_rays;
 		cudaStream_t s = c->copy_streams[k];
 		char* h = (char*)rays + off * stride;
-		CUDA_TRY( cudaMemcpy2DAsync( c->d_stage[k], 64, h, stride, 64, cnt, cudaMemcpyHostToDevice, s ) );
+		char* hd = dev_alias ? dev_alias + off * stride : 0;
+		TRY( stage_in( c, k, h, hd, stride, cnt, s ) );
 		TRY( trace_dispatch( b, layout, c->d_stage[k], 64, (char*)c->d_stage[k] + 48, 64, 0, cnt, false, s ) );
-		CUDA_TRY( cudaMemcpy2DAsync( h + 48, stride, (char*)c->d_stage[k] + 48, 64, 16, cnt, cudaMemcpyDeviceToHost, s ) );
+		if (hd && (stride & 15) == 0)
+		{
+			k_scatter_hits<<<(uint32_t)((cnt + 255) / 256), 256, 0, s>>>( (const float4*)c->d_stage[k], (float4*)hd, stride / 16, cnt );
+			LAUNCHED();
+		}
+		else CUDA_TRY( cudaMemcpy2DAsync( h + 48, stride, (char*)c->d_stage[k] + 48, 64, 16, cnt, cudaMemcpyDeviceToHost, s ) );
 	}
 	for (int i = 0; i < 3; i++) CUDA_TRY( cudaStreamSynchronize( c->copy_streams[i] ) );
 	return TBVH_OK;
@@ -376,13 +419,14 @@ int tbvh_occluded( tbvh_bvh b, int layout, const void* rays, uint32_t stride, ui
 	CUDA_TRY( cudaSetDevice( b->ctx->device ) );
 	tbvh_ctx c = b->ctx;
 	TRY( ensure_stage( c ) );
+	const char* dev_alias = (const char*)mapped_alias( rays );
 	int k = 0;
 	for (uint64_t off = 0; off < n; off += c->stage_rays, k = (k + 1) % 3)
 	{
 		const uint64_t cnt = n - off < c->stage_rays ? n - off : c->stage_rays;
 		cudaStream_t s = c->copy_streams[k];
 		const char* h = (const char*)rays + off * stride;
-		CUDA_TRY( cudaMemcpy2DAsync( c->d_stage[k], 64, h, stride, 64, cnt, cudaMemcpyHostToDevice, s ) );
+		TRY( stage_in( c, k, h, dev_alias ? dev_alias + off * stride : 0, stride, cnt, s ) );
 		TRY( trace_dispatch( b, layout, c->d_stage[k], 64, 0, 0, (uint32_t*)c->d_stage_bits[k], cnt, true, s ) );
 		CUDA_TRY( cudaMemcpyAsync( bits + off / 32, c->d_stage_bits[k], ((cnt + 31) / 32) * 4, cudaMemcpyDeviceToHost, s ) );
 	}

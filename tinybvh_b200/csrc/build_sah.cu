@@ -671,7 +671,7 @@ __global__ void k_relayout( BuildArgs A, const uint32_t tmp_count, const uint32_
 
 // ---------------------------------------------------------------------------------------------- host driver
 
-static int exclusive_scan( const uint32_t* in, uint32_t* out, uint32_t* tile_sum, uint32_t n, cudaStream_t s )
+int exclusive_scan( const uint32_t* in, uint32_t* out, uint32_t* tile_sum, uint32_t n, cudaStream_t s )
 {
 	const uint32_t tiles = (n + SCAN_TILE - 1) / SCAN_TILE;
 	k_scan_tiles<<<tiles, 256, 0, s>>>( in, tile_sum, n );
