@@ -63,8 +63,9 @@ def _ptr(a: np.ndarray):
 
 
 def _view(addr, dtype, count):
+    """COPY of `count` records at `addr` (a copy, so the array outlives the reference object that owns the memory)."""
     buf = (C.c_char * (np.dtype(dtype).itemsize * count)).from_address(addr)
-    return np.frombuffer(buf, dtype=dtype, count=count)
+    return np.frombuffer(buf, dtype=dtype, count=count).copy()
 
 
 class _Traceable:

@@ -2,6 +2,7 @@
 // traversal pipeline.  Kernels live in trace_bvh2.cu / trace_cwbvh.cu / build_sah.cu / convert.cu.
 #include "common.cuh"
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 #include <vector>
 #include <new>
@@ -49,6 +50,18 @@ int tbvh_ctx_create( int device, tbvh_ctx* out )
 	c->sm_count = prop.multiProcessorCount;
 	CUDA_TRY( cudaStreamCreateWithFlags( &c->stream, cudaStreamNonBlocking ) );
 	for (int i = 0; i < 3; i++) CUDA_TRY( cudaStreamCreateWithFlags( &c->copy_streams[i], cudaStreamNonBlocking ) );
+	for (int i = 0; i < 4; i++) CUDA_TRY( cudaStreamCreateWithFlags( &c->aux_streams[i], cudaStreamNonBlocking ) );
+	for (int i = 0; i < 3; i++)
+	{
+		CUDA_TRY( cudaEventCreateWithFlags( &c->ev_done[i], cudaEventDisableTiming ) );
+		for (int p = 0; p < 4; p++) CUDA_TRY( cudaEventCreateWithFlags( &c->ev_part[i][p], cudaEventDisableTiming ) );
+	}
+	const char* hp = getenv( "TBVH_HOST_PATH" );
+	c->host_path = hp && !strcmp( hp, "zerocopy" ) ? 1 : 0;
+	const char* sp = getenv( "TBVH_H2D_SPLIT" );
+	c->h2d_split = sp ? atoi( sp ) : 1;
+	if (c->h2d_split < 1) c->h2d_split = 1;
+	if (c->h2d_split > 4) c->h2d_split = 4;
 	*out = c;
 	return TBVH_OK;
 }
@@ -375,11 +388,28 @@ static void* mapped_alias( const void* host )
 
 static int stage_in( tbvh_ctx c, int k, const char* h, const char* h_dev, uint32_t stride, uint64_t cnt, cudaStream_t s )
 {
-	if (h_dev && (stride & 15) == 0)
+	if (c->host_path == 1 && h_dev && (stride & 15) == 0)
 	{
 		const uint64_t threads = cnt * 4;
 		k_gather_rays<<<(uint32_t)((threads + 255) / 256), 256, 0, s>>>( (const float4*)h_dev, stride / 16, (float4*)c->d_stage[k], cnt );
 		LAUNCHED();
+		return TBVH_OK;
+	}
+	if (c->h2d_split > 1 && cnt >= 4096)
+	{
+		// split the rows of this chunk over several streams (copy engines); the chunk's stream waits for all parts, and
+		// the parts wait until the previous user of this staging buffer is done
+		const uint64_t per = (cnt + c->h2d_split - 1) / c->h2d_split;
+		CUDA_TRY( cudaEventRecord( c->ev_done[k], s ) );
+		for (int p = 0; p < c->h2d_split; p++)
+		{
+			const uint64_t a = per * p, e = a + per < cnt ? a + per : cnt;
+			if (a >= e) break;
+			CUDA_TRY( cudaStreamWaitEvent( c->aux_streams[p], c->ev_done[k], 0 ) );
+			CUDA_TRY( cudaMemcpy2DAsync( (char*)c->d_stage[k] + a * 64, 64, h + a * stride, stride, 64, e - a, cudaMemcpyHostToDevice, c->aux_streams[p] ) );
+			CUDA_TRY( cudaEventRecord( c->ev_part[k][p], c->aux_streams[p] ) );
+			CUDA_TRY( cudaStreamWaitEvent( s, c->ev_part[k][p], 0 ) );
+		}
 		return TBVH_OK;
 	}
 	CUDA_TRY( cudaMemcpy2DAsync( c->d_stage[k], 64, h, stride, 64, cnt, cudaMemcpyHostToDevice, s ) );
@@ -402,7 +432,7 @@ int tbvh_intersect( tbvh_bvh b, int layout, void* rays, uint32_t stride, uint64_
 		char* hd = dev_alias ? dev_alias + off * stride : 0;
 		TRY( stage_in( c, k, h, hd, stride, cnt, s ) );
 		TRY( trace_dispatch( b, layout, c->d_stage[k], 64, (char*)c->d_stage[k] + 48, 64, 0, cnt, false, s ) );
-		if (hd && (stride & 15) == 0)
+		if (c->host_path == 1 && hd && (stride & 15) == 0)
 		{
 			k_scatter_hits<<<(uint32_t)((cnt + 255) / 256), 256, 0, s>>>( (const float4*)c->d_stage[k], (float4*)hd, stride / 16, cnt );
 			LAUNCHED();

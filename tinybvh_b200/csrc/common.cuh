@@ -24,6 +24,13 @@ struct tbvh_ctx_t
 	void* d_stage[3] = { 0, 0, 0 };  // staging ray chunks for the host path
 	void* d_stage_bits[3] = { 0, 0, 0 };
 	size_t stage_rays = 0;
+	// host-path tuning (env TBVH_HOST_PATH = copy2d | zerocopy, TBVH_H2D_SPLIT = 1..4): the inbound 2D copy of a chunk
+	// can be split over several streams so more than one copy engine works on it
+	int host_path = 0;               // 0 = copy engine (cudaMemcpy2DAsync), 1 = copy kernels through the pinned mapping
+	int h2d_split = 1;
+	cudaStream_t aux_streams[4] = { 0, 0, 0, 0 };
+	cudaEvent_t ev_done[3] = { 0, 0, 0 };
+	cudaEvent_t ev_part[3][4] = {};
 };
 
 struct tbvh_bvh_t
