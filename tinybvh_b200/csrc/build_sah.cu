@@ -17,6 +17,7 @@
 //   relayout        DFS-preorder numbering from (first, depth) of every interior node: rank = #interior nodes that
 //                   start earlier + position in the chain of nodes starting at the same primitive
 #include "common.cuh"
+#include <stdlib.h>
 #include <string.h>
 #include <vector>
 
@@ -52,6 +53,7 @@ struct BuildArgs
 	SmallRoot* small;
 	Counters* ctr;
 	uint32_t n;
+	uint32_t small_t;        // runtime switch point large phase -> warp subtrees (<= SMALL_T; env TBVH_SMALL_T for tuning)
 	float c_trav, c_int;
 };
 
@@ -211,7 +213,7 @@ __global__ void k_init_root( BuildArgs A )
 	A.tmp_nodes[0] = mn, A.tmp_nodes[1] = mx;
 	A.tmp_nodes[2] = make_float4( 0, 0, 0, 0 ), A.tmp_nodes[3] = make_float4( 0, 0, 0, 0 ); // node 1 stays unused (:2285)
 	A.node_first[0] = 0, A.node_depth[0] = 0, A.node_first[1] = 0, A.node_depth[1] = 0;
-	if (A.n > SMALL_T)
+	if (A.n > A.small_t)
 	{
 		A.lvl[0][0] = LargeNode{ 0, 0, A.n, 0 };
 		A.chunk_start[0] = 0, A.chunk_start[1] = (A.n + CHUNK - 1) / CHUNK;
@@ -281,7 +283,7 @@ __global__ void __launch_bounds__( CHUNK ) k_bin( BuildArgs A, const LargeNode* 
 // append the two children of a split node: bigger than SMALL_T -> next level's list, else -> warp-built subtree
 __device__ __forceinline__ void emit_child( BuildArgs& A, LargeNode* next, const uint32_t tmp, const uint32_t first, const uint32_t count, const uint32_t depth, const uint32_t out_buf )
 {
-	if (count > SMALL_T) next[atomicAdd( &A.ctr->next_large, 1u )] = LargeNode{ tmp, first, count, depth };
+	if (count > A.small_t) next[atomicAdd( &A.ctr->next_large, 1u )] = LargeNode{ tmp, first, count, depth };
 	else A.small[atomicAdd( &A.ctr->small_roots, 1u )] = SmallRoot{ tmp, first, count, depth | (out_buf << 16) };
 }
 
@@ -692,7 +694,12 @@ int build_sah_launch( tbvh_bvh b, float c_trav, float c_int )
 	std::vector<void*> scratch;
 	BuildArgs A = {};
 	A.verts = b->d_verts, A.n = n, A.c_trav = c_trav, A.c_int = c_int;
-	const size_t max_nodes = (size_t)2 * n + 2, max_large = n / SMALL_T + 2;
+	{
+		const char* e = getenv( "TBVH_SMALL_T" );
+		const int t = e ? atoi( e ) : SMALL_T;
+		A.small_t = (uint32_t)(t < 8 ? 8 : t > SMALL_T ? SMALL_T : t);
+	}
+	const size_t max_nodes = (size_t)2 * n + 2, max_large = n / A.small_t + 2;
 	int rc = TBVH_OK;
 	uint32_t* tile_sum = 0;
 	Counters* h_ctr = 0;
@@ -720,7 +727,7 @@ int build_sah_launch( tbvh_bvh b, float c_trav, float c_int )
 		k_init_counters<<<1, 1, 0, s>>>( A ); LAUNCHED();
 		k_fragments<<<(n + 255) / 256, 256, 0, s>>>( A ); LAUNCHED();
 		k_init_root<<<1, 256, 0, s>>>( A ); LAUNCHED();
-		uint32_t num = n > SMALL_T ? 1 : 0, chunks = (n + CHUNK - 1) / CHUNK, level = 0;
+		uint32_t num = n > A.small_t ? 1 : 0, chunks = (n + CHUNK - 1) / CHUNK, level = 0;
 		while (num)
 		{
 			const LargeNode* cur = A.lvl[level & 1];

@@ -159,4 +159,4 @@ int bvh_to_bvh_gpu( tbvh_bvh b, cudaStream_t s )
 	return rc;
 }
 
-int bvh_to_cwbvh( tbvh_bvh b, cudaStream_t s ) { tbvh_set_error( "BVH -> CWBVH conversion not implemented yet" ); return TBVH_E_UNSUPPORTED; }
+// bvh_to_cwbvh lives in convert_cwbvh.cu

@@ -13,11 +13,14 @@
 // record in the leaf-ordered triangle array (3 x float4 per triangle: v0|primIdx, e1, e2), so a leaf costs no node
 // fetch and no primIdx indirection.
 #include "common.cuh"
+#include <stdlib.h>
 
 struct Ray64 { float4 o, d, rd, hit; }; // O|mask, D|instIdx, rD|pad, t,u,v,prim
 
-template <bool ANYHIT, bool STATS>
-__global__ void __launch_bounds__( 128 ) k_trace_bvh2( const float4* __restrict__ nodes, const float4* __restrict__ tris,
+// MINB = minimum resident CTAs per SM asked of ptxas: 10 -> 40 warps / SM (no spills), 12 -> 48 warps (40 registers, a few
+// spilled bytes), 16 -> 64 warps (32 registers).  Selected at run time by TBVH_TRACE_VARIANT (0/1/2) for A/B measurements.
+template <bool ANYHIT, bool STATS, int MINB>
+__global__ void __launch_bounds__( 128, MINB ) k_trace_bvh2( const float4* __restrict__ nodes, const float4* __restrict__ tris,
 	const char* rays, const uint32_t stride, char* hits, const uint32_t hit_stride, // may alias (in-place hits): plain loads
 	uint32_t* __restrict__ bits, const uint64_t n, const uint32_t root_ref, const uint32_t root_count,
 	unsigned long long* __restrict__ stats )
@@ -119,10 +122,14 @@ int bvh2_trace_launch( tbvh_bvh b, const void* d_rays, uint32_t stride, void* d_
 	const uint64_t grid = (n + block - 1) / block;
 	if (grid > 0x7fffffffull) { tbvh_set_error( "ray batch too large for one launch" ); return TBVH_E_ARG; }
 	if (b->stats) CUDA_TRY( cudaMemsetAsync( b->d_stats, 0, 16, s ) );
-	#define LAUNCH( A, S ) k_trace_bvh2<A, S><<<(uint32_t)grid, block, 0, s>>>( b->d_trav, b->d_leaf_tris, (const char*)d_rays, stride, \
+	static int variant = -1;
+	if (variant < 0) { const char* e = getenv( "TBVH_TRACE_VARIANT" ); variant = e ? atoi( e ) : 0; }
+	#define LAUNCH( A, S, M ) k_trace_bvh2<A, S, M><<<(uint32_t)grid, block, 0, s>>>( b->d_trav, b->d_leaf_tris, (const char*)d_rays, stride, \
 		(char*)d_hits, hit_stride, d_bits, n, root_ref, root_count, b->d_stats )
-	if (anyhit) { if (b->stats) LAUNCH( true, true ); else LAUNCH( true, false ); }
-	else { if (b->stats) LAUNCH( false, true ); else LAUNCH( false, false ); }
+	if (b->stats) { if (anyhit) LAUNCH( true, true, 10 ); else LAUNCH( false, true, 10 ); }
+	else if (variant == 1) { if (anyhit) LAUNCH( true, false, 12 ); else LAUNCH( false, false, 12 ); }
+	else if (variant == 2) { if (anyhit) LAUNCH( true, false, 16 ); else LAUNCH( false, false, 16 ); }
+	else { if (anyhit) LAUNCH( true, false, 10 ); else LAUNCH( false, false, 10 ); }
 	#undef LAUNCH
 	LAUNCHED();
 	return TBVH_OK;

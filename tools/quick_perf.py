@@ -31,11 +31,18 @@ def main():
     scene = sys.argv[1] if len(sys.argv) > 1 else "sponza"
     res = int(sys.argv[2]) if len(sys.argv) > 2 else 512
     v, label = scenes.load_scene(scene)
-    t0 = time.time()
-    o = util.oracle_bvh(v)
-    print(f"{label}: {v.shape[0] // 3} tris, oracle build {time.time() - t0:.2f}s, nodes {o.nodes.shape[0]}")
-    e = api.BVH().upload(o.nodes, o.prim_idx, v)
-    print("depth", e.info().max_depth)
+    e = api.BVH().Build(v)
+    e = api.BVH().Build(v)
+    i = e.info()
+    print(f"{label}: {v.shape[0] // 3} tris, GPU build {i.build_ms:.3f} ms ({v.shape[0] // 3 / i.build_ms / 1e3:.1f} Mtris/s), nodes {i.used_nodes}, depth {i.max_depth}, "
+          f"variant {os.environ.get('TBVH_TRACE_VARIANT', '0')} small_t {os.environ.get('TBVH_SMALL_T', '256')}")
+    layout = sys.argv[3] if len(sys.argv) > 3 else "bvh"
+    if layout == "cwbvh":
+        import ctypes as C
+        t0 = time.time()
+        api.check(api._lib.lib().tbvh_convert(e.h, api.LAYOUT_CWBVH))
+        print(f"CWBVH conversion on device: {(time.time() - t0) * 1e3:.1f} ms wall, {e.info().used_blocks // 5} nodes")
+        e.layout = api.LAYOUT_CWBVH
     lo, hi = scenes.scene_bounds(v)
     if scene == "sponza":
         eye, view = R.SPONZA_EYES[0], R.SPONZA_VIEWS[0]
@@ -83,7 +90,8 @@ def main():
     print(f"host path e2e (pinned, 128B stride): {n / (t2 - t1) / 1e6:.1f} Mrays/s (first {n / (t1 - t0) / 1e6:.1f})")
     # CPU reference on a sample
     from oracle import refpy
-    if refpy.available():
+    if refpy.available() and "--cpu" in sys.argv:
+        o = util.oracle_bvh(v)
         smp = prim[: min(n, 1 << 20)].copy()
         t0 = time.time()
         o.intersect(smp, threads=0)
