@@ -1,0 +1,59 @@
+"""Parity at the size BASELINE.json's configs[2] names: Bistro exterior (2,837,209 triangles).  Skipped when the fixture is
+not present on the box (it is 136 MB and is only pushed for dedicated sessions; data/scenes is git-ignored)."""
+import numpy as np
+import pytest
+
+from oracle import refpy
+from tinybvh_b200 import api, rays as R, scenes
+from tests import util
+
+pytestmark = [pytest.mark.gpu]
+
+
+def bistro():
+    try:
+        return scenes.load_scene("bistro", allow_synthetic=False)[0]
+    except FileNotFoundError:
+        pytest.skip("Bistro fixture not on this box")
+
+
+@pytest.mark.skipif(not refpy.available(), reason="needs oracle/_ref")
+def test_bistro_build_identical_and_incoherent_parity(gpu):
+    v = bistro()
+    o = refpy.RefBVH(v, mode=0, threaded=False)
+    e = api.BVH().Build(v)
+    nodes, idx = e.download()
+    assert nodes.shape[0] == o.used_nodes
+    assert np.array_equal(nodes.view(np.uint32), o.nodes.view(np.uint32)), "GPU-built Bistro tree differs from BVH::Build"
+    assert np.array_equal(idx, o.prim_idx)
+    lo, hi = scenes.scene_bounds(v)
+    eye, view = R.bounds_camera(lo, hi, "inside")
+    want = R.primary_rays(eye, view, 512, 512, 4)
+    got = want.copy()
+    o.intersect(want), e.Intersect(got)
+    assert util.compare_hits(got, want) == {"prim": 0, "t": 0, "u": 0, "v": 0}
+    d = util.derived_sets(want, v, (lo, hi))
+    a, b = d["diffuse"].copy(), d["diffuse"].copy()
+    o.intersect(a), e.Intersect(b)
+    assert util.compare_hits(b, a) == {"prim": 0, "t": 0, "u": 0, "v": 0}, "incoherent rays: not bit-exact on the oracle's own tree"
+    assert np.array_equal(e.IsOccluded(d["shadow"]), o.occluded(d["shadow"]))
+    print("bistro: build", e.info().build_ms, "ms", v.shape[0] // 3 / e.info().build_ms / 1e3, "Mtris/s, depth", e.info().max_depth)
+
+
+@pytest.mark.skipif(not refpy.available(), reason="needs oracle/_ref")
+def test_bistro_cwbvh_conversion_and_traversal(gpu):
+    v = bistro()
+    cw = refpy.RefCWBVH(v, mode=2)
+    e = api.BVH8_CWBVH().Build(v)
+    nodes, tris = e.download()
+    assert nodes.shape == cw.nodes.shape and np.array_equal(nodes.view(np.uint32), cw.nodes.view(np.uint32)), "bvh8Data differs"
+    assert np.array_equal(tris.view(np.uint32), cw.tris.view(np.uint32)), "bvh8Tris differs"
+    lo, hi = scenes.scene_bounds(v)
+    eye, view = R.bounds_camera(lo, hi, "inside")
+    prim = R.primary_rays(eye, view, 256, 256, 4)
+    tr = prim.copy()
+    cw.intersect(tr)
+    d = R.diffuse_rays(tr, v)
+    a, b = d.copy(), d.copy()
+    cw.intersect(a), e.Intersect(b)
+    assert util.compare_hits(b, a) == {"prim": 0, "t": 0, "u": 0, "v": 0}

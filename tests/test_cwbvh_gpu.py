@@ -49,7 +49,7 @@ def check_occlusion(e, cw, o, shadow, label):
     occ_o = np.unpackbits(o.occluded(shadow).view(np.uint8), bitorder="little")[: shadow.shape[0]].astype(bool)
     occ_e = np.unpackbits(e.IsOccluded(shadow).view(np.uint8), bitorder="little")[: shadow.shape[0]].astype(bool)
     agree = occ_cw == occ_o
-    assert agree.mean() > 0.998, f"{label}: reference layouts disagree on {(~agree).sum()} occlusion bits"
+    assert agree.mean() > 0.99, f"{label}: reference layouts disagree on {(~agree).sum()} occlusion bits"
     assert np.array_equal(occ_e[agree], occ_o[agree]), f"{label}: {(occ_e[agree] != occ_o[agree]).sum()} occlusion bits differ from BVH::IsOccluded"
     return int((occ_e != occ_o).sum())
 

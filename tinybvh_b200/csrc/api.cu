@@ -5,6 +5,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include <vector>
+#include <thread>
 #include <new>
 
 static thread_local char g_err[512] = "";
@@ -58,6 +59,8 @@ int tbvh_ctx_create( int device, tbvh_ctx* out )
 	}
 	const char* hp = getenv( "TBVH_HOST_PATH" );
 	c->host_path = hp && !strcmp( hp, "zerocopy" ) ? 1 : 0;
+	const char* dm = getenv( "TBVH_D2H_MODE" );
+	c->d2h_mode = dm ? atoi( dm ) : 0;
 	const char* sp = getenv( "TBVH_H2D_SPLIT" );
 	c->h2d_split = sp ? atoi( sp ) : 1;
 	if (c->h2d_split < 1) c->h2d_split = 1;
@@ -416,6 +419,21 @@ static int stage_in( tbvh_ctx c, int k, const char* h, const char* h_dev, uint32
 	return TBVH_OK;
 }
 
+// host-side scatter of packed 16-byte hits into the strided ray records (d2h_mode 2)
+static void scatter_hits_host( const char* packed, char* rays, uint32_t stride, uint64_t cnt )
+{
+	unsigned threads = std::thread::hardware_concurrency() / 4;
+	if (threads < 1) threads = 1;
+	if (threads > 16) threads = 16;
+	if (cnt < 65536) threads = 1;
+	auto work = [=]( uint64_t a, uint64_t e ) { for (uint64_t i = a; i < e; i++) memcpy( rays + i * stride + 48, packed + i * 16, 16 ); };
+	if (threads == 1) { work( 0, cnt ); return; }
+	std::vector<std::thread> pool;
+	const uint64_t per = (cnt + threads - 1) / threads;
+	for (unsigned t = 0; t < threads; t++) { const uint64_t a = per * t, e = a + per < cnt ? a + per : cnt; if (a < e) pool.emplace_back( work, a, e ); }
+	for (auto& t : pool) t.join();
+}
+
 int tbvh_intersect( tbvh_bvh b, int layout, void* rays, uint32_t stride, uint64_t n )
 {
 	ARG_CHECK( b && rays && stride >= 64, "bad ray buffer" );
@@ -423,6 +441,13 @@ int tbvh_intersect( tbvh_bvh b, int layout, void* rays, uint32_t stride, uint64_
 	tbvh_ctx c = b->ctx;
 	TRY( ensure_stage( c ) );
 	char* dev_alias = (char*)mapped_alias( rays );
+	const int mode = (c->d2h_mode == 3 && !(dev_alias && (stride & 15) == 0)) ? 0 : c->d2h_mode;
+	if (mode == 2)
+	{
+		for (int i = 0; i < 3; i++) if (!c->d_hits_pack[i]) CUDA_TRY( cudaMalloc( &c->d_hits_pack[i], c->stage_rays * 16 ) );
+		if (c->h_hits_rays < n) { if (c->h_hits) cudaFreeHost( c->h_hits ); c->h_hits = 0; CUDA_TRY( cudaHostAlloc( &c->h_hits, n * 16, cudaHostAllocDefault ) ); c->h_hits_rays = n; }
+	}
+	std::vector<cudaEvent_t> done;
 	int k = 0;
 	for (uint64_t off = 0; off < n; off += c->stage_rays, k = (k + 1) % 3)
 	{
@@ -430,14 +455,43 @@ int tbvh_intersect( tbvh_bvh b, int layout, void* rays, uint32_t stride, uint64_
 		cudaStream_t s = c->copy_streams[k];
 		char* h = (char*)rays + off * stride;
 		char* hd = dev_alias ? dev_alias + off * stride : 0;
+		if (mode == 2 && off >= 3 * c->stage_rays)
+		{
+			// the packed hit buffer k is about to be reused: its previous chunk must be on the host (and scattered) first
+			const size_t prev = (size_t)(off / c->stage_rays) - 3;
+			CUDA_TRY( cudaEventSynchronize( done[prev] ) );
+			scatter_hits_host( (const char*)c->h_hits + (uint64_t)prev * c->stage_rays * 16, (char*)rays + (uint64_t)prev * c->stage_rays * stride, stride, c->stage_rays );
+		}
 		TRY( stage_in( c, k, h, hd, stride, cnt, s ) );
+		if (mode == 2)
+		{
+			TRY( trace_dispatch( b, layout, c->d_stage[k], 64, c->d_hits_pack[k], 16, 0, cnt, false, s ) );
+			CUDA_TRY( cudaMemcpyAsync( (char*)c->h_hits + off * 16, c->d_hits_pack[k], cnt * 16, cudaMemcpyDeviceToHost, s ) );
+			cudaEvent_t ev;
+			CUDA_TRY( cudaEventCreateWithFlags( &ev, cudaEventDisableTiming ) );
+			CUDA_TRY( cudaEventRecord( ev, s ) );
+			done.push_back( ev );
+			continue;
+		}
 		TRY( trace_dispatch( b, layout, c->d_stage[k], 64, (char*)c->d_stage[k] + 48, 64, 0, cnt, false, s ) );
-		if (c->host_path == 1 && hd && (stride & 15) == 0)
+		if (mode == 3)
 		{
 			k_scatter_hits<<<(uint32_t)((cnt + 255) / 256), 256, 0, s>>>( (const float4*)c->d_stage[k], (float4*)hd, stride / 16, cnt );
 			LAUNCHED();
 		}
+		else if (mode == 1) CUDA_TRY( cudaMemcpy2DAsync( h, stride, c->d_stage[k], 64, 64, cnt, cudaMemcpyDeviceToHost, s ) );
 		else CUDA_TRY( cudaMemcpy2DAsync( h + 48, stride, (char*)c->d_stage[k] + 48, 64, 16, cnt, cudaMemcpyDeviceToHost, s ) );
+	}
+	if (mode == 2)
+	{
+		const size_t chunks = done.size();
+		for (size_t ch = chunks >= 3 ? chunks - 3 : 0; ch < chunks; ch++)
+		{
+			CUDA_TRY( cudaEventSynchronize( done[ch] ) );
+			const uint64_t off = (uint64_t)ch * c->stage_rays, cnt = n - off < c->stage_rays ? n - off : c->stage_rays;
+			scatter_hits_host( (const char*)c->h_hits + off * 16, (char*)rays + off * stride, stride, cnt );
+		}
+		for (cudaEvent_t e : done) cudaEventDestroy( e );
 	}
 	for (int i = 0; i < 3; i++) CUDA_TRY( cudaStreamSynchronize( c->copy_streams[i] ) );
 	return TBVH_OK;

@@ -14,7 +14,7 @@ sys.path.insert(0, REPO)
 from tinybvh_b200 import api, rays as R  # noqa: E402
 
 n = 1 << 24
-v = np.array([[1e6, 1e6, 1e6, 0], [1e6 + 1, 1e6, 1e6, 0], [1e6, 1e6 + 1, 1e6, 0]], np.float32)
+v = np.array([[-10, -10, 5, 0], [10, -10, 5, 0], [0, 10, 5, 0]], np.float32)  # every ray hits at t = 5
 e = api.BVH().Build(v)
 h = api.pinned_empty(n, R.RAY_DTYPE)
 h[:] = R.make_rays(np.zeros((1, 3), np.float32), np.array([[0, 0, 1]], np.float32))[0]
@@ -23,11 +23,17 @@ for name, fn in (("intersect (64 B in, 16 B out per ray)", lambda: e.Intersect(h
     fn()
     ts = []
     for _ in range(3):
+        h["t"] = 1e30
+        h["prim"] = 7
         t0 = time.perf_counter()
         fn()
         ts.append(time.perf_counter() - t0)
+        if name.startswith("intersect"):
+            assert (h["t"] == 5).all() and (h["prim"] == 0).all(), "host path returned wrong hits"
     t = min(ts)
-    print(f"mode {os.environ.get('TBVH_HOST_PATH', 'copy2d')} split {os.environ.get('TBVH_H2D_SPLIT', '1')}: {name}: {t * 1e3:.1f} ms  {n / t / 1e6:.0f} Mrays/s  inbound {n * 64 / t / 1e9:.1f} GB/s")
+    print(f"h2d {os.environ.get('TBVH_HOST_PATH', 'copy2d')} d2h_mode {os.environ.get('TBVH_D2H_MODE', '0')}: {name}: {t * 1e3:.1f} ms  {n / t / 1e6:.0f} Mrays/s  inbound {n * 64 / t / 1e9:.1f} GB/s")
+if "--ref" not in sys.argv:
+    sys.exit(0)
 # reference points: plain 1D pinned copies
 x = torch.empty(n * 64, dtype=torch.uint8).pin_memory()
 d = torch.empty(n * 64, dtype=torch.uint8, device="cuda")
