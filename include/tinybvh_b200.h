@@ -62,6 +62,11 @@ int tbvh_ctx_create( int device, tbvh_ctx* out );
 int tbvh_ctx_destroy( tbvh_ctx ctx );
 const char* tbvh_last_error( void );
 int tbvh_device_count( void );
+/* tuning knobs (no reference counterpart; defaults are the measured best): "trace_variant" 0 = generic BVH2 kernel,
+ * 3 = octant-switch, 4 = persistent warps; "small_t" builder switch point (8..256); "d2h_mode" / "h2d_split" / "host_path"
+ * select how the host-buffer path moves ray records and hits across PCIe.  Environment variables TBVH_<KEY> set the
+ * defaults at context creation. */
+int tbvh_set_option( tbvh_ctx ctx, const char* key, int value );
 /* pinned host memory for ray buffers (replaces tinybvh::malloc64 / BVHContext::malloc for rays, tiny_bvh.h:261-292, 763-768) */
 int tbvh_host_alloc( size_t bytes, void** out );
 int tbvh_host_free( void* p );

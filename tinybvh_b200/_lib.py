@@ -31,6 +31,7 @@ SYMBOLS = {
     "tbvh_ctx_destroy": (i32, [vp]),
     "tbvh_last_error": (C.c_char_p, []),
     "tbvh_device_count": (i32, []),
+    "tbvh_set_option": (i32, [vp, C.c_char_p, i32]),
     "tbvh_host_alloc": (i32, [sz, C.POINTER(vp)]),
     "tbvh_host_free": (i32, [vp]),
     "tbvh_host_register": (i32, [vp, sz]),

@@ -30,6 +30,11 @@ def context(device: int = 0):
     return _contexts[device]
 
 
+def set_option(key: str, value: int, device: int = 0) -> None:
+    """Tuning knob of the engine context (tbvh_set_option): trace_variant, small_t, d2h_mode, h2d_split, host_path."""
+    check(_lib.lib().tbvh_set_option(context(device), key.encode(), int(value)))
+
+
 def device_count() -> int:
     return _lib.lib().tbvh_device_count()
 

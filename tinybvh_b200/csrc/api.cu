@@ -59,6 +59,10 @@ int tbvh_ctx_create( int device, tbvh_ctx* out )
 	}
 	const char* hp = getenv( "TBVH_HOST_PATH" );
 	c->host_path = hp && !strcmp( hp, "zerocopy" ) ? 1 : 0;
+	const char* tv = getenv( "TBVH_TRACE_VARIANT" );
+	c->trace_variant = tv ? atoi( tv ) : 0;
+	const char* st = getenv( "TBVH_SMALL_T" );
+	c->small_t = st ? atoi( st ) : 128;
 	const char* dm = getenv( "TBVH_D2H_MODE" );
 	c->d2h_mode = dm ? atoi( dm ) : 0;
 	const char* sp = getenv( "TBVH_H2D_SPLIT" );
@@ -76,6 +80,18 @@ int tbvh_ctx_destroy( tbvh_ctx c )
 	for (int i = 0; i < 3; i++) { if (c->d_stage[i]) cudaFree( c->d_stage[i] ); if (c->d_stage_bits[i]) cudaFree( c->d_stage_bits[i] ); cudaStreamDestroy( c->copy_streams[i] ); }
 	cudaStreamDestroy( c->stream );
 	delete c;
+	return TBVH_OK;
+}
+
+int tbvh_set_option( tbvh_ctx c, const char* key, int value )
+{
+	ARG_CHECK( c && key, "NULL argument" );
+	if (!strcmp( key, "trace_variant" )) c->trace_variant = value;
+	else if (!strcmp( key, "small_t" )) c->small_t = value;
+	else if (!strcmp( key, "d2h_mode" )) c->d2h_mode = value;
+	else if (!strcmp( key, "h2d_split" )) c->h2d_split = value < 1 ? 1 : value > 4 ? 4 : value;
+	else if (!strcmp( key, "host_path" )) c->host_path = value;
+	else { tbvh_set_error( "tbvh_set_option: unknown key '%s'", key ); return TBVH_E_ARG; }
 	return TBVH_OK;
 }
 
@@ -422,9 +438,11 @@ static int stage_in( tbvh_ctx c, int k, const char* h, const char* h_dev, uint32
 // host-side scatter of packed 16-byte hits into the strided ray records (d2h_mode 2)
 static void scatter_hits_host( const char* packed, char* rays, uint32_t stride, uint64_t cnt )
 {
-	unsigned threads = std::thread::hardware_concurrency() / 4;
+	static int env_threads = -1;
+	if (env_threads < 0) { const char* e = getenv( "TBVH_SCATTER_THREADS" ); env_threads = e ? atoi( e ) : 0; }
+	unsigned threads = env_threads > 0 ? (unsigned)env_threads : std::thread::hardware_concurrency() / 4;
 	if (threads < 1) threads = 1;
-	if (threads > 16) threads = 16;
+	if (threads > 64) threads = 64;
 	if (cnt < 65536) threads = 1;
 	auto work = [=]( uint64_t a, uint64_t e ) { for (uint64_t i = a; i < e; i++) memcpy( rays + i * stride + 48, packed + i * 16, 16 ); };
 	if (threads == 1) { work( 0, cnt ); return; }
@@ -447,7 +465,6 @@ int tbvh_intersect( tbvh_bvh b, int layout, void* rays, uint32_t stride, uint64_
 		for (int i = 0; i < 3; i++) if (!c->d_hits_pack[i]) CUDA_TRY( cudaMalloc( &c->d_hits_pack[i], c->stage_rays * 16 ) );
 		if (c->h_hits_rays < n) { if (c->h_hits) cudaFreeHost( c->h_hits ); c->h_hits = 0; CUDA_TRY( cudaHostAlloc( &c->h_hits, n * 16, cudaHostAllocDefault ) ); c->h_hits_rays = n; }
 	}
-	std::vector<cudaEvent_t> done;
 	int k = 0;
 	for (uint64_t off = 0; off < n; off += c->stage_rays, k = (k + 1) % 3)
 	{
@@ -455,22 +472,11 @@ int tbvh_intersect( tbvh_bvh b, int layout, void* rays, uint32_t stride, uint64_
 		cudaStream_t s = c->copy_streams[k];
 		char* h = (char*)rays + off * stride;
 		char* hd = dev_alias ? dev_alias + off * stride : 0;
-		if (mode == 2 && off >= 3 * c->stage_rays)
-		{
-			// the packed hit buffer k is about to be reused: its previous chunk must be on the host (and scattered) first
-			const size_t prev = (size_t)(off / c->stage_rays) - 3;
-			CUDA_TRY( cudaEventSynchronize( done[prev] ) );
-			scatter_hits_host( (const char*)c->h_hits + (uint64_t)prev * c->stage_rays * 16, (char*)rays + (uint64_t)prev * c->stage_rays * stride, stride, c->stage_rays );
-		}
 		TRY( stage_in( c, k, h, hd, stride, cnt, s ) );
 		if (mode == 2)
 		{
 			TRY( trace_dispatch( b, layout, c->d_stage[k], 64, c->d_hits_pack[k], 16, 0, cnt, false, s ) );
 			CUDA_TRY( cudaMemcpyAsync( (char*)c->h_hits + off * 16, c->d_hits_pack[k], cnt * 16, cudaMemcpyDeviceToHost, s ) );
-			cudaEvent_t ev;
-			CUDA_TRY( cudaEventCreateWithFlags( &ev, cudaEventDisableTiming ) );
-			CUDA_TRY( cudaEventRecord( ev, s ) );
-			done.push_back( ev );
 			continue;
 		}
 		TRY( trace_dispatch( b, layout, c->d_stage[k], 64, (char*)c->d_stage[k] + 48, 64, 0, cnt, false, s ) );
@@ -484,14 +490,11 @@ int tbvh_intersect( tbvh_bvh b, int layout, void* rays, uint32_t stride, uint64_
 	}
 	if (mode == 2)
 	{
-		const size_t chunks = done.size();
-		for (size_t ch = chunks >= 3 ? chunks - 3 : 0; ch < chunks; ch++)
-		{
-			CUDA_TRY( cudaEventSynchronize( done[ch] ) );
-			const uint64_t off = (uint64_t)ch * c->stage_rays, cnt = n - off < c->stage_rays ? n - off : c->stage_rays;
-			scatter_hits_host( (const char*)c->h_hits + off * 16, (char*)rays + off * stride, stride, cnt );
-		}
-		for (cudaEvent_t e : done) cudaEventDestroy( e );
+		// every chunk's packed hits land in h_hits (each chunk has its own slice of it, so nothing is overwritten); wait for
+		// them all, then scatter the 16-byte hits into the strided records with a handful of host threads
+		for (int i = 0; i < 3; i++) CUDA_TRY( cudaStreamSynchronize( c->copy_streams[i] ) );
+		scatter_hits_host( (const char*)c->h_hits, (char*)rays, stride, n );
+		return TBVH_OK;
 	}
 	for (int i = 0; i < 3; i++) CUDA_TRY( cudaStreamSynchronize( c->copy_streams[i] ) );
 	return TBVH_OK;

@@ -695,8 +695,7 @@ int build_sah_launch( tbvh_bvh b, float c_trav, float c_int )
 	BuildArgs A = {};
 	A.verts = b->d_verts, A.n = n, A.c_trav = c_trav, A.c_int = c_int;
 	{
-		const char* e = getenv( "TBVH_SMALL_T" );
-		const int t = e ? atoi( e ) : 128; // measured on B200: 128 beats 64 and 256 (profiles/README.md)
+		const int t = b->ctx->small_t; // measured on B200: 128 beats 64 and 256 (profiles/README.md)
 		A.small_t = (uint32_t)(t < 8 ? 8 : t > SMALL_T ? SMALL_T : t);
 	}
 	const size_t max_nodes = (size_t)2 * n + 2, max_large = n / A.small_t + 2;
