@@ -177,8 +177,12 @@ def run_reference(args):
 
 
 def data_label(label):
-    return ("synthetic procedural scene of the same triangle count (fixture not found)" if label.startswith("synthetic")
-            else f"reference fixture testdata/{scenes.SCENES[label][0][0]} (triangle soup), rays generated synthetically (speedtest camera pattern)")
+    if label.startswith("synthetic"):
+        return "synthetic procedural scene of the same triangle count (fixture not found)"
+    if label == "lucy_dragon_x29":
+        return "reference fixtures testdata/lucy.bin + xyzrgb_dragon.bin replicated 29x on a grid (10,145,708 triangles), rays generated synthetically"
+    files = "+".join(scenes.SCENES[label][0])
+    return f"reference fixture testdata/{files} (triangle soup), rays generated synthetically (speedtest camera pattern)"
 
 
 def workload_name(args, label):
@@ -310,12 +314,22 @@ def run_ours(args):
         eng.IsOccluded(h_shadow, bits=h_bits)
     te1 = time.perf_counter()
     e2e_ms = (te1 - te0) * 1e3
+    # the same with the packed-hits entry point (tbvh_intersect_packed): the return trip is one contiguous copy per chunk
+    h_hits = api.pinned_empty(n, R.HIT_DTYPE)
+    eng.IntersectPacked(h_prim, hits=h_hits)
+    barrier()
+    tp0 = time.perf_counter()
+    for _ in range(args.steps):
+        eng.IntersectPacked(h_prim, hits=h_hits)
+        eng.IsOccluded(h_shadow, bits=h_bits)
+    tp1 = time.perf_counter()
+    e2e_packed_ms = (tp1 - tp0) * 1e3
     clk = clocks.stop() if clocks else None
 
-    t = torch.tensor([total_ms, e2e_ms, prim_ms, shad_ms], dtype=torch.float64, device=dev)
+    t = torch.tensor([total_ms, e2e_ms, prim_ms, shad_ms, e2e_packed_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    total_ms, e2e_ms, prim_ms, shad_ms = [float(x) for x in t.cpu()]
+    total_ms, e2e_ms, prim_ms, shad_ms, e2e_packed_ms = [float(x) for x in t.cpu()]
 
     if rank == 0:
         rays_per_step = 2 * n * world
@@ -353,7 +367,9 @@ def run_ours(args):
                          "note": "traversal is latency/issue bound, not HBM bound (SURVEY 8d): see DESIGN.md for the L2-side accounting"},
             "e2e": {"value": rays_per_step / (e2e_ms / args.steps) / 1e3, "unit": "Mrays/s", "h2d_bytes_per_step": 2 * n * 64,
                     "d2h_bytes_per_step": n * 16 + ((n + 31) // 32) * 4, "ms_per_step": e2e_ms / args.steps,
-                    "api": "tbvh_intersect + tbvh_occluded on pinned 128-byte host Ray records"},
+                    "api": "tbvh_intersect + tbvh_occluded on pinned 128-byte host Ray records (hits written in place into Ray.hit)",
+                    "packed_hits_value": rays_per_step / (e2e_packed_ms / args.steps) / 1e3,
+                    "packed_hits_api": "tbvh_intersect_packed + tbvh_occluded: same inputs, hits returned as a packed 16-byte array"},
             "gpu_launches": int(launches),
             "clocks": clk,
         }

@@ -106,6 +106,10 @@ int tbvh_download_cwbvh( tbvh_bvh bvh, void* bvh8_data, void* bvh8_tris, int spa
  * batch kernels batch_ailalaine (traverse_bvh2.cl:209) / batch_cwbvh (traverse_cwbvh.cl:554) for a whole batch:
  * host records, in place - copies bytes 0..63 in, writes t,u,v,prim back to bytes 48..63 of every record. */
 int tbvh_intersect( tbvh_bvh bvh, int layout, void* rays, uint32_t stride, uint64_t n );
+/* same traversal, hits delivered as a packed array of 16-byte (t,u,v,prim) records instead of being scattered into the
+ * 128-byte ray records: the return trip becomes one contiguous copy per chunk (the in-place form pays a strided
+ * 16-byte-row copy).  `rays` is not modified. */
+int tbvh_intersect_packed( tbvh_bvh bvh, int layout, const void* rays, uint32_t stride, uint64_t n, void* hits );
 /* BVH::IsOccluded( const Ray& ) tiny_bvh.h:3382 / isoccluded_cwbvh (traverse_cwbvh.cl:343) for a batch:
  * bits[i>>5] bit (i&31) = occluded; (n+31)/32 words are written. */
 int tbvh_occluded( tbvh_bvh bvh, int layout, const void* rays, uint32_t stride, uint64_t n, uint32_t* bits );

@@ -74,6 +74,11 @@ public:
 		TBVH_FATAL_IF( tbvh_intersect( h, layout, rays, (uint32_t)sizeof( RayT ), n ), "Intersect" );
 		return 0;
 	}
+	// batch traversal with packed results: hits[i] = { t, u, v, prim } (16 bytes), rays untouched - the fast return path
+	template <class RayT> void Intersect( const RayT* rays, uint64_t n, void* hits16 ) const
+	{
+		TBVH_FATAL_IF( tbvh_intersect_packed( h, layout, rays, (uint32_t)sizeof( RayT ), n, hits16 ), "Intersect (packed)" );
+	}
 	template <class RayT> void IsOccluded( const RayT* rays, uint64_t n, uint32_t* bits ) const
 	{
 		TBVH_FATAL_IF( tbvh_occluded( h, layout, rays, (uint32_t)sizeof( RayT ), n, bits ), "IsOccluded" );

@@ -47,7 +47,7 @@ def test_trace_variants_are_bit_exact(gpu, world, variant):
         m = d["shadow"].shape[0] - 37
         assert np.array_equal(e.IsOccluded(d["shadow"][:m].copy()), util.oracle_bvh(v).occluded(d["shadow"][:m].copy()))
     finally:
-        api.set_option("trace_variant", 0)
+        api.set_option("trace_variant", 3)
 
 
 @pytest.mark.parametrize("mode", [0, 1, 2, 3])
@@ -64,6 +64,8 @@ def test_host_path_modes_return_the_same_hits(gpu, world, mode):
         pageable = primary.copy()
         e.Intersect(pageable)
         assert util.compare_hits(pageable, want["primary"]) == ZERO, f"d2h_mode {mode} (pageable)"
+        hits = e.IntersectPacked(primary)   # packed return path: rays untouched, 16-byte hits
+        assert np.array_equal(hits["t"].view(np.uint32), want["primary"]["t"].view(np.uint32)) and np.array_equal(hits["prim"], want["primary"]["prim"])
         api.pinned_free(pinned)
     finally:
         api.set_option("d2h_mode", 0)

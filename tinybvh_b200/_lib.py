@@ -48,6 +48,7 @@ SYMBOLS = {
     "tbvh_download_bvh_gpu": (i32, [vp, vp, i32]),
     "tbvh_download_cwbvh": (i32, [vp, vp, vp, i32]),
     "tbvh_intersect": (i32, [vp, i32, vp, u32, u64]),
+    "tbvh_intersect_packed": (i32, [vp, i32, vp, u32, u64, vp]),
     "tbvh_occluded": (i32, [vp, i32, vp, u32, u64, vp]),
     "tbvh_intersect_device": (i32, [vp, i32, vp, u32, vp, u64, vp]),
     "tbvh_occluded_device": (i32, [vp, i32, vp, u32, vp, u64, vp]),

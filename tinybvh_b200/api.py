@@ -107,6 +107,15 @@ class _Base:
         check(L.tbvh_intersect(self.h, self.layout, _np_ptr(rays), rays.dtype.itemsize, rays.shape[0]))
         return rays
 
+    def IntersectPacked(self, rays, hits=None):
+        """Host path with packed results: rays untouched, hits -> HIT_DTYPE array (tbvh_intersect_packed)."""
+        from .rays import HIT_DTYPE
+        assert not _is_torch(rays) and rays.dtype.itemsize in (64, 128) and rays.flags.c_contiguous
+        if hits is None:
+            hits = np.zeros(rays.shape[0], HIT_DTYPE)
+        check(_lib.lib().tbvh_intersect_packed(self.h, self.layout, _np_ptr(rays), rays.dtype.itemsize, rays.shape[0], _np_ptr(hits)))
+        return hits
+
     def IsOccluded(self, rays, bits=None, stream=None):
         """Any hit within [0, ray.hit.t] per ray -> uint32 bit mask, bit (i&31) of word i>>5."""
         L = _lib.lib()

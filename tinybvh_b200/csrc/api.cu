@@ -60,7 +60,7 @@ int tbvh_ctx_create( int device, tbvh_ctx* out )
 	const char* hp = getenv( "TBVH_HOST_PATH" );
 	c->host_path = hp && !strcmp( hp, "zerocopy" ) ? 1 : 0;
 	const char* tv = getenv( "TBVH_TRACE_VARIANT" );
-	c->trace_variant = tv ? atoi( tv ) : 0;
+	c->trace_variant = tv ? atoi( tv ) : 3; // octant switch: +5 % on camera / shadow rays, -3 % on diffuse (profiles/README.md)
 	const char* st = getenv( "TBVH_SMALL_T" );
 	c->small_t = st ? atoi( st ) : 128;
 	const char* dm = getenv( "TBVH_D2H_MODE" );
@@ -452,17 +452,28 @@ static void scatter_hits_host( const char* packed, char* rays, uint32_t stride, 
 	for (auto& t : pool) t.join();
 }
 
-int tbvh_intersect( tbvh_bvh b, int layout, void* rays, uint32_t stride, uint64_t n )
+static int intersect_host( tbvh_bvh b, int layout, void* rays, uint32_t stride, uint64_t n, void* packed_hits );
+
+int tbvh_intersect( tbvh_bvh b, int layout, void* rays, uint32_t stride, uint64_t n ) { return intersect_host( b, layout, rays, stride, n, 0 ); }
+
+int tbvh_intersect_packed( tbvh_bvh b, int layout, const void* rays, uint32_t stride, uint64_t n, void* hits )
+{
+	ARG_CHECK( hits, "hits == NULL" );
+	return intersect_host( b, layout, (void*)rays, stride, n, hits );
+}
+
+static int intersect_host( tbvh_bvh b, int layout, void* rays, uint32_t stride, uint64_t n, void* packed_hits )
 {
 	ARG_CHECK( b && rays && stride >= 64, "bad ray buffer" );
 	CUDA_TRY( cudaSetDevice( b->ctx->device ) );
 	tbvh_ctx c = b->ctx;
 	TRY( ensure_stage( c ) );
 	char* dev_alias = (char*)mapped_alias( rays );
-	const int mode = (c->d2h_mode == 3 && !(dev_alias && (stride & 15) == 0)) ? 0 : c->d2h_mode;
+	const int mode = packed_hits ? 4 : (c->d2h_mode == 3 && !(dev_alias && (stride & 15) == 0)) ? 0 : c->d2h_mode;
+	if (mode == 2 || mode == 4)
+		for (int i = 0; i < 3; i++) if (!c->d_hits_pack[i]) CUDA_TRY( cudaMalloc( &c->d_hits_pack[i], c->stage_rays * 16 ) );
 	if (mode == 2)
 	{
-		for (int i = 0; i < 3; i++) if (!c->d_hits_pack[i]) CUDA_TRY( cudaMalloc( &c->d_hits_pack[i], c->stage_rays * 16 ) );
 		if (c->h_hits_rays < n) { if (c->h_hits) cudaFreeHost( c->h_hits ); c->h_hits = 0; CUDA_TRY( cudaHostAlloc( &c->h_hits, n * 16, cudaHostAllocDefault ) ); c->h_hits_rays = n; }
 	}
 	int k = 0;
@@ -473,10 +484,12 @@ int tbvh_intersect( tbvh_bvh b, int layout, void* rays, uint32_t stride, uint64_
 		char* h = (char*)rays + off * stride;
 		char* hd = dev_alias ? dev_alias + off * stride : 0;
 		TRY( stage_in( c, k, h, hd, stride, cnt, s ) );
-		if (mode == 2)
+		if (mode == 2 || mode == 4)
 		{
+			// hits leave the device packed (16 B per ray, one contiguous copy per chunk): into the caller's packed array
+			// (tbvh_intersect_packed) or into pinned staging for the host-side scatter (d2h_mode 2)
 			TRY( trace_dispatch( b, layout, c->d_stage[k], 64, c->d_hits_pack[k], 16, 0, cnt, false, s ) );
-			CUDA_TRY( cudaMemcpyAsync( (char*)c->h_hits + off * 16, c->d_hits_pack[k], cnt * 16, cudaMemcpyDeviceToHost, s ) );
+			CUDA_TRY( cudaMemcpyAsync( (char*)(mode == 4 ? packed_hits : c->h_hits) + off * 16, c->d_hits_pack[k], cnt * 16, cudaMemcpyDeviceToHost, s ) );
 			continue;
 		}
 		TRY( trace_dispatch( b, layout, c->d_stage[k], 64, (char*)c->d_stage[k] + 48, 64, 0, cnt, false, s ) );

@@ -22,7 +22,7 @@
 #include <vector>
 
 #define BINS 8
-#define SMALL_T 256          // subtrees of at most this many primitives are built by one warp
+#define SMALL_T 128          // capacity of the warp kernel: subtrees of at most this many primitives (run-time switch point <= this)
 #define CHUNK 256            // primitives per CTA in the large phase
 #define BIN_WORDS 168        // 3 axes x 8 bins x (3 min keys, 3 max keys, count)
 #define SCAN_TILE 2048
@@ -170,6 +170,27 @@ __device__ __forceinline__ uint32_t partition_dest( const uint32_t rel, const ui
 	return n - 1 - r;
 }
 
+// Warp-aggregated update of a bin table held in shared memory: lanes that fall into the same bin first reduce their
+// six box keys with REDUX (match.any + redux.sync.min/max), then ONE lane per distinct bin issues the seven shared
+// atomics.  Neighbouring primitives usually share a bin, so this cuts the shared-atomic traffic (the limiter of the
+// per-primitive version: 73 % L1TEX at 7 % issue, profiles/r1_build_ncu.txt) by an order of magnitude.
+// Lanes without a primitive pass valid = false (they join the votes with neutral values).
+__device__ __forceinline__ void bin_update_aggregated( uint32_t* bins /* one axis: BINS * 7 words */, const bool valid, const uint32_t bin,
+	const uint32_t kmn0, const uint32_t kmn1, const uint32_t kmn2, const uint32_t kmx0, const uint32_t kmx1, const uint32_t kmx2 )
+{
+	const uint32_t key = valid ? bin : 0xffu;
+	const uint32_t m = __match_any_sync( 0xffffffffu, key );
+	const uint32_t a0 = __reduce_min_sync( m, kmn0 ), a1 = __reduce_min_sync( m, kmn1 ), a2 = __reduce_min_sync( m, kmn2 );
+	const uint32_t b0 = __reduce_max_sync( m, kmx0 ), b1 = __reduce_max_sync( m, kmx1 ), b2 = __reduce_max_sync( m, kmx2 );
+	if (valid && (threadIdx.x & 31) == (uint32_t)(__ffs( m ) - 1))
+	{
+		uint32_t* w = bins + bin * 7;
+		atomicMin( w + 0, a0 ), atomicMin( w + 1, a1 ), atomicMin( w + 2, a2 );
+		atomicMax( w + 3, b0 ), atomicMax( w + 4, b1 ), atomicMax( w + 5, b2 );
+		atomicAdd( w + 6, (uint32_t)__popc( m ) );
+	}
+}
+
 // ---------------------------------------------------------------------------------------------- fragments
 
 __global__ void __launch_bounds__( 256 ) k_fragments( BuildArgs A )
@@ -248,26 +269,21 @@ __global__ void __launch_bounds__( CHUNK ) k_bin( BuildArgs A, const LargeNode* 
 	const uint32_t j = s_slot;
 	const LargeNode nd = cur[j];
 	const uint32_t off = (blockIdx.x - __ldg( A.chunk_start + j )) * CHUNK + threadIdx.x;
-	if (off < nd.count)
+	const bool valid = off < nd.count;
+	uint32_t b3[3] = { 0, 0, 0 }, kmn[3] = { 0xffffffffu, 0xffffffffu, 0xffffffffu }, kmx[3] = { 0, 0, 0 };
+	if (valid)
 	{
 		const float4 nmin = __ldg( A.tmp_nodes + (size_t)nd.tmp * 2 ), nmax = __ldg( A.tmp_nodes + (size_t)nd.tmp * 2 + 1 );
 		const uint32_t p = nd.first + off, fi = __ldg( idx_in + p );
 		const float4 fmn = __ldg( A.frag_min + fi ), fmx = __ldg( A.frag_max + fi );
-		const uint32_t bx = bin_of( fmn.x, fmx.x, nmin.x, __fdiv_rn( (float)BINS, __fsub_rn( nmax.x, nmin.x ) ) );
-		const uint32_t by = bin_of( fmn.y, fmx.y, nmin.y, __fdiv_rn( (float)BINS, __fsub_rn( nmax.y, nmin.y ) ) );
-		const uint32_t bz = bin_of( fmn.z, fmx.z, nmin.z, __fdiv_rn( (float)BINS, __fsub_rn( nmax.z, nmin.z ) ) );
-		A.bin_ids[p] = (uint16_t)(bx | (by << 3) | (bz << 6));
-		const uint32_t kmn[3] = { f2key( fmn.x ), f2key( fmn.y ), f2key( fmn.z ) }, kmx[3] = { f2key( fmx.x ), f2key( fmx.y ), f2key( fmx.z ) };
-		const uint32_t b3[3] = { bx, by, bz };
-		#pragma unroll
-		for (int a = 0; a < 3; a++)
-		{
-			uint32_t* w = s_bins + (a * BINS + b3[a]) * 7;
-			atomicMin( w + 0, kmn[0] ), atomicMin( w + 1, kmn[1] ), atomicMin( w + 2, kmn[2] );
-			atomicMax( w + 3, kmx[0] ), atomicMax( w + 4, kmx[1] ), atomicMax( w + 5, kmx[2] );
-			atomicAdd( w + 6, 1u );
-		}
+		b3[0] = bin_of( fmn.x, fmx.x, nmin.x, __fdiv_rn( (float)BINS, __fsub_rn( nmax.x, nmin.x ) ) );
+		b3[1] = bin_of( fmn.y, fmx.y, nmin.y, __fdiv_rn( (float)BINS, __fsub_rn( nmax.y, nmin.y ) ) );
+		b3[2] = bin_of( fmn.z, fmx.z, nmin.z, __fdiv_rn( (float)BINS, __fsub_rn( nmax.z, nmin.z ) ) );
+		A.bin_ids[p] = (uint16_t)(b3[0] | (b3[1] << 3) | (b3[2] << 6));
+		kmn[0] = f2key( fmn.x ), kmn[1] = f2key( fmn.y ), kmn[2] = f2key( fmn.z ), kmx[0] = f2key( fmx.x ), kmx[1] = f2key( fmx.y ), kmx[2] = f2key( fmx.z );
 	}
+	#pragma unroll
+	for (int a = 0; a < 3; a++) bin_update_aggregated( s_bins + a * BINS * 7, valid, b3[a], kmn[0], kmn[1], kmn[2], kmx[0], kmx[1], kmx[2] );
 	__syncthreads();
 	if (threadIdx.x < BIN_WORDS)
 	{
@@ -330,9 +346,10 @@ __global__ void __launch_bounds__( CHUNK ) k_flags( BuildArgs A, const LargeNode
 	const LargeNode nd = cur[j];
 	const SplitInfo sp = A.split[j];
 	const uint32_t off = (blockIdx.x - __ldg( A.chunk_start + j )) * CHUNK + threadIdx.x;
-	if (off >= nd.count) return;
+	// flags live in CHUNK SPACE (index = chunk * CHUNK + lane): the scan then costs O(active primitives) per level, and a
+	// node's flags stay contiguous because its chunks are; padding lanes of a node's last chunk carry 0
 	const uint32_t p = nd.first + off;
-	A.flags[p] = (sp.did && ((((uint32_t)A.bin_ids[p]) >> (3 * sp.axis)) & 7u) <= sp.pos) ? 1u : 0u;
+	A.flags[(size_t)blockIdx.x * CHUNK + threadIdx.x] = (off < nd.count && sp.did && ((((uint32_t)A.bin_ids[p]) >> (3 * sp.axis)) & 7u) <= sp.pos) ? 1u : 0u;
 }
 
 // exclusive scan of flags[0..n) into scan[0..n] (scan[n] = total): tile sums, one-block spine, apply
@@ -408,8 +425,8 @@ __global__ void __launch_bounds__( CHUNK ) k_posbl( BuildArgs A, const LargeNode
 	const SplitInfo sp = A.split[j];
 	const uint32_t off = (blockIdx.x - __ldg( A.chunk_start + j )) * CHUNK + threadIdx.x;
 	if (!sp.did || off >= nd.count || off < sp.L) return;
-	const uint32_t p = nd.first + off;
-	if (A.flags[p]) A.pos_bl[nd.first + (A.scan[nd.first + nd.count] - A.scan[p + 1])] = off; // BL_k, k = lefts behind it
+	const size_t sb = (size_t)__ldg( A.chunk_start + j ) * CHUNK; // this node's base in chunk space
+	if (A.flags[sb + off]) A.pos_bl[nd.first + (A.scan[sb + nd.count] - A.scan[sb + off + 1])] = off; // BL_k, k = lefts behind it
 }
 
 __global__ void __launch_bounds__( CHUNK ) k_scatter( BuildArgs A, const LargeNode* __restrict__ cur, const uint32_t num,
@@ -423,12 +440,13 @@ __global__ void __launch_bounds__( CHUNK ) k_scatter( BuildArgs A, const LargeNo
 	const SplitInfo sp = A.split[j];
 	const uint32_t off = (blockIdx.x - __ldg( A.chunk_start + j )) * CHUNK + threadIdx.x;
 	if (!sp.did || off >= nd.count) return;
-	const uint32_t p = nd.first + off, s0 = A.scan[nd.first];
-	const uint32_t lefts_before = A.scan[p] - s0, lefts_in_F = A.scan[nd.first + sp.L] - s0;
+	const size_t sb = (size_t)__ldg( A.chunk_start + j ) * CHUNK; // this node's base in chunk space
+	const uint32_t p = nd.first + off, s0 = A.scan[sb];
+	const uint32_t lefts_before = A.scan[sb + off] - s0, lefts_in_F = A.scan[sb + sp.L] - s0;
 	const uint32_t m = sp.L - lefts_in_F;
-	const bool extra = sp.L < nd.count && A.flags[nd.first + sp.L] == 0;
+	const bool extra = sp.L < nd.count && A.flags[sb + sp.L] == 0;
 	uint32_t pull;
-	const uint32_t dest = partition_dest( off, nd.count, sp.L, A.flags[p] != 0, lefts_before, m, extra, A.pos_bl + nd.first, &pull );
+	const uint32_t dest = partition_dest( off, nd.count, sp.L, A.flags[sb + off] != 0, lefts_before, m, extra, A.pos_bl + nd.first, &pull );
 	if (dest != 0xffffffffu) idx_out[nd.first + dest] = idx_in[p];
 	if (pull != 0xffffffffu) idx_out[p] = idx_in[nd.first + pull];
 }
@@ -476,7 +494,9 @@ __global__ void k_bins_init( uint32_t* bins, const uint32_t words )
 #define SMALL_WARPS 8
 struct SmallSmem
 {
-	uint32_t idx[2][SMALL_T];
+	uint32_t gid[SMALL_T];            // global primitive index of each local slot
+	float fmn[SMALL_T][3], fmx[SMALL_T][3]; // the subtree's fragment boxes, staged once (every level re-reads them)
+	uint16_t idx[2][SMALL_T];         // ping-pong order of local slots
 	uint16_t bid[SMALL_T];
 	uint16_t posbl[SMALL_T];
 	uint32_t fw[SMALL_T / 32];
@@ -496,7 +516,13 @@ __global__ void __launch_bounds__( SMALL_WARPS * 32 ) k_build_small( BuildArgs A
 	SmallSmem& S = S_all[wid];
 	const SmallRoot root = A.small[r];
 	const uint32_t* src = A.idx[root.depth_buf >> 16];
-	for (uint32_t k = lane; k < root.count; k += 32) S.idx[0][k] = src[root.first + k];
+	for (uint32_t k = lane; k < root.count; k += 32)
+	{
+		const uint32_t fi = src[root.first + k];
+		const float4 mn = __ldg( A.frag_min + fi ), mx = __ldg( A.frag_max + fi );
+		S.gid[k] = fi, S.idx[0][k] = (uint16_t)k;
+		S.fmn[k][0] = mn.x, S.fmn[k][1] = mn.y, S.fmn[k][2] = mn.z, S.fmx[k][0] = mx.x, S.fmx[k][1] = mx.y, S.fmx[k][2] = mx.z;
+	}
 	const float4 rmin = A.tmp_nodes[0], rmax = A.tmp_nodes[1];
 	const float3 min_dim = make_float3( __fmul_rn( __fsub_rn( rmax.x, rmin.x ), 1e-20f ), __fmul_rn( __fsub_rn( rmax.y, rmin.y ), 1e-20f ), __fmul_rn( __fsub_rn( rmax.z, rmin.z ), 1e-20f ) );
 	uint32_t sp = 0, local_max_depth = 0;
@@ -509,28 +535,28 @@ __global__ void __launch_bounds__( SMALL_WARPS * 32 ) k_build_small( BuildArgs A
 		__syncwarp();
 		const float4 nmin = A.tmp_nodes[(size_t)tmp * 2], nmax = A.tmp_nodes[(size_t)tmp * 2 + 1];
 		const float rpx = __fdiv_rn( (float)BINS, __fsub_rn( nmax.x, nmin.x ) ), rpy = __fdiv_rn( (float)BINS, __fsub_rn( nmax.y, nmin.y ) ), rpz = __fdiv_rn( (float)BINS, __fsub_rn( nmax.z, nmin.z ) );
-		for (uint32_t k = lane; k < n; k += 32)
+		for (uint32_t base = 0; base < n; base += 32) // whole warp iterates together: the aggregated update votes
 		{
-			const uint32_t fi = S.idx[buf][lo + k];
-			const float4 fmn = __ldg( A.frag_min + fi ), fmx = __ldg( A.frag_max + fi );
-			const uint32_t b3[3] = { bin_of( fmn.x, fmx.x, nmin.x, rpx ), bin_of( fmn.y, fmx.y, nmin.y, rpy ), bin_of( fmn.z, fmx.z, nmin.z, rpz ) };
-			S.bid[lo + k] = (uint16_t)(b3[0] | (b3[1] << 3) | (b3[2] << 6));
-			const uint32_t kmn[3] = { f2key( fmn.x ), f2key( fmn.y ), f2key( fmn.z ) }, kmx[3] = { f2key( fmx.x ), f2key( fmx.y ), f2key( fmx.z ) };
-			#pragma unroll
-			for (int a = 0; a < 3; a++)
+			const uint32_t k = base + lane;
+			const bool valid = k < n;
+			uint32_t b3[3] = { 0, 0, 0 }, kmn[3] = { 0xffffffffu, 0xffffffffu, 0xffffffffu }, kmx[3] = { 0, 0, 0 };
+			if (valid)
 			{
-				uint32_t* w = S.bins + (a * BINS + b3[a]) * 7;
-				atomicMin( w + 0, kmn[0] ), atomicMin( w + 1, kmn[1] ), atomicMin( w + 2, kmn[2] );
-				atomicMax( w + 3, kmx[0] ), atomicMax( w + 4, kmx[1] ), atomicMax( w + 5, kmx[2] );
-				atomicAdd( w + 6, 1u );
+				const uint32_t sl = S.idx[buf][lo + k];
+				const float mnx = S.fmn[sl][0], mny = S.fmn[sl][1], mnz = S.fmn[sl][2], mxx = S.fmx[sl][0], mxy = S.fmx[sl][1], mxz = S.fmx[sl][2];
+				b3[0] = bin_of( mnx, mxx, nmin.x, rpx ), b3[1] = bin_of( mny, mxy, nmin.y, rpy ), b3[2] = bin_of( mnz, mxz, nmin.z, rpz );
+				S.bid[lo + k] = (uint16_t)(b3[0] | (b3[1] << 3) | (b3[2] << 6));
+				kmn[0] = f2key( mnx ), kmn[1] = f2key( mny ), kmn[2] = f2key( mnz ), kmx[0] = f2key( mxx ), kmx[1] = f2key( mxy ), kmx[2] = f2key( mxz );
 			}
+			#pragma unroll
+			for (int a = 0; a < 3; a++) bin_update_aggregated( S.bins + a * BINS * 7, valid, b3[a], kmn[0], kmn[1], kmn[2], kmx[0], kmx[1], kmx[2] );
 		}
 		__syncwarp();
 		const SweepResult R = sweep_node( S.bins, nmin, nmax, n, min_dim, A.c_trav, A.c_int );
 		bool pop = false;
 		if (!R.split)
 		{
-			for (uint32_t k = lane; k < n; k += 32) A.idx_final[root.first + lo + k] = S.idx[buf][lo + k];
+			for (uint32_t k = lane; k < n; k += 32) A.idx_final[root.first + lo + k] = S.gid[S.idx[buf][lo + k]];
 			pop = true;
 		}
 		else
@@ -712,16 +738,17 @@ int build_sah_launch( tbvh_bvh b, float c_trav, float c_int )
 		DEV_ALLOC( A.frag_min, (size_t)n * 16 ); DEV_ALLOC( A.frag_max, (size_t)n * 16 );
 		DEV_ALLOC( A.idx[0], (size_t)n * 4 ); DEV_ALLOC( A.idx[1], (size_t)n * 4 );
 		DEV_ALLOC( A.bin_ids, (size_t)n * 2 );
-		DEV_ALLOC( A.flags, ((size_t)n + 1) * 4 ); DEV_ALLOC( A.scan, ((size_t)n + 1) * 4 ); DEV_ALLOC( A.pos_bl, ((size_t)n + 1) * 4 );
+		// chunk space: at most n / CHUNK + (#large nodes) chunks per level
+		const size_t flag_words = (size_t)n + (size_t)CHUNK * (max_large + 1) + 1;
+		DEV_ALLOC( A.flags, flag_words * 4 ); DEV_ALLOC( A.scan, flag_words * 4 ); DEV_ALLOC( A.pos_bl, ((size_t)n + 1) * 4 );
 		DEV_ALLOC( A.tmp_nodes, max_nodes * 32 ); DEV_ALLOC( A.node_first, max_nodes * 4 ); DEV_ALLOC( A.node_depth, max_nodes * 4 );
 		DEV_ALLOC( A.lvl[0], max_large * sizeof( LargeNode ) ); DEV_ALLOC( A.lvl[1], max_large * sizeof( LargeNode ) );
 		DEV_ALLOC( A.chunk_start, (max_large + 1) * 4 ); DEV_ALLOC( A.bins, max_large * BIN_WORDS * 4 ); DEV_ALLOC( A.split, max_large * sizeof( SplitInfo ) );
 		DEV_ALLOC( A.small, ((size_t)n + 1) * sizeof( SmallRoot ) );
 		DEV_ALLOC( A.ctr, sizeof( Counters ) );
-		DEV_ALLOC( tile_sum, ((size_t)n / SCAN_TILE + 2) * 4 );
+		DEV_ALLOC( tile_sum, (flag_words / SCAN_TILE + 2) * 4 );
 		CUDA_TRY( cudaMallocHost( &h_ctr, sizeof( Counters ) ) );
 		CUDA_TRY( cudaEventCreate( &e0 ) ); CUDA_TRY( cudaEventCreate( &e1 ) );
-		CUDA_TRY( cudaMemsetAsync( A.flags, 0, ((size_t)n + 1) * 4, s ) ); // stale flags are harmless, uninitialised ones are not tidy
 		CUDA_TRY( cudaEventRecord( e0, s ) );
 		k_init_counters<<<1, 1, 0, s>>>( A ); LAUNCHED();
 		k_fragments<<<(n + 255) / 256, 256, 0, s>>>( A ); LAUNCHED();
@@ -736,7 +763,7 @@ int build_sah_launch( tbvh_bvh b, float c_trav, float c_int )
 			k_bin<<<chunks, CHUNK, 0, s>>>( A, cur, num, idx_in ); LAUNCHED();
 			k_sweep<<<(num * 32 + 255) / 256, 256, 0, s>>>( A, cur, next, num, idx_in, (level + 1) & 1 ); LAUNCHED();
 			k_flags<<<chunks, CHUNK, 0, s>>>( A, cur, num ); LAUNCHED();
-			{ const int r = exclusive_scan( A.flags, A.scan, tile_sum, n, s ); if (r != TBVH_OK) return r; }
+			{ const int r = exclusive_scan( A.flags, A.scan, tile_sum, chunks * CHUNK, s ); if (r != TBVH_OK) return r; }
 			k_posbl<<<chunks, CHUNK, 0, s>>>( A, cur, num ); LAUNCHED();
 			k_scatter<<<chunks, CHUNK, 0, s>>>( A, cur, num, idx_in, idx_out ); LAUNCHED();
 			k_prepare_level<<<1, 1024, 0, s>>>( A, next ); LAUNCHED();

@@ -142,6 +142,11 @@ def load_scene(name: str, allow_synthetic: bool = True):
     if name.startswith("synthetic:"):
         n = int(name.split(":")[1])
         return procedural_scene(n), name
+    if name == "lucy_dragon_x29":
+        # BASELINE.json configs[4] says "~10M tris combined"; the shipped fixtures total 349,852, so the mesh is replicated
+        # 29x on a 4x4x2 grid with pitch 1.1 x bbox extent -> 10,145,708 triangles
+        base, label = load_scene("lucy_dragon", allow_synthetic)
+        return replicate_grid(base, 29), ("lucy_dragon_x29" if label == "lucy_dragon" else "synthetic:lucy_dragon_x29")
     files, ntris = SCENES[name]
     paths = [_find(f) for f in files]
     if all(paths):

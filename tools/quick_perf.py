@@ -60,11 +60,11 @@ def main():
     best, med = timeit(lambda: e.Intersect(dprim, hits=hits))
     print(f"primary  closest: best {best:.3f} ms  {n / best / 1e3:.1f} Mrays/s (median {n / med / 1e3:.1f})")
     if layout == "bvh":
-        for var in (3, 4):
+        for var in (0, 4):
             api.set_option("trace_variant", var)
             best, med = timeit(lambda: e.Intersect(dprim, hits=hits))
             print(f"primary  closest variant {var}: best {best:.3f} ms  {n / best / 1e3:.1f} Mrays/s")
-        api.set_option("trace_variant", 0)
+        api.set_option("trace_variant", 3)
     # shadow + diffuse from traced primaries (host side generation)
     traced = prim.copy()
     h = hits.cpu().numpy()
@@ -84,13 +84,13 @@ def main():
     steps, tris = e.get_stats()
     e.set_stats(False)
     if layout == "bvh":
-        for var in (3, 4):
+        for var in (0, 4):
             api.set_option("trace_variant", var)
             best, med = timeit(lambda: e.IsOccluded(dsh, bits=bits))
             print(f"shadow   anyhit  variant {var}: best {best:.3f} ms  {n / best / 1e3:.1f} Mrays/s")
             best, med = timeit(lambda: e.Intersect(ddf, hits=hits))
             print(f"diffuse  closest variant {var}: best {best:.3f} ms  {n / best / 1e3:.1f} Mrays/s")
-        api.set_option("trace_variant", 0)
+        api.set_option("trace_variant", 3)
     best, med = timeit(lambda: e.Intersect(ddf, hits=hits))
     print(f"diffuse  closest: best {best:.3f} ms  {n / best / 1e3:.1f} Mrays/s (median {n / med / 1e3:.1f})  {steps / n:.1f} steps/ray {tris / n:.2f} tris/ray")
     # host path (pinned) e2e
