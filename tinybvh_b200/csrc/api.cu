@@ -88,6 +88,7 @@ int tbvh_set_option( tbvh_ctx c, const char* key, int value )
 	ARG_CHECK( c && key, "NULL argument" );
 	if (!strcmp( key, "trace_variant" )) c->trace_variant = value;
 	else if (!strcmp( key, "small_t" )) c->small_t = value;
+	else if (!strcmp( key, "small_mode" )) c->small_mode = value & 3;
 	else if (!strcmp( key, "d2h_mode" )) c->d2h_mode = value;
 	else if (!strcmp( key, "h2d_split" )) c->h2d_split = value < 1 ? 1 : value > 4 ? 4 : value;
 	else if (!strcmp( key, "host_path" )) c->host_path = value;

@@ -492,10 +492,10 @@ __global__ void k_bins_init( uint32_t* bins, const uint32_t words )
 // ---------------------------------------------------------------------------------------------- small subtrees
 
 #define SMALL_WARPS 8
-struct SmallSmem
+template <bool FRAGS> struct SmallSmemT
 {
 	uint32_t gid[SMALL_T];            // global primitive index of each local slot
-	float fmn[SMALL_T][3], fmx[SMALL_T][3]; // the subtree's fragment boxes, staged once (every level re-reads them)
+	float fmn[FRAGS ? SMALL_T : 1][3], fmx[FRAGS ? SMALL_T : 1][3]; // FRAGS: the subtree's fragment boxes, staged once
 	uint16_t idx[2][SMALL_T];         // ping-pong order of local slots
 	uint16_t bid[SMALL_T];
 	uint16_t posbl[SMALL_T];
@@ -504,8 +504,13 @@ struct SmallSmem
 	uint32_t st_tmp[12]; uint32_t st_rng[12]; uint32_t st_db[12]; // stack: tmp node, lo | n << 16, depth | buf << 16
 };
 
+// FRAGS: stage the subtree's fragment boxes in shared memory (no global gathers per level, fewer resident warps).
+// AGG:   warp-aggregated bin updates for batches of a node with >= 64 primitives (small nodes use plain shared atomics:
+//        with a handful of active lanes the match/redux sequence costs more than the conflicts it removes).
+template <bool FRAGS, bool AGG>
 __global__ void __launch_bounds__( SMALL_WARPS * 32 ) k_build_small( BuildArgs A, const uint32_t num_roots )
 {
+	typedef SmallSmemT<FRAGS> SmallSmem;
 	// One warp builds a whole subtree of <= SMALL_T primitives: the reference's loop (:2347-2445) with the primitives
 	// of the current node spread over the lanes.  The smaller child is continued, the larger pushed, so the stack
 	// stays below log2(SMALL_T)+2 entries; order of work does not matter because numbering is fixed afterwards.
@@ -519,9 +524,12 @@ __global__ void __launch_bounds__( SMALL_WARPS * 32 ) k_build_small( BuildArgs A
 	for (uint32_t k = lane; k < root.count; k += 32)
 	{
 		const uint32_t fi = src[root.first + k];
-		const float4 mn = __ldg( A.frag_min + fi ), mx = __ldg( A.frag_max + fi );
 		S.gid[k] = fi, S.idx[0][k] = (uint16_t)k;
-		S.fmn[k][0] = mn.x, S.fmn[k][1] = mn.y, S.fmn[k][2] = mn.z, S.fmx[k][0] = mx.x, S.fmx[k][1] = mx.y, S.fmx[k][2] = mx.z;
+		if (FRAGS)
+		{
+			const float4 mn = __ldg( A.frag_min + fi ), mx = __ldg( A.frag_max + fi );
+			S.fmn[k][0] = mn.x, S.fmn[k][1] = mn.y, S.fmn[k][2] = mn.z, S.fmx[k][0] = mx.x, S.fmx[k][1] = mx.y, S.fmx[k][2] = mx.z;
+		}
 	}
 	const float4 rmin = A.tmp_nodes[0], rmax = A.tmp_nodes[1];
 	const float3 min_dim = make_float3( __fmul_rn( __fsub_rn( rmax.x, rmin.x ), 1e-20f ), __fmul_rn( __fsub_rn( rmax.y, rmin.y ), 1e-20f ), __fmul_rn( __fsub_rn( rmax.z, rmin.z ), 1e-20f ) );
@@ -543,13 +551,33 @@ __global__ void __launch_bounds__( SMALL_WARPS * 32 ) k_build_small( BuildArgs A
 			if (valid)
 			{
 				const uint32_t sl = S.idx[buf][lo + k];
-				const float mnx = S.fmn[sl][0], mny = S.fmn[sl][1], mnz = S.fmn[sl][2], mxx = S.fmx[sl][0], mxy = S.fmx[sl][1], mxz = S.fmx[sl][2];
+				float mnx, mny, mnz, mxx, mxy, mxz;
+				if (FRAGS) mnx = S.fmn[sl][0], mny = S.fmn[sl][1], mnz = S.fmn[sl][2], mxx = S.fmx[sl][0], mxy = S.fmx[sl][1], mxz = S.fmx[sl][2];
+				else
+				{
+					const float4 mn = __ldg( A.frag_min + S.gid[sl] ), mx = __ldg( A.frag_max + S.gid[sl] );
+					mnx = mn.x, mny = mn.y, mnz = mn.z, mxx = mx.x, mxy = mx.y, mxz = mx.z;
+				}
 				b3[0] = bin_of( mnx, mxx, nmin.x, rpx ), b3[1] = bin_of( mny, mxy, nmin.y, rpy ), b3[2] = bin_of( mnz, mxz, nmin.z, rpz );
 				S.bid[lo + k] = (uint16_t)(b3[0] | (b3[1] << 3) | (b3[2] << 6));
 				kmn[0] = f2key( mnx ), kmn[1] = f2key( mny ), kmn[2] = f2key( mnz ), kmx[0] = f2key( mxx ), kmx[1] = f2key( mxy ), kmx[2] = f2key( mxz );
 			}
-			#pragma unroll
-			for (int a = 0; a < 3; a++) bin_update_aggregated( S.bins + a * BINS * 7, valid, b3[a], kmn[0], kmn[1], kmn[2], kmx[0], kmx[1], kmx[2] );
+			if (AGG && n >= 64)
+			{
+				#pragma unroll
+				for (int a = 0; a < 3; a++) bin_update_aggregated( S.bins + a * BINS * 7, valid, b3[a], kmn[0], kmn[1], kmn[2], kmx[0], kmx[1], kmx[2] );
+			}
+			else if (valid)
+			{
+				#pragma unroll
+				for (int a = 0; a < 3; a++)
+				{
+					uint32_t* w = S.bins + (a * BINS + b3[a]) * 7;
+					atomicMin( w + 0, kmn[0] ), atomicMin( w + 1, kmn[1] ), atomicMin( w + 2, kmn[2] );
+					atomicMax( w + 3, kmx[0] ), atomicMax( w + 4, kmx[1] ), atomicMax( w + 5, kmx[2] );
+					atomicAdd( w + 6, 1u );
+				}
+			}
 		}
 		__syncwarp();
 		const SweepResult R = sweep_node( S.bins, nmin, nmax, n, min_dim, A.c_trav, A.c_int );
@@ -782,7 +810,15 @@ int build_sah_launch( tbvh_bvh b, float c_trav, float c_int )
 		CUDA_TRY( cudaMemcpyAsync( h_ctr, A.ctr, sizeof( Counters ), cudaMemcpyDeviceToHost, s ) );
 		CUDA_TRY( cudaStreamSynchronize( s ) );
 		const uint32_t roots = h_ctr->small_roots;
-		if (roots) { k_build_small<<<(roots + SMALL_WARPS - 1) / SMALL_WARPS, SMALL_WARPS * 32, 0, s>>>( A, roots ); LAUNCHED(); }
+		if (roots)
+		{
+			const uint32_t g = (roots + SMALL_WARPS - 1) / SMALL_WARPS, mode = (uint32_t)b->ctx->small_mode;
+			if (mode == 0) k_build_small<false, false><<<g, SMALL_WARPS * 32, 0, s>>>( A, roots );
+			else if (mode == 1) k_build_small<true, false><<<g, SMALL_WARPS * 32, 0, s>>>( A, roots );
+			else if (mode == 2) k_build_small<false, true><<<g, SMALL_WARPS * 32, 0, s>>>( A, roots );
+			else k_build_small<true, true><<<g, SMALL_WARPS * 32, 0, s>>>( A, roots );
+			LAUNCHED();
+		}
 		CUDA_TRY( cudaMemcpyAsync( h_ctr, A.ctr, sizeof( Counters ), cudaMemcpyDeviceToHost, s ) );
 		CUDA_TRY( cudaStreamSynchronize( s ) );
 		const uint32_t tmp_count = h_ctr->tmp_nodes;
