@@ -78,10 +78,22 @@ struct SweepResult { bool split; uint32_t axis, pos, lN; float l1[3], l2[3], r1[
 
 // One warp evaluates the 21 candidate planes of a node from its bin table (ordered keys + counts) - the sweep,
 // termination test and child bounds of tiny_bvh.h:2380-2412.  All lanes return the same result.
-__device__ __forceinline__ SweepResult sweep_node( const uint32_t* bins /* BIN_WORDS, shared or global */, const float4 nmin, const float4 nmax,
+__device__ __forceinline__ SweepResult sweep_node( uint32_t* bins /* BIN_WORDS, shared or global; decoded in place */, const float4 nmin, const float4 nmax,
 	const uint32_t count, const float3 min_dim, const float c_trav, const float c_int )
 {
 	const uint32_t lane = threadIdx.x & 31;
+	// decode pass: lanes 0..23 turn the six ordered keys of "their" bin back into floats, once, instead of every one of
+	// the 7 candidate lanes of an axis decoding all 8 bins again
+	if (lane < 3 * BINS)
+	{
+		uint32_t* w = bins + lane * 7;
+		if (w[6] != 0)
+		{
+			#pragma unroll
+			for (int k = 0; k < 6; k++) w[k] = __float_as_uint( key2f( w[k] ) );
+		}
+	}
+	__syncwarp();
 	const uint32_t a = lane / 7, i = lane % 7; // lanes 0..20: axis a, plane i
 	float l1[3] = { BVH_FAR, BVH_FAR, BVH_FAR }, l2[3] = { -BVH_FAR, -BVH_FAR, -BVH_FAR };
 	float r1[3] = { BVH_FAR, BVH_FAR, BVH_FAR }, r2[3] = { -BVH_FAR, -BVH_FAR, -BVH_FAR };
@@ -98,8 +110,8 @@ __device__ __forceinline__ SweepResult sweep_node( const uint32_t* bins /* BIN_W
 				const uint32_t* w = bins + (a * BINS + b) * 7;
 				const uint32_t c = w[6];
 				if (c == 0) continue; // empty bin: the reference's +-BVH_FAR initial box, no effect on a union
-				const float mnx = key2f( w[0] ), mny = key2f( w[1] ), mnz = key2f( w[2] );
-				const float mxx = key2f( w[3] ), mxy = key2f( w[4] ), mxz = key2f( w[5] );
+				const float mnx = __uint_as_float( w[0] ), mny = __uint_as_float( w[1] ), mnz = __uint_as_float( w[2] );
+				const float mxx = __uint_as_float( w[3] ), mxy = __uint_as_float( w[4] ), mxz = __uint_as_float( w[5] );
 				if (b <= i)
 				{
 					l1[0] = fminf( l1[0], mnx ), l1[1] = fminf( l1[1], mny ), l1[2] = fminf( l1[2], mnz );

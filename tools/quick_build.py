@@ -7,11 +7,11 @@ REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, REPO)
 from tinybvh_b200 import api, scenes  # noqa: E402
 
-for scene in sys.argv[1:] or ["sponza"]:
+for scene in [a for a in sys.argv[1:] if not a.startswith("--")] or ["sponza"]:
     v, label = scenes.load_scene(scene)
     n = v.shape[0] // 3
-    for mode in (0, 1, 2, 3):
-        for t in (64, 128):
+    for mode in ((0, 1, 2, 3) if "--all" in sys.argv else (0,)):
+        for t in ((64, 128) if "--all" in sys.argv else (128,)):
             api.set_option("small_mode", mode)
             api.set_option("small_t", t)
             best = 1e9
