@@ -20,7 +20,12 @@ __device__ __forceinline__ uint32_t sign_extend_s8x4( const uint32_t x )
 	return v;
 }
 
-__device__ __forceinline__ float byte_f( const uint32_t w, const int i ) { return (float)((w >> (8 * i)) & 0xffu); }
+// (float)byte i of w without the quarter-rate I2F: splice the byte under the mantissa of 2^23 (one PRMT) and subtract 2^23
+// (exact).  The node step converts 48 bytes; with I2F the conversion unit, not the issue slots, bounded the kernel.
+__device__ __forceinline__ float byte_f( const uint32_t w, const int i )
+{
+	return __fsub_rn( __uint_as_float( __byte_perm( w, 0x4b000000u, 0x7650u | (uint32_t)i ) ), 8388608.0f );
+}
 
 // 4 children: quantised bounds words (lo/hi per axis, already swizzled by ray sign) -> hit bits
 __device__ __forceinline__ uint32_t slab4( const uint32_t meta4, const uint32_t octinv4, const uint32_t lox, const uint32_t loy, const uint32_t loz,
