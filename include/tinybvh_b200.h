@@ -83,6 +83,14 @@ int tbvh_bvh_info( tbvh_bvh bvh, tbvh_info* out );
  * (the reference keeps a pointer: "we're not copying this data").  c_trav / c_int = BVHBase::c_trav, c_int. */
 int tbvh_build( tbvh_bvh bvh, const void* verts, uint32_t stride, uint32_t prim_count, int space, float c_trav, float c_int );
 
+/* The same builder with the decisions of BVH::BuildAVX (tiny_bvh.h:6400-6671) - the builder BuildDefault (:1817-1832) picks
+ * on x86, i.e. what BVH_GPU::Build, BVH8_CWBVH::Build and BVH8_CPU::Build construct their trees with.  It differs from
+ * BVH::Build in bin rounding, the partition's bin function, minDim and the plane tie-break order; the trees are
+ * "nearly identical" (:6352) but not byte-identical, so both flavours exist. */
+#define TBVH_BUILD_REFERENCE 0   /* BVH::Build */
+#define TBVH_BUILD_AVX 1         /* BVH::BuildAVX / BuildDefault */
+int tbvh_build_flavour( tbvh_bvh bvh, const void* verts, uint32_t stride, uint32_t prim_count, int space, float c_trav, float c_int, int flavour );
+
 /* consume a tree built elsewhere, in the reference's own layouts (the public members bvhNode / primIdx /
  * verts of tiny_bvh.h:952-964, BVH_GPU::bvhNode :1124, BVH8_CWBVH::bvh8Data / bvh8Tris :1356-1357) */
 int tbvh_upload_bvh( tbvh_bvh bvh, const void* nodes32, uint32_t used_nodes, const uint32_t* prim_idx, uint32_t idx_count,

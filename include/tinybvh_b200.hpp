@@ -115,6 +115,12 @@ public:
 		TBVH_FATAL_IF( tbvh_build( h, vertices, (uint32_t)sizeof( Vec4 ), primCount, TBVH_HOST, c_trav, c_int ), "BVH::Build" );
 		sync_info();
 	}
+	// BVH::BuildAVX( const bvhvec4*, uint32_t ) tiny_bvh.h:6400 - the flavour BuildDefault picks on x86
+	template <class Vec4> void BuildAVX( const Vec4* vertices, const uint32_t primCount )
+	{
+		TBVH_FATAL_IF( tbvh_build_flavour( h, vertices, (uint32_t)sizeof( Vec4 ), primCount, TBVH_HOST, c_trav, c_int, TBVH_BUILD_AVX ), "BVH::BuildAVX" );
+		sync_info();
+	}
 	template <class Vec4> void BuildHQ( const Vec4*, const uint32_t )
 	{
 		fprintf( stderr, "Fatal error in tinybvh_b200 BVH::BuildHQ: the SBVH builder (tiny_bvh.h:2623) is not implemented on the GPU and there is no CPU fallback.\n" );
@@ -135,7 +141,8 @@ public:
 	BVH_GPU() : BVHBase( TBVH_LAYOUT_BVH_GPU ) {}
 	template <class Vec4> void Build( const Vec4* vertices, const uint32_t primCount )
 	{
-		TBVH_FATAL_IF( tbvh_build( h, vertices, (uint32_t)sizeof( Vec4 ), primCount, TBVH_HOST, c_trav, c_int ), "BVH_GPU::Build" );
+		// BVH_GPU::Build -> bvh.BuildDefault = BuildAVX on x86 (tiny_bvh.h:1817-1832)
+		TBVH_FATAL_IF( tbvh_build_flavour( h, vertices, (uint32_t)sizeof( Vec4 ), primCount, TBVH_HOST, c_trav, c_int, TBVH_BUILD_AVX ), "BVH_GPU::Build" );
 		TBVH_FATAL_IF( tbvh_convert( h, TBVH_LAYOUT_BVH_GPU ), "BVH_GPU::Build" );
 		sync_info();
 	}
@@ -156,7 +163,8 @@ public:
 	uint32_t usedBlocks = 0;
 	template <class Vec4> void Build( const Vec4* vertices, const uint32_t primCount )
 	{
-		TBVH_FATAL_IF( tbvh_build( h, vertices, (uint32_t)sizeof( Vec4 ), primCount, TBVH_HOST, c_trav, c_int ), "BVH8_CWBVH::Build" );
+		// BVH8_CWBVH::Build -> bvh8.bvh.BuildDefault = BuildAVX on x86 (tiny_bvh.h:5830)
+		TBVH_FATAL_IF( tbvh_build_flavour( h, vertices, (uint32_t)sizeof( Vec4 ), primCount, TBVH_HOST, c_trav, c_int, TBVH_BUILD_AVX ), "BVH8_CWBVH::Build" );
 		TBVH_FATAL_IF( tbvh_convert( h, TBVH_LAYOUT_CWBVH ), "BVH8_CWBVH::Build" );
 		sync_info(), usedBlocks = Info().used_blocks;
 	}

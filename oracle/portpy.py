@@ -32,6 +32,7 @@ def lib():
         L = C.CDLL(PORT_SO)
         vp, u32, u64, i32, f32 = C.c_void_p, C.c_uint32, C.c_uint64, C.c_int, C.c_float
         L.orc_build.restype, L.orc_build.argtypes = u32, [vp, u32, vp, vp, f32, f32]
+        L.orc_build_avx.restype, L.orc_build_avx.argtypes = u32, [vp, u32, vp, vp, f32, f32]
         L.orc_intersect.restype, L.orc_intersect.argtypes = None, [vp, vp, vp, vp, u64, i32]
         L.orc_occluded.restype, L.orc_occluded.argtypes = None, [vp, vp, vp, vp, u64, vp, i32]
         L.orc_tri_test.restype, L.orc_tri_test.argtypes = i32, [vp] * 5 + [f32] + [vp] * 3
@@ -48,7 +49,7 @@ def _ptr(a):
 class PortBVH:
     """orc_build + orc_intersect / orc_occluded: restatement of BVH::Build + Intersect / IsOccluded."""
 
-    def __init__(self, verts=None, c_trav: float = 1.0, c_int: float = 1.0, nodes=None, prim_idx=None):
+    def __init__(self, verts=None, c_trav: float = 1.0, c_int: float = 1.0, nodes=None, prim_idx=None, avx: bool = False):
         self.verts = np.ascontiguousarray(verts, np.float32).reshape(-1, 4)
         n = self.verts.shape[0] // 3
         if nodes is not None:
@@ -57,7 +58,8 @@ class PortBVH:
             return
         nodes = np.zeros(max(2 * n, 2), NODE32)
         self.prim_idx = np.zeros(n, np.uint32)
-        used = lib().orc_build(_ptr(self.verts), n, _ptr(nodes), _ptr(self.prim_idx), c_trav, c_int)
+        fn = lib().orc_build_avx if avx else lib().orc_build
+        used = fn(_ptr(self.verts), n, _ptr(nodes), _ptr(self.prim_idx), c_trav, c_int)
         self.nodes = nodes[:used].copy()
 
     used_nodes = property(lambda s: s.nodes.shape[0])

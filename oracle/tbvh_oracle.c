@@ -46,7 +46,28 @@ static inline int bin_of( float bmin, float bmax, float nmin, float rpd )
 	return bi > 0 ? (bi < BVHBINS - 1 ? bi : BVHBINS - 1) : 0;  /* tinybvh_clamp :458 */
 }
 
-uint32_t orc_build( const float* verts, uint32_t primCount, orc_node* nodes, uint32_t* primIdx, float c_trav, float c_int )
+/* BuildAVXBinTask :6500-6502: cvtps2dq( fma( (bmax+bmin) - 2*nmin, rpd, -0.5 ) ), clamped to [0,7]; cvtps2dq rounds to nearest even
+ * and yields INT_MIN for NaN / out of range */
+static inline int bin_of_avx( float bmin, float bmax, float nmin2, float rpd )
+{
+	const float f = fmaf( (bmax + bmin) - nmin2, rpd, -0.5f );
+	int bi = (f != f || f >= 2147483648.0f || f < -2147483648.0f) ? (int)0x80000000 : (int)lrintf( f );
+	return bi > 0 ? (bi < BVHBINS - 1 ? bi : BVHBINS - 1) : 0;
+}
+/* BuildAVXSubtree :6629: (uint32_t)((bmax + bmin - nmin) * rpd) - 64-bit cvttss2si, low 32 bits, no clamp */
+static inline uint32_t part_bin_avx( float bmin, float bmax, float nmin2, float rpd )
+{
+	const float f = (bmax + bmin - nmin2) * rpd;
+	const long long v = (f != f || f >= 9223372036854775808.0f || f < -9223372036854775808.0f) ? (long long)0x8000000000000000ull : (long long)f;
+	return (uint32_t)v;
+}
+
+/* flavour 0: BVH::Build (:2332-2461).  flavour 1: BVH::BuildAVX (:6400-6671) - the builder BuildDefault (:1817-1832), and with it
+ * every derived layout's Build(), runs on x86.  Same algorithm; it differs in: the bin index (round-to-nearest of
+ * fma(bmax+bmin-2*nmin, 3.99992/extent, -0.5), rpd = 0 on a zero extent); the partition's own bin function (truncation,
+ * no -0.5, no clamp) which also decides the child counts; minDim = 1e-7 * root extent; planes tried in the order
+ * 3,2,4,5,1,0,6 with both sides non-empty; cost = fma(lN, areaL, rN*areaR). */
+static uint32_t build_impl( const float* verts, uint32_t primCount, orc_node* nodes, uint32_t* primIdx, float c_trav, float c_int, int flavour )
 {
 	orc_fragment* fragment = (orc_fragment*)malloc( (size_t)primCount * sizeof( orc_fragment ) );
 	memset( &nodes[1], 0, sizeof( orc_node ) ); /* node 1 unused, :2285 */
@@ -69,7 +90,8 @@ uint32_t orc_build( const float* verts, uint32_t primCount, orc_node* nodes, uin
 	uint32_t newNodePtr = 2;
 	/* Build(nodeIdx, depth) :2332-2461, non-threaded numbering */
 	uint32_t task[256], taskCount = 0, nodeIdx = 0;
-	float minDim[3] = { (rmax[0] - rmin[0]) * 1e-20f, (rmax[1] - rmin[1]) * 1e-20f, (rmax[2] - rmin[2]) * 1e-20f };
+	const float mdf = flavour ? 1e-7f : 1e-20f;
+	float minDim[3] = { (rmax[0] - rmin[0]) * mdf, (rmax[1] - rmin[1]) * mdf, (rmax[2] - rmin[2]) * mdf };
 	float bestLMin[3] = { 0 }, bestLMax[3] = { 0 }, bestRMin[3] = { 0 }, bestRMax[3] = { 0 };
 	while (1)
 	{
@@ -82,14 +104,19 @@ uint32_t orc_build( const float* verts, uint32_t primCount, orc_node* nodes, uin
 			for (int a = 0; a < 3; a++) for (int i = 0; i < BVHBINS; i++) for (int k = 0; k < 3; k++)
 				binMin[a][i][k] = BVH_FAR, binMax[a][i][k] = -BVH_FAR;
 			memset( count, 0, sizeof( count ) );
-			float rpd3[3];
-			for (int a = 0; a < 3; a++) rpd3[a] = (float)BVHBINS / (nmax3[a] - nmin3[a]);
+			float rpd3[3], nmin2[3] = { 0, 0, 0 };
+			for (int a = 0; a < 3; a++)
+			{
+				if (!flavour) { rpd3[a] = (float)BVHBINS / (nmax3[a] - nmin3[a]); continue; }
+				const float d = nmax3[a] - nmin3[a]; /* :6557-6559 */
+				nmin2[a] = nmin3[a] * 2.0f, rpd3[a] = d == 0 ? 0.0f : (BVHBINS * 0.49999f) / d;
+			}
 			for (uint32_t i = 0; i < node->triCount; i++) /* binning :2357-2376 */
 			{
 				const orc_fragment* f = &fragment[primIdx[node->leftFirst + i]];
 				for (int a = 0; a < 3; a++)
 				{
-					const int bi = bin_of( f->bmin[a], f->bmax[a], nmin3[a], rpd3[a] );
+					const int bi = flavour ? bin_of_avx( f->bmin[a], f->bmax[a], nmin2[a], rpd3[a] ) : bin_of( f->bmin[a], f->bmax[a], nmin3[a], rpd3[a] );
 					for (int k = 0; k < 3; k++)
 						binMin[a][bi][k] = fminf_( binMin[a][bi][k], f->bmin[k] ),
 						binMax[a][bi][k] = fmaxf_( binMax[a][bi][k], f->bmax[k] );
@@ -102,6 +129,40 @@ uint32_t orc_build( const float* verts, uint32_t primCount, orc_node* nodes, uin
 			uint32_t bestAxis = 0, bestPos = 0;
 			for (int a = 0; a < 3; a++) if ((nmax3[a] - nmin3[a]) > minDim[a])
 			{
+				if (flavour)
+				{
+					/* :6597-6621 - prefix / suffix unions, then the planes in the order 3,2,4,5,1,0,6 */
+					static const int order[7] = { 3, 2, 4, 5, 1, 0, 6 };
+					float lmn[7][3], lmx[7][3], rmn[7][3], rmx[7][3];
+					uint32_t lNs[7], rNs[7];
+					float a1[3] = { BVH_FAR, BVH_FAR, BVH_FAR }, a2[3] = { -BVH_FAR, -BVH_FAR, -BVH_FAR };
+					float b1[3] = { BVH_FAR, BVH_FAR, BVH_FAR }, b2[3] = { -BVH_FAR, -BVH_FAR, -BVH_FAR };
+					uint32_t ln = 0, rn = 0;
+					for (int i = 0; i < 7; i++)
+					{
+						for (int k = 0; k < 3; k++)
+						{
+							lmn[i][k] = a1[k] = fminf_( a1[k], binMin[a][i][k] ), lmx[i][k] = a2[k] = fmaxf_( a2[k], binMax[a][i][k] );
+							rmn[6 - i][k] = b1[k] = fminf_( b1[k], binMin[a][7 - i][k] ), rmx[6 - i][k] = b2[k] = fmaxf_( b2[k], binMax[a][7 - i][k] );
+						}
+						ln += count[a][i], rn += count[a][7 - i];
+						lNs[i] = ln, rNs[6 - i] = rn;
+					}
+					for (int o = 0; o < 7; o++)
+					{
+						const int i = order[o];
+						if (lNs[i] == 0 || rNs[i] == 0) continue; /* PROCESS_PLANE: lN * rN != 0 */
+						const float aL = half_area( lmx[i][0] - lmn[i][0], lmx[i][1] - lmn[i][1], lmx[i][2] - lmn[i][2] );
+						const float aR = half_area( rmx[i][0] - rmn[i][0], rmx[i][1] - rmn[i][1], rmx[i][2] - rmn[i][2] );
+						const float C = fmaf( (float)lNs[i], aL, aR * (float)rNs[i] );
+						if (C < splitCost)
+						{
+							splitCost = C, bestAxis = a, bestPos = i;
+							for (int k = 0; k < 3; k++) bestLMin[k] = lmn[i][k], bestLMax[k] = lmx[i][k], bestRMin[k] = rmn[i][k], bestRMax[k] = rmx[i][k];
+						}
+					}
+					continue;
+				}
 				float lBMin[BVHBINS - 1][3], rBMin[BVHBINS - 1][3], lBMax[BVHBINS - 1][3], rBMax[BVHBINS - 1][3];
 				float l1[3] = { BVH_FAR, BVH_FAR, BVH_FAR }, l2[3] = { -BVH_FAR, -BVH_FAR, -BVH_FAR };
 				float r1[3] = { BVH_FAR, BVH_FAR, BVH_FAR }, r2[3] = { -BVH_FAR, -BVH_FAR, -BVH_FAR };
@@ -147,8 +208,8 @@ uint32_t orc_build( const float* verts, uint32_t primCount, orc_node* nodes, uin
 			for (uint32_t i = 0; i < node->triCount; i++)
 			{
 				const orc_fragment* f = &fragment[primIdx[src]];
-				const int bi = bin_of( f->bmin[bestAxis], f->bmax[bestAxis], nmin, rpd );
-				if ((uint32_t)bi <= bestPos) src++;
+				const uint32_t bi = flavour ? part_bin_avx( f->bmin[bestAxis], f->bmax[bestAxis], nmin2[bestAxis], rpd ) : (uint32_t)bin_of( f->bmin[bestAxis], f->bmax[bestAxis], nmin, rpd );
+				if (bi <= bestPos) src++;
 				else { uint32_t t = primIdx[src]; primIdx[src] = primIdx[--j], primIdx[j] = t; }
 			}
 			const uint32_t leftCount = src - node->leftFirst, rightCount = node->triCount - leftCount;
@@ -168,6 +229,15 @@ uint32_t orc_build( const float* verts, uint32_t primCount, orc_node* nodes, uin
 	}
 	free( fragment );
 	return newNodePtr;
+}
+
+uint32_t orc_build( const float* verts, uint32_t primCount, orc_node* nodes, uint32_t* primIdx, float c_trav, float c_int )
+{
+	return build_impl( verts, primCount, nodes, primIdx, c_trav, c_int, 0 );
+}
+uint32_t orc_build_avx( const float* verts, uint32_t primCount, orc_node* nodes, uint32_t* primIdx, float c_trav, float c_int )
+{
+	return build_impl( verts, primCount, nodes, primIdx, c_trav, c_int, 1 );
 }
 
 /* -------------------------------------------------------------------------------------------- traversal */

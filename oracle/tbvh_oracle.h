@@ -23,6 +23,8 @@ typedef struct { float lmin[3]; uint32_t left; float lmax[3]; uint32_t right; fl
 /* BVH::PrepareBuild (:2261) + BVH::Build(nodeIdx,depth) (:2332), single-threaded numbering.
  * verts: primCount*3 float4; nodes: room for 2*primCount; primIdx: room for primCount. Returns usedNodes. */
 uint32_t orc_build( const float* verts, uint32_t primCount, orc_node* nodes, uint32_t* primIdx, float c_trav, float c_int );
+/* BVH::PrepareAVXBuild (:6424) + BVH::BuildAVXSubtree (:6529) = what BuildDefault (:1817) runs on x86, single-threaded numbering */
+uint32_t orc_build_avx( const float* verts, uint32_t primCount, orc_node* nodes, uint32_t* primIdx, float c_trav, float c_int );
 
 /* BVH::Intersect (:3222,:3247) / BVH::IsOccluded (:3382,:3407) over 128-byte host Ray records, in place.
  * threads<=0 -> all cores (OpenMP). */

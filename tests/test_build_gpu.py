@@ -71,3 +71,22 @@ def test_rebuild_is_deterministic(gpu):
     a = api.BVH().Build(v).download()
     b = api.BVH().Build(v).download()
     assert np.array_equal(a[0].view(np.uint8), b[0].view(np.uint8)) and np.array_equal(a[1], b[1])
+
+
+@pytest.mark.parametrize("ntris,seed", [(1, 81), (2, 82), (129, 83), (1000, 84), (70000, 85), (300000, 86)])
+def test_build_avx_flavour_matches_reference(gpu, ntris, seed):
+    """BVH::BuildAVX (what BuildDefault runs on x86): same tree as the reference's, byte for byte."""
+    from oracle import portpy, refpy
+    v = scenes.procedural_scene(ntris, seed)
+    o = refpy.RefBVH(v, mode=1, threaded=False) if refpy.available() else portpy.PortBVH(v, avx=True)
+    e = api.BVH().BuildAVX(v)
+    assert_same_tree(e, o.nodes, o.prim_idx, f"BuildAVX {ntris} tris")
+
+
+@pytest.mark.parametrize("scene", ["bunny", "sponza"])
+def test_build_avx_flavour_fixtures(gpu, scene):
+    from oracle import portpy, refpy
+    v, label = scenes.load_scene(scene)
+    o = refpy.RefBVH(v, mode=1, threaded=False) if refpy.available() else portpy.PortBVH(v, avx=True)
+    e = api.BVH().BuildAVX(v)
+    assert_same_tree(e, o.nodes, o.prim_idx, "BuildAVX " + label)

@@ -4,6 +4,7 @@ import pytest
 
 from oracle import refpy
 from tinybvh_b200 import api, scenes
+from tinybvh_b200._lib import BUILD_AVX, BUILD_REFERENCE
 from tests import golden_util as G
 from tests import util
 
@@ -20,17 +21,23 @@ def diff_nodes(got, want, words):
 @pytest.mark.parametrize("path", G.golden_files(), ids=lambda p: p.split("/")[-1])
 def test_bvh_gpu_conversion_matches_golden(gpu, path):
     g = G.load(path)
-    e = api.BVH_GPU().Build(g["verts"])
+    e = api.BVH_GPU()
+    e.build_flavour = BUILD_REFERENCE   # the golden vectors hold BVH_GPU::ConvertFrom of the scalar BVH::Build tree
+    e.Build(g["verts"])
     diff_nodes(e.download(), g["nodes_gpu"].view(np.uint8).view(api.NODE64).reshape(-1), 16)
 
 
 @pytest.mark.skipif(not refpy.available(), reason="needs oracle/_ref")
 @pytest.mark.parametrize("ntris,seed", [(5, 51), (999, 52), (120000, 53)])
-def test_bvh_gpu_conversion_matches_reference(gpu, ntris, seed):
+@pytest.mark.parametrize("flavour", [BUILD_REFERENCE, BUILD_AVX])
+def test_bvh_gpu_conversion_matches_reference(gpu, ntris, seed, flavour):
+    """flavour AVX = BVH_GPU::Build itself (BuildDefault -> BuildAVX, then ConvertFrom); REFERENCE = ConvertFrom(BVH::Build)."""
     v = scenes.procedural_scene(ntris, seed)
-    ref = refpy.RefBVH(v, mode=0, threaded=False)
+    ref = refpy.RefBVH(v, mode=1 if flavour == BUILD_AVX else 0, threaded=False)
     want = refpy.RefBVHGPU(ref).nodes
-    e = api.BVH_GPU().Build(v)
+    e = api.BVH_GPU()
+    e.build_flavour = flavour
+    e.Build(v)
     diff_nodes(e.download(), want, 16)
     # the converted layout traverses like the source tree
     sets, _ = util.ray_sets(v, res=48)
@@ -66,10 +73,15 @@ def diff_blob(got, want, name, row_bytes):
 
 @pytest.mark.skipif(not refpy.available(), reason="needs oracle/_ref")
 @pytest.mark.parametrize("ntris,seed", [(1, 61), (3, 62), (4, 63), (40, 64), (2000, 65), (60000, 66)])
-def test_cwbvh_conversion_matches_reference(gpu, ntris, seed):
+@pytest.mark.parametrize("flavour", [BUILD_REFERENCE, BUILD_AVX])
+def test_cwbvh_conversion_matches_reference(gpu, ntris, seed, flavour):
+    """flavour AVX: byte-identical to BVH8_CWBVH::Build itself (mode 0: BuildDefault = BuildAVX, Compact, SplitLeafs, collapse,
+    encode); REFERENCE: the same chain over the scalar BVH::Build tree (mode 2)."""
     v = scenes.procedural_scene(ntris, seed)
-    cw = refpy.RefCWBVH(v, mode=2)
-    e = api.BVH8_CWBVH().Build(v)
+    cw = refpy.RefCWBVH(v, mode=0 if flavour == BUILD_AVX else 2)
+    e = api.BVH8_CWBVH()
+    e.build_flavour = flavour
+    e.Build(v)
     nodes, tris = e.download()
     diff_blob(nodes, cw.nodes, "bvh8Data (80-byte nodes)", 80)
     diff_blob(tris, cw.tris, "bvh8Tris (48-byte triangles)", 48)
@@ -79,7 +91,7 @@ def test_cwbvh_conversion_matches_reference(gpu, ntris, seed):
 @pytest.mark.parametrize("scene", ["bunny", "sponza"])
 def test_cwbvh_conversion_fixtures(gpu, scene):
     v, label = scenes.load_scene(scene)
-    cw = refpy.RefCWBVH(v, mode=2)
+    cw = refpy.RefCWBVH(v, mode=0)      # BVH8_CWBVH::Build as the reference runs it (threaded BuildAVX underneath)
     e = api.BVH8_CWBVH().Build(v)
     nodes, tris = e.download()
     diff_blob(nodes, cw.nodes, label + " bvh8Data", 80)

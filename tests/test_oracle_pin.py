@@ -78,3 +78,15 @@ def test_primary_ray_pattern():
     # first 256 rays = first 4x4-pixel tile, 16 samples per pixel (tiny_bvh_speedtest.cpp:527-540)
     assert np.allclose(r["O"], R.SPONZA_EYES[0])
     assert np.allclose(np.linalg.norm(r["D"], axis=1), 1, atol=1e-6)
+
+
+@pytest.mark.skipif(not refpy.available(), reason="oracle/_ref not built (needs /root/reference)")
+@pytest.mark.parametrize("ntris,seed", [(20000, 5), (777, 6), (3, 7)])
+def test_port_avx_flavour_matches_reference(ntris, seed):
+    """orc_build_avx restates BVH::BuildAVX (the BuildDefault builder on x86): byte-identical trees."""
+    v = scenes.procedural_scene(ntris, seed)
+    ref = refpy.RefBVH(v, mode=1, threaded=False)
+    port = portpy.PortBVH(v, avx=True)
+    assert ref.used_nodes == port.used_nodes
+    assert np.array_equal(ref.nodes.view(np.uint8), port.nodes.view(np.uint8))
+    assert np.array_equal(ref.prim_idx, port.prim_idx)

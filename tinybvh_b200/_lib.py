@@ -11,6 +11,7 @@ SO = os.path.join(HERE, "libtinybvh_b200.so")
 
 OK, HOST, DEVICE = 0, 0, 1
 LAYOUT_BVH, LAYOUT_BVH_GPU, LAYOUT_CWBVH = 1, 5, 10
+BUILD_REFERENCE, BUILD_AVX = 0, 1
 
 
 class TbvhError(RuntimeError):
@@ -40,6 +41,7 @@ SYMBOLS = {
     "tbvh_bvh_destroy": (i32, [vp]),
     "tbvh_bvh_info": (i32, [vp, C.POINTER(Info)]),
     "tbvh_build": (i32, [vp, vp, u32, u32, i32, f32, f32]),
+    "tbvh_build_flavour": (i32, [vp, vp, u32, u32, i32, f32, f32, i32]),
     "tbvh_upload_bvh": (i32, [vp, vp, u32, vp, u32, vp, u32, u32, i32]),
     "tbvh_upload_bvh_gpu": (i32, [vp, vp, u32, vp, u32, vp, u32, u32, i32]),
     "tbvh_upload_cwbvh": (i32, [vp, vp, u32, vp, u32, i32]),

@@ -63,6 +63,7 @@ def _verts_arg(verts):
 
 class _Base:
     layout = LAYOUT_BVH
+    build_flavour = _lib.BUILD_AVX   # derived layouts build through BuildDefault; set to _lib.BUILD_REFERENCE for BVH::Build's tree
 
     def __init__(self, device: int = 0):
         self.device = device
@@ -155,6 +156,12 @@ class BVH(_Base):
         check(_lib.lib().tbvh_build(self.h, p, stride, n, space, self.c_trav, self.c_int))
         return self
 
+    def BuildAVX(self, vertices, primCount: int = 0):
+        """BVH::BuildAVX (tiny_bvh.h:6400) - the flavour BuildDefault uses on x86."""
+        p, stride, nv, space, keep = _verts_arg(vertices)
+        check(_lib.lib().tbvh_build_flavour(self.h, p, stride, primCount or nv // 3, space, self.c_trav, self.c_int, _lib.BUILD_AVX))
+        return self
+
     def BuildHQ(self, vertices, primCount: int = 0):
         raise TbvhError("BVH::BuildHQ (SBVH, tiny_bvh.h:2623) is not implemented on the GPU yet; no CPU fallback")
 
@@ -182,7 +189,8 @@ class BVH_GPU(_Base):
 
     def Build(self, vertices, primCount: int = 0):
         p, stride, nv, space, keep = _verts_arg(vertices)
-        check(_lib.lib().tbvh_build(self.h, p, stride, primCount or nv // 3, space, self.c_trav, self.c_int))
+        # BVH_GPU::Build -> bvh.BuildDefault (tiny_bvh.h:4580-4590) = BuildAVX on x86, then ConvertFrom
+        check(_lib.lib().tbvh_build_flavour(self.h, p, stride, primCount or nv // 3, space, self.c_trav, self.c_int, self.build_flavour))
         check(_lib.lib().tbvh_convert(self.h, LAYOUT_BVH_GPU))
         return self
 
@@ -207,7 +215,8 @@ class BVH8_CWBVH(_Base):
 
     def Build(self, vertices, primCount: int = 0):
         p, stride, nv, space, keep = _verts_arg(vertices)
-        check(_lib.lib().tbvh_build(self.h, p, stride, primCount or nv // 3, space, self.c_trav, self.c_int))
+        # BVH8_CWBVH::Build -> bvh8.bvh.BuildDefault (tiny_bvh.h:5830) = BuildAVX on x86, then the conversion chain
+        check(_lib.lib().tbvh_build_flavour(self.h, p, stride, primCount or nv // 3, space, self.c_trav, self.c_int, self.build_flavour))
         check(_lib.lib().tbvh_convert(self.h, LAYOUT_CWBVH))
         return self
 

@@ -289,15 +289,21 @@ int tbvh_upload_cwbvh( tbvh_bvh b, const void* bvh8_data, uint32_t used_blocks, 
 	return TBVH_OK;
 }
 
-int tbvh_build( tbvh_bvh b, const void* verts, uint32_t stride, uint32_t prim_count, int space, float c_trav, float c_int )
+int tbvh_build_flavour( tbvh_bvh b, const void* verts, uint32_t stride, uint32_t prim_count, int space, float c_trav, float c_int, int flavour )
 {
 	ARG_CHECK( b, "NULL handle" );
+	ARG_CHECK( flavour == TBVH_BUILD_REFERENCE || flavour == TBVH_BUILD_AVX, "unknown builder flavour" );
 	CUDA_TRY( cudaSetDevice( b->ctx->device ) );
 	free_layouts( b );
 	TRY( upload_verts( b, verts, stride, prim_count, space, b->ctx->stream ) );
-	TRY( build_sah_launch( b, c_trav, c_int ) );
+	TRY( build_sah_launch( b, c_trav, c_int, flavour ) );
 	b->info.layouts = 1u << TBVH_LAYOUT_BVH;
 	return TBVH_OK;
+}
+
+int tbvh_build( tbvh_bvh b, const void* verts, uint32_t stride, uint32_t prim_count, int space, float c_trav, float c_int )
+{
+	return tbvh_build_flavour( b, verts, stride, prim_count, space, c_trav, c_int, TBVH_BUILD_REFERENCE );
 }
 
 int tbvh_convert( tbvh_bvh b, int to_layout )

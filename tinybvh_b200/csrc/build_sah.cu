@@ -25,6 +25,8 @@
 #define SMALL_T 128          // capacity of the warp kernel: subtrees of at most this many primitives (run-time switch point <= this)
 #define CHUNK 256            // primitives per CTA in the large phase
 #define BIN_WORDS 168        // 3 axes x 8 bins x (3 min keys, 3 max keys, count)
+#define BIN_STRIDE 192       // + 3 x 8 counts of the PARTITION's own bin function (BuildAVX flavour, see bin_part_avx)
+__device__ __forceinline__ uint32_t bin_init_word( const uint32_t k ) { return (k < BIN_WORDS && (k % 7) < 3) ? 0xffffffffu : 0u; }
 #define SCAN_TILE 2048
 
 struct LargeNode { uint32_t tmp, first, count, depth; };
@@ -53,6 +55,7 @@ struct BuildArgs
 	SmallRoot* small;
 	Counters* ctr;
 	uint32_t n;
+	uint32_t flavour;        // 0 = BVH::Build (scalar reference builder), 1 = BVH::BuildAVX (what BuildDefault runs on x86)
 	uint32_t small_t;        // runtime switch point large phase -> warp subtrees (<= SMALL_T; env TBVH_SMALL_T for tuning)
 	float c_trav, c_int;
 };
@@ -68,6 +71,24 @@ __device__ __forceinline__ uint32_t bin_of( const float bmin, const float bmax, 
 	return (uint32_t)min( max( bi, 0 ), BINS - 1 );
 }
 
+// BuildAVX flavour (tiny_bvh.h:6500-6502, :6557-6559): nmin2 = 2 * node min, rpd = (8 * 0.49999f) / extent (0 on a zero extent);
+// binning bin = clamp( cvtps2dq( fma( (bmax+bmin) - nmin2, rpd, -0.5 ) ), 0, 7 )  (round to nearest even; INT_MIN when out of range)
+__device__ __forceinline__ float rpd_avx( const float ext ) { return ext == 0 ? 0.0f : __fdiv_rn( __fmul_rn( 8.0f, 0.49999f ), ext ); }
+__device__ __forceinline__ uint32_t bin_of_avx( const float bmin, const float bmax, const float nmin2, const float rpd )
+{
+	const float f = __fmaf_rn( __fsub_rn( __fadd_rn( bmax, bmin ), nmin2 ), rpd, -0.5f );
+	const int bi = (f >= 2147483648.0f) ? 0 : __float2int_rn( f );
+	return (uint32_t)min( max( bi, 0 ), BINS - 1 );
+}
+// the partition's own bin (:6629): (uint32_t)((bmax + bmin - nmin2) * rpd) through a 64-bit truncation, not clamped; only
+// "<= bestPos" (bestPos <= 6) is ever asked of it, so 7 stands for everything above
+__device__ __forceinline__ uint32_t bin_part_avx( const float bmin, const float bmax, const float nmin2, const float rpd )
+{
+	const float f = __fmul_rn( __fsub_rn( __fadd_rn( bmax, bmin ), nmin2 ), rpd );
+	const long long v = (f != f || f >= 9223372036854775808.0f || f < -9223372036854775808.0f) ? (long long)0x8000000000000000ull : __float2ll_rz( f );
+	return min( (uint32_t)v, 7u );
+}
+
 // BVHBase::SA / tinybvh_half_area in the oracle's pairing (tiny_bvh.h:8477, :460)
 __device__ __forceinline__ float half_area( const float ex, const float ey, const float ez )
 {
@@ -79,7 +100,7 @@ struct SweepResult { bool split; uint32_t axis, pos, lN; float l1[3], l2[3], r1[
 // One warp evaluates the 21 candidate planes of a node from its bin table (ordered keys + counts) - the sweep,
 // termination test and child bounds of tiny_bvh.h:2380-2412.  All lanes return the same result.
 __device__ __forceinline__ SweepResult sweep_node( uint32_t* bins /* BIN_WORDS, shared or global; decoded in place */, const float4 nmin, const float4 nmax,
-	const uint32_t count, const float3 min_dim, const float c_trav, const float c_int )
+	const uint32_t count, const float3 min_dim, const float c_trav, const float c_int, const uint32_t flavour )
 {
 	const uint32_t lane = threadIdx.x & 31;
 	// decode pass: lanes 0..23 turn the six ordered keys of "their" bin back into floats, once, instead of every one of
@@ -94,7 +115,9 @@ __device__ __forceinline__ SweepResult sweep_node( uint32_t* bins /* BIN_WORDS, 
 		}
 	}
 	__syncwarp();
-	const uint32_t a = lane / 7, i = lane % 7; // lanes 0..20: axis a, plane i
+	// lanes 0..20: axis a, plane i.  The lane index is also the tie-break priority: planes 0..6 for BVH::Build (:2396-2404),
+	// 3,2,4,5,1,0,6 for BuildAVX (:6614-6620).
+	const uint32_t a = lane / 7, i = flavour ? ((0x6015423u >> (4 * (lane % 7))) & 7u) : lane % 7;
 	float l1[3] = { BVH_FAR, BVH_FAR, BVH_FAR }, l2[3] = { -BVH_FAR, -BVH_FAR, -BVH_FAR };
 	float r1[3] = { BVH_FAR, BVH_FAR, BVH_FAR }, r2[3] = { -BVH_FAR, -BVH_FAR, -BVH_FAR };
 	uint32_t lN = 0, rN = 0;
@@ -123,9 +146,26 @@ __device__ __forceinline__ SweepResult sweep_node( uint32_t* bins /* BIN_WORDS, 
 					r2[0] = fmaxf( r2[0], mxx ), r2[1] = fmaxf( r2[1], mxy ), r2[2] = fmaxf( r2[2], mxz ), rN += c;
 				}
 			}
-			const float ANL = lN == 0 ? BVH_FAR : __fmul_rn( half_area( __fsub_rn( l2[0], l1[0] ), __fsub_rn( l2[1], l1[1] ), __fsub_rn( l2[2], l1[2] ) ), __uint2float_rn( lN ) );
-			const float ANR = rN == 0 ? BVH_FAR : __fmul_rn( half_area( __fsub_rn( r2[0], r1[0] ), __fsub_rn( r2[1], r1[1] ), __fsub_rn( r2[2], r1[2] ) ), __uint2float_rn( rN ) );
-			C = __fadd_rn( ANL, ANR );
+			const float aL = half_area( __fsub_rn( l2[0], l1[0] ), __fsub_rn( l2[1], l1[1] ), __fsub_rn( l2[2], l1[2] ) );
+			const float aR = half_area( __fsub_rn( r2[0], r1[0] ), __fsub_rn( r2[1], r1[1] ), __fsub_rn( r2[2], r1[2] ) );
+			if (flavour)
+			{
+				// PROCESS_PLANE (:6394-6396): both sides non-empty, cost = fma( lN, areaL, areaR * rN )
+				if (lN != 0 && rN != 0) C = __fmaf_rn( __uint2float_rn( lN ), aL, __fmul_rn( aR, __uint2float_rn( rN ) ) );
+			}
+			else
+			{
+				const float ANL = lN == 0 ? BVH_FAR : __fmul_rn( aL, __uint2float_rn( lN ) );
+				const float ANR = rN == 0 ? BVH_FAR : __fmul_rn( aR, __uint2float_rn( rN ) );
+				C = __fadd_rn( ANL, ANR );
+			}
+			if (flavour)
+			{
+				// the partition decides the child sizes with its own bin function: left count = its histogram up to plane i
+				uint32_t pl = 0;
+				for (uint32_t b = 0; b <= i; b++) pl += bins[BIN_WORDS + a * BINS + b];
+				lN = pl;
+			}
 		}
 	}
 	// first strict minimum below BVH_FAR in (axis, plane) order == lowest lane holding the warp minimum
@@ -138,9 +178,11 @@ __device__ __forceinline__ SweepResult sweep_node( uint32_t* bins /* BIN_WORDS, 
 	const float splitCost = __fmaf_rn( __fmul_rn( c_int, rSAV ), splitCostIn, c_trav );
 	const float noSplitCost = __fmul_rn( __uint2float_rn( count ), c_int );
 	SweepResult R;
-	R.split = found && !(splitCost >= noSplitCost);
-	R.axis = win / 7, R.pos = win % 7;
+	R.axis = win / 7, R.pos = __shfl_sync( 0xffffffffu, i, win );
 	R.lN = __shfl_sync( 0xffffffffu, lN, win );
+	// BuildAVX: if its partition puts everything on one side the reference leaves the node a leaf (:6639; it has by then
+	// permuted primIdx and burnt two node slots - "should not happen", not reproduced)
+	R.split = found && !(splitCost >= noSplitCost) && R.lN != 0 && R.lN != count;
 	#pragma unroll
 	for (int k = 0; k < 3; k++)
 	{
@@ -251,7 +293,7 @@ __global__ void k_init_root( BuildArgs A )
 		A.lvl[0][0] = LargeNode{ 0, 0, A.n, 0 };
 		A.chunk_start[0] = 0, A.chunk_start[1] = (A.n + CHUNK - 1) / CHUNK;
 		c->total_chunks = (A.n + CHUNK - 1) / CHUNK;
-		for (int k = threadIdx.x; k < BIN_WORDS; k += blockDim.x) A.bins[k] = (k % 7) < 3 ? 0xffffffffu : 0u;
+		for (int k = threadIdx.x; k < BIN_STRIDE; k += blockDim.x) A.bins[k] = bin_init_word( k );
 	}
 	else if (threadIdx.x == 0)
 	{
@@ -273,10 +315,10 @@ __device__ __forceinline__ uint32_t find_slot( const uint32_t* __restrict__ chun
 __global__ void __launch_bounds__( CHUNK ) k_bin( BuildArgs A, const LargeNode* __restrict__ cur, const uint32_t num, const uint32_t* __restrict__ idx_in )
 {
 	// binning :2357-2376 for one 256-primitive chunk of one node: shared-memory table, then one flush per CTA
-	__shared__ uint32_t s_bins[BIN_WORDS];
+	__shared__ uint32_t s_bins[BIN_STRIDE];
 	__shared__ uint32_t s_slot;
 	if (threadIdx.x == 0) s_slot = find_slot( A.chunk_start, num, blockIdx.x );
-	for (int k = threadIdx.x; k < BIN_WORDS; k += CHUNK) s_bins[k] = (k % 7) < 3 ? 0xffffffffu : 0u;
+	for (int k = threadIdx.x; k < BIN_STRIDE; k += CHUNK) s_bins[k] = bin_init_word( k );
 	__syncthreads();
 	const uint32_t j = s_slot;
 	const LargeNode nd = cur[j];
@@ -288,10 +330,23 @@ __global__ void __launch_bounds__( CHUNK ) k_bin( BuildArgs A, const LargeNode* 
 		const float4 nmin = __ldg( A.tmp_nodes + (size_t)nd.tmp * 2 ), nmax = __ldg( A.tmp_nodes + (size_t)nd.tmp * 2 + 1 );
 		const uint32_t p = nd.first + off, fi = __ldg( idx_in + p );
 		const float4 fmn = __ldg( A.frag_min + fi ), fmx = __ldg( A.frag_max + fi );
-		b3[0] = bin_of( fmn.x, fmx.x, nmin.x, __fdiv_rn( (float)BINS, __fsub_rn( nmax.x, nmin.x ) ) );
-		b3[1] = bin_of( fmn.y, fmx.y, nmin.y, __fdiv_rn( (float)BINS, __fsub_rn( nmax.y, nmin.y ) ) );
-		b3[2] = bin_of( fmn.z, fmx.z, nmin.z, __fdiv_rn( (float)BINS, __fsub_rn( nmax.z, nmin.z ) ) );
-		A.bin_ids[p] = (uint16_t)(b3[0] | (b3[1] << 3) | (b3[2] << 6));
+		if (A.flavour)
+		{
+			const float rx = rpd_avx( __fsub_rn( nmax.x, nmin.x ) ), ry = rpd_avx( __fsub_rn( nmax.y, nmin.y ) ), rz = rpd_avx( __fsub_rn( nmax.z, nmin.z ) );
+			const float mx2 = __fmul_rn( nmin.x, 2.0f ), my2 = __fmul_rn( nmin.y, 2.0f ), mz2 = __fmul_rn( nmin.z, 2.0f );
+			b3[0] = bin_of_avx( fmn.x, fmx.x, mx2, rx ), b3[1] = bin_of_avx( fmn.y, fmx.y, my2, ry ), b3[2] = bin_of_avx( fmn.z, fmx.z, mz2, rz );
+			// the partition's bins: what k_flags compares with the split plane, and what sizes the children
+			const uint32_t p0 = bin_part_avx( fmn.x, fmx.x, mx2, rx ), p1 = bin_part_avx( fmn.y, fmx.y, my2, ry ), p2 = bin_part_avx( fmn.z, fmx.z, mz2, rz );
+			A.bin_ids[p] = (uint16_t)(p0 | (p1 << 3) | (p2 << 6));
+			atomicAdd( s_bins + BIN_WORDS + p0, 1u ), atomicAdd( s_bins + BIN_WORDS + BINS + p1, 1u ), atomicAdd( s_bins + BIN_WORDS + 2 * BINS + p2, 1u );
+		}
+		else
+		{
+			b3[0] = bin_of( fmn.x, fmx.x, nmin.x, __fdiv_rn( (float)BINS, __fsub_rn( nmax.x, nmin.x ) ) );
+			b3[1] = bin_of( fmn.y, fmx.y, nmin.y, __fdiv_rn( (float)BINS, __fsub_rn( nmax.y, nmin.y ) ) );
+			b3[2] = bin_of( fmn.z, fmx.z, nmin.z, __fdiv_rn( (float)BINS, __fsub_rn( nmax.z, nmin.z ) ) );
+			A.bin_ids[p] = (uint16_t)(b3[0] | (b3[1] << 3) | (b3[2] << 6));
+		}
 		kmn[0] = f2key( fmn.x ), kmn[1] = f2key( fmn.y ), kmn[2] = f2key( fmn.z ), kmx[0] = f2key( fmx.x ), kmx[1] = f2key( fmx.y ), kmx[2] = f2key( fmx.z );
 	}
 	#pragma unroll
@@ -302,10 +357,11 @@ __global__ void __launch_bounds__( CHUNK ) k_bin( BuildArgs A, const LargeNode* 
 		const uint32_t k = threadIdx.x, bin = k / 7, f = k % 7;
 		if (s_bins[bin * 7 + 6] != 0)
 		{
-			uint32_t* g = A.bins + (size_t)j * BIN_WORDS + k;
+			uint32_t* g = A.bins + (size_t)j * BIN_STRIDE + k;
 			if (f < 3) atomicMin( g, s_bins[k] ); else if (f < 6) atomicMax( g, s_bins[k] ); else atomicAdd( g, s_bins[k] );
 		}
 	}
+	else if (threadIdx.x < BIN_STRIDE && A.flavour && s_bins[threadIdx.x] != 0) atomicAdd( A.bins + (size_t)j * BIN_STRIDE + threadIdx.x, s_bins[threadIdx.x] );
 }
 
 // append the two children of a split node: bigger than SMALL_T -> next level's list, else -> warp-built subtree
@@ -323,8 +379,9 @@ __global__ void __launch_bounds__( 256 ) k_sweep( BuildArgs A, const LargeNode* 
 	const LargeNode nd = cur[j];
 	const float4 nmin = A.tmp_nodes[(size_t)nd.tmp * 2], nmax = A.tmp_nodes[(size_t)nd.tmp * 2 + 1];
 	const float4 rmin = A.tmp_nodes[0], rmax = A.tmp_nodes[1];
-	const float3 min_dim = make_float3( __fmul_rn( __fsub_rn( rmax.x, rmin.x ), 1e-20f ), __fmul_rn( __fsub_rn( rmax.y, rmin.y ), 1e-20f ), __fmul_rn( __fsub_rn( rmax.z, rmin.z ), 1e-20f ) );
-	const SweepResult R = sweep_node( A.bins + (size_t)j * BIN_WORDS, nmin, nmax, nd.count, min_dim, A.c_trav, A.c_int );
+	const float mdf = A.flavour ? 1e-7f : 1e-20f; // minDim (:2346 / :6555)
+	const float3 min_dim = make_float3( __fmul_rn( __fsub_rn( rmax.x, rmin.x ), mdf ), __fmul_rn( __fsub_rn( rmax.y, rmin.y ), mdf ), __fmul_rn( __fsub_rn( rmax.z, rmin.z ), mdf ) );
+	const SweepResult R = sweep_node( A.bins + (size_t)j * BIN_STRIDE, nmin, nmax, nd.count, min_dim, A.c_trav, A.c_int, A.flavour );
 	if (!R.split)
 	{
 		// leaf: its range is final (tiny_bvh.h:2409-2412); publish the order it has in the current buffer
@@ -498,7 +555,7 @@ __global__ void __launch_bounds__( 1024 ) k_prepare_level( BuildArgs A, const La
 __global__ void k_bins_init( uint32_t* bins, const uint32_t words )
 {
 	const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
-	if (k < words) bins[k] = (k % 7) < 3 ? 0xffffffffu : 0u; // BIN_WORDS is a multiple of 7, so k % 7 is the field
+	if (k < words) bins[k] = bin_init_word( k % BIN_STRIDE );
 }
 
 // ---------------------------------------------------------------------------------------------- small subtrees
@@ -512,7 +569,7 @@ template <bool FRAGS> struct SmallSmemT
 	uint16_t bid[SMALL_T];
 	uint16_t posbl[SMALL_T];
 	uint32_t fw[SMALL_T / 32];
-	uint32_t bins[BIN_WORDS];
+	uint32_t bins[BIN_STRIDE];
 	uint32_t st_tmp[12]; uint32_t st_rng[12]; uint32_t st_db[12]; // stack: tmp node, lo | n << 16, depth | buf << 16
 };
 
@@ -544,17 +601,20 @@ __global__ void __launch_bounds__( SMALL_WARPS * 32 ) k_build_small( BuildArgs A
 		}
 	}
 	const float4 rmin = A.tmp_nodes[0], rmax = A.tmp_nodes[1];
-	const float3 min_dim = make_float3( __fmul_rn( __fsub_rn( rmax.x, rmin.x ), 1e-20f ), __fmul_rn( __fsub_rn( rmax.y, rmin.y ), 1e-20f ), __fmul_rn( __fsub_rn( rmax.z, rmin.z ), 1e-20f ) );
+	const float mdf = A.flavour ? 1e-7f : 1e-20f; // minDim (:2346 / :6555)
+	const float3 min_dim = make_float3( __fmul_rn( __fsub_rn( rmax.x, rmin.x ), mdf ), __fmul_rn( __fsub_rn( rmax.y, rmin.y ), mdf ), __fmul_rn( __fsub_rn( rmax.z, rmin.z ), mdf ) );
 	uint32_t sp = 0, local_max_depth = 0;
 	uint32_t tmp = root.tmp, lo = 0, n = root.count, depth = root.depth_buf & 0xffffu, buf = 0;
 	__syncwarp();
 	while (true)
 	{
 		// ---- bin the node's primitives (:2357-2376)
-		for (uint32_t k = lane; k < BIN_WORDS; k += 32) S.bins[k] = (k % 7) < 3 ? 0xffffffffu : 0u;
+		for (uint32_t k = lane; k < BIN_STRIDE; k += 32) S.bins[k] = bin_init_word( k );
 		__syncwarp();
 		const float4 nmin = A.tmp_nodes[(size_t)tmp * 2], nmax = A.tmp_nodes[(size_t)tmp * 2 + 1];
-		const float rpx = __fdiv_rn( (float)BINS, __fsub_rn( nmax.x, nmin.x ) ), rpy = __fdiv_rn( (float)BINS, __fsub_rn( nmax.y, nmin.y ) ), rpz = __fdiv_rn( (float)BINS, __fsub_rn( nmax.z, nmin.z ) );
+		const float ex_ = __fsub_rn( nmax.x, nmin.x ), ey_ = __fsub_rn( nmax.y, nmin.y ), ez_ = __fsub_rn( nmax.z, nmin.z );
+		const float rpx = A.flavour ? rpd_avx( ex_ ) : __fdiv_rn( (float)BINS, ex_ ), rpy = A.flavour ? rpd_avx( ey_ ) : __fdiv_rn( (float)BINS, ey_ ), rpz = A.flavour ? rpd_avx( ez_ ) : __fdiv_rn( (float)BINS, ez_ );
+		const float mx2 = __fmul_rn( nmin.x, 2.0f ), my2 = __fmul_rn( nmin.y, 2.0f ), mz2 = __fmul_rn( nmin.z, 2.0f );
 		for (uint32_t base = 0; base < n; base += 32) // whole warp iterates together: the aggregated update votes
 		{
 			const uint32_t k = base + lane;
@@ -570,8 +630,18 @@ __global__ void __launch_bounds__( SMALL_WARPS * 32 ) k_build_small( BuildArgs A
 					const float4 mn = __ldg( A.frag_min + S.gid[sl] ), mx = __ldg( A.frag_max + S.gid[sl] );
 					mnx = mn.x, mny = mn.y, mnz = mn.z, mxx = mx.x, mxy = mx.y, mxz = mx.z;
 				}
-				b3[0] = bin_of( mnx, mxx, nmin.x, rpx ), b3[1] = bin_of( mny, mxy, nmin.y, rpy ), b3[2] = bin_of( mnz, mxz, nmin.z, rpz );
-				S.bid[lo + k] = (uint16_t)(b3[0] | (b3[1] << 3) | (b3[2] << 6));
+				if (A.flavour)
+				{
+					b3[0] = bin_of_avx( mnx, mxx, mx2, rpx ), b3[1] = bin_of_avx( mny, mxy, my2, rpy ), b3[2] = bin_of_avx( mnz, mxz, mz2, rpz );
+					const uint32_t p0 = bin_part_avx( mnx, mxx, mx2, rpx ), p1 = bin_part_avx( mny, mxy, my2, rpy ), p2 = bin_part_avx( mnz, mxz, mz2, rpz );
+					S.bid[lo + k] = (uint16_t)(p0 | (p1 << 3) | (p2 << 6));
+					atomicAdd( S.bins + BIN_WORDS + p0, 1u ), atomicAdd( S.bins + BIN_WORDS + BINS + p1, 1u ), atomicAdd( S.bins + BIN_WORDS + 2 * BINS + p2, 1u );
+				}
+				else
+				{
+					b3[0] = bin_of( mnx, mxx, nmin.x, rpx ), b3[1] = bin_of( mny, mxy, nmin.y, rpy ), b3[2] = bin_of( mnz, mxz, nmin.z, rpz );
+					S.bid[lo + k] = (uint16_t)(b3[0] | (b3[1] << 3) | (b3[2] << 6));
+				}
 				kmn[0] = f2key( mnx ), kmn[1] = f2key( mny ), kmn[2] = f2key( mnz ), kmx[0] = f2key( mxx ), kmx[1] = f2key( mxy ), kmx[2] = f2key( mxz );
 			}
 			if (AGG && n >= 64)
@@ -592,7 +662,7 @@ __global__ void __launch_bounds__( SMALL_WARPS * 32 ) k_build_small( BuildArgs A
 			}
 		}
 		__syncwarp();
-		const SweepResult R = sweep_node( S.bins, nmin, nmax, n, min_dim, A.c_trav, A.c_int );
+		const SweepResult R = sweep_node( S.bins, nmin, nmax, n, min_dim, A.c_trav, A.c_int, A.flavour );
 		bool pop = false;
 		if (!R.split)
 		{
@@ -753,13 +823,13 @@ int exclusive_scan( const uint32_t* in, uint32_t* out, uint32_t* tile_sum, uint3
 
 #define DEV_ALLOC( ptr, bytes ) do { CUDA_TRY( cudaMalloc( (void**)&(ptr), (bytes) ) ); scratch.push_back( (void*)(ptr) ); } while (0)
 
-int build_sah_launch( tbvh_bvh b, float c_trav, float c_int )
+int build_sah_launch( tbvh_bvh b, float c_trav, float c_int, int flavour )
 {
 	const uint32_t n = b->info.prim_count;
 	cudaStream_t s = b->ctx->stream;
 	std::vector<void*> scratch;
 	BuildArgs A = {};
-	A.verts = b->d_verts, A.n = n, A.c_trav = c_trav, A.c_int = c_int;
+	A.verts = b->d_verts, A.n = n, A.c_trav = c_trav, A.c_int = c_int, A.flavour = (uint32_t)flavour;
 	{
 		const int t = b->ctx->small_t; // measured on B200: 128 beats 64 and 256 (profiles/README.md)
 		A.small_t = (uint32_t)(t < 8 ? 8 : t > SMALL_T ? SMALL_T : t);
@@ -783,7 +853,7 @@ int build_sah_launch( tbvh_bvh b, float c_trav, float c_int )
 		DEV_ALLOC( A.flags, flag_words * 4 ); DEV_ALLOC( A.scan, flag_words * 4 ); DEV_ALLOC( A.pos_bl, ((size_t)n + 1) * 4 );
 		DEV_ALLOC( A.tmp_nodes, max_nodes * 32 ); DEV_ALLOC( A.node_first, max_nodes * 4 ); DEV_ALLOC( A.node_depth, max_nodes * 4 );
 		DEV_ALLOC( A.lvl[0], max_large * sizeof( LargeNode ) ); DEV_ALLOC( A.lvl[1], max_large * sizeof( LargeNode ) );
-		DEV_ALLOC( A.chunk_start, (max_large + 1) * 4 ); DEV_ALLOC( A.bins, max_large * BIN_WORDS * 4 ); DEV_ALLOC( A.split, max_large * sizeof( SplitInfo ) );
+		DEV_ALLOC( A.chunk_start, (max_large + 1) * 4 ); DEV_ALLOC( A.bins, max_large * BIN_STRIDE * 4 ); DEV_ALLOC( A.split, max_large * sizeof( SplitInfo ) );
 		DEV_ALLOC( A.small, ((size_t)n + 1) * sizeof( SmallRoot ) );
 		DEV_ALLOC( A.ctr, sizeof( Counters ) );
 		DEV_ALLOC( tile_sum, (flag_words / SCAN_TILE + 2) * 4 );
@@ -813,7 +883,7 @@ int build_sah_launch( tbvh_bvh b, float c_trav, float c_int )
 			if (num > max_large) { tbvh_set_error( "build: level list overflow (%u > %zu)", num, max_large ); return TBVH_E_LIMIT; }
 			if (num)
 			{
-				k_bins_init<<<(num * BIN_WORDS + 255) / 256, 256, 0, s>>>( A.bins, num * BIN_WORDS ); LAUNCHED();
+				k_bins_init<<<(num * BIN_STRIDE + 255) / 256, 256, 0, s>>>( A.bins, num * BIN_STRIDE ); LAUNCHED();
 				CUDA_TRY( cudaMemsetAsync( &A.ctr->next_large, 0, 4, s ) );
 			}
 			level++;
