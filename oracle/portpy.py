@@ -20,8 +20,8 @@ NODE64 = np.dtype([("lmin", "3f4"), ("left", "u4"), ("lmax", "3f4"), ("right", "
 
 
 def build_lib(force: bool = False):
-    src = os.path.join(_HERE, "tbvh_oracle.c")
-    if force or not os.path.isfile(PORT_SO) or os.path.getmtime(PORT_SO) < os.path.getmtime(src):
+    srcs = [os.path.join(_HERE, f) for f in ("tbvh_oracle.c", "tbvh_oracle_hq.c", "tbvh_oracle.h")]
+    if force or not os.path.isfile(PORT_SO) or any(os.path.getmtime(PORT_SO) < os.path.getmtime(s) for s in srcs):
         subprocess.check_call(["make", "-C", _HERE, "port"], stdout=subprocess.DEVNULL)
 
 
@@ -33,6 +33,9 @@ def lib():
         vp, u32, u64, i32, f32 = C.c_void_p, C.c_uint32, C.c_uint64, C.c_int, C.c_float
         L.orc_build.restype, L.orc_build.argtypes = u32, [vp, u32, vp, vp, f32, f32]
         L.orc_build_avx.restype, L.orc_build_avx.argtypes = u32, [vp, u32, vp, vp, f32, f32]
+        L.orc_build_hq.restype, L.orc_build_hq.argtypes = u32, [vp, u32, vp, vp, vp, vp, f32, f32]
+        L.orc_clip_frag.restype, L.orc_clip_frag.argtypes = i32, [vp, vp, vp, vp, vp, vp, u32]
+        L.orc_split_frag.restype, L.orc_split_frag.argtypes = None, [vp, vp, vp, vp, vp, u32, f32, vp, vp]
         L.orc_intersect.restype, L.orc_intersect.argtypes = None, [vp, vp, vp, vp, u64, i32]
         L.orc_occluded.restype, L.orc_occluded.argtypes = None, [vp, vp, vp, vp, u64, vp, i32]
         L.orc_tri_test.restype, L.orc_tri_test.argtypes = i32, [vp] * 5 + [f32] + [vp] * 3
@@ -82,6 +85,35 @@ class PortBVH:
 
     def sah_cost(self, c_trav=1.0, c_int=1.0):
         return float(lib().orc_sah_cost(_ptr(self.nodes), 0, c_trav, c_int))
+
+
+def build_hq(verts, c_trav: float = 1.0, c_int: float = 1.0):
+    """orc_build_hq: restatement of BVH::BuildHQ + Compact -> (nodes, primIdx[:usedIdx], idxCount)."""
+    v = np.ascontiguousarray(verts, np.float32).reshape(-1, 4)
+    n = v.shape[0] // 3
+    nodes = np.zeros(3 * n + 2, NODE32)
+    idx = np.zeros(n + n // 2 + 1, np.uint32)
+    ic, ui = C.c_uint32(), C.c_uint32()
+    used = lib().orc_build_hq(_ptr(v), n, _ptr(nodes), _ptr(idx), C.byref(ic), C.byref(ui), c_trav, c_int)
+    return nodes[:used].copy(), idx[:ui.value].copy(), ic.value
+
+
+FRAGMENT = np.dtype([("bmin", "3f4"), ("primIdx", "u4"), ("bmax", "3f4"), ("clipped", "u4")])
+
+
+def clip_frag(verts, frag, bmin, bmax, min_dim, axis):
+    out = np.zeros(1, FRAGMENT)
+    a = [np.ascontiguousarray(x, np.float32) for x in (bmin, bmax, min_dim)]
+    ok = lib().orc_clip_frag(_ptr(verts), _ptr(frag), _ptr(out), _ptr(a[0]), _ptr(a[1]), _ptr(a[2]), int(axis))
+    return bool(ok), out
+
+
+def split_frag(verts, frag, min_dim, axis, pos):
+    l, r = np.zeros(1, FRAGMENT), np.zeros(1, FRAGMENT)
+    lo, ro = C.c_int(), C.c_int()
+    md = np.ascontiguousarray(min_dim, np.float32)
+    lib().orc_split_frag(_ptr(verts), _ptr(frag), _ptr(l), _ptr(r), _ptr(md), int(axis), float(pos), C.byref(lo), C.byref(ro))
+    return bool(lo.value), bool(ro.value), l, r
 
 
 def tri_test(O, D, v0, v1, v2, tmax):

@@ -98,6 +98,22 @@ void ref_bvh_occluded( void* h, const void* rays, uint64_t n, uint32_t* bits, in
 	for (uint64_t i = 0; i < n; i++) if (o[i]) bits[i >> 5] |= 1u << (i & 31);
 }
 
+// SBVH helpers, exposed so the restatement's clip_frag / split_frag can be pinned function by function
+int ref_clip_frag( void* h, const void* orig, void* out, const float* bmin, const float* bmax, const float* minDim, uint32_t axis )
+{
+	const BVH* b = (BVH*)h;
+	return b->ClipFrag( *(const BVHBase::Fragment*)orig, *(BVHBase::Fragment*)out, bvhvec3( bmin[0], bmin[1], bmin[2] ), bvhvec3( bmax[0], bmax[1], bmax[2] ),
+		bvhvec3( minDim[0], minDim[1], minDim[2] ), axis ) ? 1 : 0;
+}
+void ref_split_frag( void* h, const void* orig, void* left, void* right, const float* minDim, uint32_t axis, float pos, int* lok, int* rok )
+{
+	const BVH* b = (BVH*)h;
+	bool l = false, r = false;
+	const bvhvec3 md( minDim[0], minDim[1], minDim[2] );
+	b->SplitFrag( *(const BVHBase::Fragment*)orig, *(BVHBase::Fragment*)left, *(BVHBase::Fragment*)right, md, axis, pos, l, r );
+	*lok = l, *rok = r;
+}
+
 // ---------------------------------------------------------------- BVH_GPU (Aila-Laine 64-byte nodes)
 void* ref_bvhgpu_from_bvh( void* bvh, int compact )
 {

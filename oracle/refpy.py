@@ -40,6 +40,8 @@ def lib():
             "ref_bvh_from_arrays": (vp, [vp, u32, vp, u32, vp, u32]),
             "ref_bvh_intersect": (None, [vp, vp, u64, i32]),
             "ref_bvh_occluded": (None, [vp, vp, u64, vp, i32]),
+            "ref_clip_frag": (i32, [vp, vp, vp, vp, vp, vp, u32]),
+            "ref_split_frag": (None, [vp, vp, vp, vp, vp, u32, C.c_float, vp, vp]),
             "ref_bvhgpu_from_bvh": (vp, [vp, i32]), "ref_bvhgpu_destroy": (None, [vp]),
             "ref_bvhgpu_used_nodes": (u32, [vp]), "ref_bvhgpu_nodes": (vp, [vp]),
             "ref_bvhgpu_intersect": (None, [vp, vp, u64, i32]),
@@ -56,6 +58,9 @@ def lib():
             fn.restype, fn.argtypes = res, args
         _lib = L
     return _lib
+
+
+FRAGMENT = np.dtype([("bmin", "3f4"), ("primIdx", "u4"), ("bmax", "3f4"), ("clipped", "u4")])  # BVHBase::Fragment :764
 
 
 def _ptr(a: np.ndarray):
@@ -118,6 +123,21 @@ class RefBVH(_Traceable):
     tri_count = property(lambda s: lib().ref_bvh_tri_count(s.h))
     nodes = property(lambda s: _view(lib().ref_bvh_nodes(s.h), NODE32, s.used_nodes))
     prim_idx = property(lambda s: _view(lib().ref_bvh_prim_idx(s.h), np.uint32, s.idx_count))
+
+    def clip_frag(self, frag, bmin, bmax, min_dim, axis):
+        """BVH::ClipFrag (:8614) on one FRAGMENT record -> (has_verts, new fragment)."""
+        out = np.zeros(1, FRAGMENT)
+        a = [np.ascontiguousarray(x, np.float32) for x in (bmin, bmax, min_dim)]
+        ok = lib().ref_clip_frag(self.h, _ptr(frag), _ptr(out), _ptr(a[0]), _ptr(a[1]), _ptr(a[2]), int(axis))
+        return bool(ok), out
+
+    def split_frag(self, frag, min_dim, axis, pos):
+        """BVH::SplitFrag (:8731) -> (left_ok, right_ok, left, right)."""
+        l, r = np.zeros(1, FRAGMENT), np.zeros(1, FRAGMENT)
+        lo, ro = C.c_int(), C.c_int()
+        md = np.ascontiguousarray(min_dim, np.float32)
+        lib().ref_split_frag(self.h, _ptr(frag), _ptr(l), _ptr(r), _ptr(md), int(axis), float(pos), C.byref(lo), C.byref(ro))
+        return bool(lo.value), bool(ro.value), l, r
 
     def sah_cost(self):
         return float(lib().ref_bvh_sah_cost(self.h))

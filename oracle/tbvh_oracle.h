@@ -26,6 +26,15 @@ uint32_t orc_build( const float* verts, uint32_t primCount, orc_node* nodes, uin
 /* BVH::PrepareAVXBuild (:6424) + BVH::BuildAVXSubtree (:6529) = what BuildDefault (:1817) runs on x86, single-threaded numbering */
 uint32_t orc_build_avx( const float* verts, uint32_t primCount, orc_node* nodes, uint32_t* primIdx, float c_trav, float c_int );
 
+/* BVH::BuildHQ (SBVH, :2623-3040) + Compact (:3733), single-threaded; tbvh_oracle_hq.c.  nodes: room for 3*primCount+2,
+ * primIdx: room for primCount + primCount/2.  Returns usedNodes. */
+uint32_t orc_build_hq( const float* verts, uint32_t primCount, orc_node* nodes, uint32_t* primIdx, uint32_t* idxCount, uint32_t* usedIdx, float c_trav, float c_int );
+
+/* test hooks for the two geometric helpers of the SBVH build: BVH::ClipFrag (:8614) and BVH::SplitFrag (:8731) on one
+ * 32-byte Fragment record {bmin[3], primIdx, bmax[3], clipped} (:764) */
+int orc_clip_frag( const float* verts, const void* orig, void* out, const float* bmin, const float* bmax, const float* minDim, uint32_t axis );
+void orc_split_frag( const float* verts, const void* orig, void* left, void* right, const float* minDim, uint32_t axis, float pos, int* leftOk, int* rightOk );
+
 /* BVH::Intersect (:3222,:3247) / BVH::IsOccluded (:3382,:3407) over 128-byte host Ray records, in place.
  * threads<=0 -> all cores (OpenMP). */
 void orc_intersect( const orc_node* nodes, const uint32_t* primIdx, const float* verts, void* rays, uint64_t n, int threads );

@@ -90,3 +90,57 @@ def test_port_avx_flavour_matches_reference(ntris, seed):
     assert ref.used_nodes == port.used_nodes
     assert np.array_equal(ref.nodes.view(np.uint8), port.nodes.view(np.uint8))
     assert np.array_equal(ref.prim_idx, port.prim_idx)
+
+
+# ---------------------------------------------------------------- BVH::BuildHQ (SBVH) restatement, oracle/tbvh_oracle_hq.c
+@pytest.mark.parametrize("path", G.golden_files(), ids=lambda p: p.split("/")[-1])
+def test_port_build_hq_matches_golden_tree(path):
+    g = G.load(path)
+    nodes, idx, idx_count = portpy.build_hq(g["verts"])
+    assert np.array_equal(nodes.view(np.uint32).reshape(-1, 8), g["hq_nodes"])
+    assert np.array_equal(idx, g["hq_prim_idx"])
+    assert idx_count == int(g["hq_idx_count"][0])
+
+
+@pytest.mark.skipif(not refpy.available(), reason="oracle/_ref not built (needs /root/reference)")
+@pytest.mark.parametrize("ntris,seed", [(20000, 21), (3000, 22), (300, 23), (2, 24)])
+def test_port_build_hq_matches_reference(ntris, seed):
+    v = scenes.procedural_scene(ntris, seed=seed)
+    ref = refpy.RefBVH(v, mode=2, threaded=False)
+    nodes, idx, idx_count = portpy.build_hq(v)
+    assert np.array_equal(nodes.view(np.uint32), ref.nodes.view(np.uint32))
+    assert np.array_equal(idx, ref.prim_idx[: idx.shape[0]]) and idx.shape[0] == int(ref.nodes["triCount"].sum())
+    assert idx_count == ref.idx_count
+    # an SBVH may reference a triangle from several leaves, but every triangle is referenced at least once
+    assert np.array_equal(np.unique(idx), np.arange(ntris))
+
+
+@pytest.mark.skipif(not refpy.available(), reason="oracle/_ref not built (needs /root/reference)")
+def test_port_clip_and_split_frag_match_reference():
+    v = scenes.procedural_scene(4000, seed=31)
+    n = v.shape[0] // 3
+    ref = refpy.RefBVH(v, mode=0, threaded=False)
+    tri = v.reshape(-1, 3, 4)[:, :, :3]
+    lo, hi = tri.min((0, 1)), tri.max((0, 1))
+    min_dim = ((hi - lo) * np.float32(1e-7)).astype(np.float32)
+    rng = np.random.default_rng(7)
+    for it in range(6000):
+        i = int(rng.integers(n))
+        fr = np.zeros(1, refpy.FRAGMENT)
+        fr["primIdx"], fr["bmin"], fr["bmax"] = i, tri[i].min(0), tri[i].max(0)
+        fr["clipped"] = it & 1
+        ext = fr["bmax"][0] - fr["bmin"][0]
+        if it & 1:  # a box a previous clip could have left
+            fr["bmin"][0] += ext * rng.random(3, np.float32) * 0.3
+            fr["bmax"][0] -= ext * rng.random(3, np.float32) * 0.3
+            ext = fr["bmax"][0] - fr["bmin"][0]
+        axis = int(rng.integers(3))
+        bmin, bmax = lo.copy(), hi.copy()
+        bmin[axis] = fr["bmin"][0][axis] + ext[axis] * rng.random() * 0.9
+        bmax[axis] = bmin[axis] + ext[axis] * rng.random() * 0.5
+        ok_r, out_r = ref.clip_frag(fr, bmin, bmax, min_dim, axis)
+        ok_p, out_p = portpy.clip_frag(v, fr, bmin, bmax, min_dim, axis)
+        assert ok_r == ok_p and out_r.tobytes() == out_p.tobytes()
+        pos = np.float32(fr["bmin"][0][axis] + ext[axis] * rng.random())
+        sr, sp = ref.split_frag(fr, min_dim, axis, pos), portpy.split_frag(v, fr, min_dim, axis, pos)
+        assert sr[:2] == sp[:2] and sr[2].tobytes() == sp[2].tobytes() and sr[3].tobytes() == sp[3].tobytes()

@@ -42,6 +42,11 @@ def make(name, verts, res):
     d["diffuse_hit"] = np.stack([df["t"].view(np.uint32), df["u"].view(np.uint32), df["v"].view(np.uint32), df["prim"]], 1)
     g = refpy.RefBVHGPU(ref)
     d["nodes_gpu"] = g.nodes.copy().view(np.uint32).reshape(-1, 16)
+    # BVH::BuildHQ (SBVH), single-threaded numbering, after its closing Compact()
+    hq = refpy.RefBVH(verts, mode=2, threaded=False)
+    d["hq_nodes"] = hq.nodes.copy().view(np.uint32).reshape(-1, 8)
+    d["hq_prim_idx"] = hq.prim_idx[: int(hq.nodes["triCount"].sum())].copy()
+    d["hq_idx_count"] = np.array([hq.idx_count], np.uint32)
     os.makedirs(OUT, exist_ok=True)
     np.savez_compressed(os.path.join(OUT, name + ".npz"), **d)
     print(name, "tris", verts.shape[0] // 3, "nodes", ref.used_nodes, "rays", prim.shape[0],
