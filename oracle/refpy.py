@@ -60,7 +60,7 @@ def lib():
     return _lib
 
 
-FRAGMENT = np.dtype([("bmin", "3f4"), ("primIdx", "u4"), ("bmax", "3f4"), ("clipped", "u4")])  # BVHBase::Fragment :764
+FRAGMENT = np.dtype([("bmin", "3f4"), ("primIdx", "u4"), ("bmax", "3f4"), ("clipped", "u4")])  # BVHBase::Fragment :792
 
 
 def _ptr(a: np.ndarray):

@@ -31,7 +31,7 @@ uint32_t orc_build_avx( const float* verts, uint32_t primCount, orc_node* nodes,
 uint32_t orc_build_hq( const float* verts, uint32_t primCount, orc_node* nodes, uint32_t* primIdx, uint32_t* idxCount, uint32_t* usedIdx, float c_trav, float c_int );
 
 /* test hooks for the two geometric helpers of the SBVH build: BVH::ClipFrag (:8614) and BVH::SplitFrag (:8731) on one
- * 32-byte Fragment record {bmin[3], primIdx, bmax[3], clipped} (:764) */
+ * 32-byte Fragment record {bmin[3], primIdx, bmax[3], clipped} (:792) */
 int orc_clip_frag( const float* verts, const void* orig, void* out, const float* bmin, const float* bmax, const float* minDim, uint32_t axis );
 void orc_split_frag( const float* verts, const void* orig, void* left, void* right, const float* minDim, uint32_t axis, float pos, int* leftOk, int* rightOk );
 
