@@ -89,6 +89,10 @@ int tbvh_build( tbvh_bvh bvh, const void* verts, uint32_t stride, uint32_t prim_
  * "nearly identical" (:6352) but not byte-identical, so both flavours exist. */
 #define TBVH_BUILD_REFERENCE 0   /* BVH::Build */
 #define TBVH_BUILD_AVX 1         /* BVH::BuildAVX / BuildDefault */
+/* BVH::BuildHQ (tiny_bvh.h:2623-3040): SBVH - object split vs. spatial split with clipping (ClipFrag :8614, SplitFrag :8731)
+ * and unsplitting, followed by Compact() (:3733).  idx_count becomes prim_count + prim_count/2 as in the reference (the
+ * leaves reference the first sum(triCount) entries; the rest is zero), used_nodes up to 3 * prim_count. */
+#define TBVH_BUILD_HQ 2          /* BVH::BuildHQ */
 int tbvh_build_flavour( tbvh_bvh bvh, const void* verts, uint32_t stride, uint32_t prim_count, int space, float c_trav, float c_int, int flavour );
 
 /* consume a tree built elsewhere, in the reference's own layouts (the public members bvhNode / primIdx /

@@ -121,10 +121,11 @@ public:
 		TBVH_FATAL_IF( tbvh_build_flavour( h, vertices, (uint32_t)sizeof( Vec4 ), primCount, TBVH_HOST, c_trav, c_int, TBVH_BUILD_AVX ), "BVH::BuildAVX" );
 		sync_info();
 	}
-	template <class Vec4> void BuildHQ( const Vec4*, const uint32_t )
+	// BVH::BuildHQ( const bvhvec4*, uint32_t ) tiny_bvh.h:2623 - SBVH (spatial splits), ends with Compact()
+	template <class Vec4> void BuildHQ( const Vec4* vertices, const uint32_t primCount )
 	{
-		fprintf( stderr, "Fatal error in tinybvh_b200 BVH::BuildHQ: the SBVH builder (tiny_bvh.h:2623) is not implemented on the GPU and there is no CPU fallback.\n" );
-		exit( 1 );
+		TBVH_FATAL_IF( tbvh_build_flavour( h, vertices, (uint32_t)sizeof( Vec4 ), primCount, TBVH_HOST, c_trav, c_int, TBVH_BUILD_HQ ), "BVH::BuildHQ" );
+		sync_info();
 	}
 	// consume / produce the reference's public arrays (bvhNode, primIdx: tiny_bvh.h:952-964)
 	template <class Vec4> void Upload( const void* bvhNode, uint32_t used, const uint32_t* primIdx, uint32_t idxCnt, const Vec4* vertices, uint32_t primCount )

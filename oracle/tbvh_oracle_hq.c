@@ -216,6 +216,7 @@ static void split_frag( const hq_t* h, const frag_t* orig, frag_t* left, frag_t*
 }
 
 typedef struct { uint32_t node, sliceStart, sliceEnd, depth; } task_t;
+uint32_t orc_hq_failed_splits = 0; /* diagnostics: low 16 bits = 'spatial split failed' leaves (:2939), high bits = those that read stale idxTmp words */
 
 /* BuildHQTask :2731-3008, non-threaded */
 static void build_hq_task( hq_t* h, uint32_t nodeIdx, uint32_t sliceStart, uint32_t sliceEnd, uint32_t* idxTmp )
@@ -342,7 +343,7 @@ static void build_hq_task( hq_t* h, uint32_t nodeIdx, uint32_t sliceStart, uint3
 					for (uint32_t i = 0; i < binCount - 1; i++)
 					{
 						const float Cspatial = split_cost( h, rSAV, AL[i], NL[i], AR[i], NR[i] );
-						if (Cspatial < minSplitCost && NL[i] + NR[i] < budget && NL[i] * NR[i] > 0)
+						if (Cspatial < minSplitCost && NL[i] + NR[i] < budget && (int32_t)((uint32_t)NL[i] * (uint32_t)NR[i]) > 0) /* 32-bit wrap-around product, as the frozen reference build computes it (imul) */
 						{
 							spatial = 1, minSplitCost = splitCost = Cspatial, bestAxis = (uint32_t)a, bestPos = i;
 							for (int k = 0; k < 3; k++) bestLMin[k] = lBMin[i][k], bestLMax[k] = lBMax[i][k], bestRMin[k] = rBMin[i][k], bestRMax[k] = rBMax[i][k];
@@ -432,6 +433,8 @@ static void build_hq_task( hq_t* h, uint32_t nodeIdx, uint32_t sliceStart, uint3
 			const uint32_t leftCount = A - sliceStart, rightCount = sliceEnd - B;
 			if (leftCount == 0 || rightCount == 0)
 			{
+				orc_hq_failed_splits++;
+				if (node->leftFirst != (leftCount ? sliceStart : B)) orc_hq_failed_splits += 1 << 16;
 				for (uint32_t i = 0; i < node->triCount; i++) primIdx[node->leftFirst + i] = fragment[primIdx[node->leftFirst + i]].primIdx;
 				node->minx = fmin_( bestLMin[0], bestRMin[0] ), node->miny = fmin_( bestLMin[1], bestRMin[1] ), node->minz = fmin_( bestLMin[2], bestRMin[2] );
 				node->maxx = fmax_( bestLMax[0], bestRMax[0] ), node->maxy = fmax_( bestLMax[1], bestRMax[1] ), node->maxz = fmax_( bestLMax[2], bestRMax[2] );

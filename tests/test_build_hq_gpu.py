@@ -1,0 +1,91 @@
+"""GPU parity of the SBVH builder: tbvh_build_flavour(TBVH_BUILD_HQ) through the C-ABI must produce the reference's
+BVH::BuildHQ tree (spatial splits, unsplitting, final Compact) byte for byte: node array and the part of primIdx the
+leaves reference.  The checker is the pinned restatement oracle/tbvh_oracle_hq.c (and the golden HQ trees)."""
+import numpy as np
+import pytest
+
+from tinybvh_b200 import api, rays as R, scenes
+from tests import golden_util as G
+from tests import util
+
+pytestmark = pytest.mark.gpu
+
+
+def hq_want(v):
+    from oracle import portpy
+    return portpy.build_hq(v)
+
+
+def assert_same_hq_tree(e, nodes_want, idx_want, idx_count_want, label=""):
+    nodes, idx = e.download()
+    info = e.info()
+    assert info.idx_count == idx_count_want and idx.shape[0] == idx_count_want, f"{label}: idxCount {info.idx_count}"
+    assert nodes.shape[0] == nodes_want.shape[0], f"{label}: usedNodes {nodes.shape[0]} != {nodes_want.shape[0]}"
+    a, b = nodes.view(np.uint32).reshape(-1, 8), np.ascontiguousarray(nodes_want).view(np.uint32).reshape(-1, 8)
+    bad = np.nonzero((a != b).any(1))[0]
+    assert bad.size == 0, f"{label}: {bad.size} nodes differ, first {bad[:5]}: got {a[bad[0]]} want {b[bad[0]]}"
+    used = idx_want.shape[0]
+    assert np.array_equal(idx[:used], idx_want), f"{label}: primIdx differs at {np.nonzero(idx[:used] != idx_want)[0][:8]}"
+    assert not idx[used:].any()
+
+
+@pytest.mark.parametrize("path", G.golden_files(), ids=lambda p: p.split("/")[-1])
+def test_build_hq_matches_golden_tree(gpu, path):
+    g = G.load(path)
+    e = api.BVH().BuildHQ(g["verts"])
+    assert_same_hq_tree(e, g["hq_nodes"].view(np.uint8).view(api.NODE32).reshape(-1), g["hq_prim_idx"], int(g["hq_idx_count"][0]), path)
+
+
+@pytest.mark.parametrize("ntris,seed", [(1, 1), (2, 2), (3, 3), (31, 4), (256, 5), (257, 6), (300, 7), (1000, 8), (5000, 9), (70000, 10), (200000, 11)])
+def test_build_hq_matches_oracle_on_seeded_scenes(gpu, ntris, seed):
+    v = scenes.procedural_scene(ntris, seed)
+    nodes, idx, ic = hq_want(v)
+    e = api.BVH().BuildHQ(v)
+    assert_same_hq_tree(e, nodes, idx, ic, f"{ntris} tris")
+    assert e.info().build_ms > 0
+
+
+@pytest.mark.parametrize("scene", ["legocar", "head", "bunny", "sponza"])
+def test_build_hq_fixtures_and_trace(gpu, scene):
+    """legocar and sponza contain 'spatial split failed' leaves (tiny_bvh.h:2939), whose content depends on the words an
+    ancestor's partition left behind in idxTmp - reproduced, not avoided."""
+    v, label = scenes.load_scene(scene)
+    nodes, idx, ic = hq_want(v)
+    e = api.BVH().BuildHQ(v)
+    assert_same_hq_tree(e, nodes, idx, ic, label)
+    # traversal of the SBVH: same hits as the oracle walking the same tree
+    from oracle import portpy
+    o = portpy.PortBVH(v, nodes=nodes, prim_idx=idx)
+    lo, hi = scenes.scene_bounds(v)
+    eye, view = (R.SPONZA_EYES[0], R.SPONZA_VIEWS[0]) if scene == "sponza" else R.bounds_camera(lo, hi, "outside")
+    want = R.primary_rays(eye, view, 128, 128, 4)
+    got = want.copy()
+    o.intersect(want), e.Intersect(got)
+    assert util.compare_hits(got, want) == {"prim": 0, "t": 0, "u": 0, "v": 0}
+
+
+def test_build_hq_degenerate_inputs(gpu):
+    one = np.array([[0, 0, 0, 0], [1, 0, 0, 0], [0, 1, 0, 0]], np.float32)
+    same = np.tile(one, (700, 1))
+    flat = scenes.procedural_scene(3000, 12)
+    flat[:, 1] = 1.5
+    base = scenes.procedural_scene(900, 13)
+    dup = np.concatenate([base, base, base[:300]])
+    # long thin triangles: the case spatial splits exist for
+    rng = np.random.default_rng(17)
+    c = rng.random((2000, 3), np.float32) * 10
+    d = (rng.random((2000, 3), np.float32) - 0.5) * np.array([8, 0.05, 0.05], np.float32)
+    w = (rng.random((2000, 3), np.float32) - 0.5) * 0.05
+    sl = np.zeros((6000, 4), np.float32)
+    sl[0::3, :3], sl[1::3, :3], sl[2::3, :3] = c - d, c + d, c + w
+    for name, v in (("identical", same), ("flat", flat), ("duplicates", dup), ("slivers", sl)):
+        nodes, idx, ic = hq_want(v)
+        e = api.BVH().BuildHQ(v)
+        assert_same_hq_tree(e, nodes, idx, ic, name)
+
+
+def test_build_hq_is_deterministic(gpu):
+    v = scenes.procedural_scene(30000, 14)
+    a = api.BVH().BuildHQ(v).download()
+    b = api.BVH().BuildHQ(v).download()
+    assert np.array_equal(a[0].view(np.uint8), b[0].view(np.uint8)) and np.array_equal(a[1], b[1])

@@ -11,7 +11,7 @@ SO = os.path.join(HERE, "libtinybvh_b200.so")
 
 OK, HOST, DEVICE = 0, 0, 1
 LAYOUT_BVH, LAYOUT_BVH_GPU, LAYOUT_CWBVH = 1, 5, 10
-BUILD_REFERENCE, BUILD_AVX = 0, 1
+BUILD_REFERENCE, BUILD_AVX, BUILD_HQ = 0, 1, 2
 
 
 class TbvhError(RuntimeError):

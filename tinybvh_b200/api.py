@@ -163,7 +163,10 @@ class BVH(_Base):
         return self
 
     def BuildHQ(self, vertices, primCount: int = 0):
-        raise TbvhError("BVH::BuildHQ (SBVH, tiny_bvh.h:2623) is not implemented on the GPU yet; no CPU fallback")
+        """BVH::BuildHQ (tiny_bvh.h:2623): SBVH with spatial splits; idxCount becomes primCount + primCount/2."""
+        p, stride, nv, space, keep = _verts_arg(vertices)
+        check(_lib.lib().tbvh_build_flavour(self.h, p, stride, primCount or nv // 3, space, self.c_trav, self.c_int, _lib.BUILD_HQ))
+        return self
 
     def upload(self, nodes, primIdx, vertices):
         """Consume a tree built elsewhere in the reference's BVH layout (bvhNode / primIdx / verts, :952-964)."""

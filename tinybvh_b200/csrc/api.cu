@@ -292,11 +292,11 @@ int tbvh_upload_cwbvh( tbvh_bvh b, const void* bvh8_data, uint32_t used_blocks, 
 int tbvh_build_flavour( tbvh_bvh b, const void* verts, uint32_t stride, uint32_t prim_count, int space, float c_trav, float c_int, int flavour )
 {
 	ARG_CHECK( b, "NULL handle" );
-	ARG_CHECK( flavour == TBVH_BUILD_REFERENCE || flavour == TBVH_BUILD_AVX, "unknown builder flavour" );
+	ARG_CHECK( flavour == TBVH_BUILD_REFERENCE || flavour == TBVH_BUILD_AVX || flavour == TBVH_BUILD_HQ, "unknown builder flavour" );
 	CUDA_TRY( cudaSetDevice( b->ctx->device ) );
 	free_layouts( b );
 	TRY( upload_verts( b, verts, stride, prim_count, space, b->ctx->stream ) );
-	TRY( build_sah_launch( b, c_trav, c_int, flavour ) );
+	if (flavour == TBVH_BUILD_HQ) TRY( build_hq_launch( b, c_trav, c_int ) ); else TRY( build_sah_launch( b, c_trav, c_int, flavour ) );
 	b->info.layouts = 1u << TBVH_LAYOUT_BVH;
 	return TBVH_OK;
 }

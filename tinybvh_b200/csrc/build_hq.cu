@@ -1,0 +1,908 @@
+// tinybvh_b200/csrc/build_hq.cu - SBVH construction (spatial splits) on sm_100a.
+//
+// Replaces BVH::BuildHQ: PrepareHQBuild (tiny_bvh.h:2648-2709), BuildHQTask (:2731-3008), SplitCostSAH (:2711), ClipFrag
+// (:8614-8729), SplitFrag (:8731-8793) and the closing Compact() (:3733-3770).  The result is the reference's own tree
+// byte for byte (tests/test_build_hq_gpu.py memcmp()s nodes and the referenced part of primIdx against it), which pins
+// down more than the split decisions:
+//   * every float operation is spelled with an _rn intrinsic in the pairing of the frozen reference build (see the
+//     header of oracle/tbvh_oracle_hq.c); nvcc's own contraction cannot change a rounding;
+//   * the "unsplitting" pass (:2895-2926) is a sequential chain over the straddling fragments of a node - each decision
+//     changes the running child bounds / counts / cost the next one is judged by.  Here the fragments of a node are
+//     classified in parallel, the straddlers are compacted in order, ONE warp walks the chain (32 straddlers fetched per
+//     step, decisions replayed from registers), and the fragments the chain decides to split are clipped in parallel;
+//   * the reference partitions into a second index array (idxTmp) inside the node's slice [sliceStart, sliceEnd) and, when a
+//     spatial split "fails" (:2939, all fragments end up on one side), builds the leaf from whatever idxTmp held at the
+//     node's old position - words written by an ancestor's partition, or the initial zeros.  That is reproduced by keeping
+//     the same two arrays with the same write discipline (left part upward from sliceStart, right part downward from
+//     sliceEnd, copy back to primIdx): what a failed node reads is then a function of its ancestors only, not of the order
+//     nodes are processed in;
+//   * node numbering after Compact() is "children of the k-th interior node in DFS preorder at 2+2k, 3+2k", leaf index
+//     ranges packed in DFS leaf order: computed here from subtree sizes (one bottom-up pass with arrival counters, one
+//     walk to the root per node).  New fragments are handed out by an atomic counter; their numbers never reach the output.
+//
+// Structure: every node is owned by one thread group for all of its steps (object bins, sweep, spatial bins with clipping,
+// sweep, partition, child bounds, emit), so no step needs inter-CTA communication:
+//   k_hq_level     level-synchronous, one 256-thread CTA per node with more than HQ_SMALL fragments
+//   k_hq_subtrees  one warp per subtree of at most HQ_SMALL fragments, depth-first with a shared-memory task stack
+#include "common.cuh"
+#include <stdlib.h>
+#include <string.h>
+#include <vector>
+
+namespace
+{
+#define HQBINS 8
+#define HQ_SMALL 256          // nodes with at most this many fragments go to the warp kernel
+#define HQ_BIG_THREADS 256
+#define HQ_SMALL_WARPS 4
+#define HQ_STACK 64
+
+struct HQTask { uint32_t node, sliceStart, sliceEnd, depth; };
+struct HQCounters
+{
+	uint32_t node_ptr;       // temp node records allocated (pairs from 2)
+	uint32_t frag_ptr;       // nextFrag
+	uint32_t next_big;       // tasks appended to the next level's list
+	uint32_t small_roots;    // subtree roots for k_hq_subtrees
+	uint32_t max_depth;
+	uint32_t failed_splits;  // ":2939 spatial split failed" leaves
+	uint32_t overflow;       // a task stack / fragment pool ran out (cannot happen within the reference's own bounds)
+	uint32_t root_key[6];
+	float root_area;
+	float min_dim[3];
+};
+
+struct HQArgs
+{
+	const float4* verts;
+	float4* frag_min; float4* frag_max;       // (bmin, primIdx) / (bmax, clipped): the reference's 32-byte Fragment (:792) as two halves
+	uint32_t* prim_idx; uint32_t* idx_tmp;    // both idx_cap words, the reference's primIdx / idxTmp
+	uint32_t* cls; uint32_t* strad; float* spos; // partition scratch, indexed like the slices
+	float4* tmp_nodes; uint32_t* parent; uint32_t* sub_int; uint32_t* sub_prims; uint32_t* arrive;
+	HQTask* lvl[2]; HQTask* small;
+	HQCounters* ctr;
+	uint32_t n, idx_cap, node_cap, lvl_cap;
+	float c_trav, c_int;
+};
+
+struct GroupSmem
+{
+	uint32_t kmin[3][HQBINS][3], kmax[3][HQBINS][3]; // bin bounds as ordered keys
+	uint32_t cntA[3][HQBINS], cntB[3][HQBINS];       // object: count / spatial: countIn, countOut
+	float cost[24]; int cNL[24], cNR[24];
+	float cb[21][12];                                // candidate child bounds: lmin, lmax, rmin, rmax
+	float best[12];
+	float splitCost;
+	uint32_t bestAxis, bestPos, bestIdx;
+	int spatial, bestNL, bestNR, hasObj, trySpatial, leaf;
+	uint32_t wtot[8];
+	uint32_t nstrad;
+	uint32_t ckey[12];                               // child bounds of a spatial partition: lmin, lmax, rmin, rmax keys
+	uint32_t lc;
+};
+
+// ---------------------------------------------------------------------------------------------- shared math
+__device__ __forceinline__ float tmin( const float a, const float b ) { return a < b ? a : b; }   // tinybvh_min :432
+__device__ __forceinline__ float tmax( const float a, const float b ) { return a > b ? a : b; }   // tinybvh_max :433
+__device__ __forceinline__ float clampf( const float x, const float a, const float b ) { return x > a ? (x < b ? x : b) : a; }
+__device__ __forceinline__ int clampi( const int x, const int a, const int b ) { return x > a ? (x < b ? x : b) : a; }
+// (int)f as x86 computes it (cvttss2si): INT_MIN for NaN and anything outside int32
+__device__ __forceinline__ int cvtt( const float f ) { return (f >= -2147483648.0f && f < 2147483648.0f) ? __float2int_rz( f ) : (int)0x80000000; }
+// tinybvh_half_area :460 / BVHBase::SA :8477, the reference build's pairing
+__device__ __forceinline__ float half_area3( const float x, const float y, const float z )
+{
+	return x < -BVH_FAR ? 0.0f : __fmaf_rn( z, x, __fmaf_rn( y, x, __fmul_rn( y, z ) ) );
+}
+// SplitCostSAH :2711 (l_quads = false)
+__device__ __forceinline__ float split_cost( const float c_trav, const float c_int, const float rAparent, const float Aleft, const int Nleft, const float Aright, const int Nright )
+{
+	return __fmaf_rn( __fmaf_rn( __int2float_rn( Nleft ), Aleft, __fmul_rn( Aright, __int2float_rn( Nright ) ) ), __fmul_rn( c_int, rAparent ), c_trav );
+}
+__device__ __forceinline__ float comp( const float4 v, const uint32_t a ) { return a == 0 ? v.x : a == 1 ? v.y : v.z; }
+
+struct Frag { float bmin[3], bmax[3]; uint32_t prim, clipped; };
+__device__ __forceinline__ Frag load_frag( const HQArgs& A, const uint32_t fi )
+{
+	const float4 a = A.frag_min[fi], b = A.frag_max[fi];
+	Frag f;
+	f.bmin[0] = a.x, f.bmin[1] = a.y, f.bmin[2] = a.z, f.prim = __float_as_uint( a.w );
+	f.bmax[0] = b.x, f.bmax[1] = b.y, f.bmax[2] = b.z, f.clipped = __float_as_uint( b.w );
+	return f;
+}
+__device__ __forceinline__ void store_frag( const HQArgs& A, const uint32_t fi, const float* bmin, const float* bmax, const uint32_t prim )
+{
+	A.frag_min[fi] = make_float4( bmin[0], bmin[1], bmin[2], __uint_as_float( prim ) );
+	A.frag_max[fi] = make_float4( bmax[0], bmax[1], bmax[2], __uint_as_float( 1u ) );
+}
+__device__ __forceinline__ void load_tri( const HQArgs& A, const uint32_t prim, float v[3][3] )
+{
+	#pragma unroll
+	for (int k = 0; k < 3; k++) { const float4 p = A.verts[(size_t)prim * 3 + k]; v[k][0] = p.x, v[k][1] = p.y, v[k][2] = p.z; }
+}
+// C = v0 + f * (v1 - v0), compiled by the reference build as fma( f, v1 - v0, v0 ) per component
+__device__ __forceinline__ void lerp3( float* C, const float* v0, const float* v1, const float f )
+{
+	#pragma unroll
+	for (int k = 0; k < 3; k++) C[k] = __fmaf_rn( f, __fsub_rn( v1[k], v0[k] ), v0[k] );
+}
+__device__ __forceinline__ void cp3( float* d, const float* s ) { d[0] = s[0], d[1] = s[1], d[2] = s[2]; }
+
+// Sutherland-Hodgman of polygon vin[0..Nin) against the slab l <= x[a] <= r, in place (result back in vin); the generic
+// loops of ClipFrag (:8630-8658, tolerance eps, unclamped f) and SplitFrag (:8744-8770, eps = 0, f clamped to [0,1]).
+template <bool CLAMP> __device__ __forceinline__ uint32_t clip_slab( float vin[16][3], float vout[16][3], uint32_t Nin, const uint32_t a, const float l, const float r, const float eps )
+{
+	uint32_t Nout = 0;
+	const float le = __fsub_rn( l, eps ), re = __fadd_rn( r, eps );
+	for (uint32_t v = 0; v < Nin; v++)
+	{
+		const float* v0 = vin[v], * v1 = vin[(v + 1) % Nin];
+		const bool v0in = v0[a] >= le, v1in = v1[a] >= le;
+		if (!(v0in || v1in)) continue; else if (v0in ^ v1in)
+		{
+			float f = __fdiv_rn( __fsub_rn( l, v0[a] ), __fsub_rn( v1[a], v0[a] ) );
+			if (CLAMP) f = clampf( f, 0.0f, 1.0f );
+			float C[3];
+			lerp3( C, v0, v1, f ), C[a] = l, cp3( vout[Nout++], C );
+		}
+		if (v1in) cp3( vout[Nout++], v1 );
+	}
+	Nin = 0;
+	for (uint32_t v = 0; v < Nout; v++)
+	{
+		const float* v0 = vout[v], * v1 = vout[(v + 1) % Nout];
+		const bool v0in = v0[a] <= re, v1in = v1[a] <= re;
+		if (!(v0in || v1in)) continue; else if (v0in ^ v1in)
+		{
+			float f = __fdiv_rn( __fsub_rn( r, v0[a] ), __fsub_rn( v1[a], v0[a] ) );
+			if (CLAMP) f = clampf( f, 0.0f, 1.0f );
+			float C[3];
+			lerp3( C, v0, v1, f ), C[a] = r, cp3( vin[Nin++], C );
+		}
+		if (v1in) cp3( vin[Nin++], v1 );
+	}
+	return Nin;
+}
+
+// BVH::ClipFrag :8614-8729: bounds of (fragment's triangle) clipped to box [bmin_in, bmax_in] ^ fragment box.
+// Returns false when nothing is left; nb_min / nb_max receive the new fragment's box either way (as the reference does).
+__device__ bool clip_frag( const HQArgs& A, const Frag& orig, float* nb_min, float* nb_max, const float* bmin_in, const float* bmax_in, const float* minDim, const uint32_t axis )
+{
+	float bmin[3], bmax[3], extent[3];
+	#pragma unroll
+	for (int a = 0; a < 3; a++) bmin[a] = tmax( bmin_in[a], orig.bmin[a] ), bmax[a] = tmin( bmax_in[a], orig.bmax[a] ), extent[a] = __fsub_rn( bmax[a], bmin[a] );
+	float mn[3] = { BVH_FAR, BVH_FAR, BVH_FAR }, mx[3] = { -BVH_FAR, -BVH_FAR, -BVH_FAR };
+	bool has;
+	if (orig.clipped)
+	{
+		float vin[16][3], vout[16][3];
+		{
+			float t[3][3];
+			load_tri( A, orig.prim, t );
+			cp3( vin[0], t[0] ), cp3( vin[1], t[1] ), cp3( vin[2], t[2] );
+		}
+		uint32_t Nin = 3;
+		for (uint32_t a = 0; a < 3; a++)
+		{
+			const float eps = minDim[a];
+			if (extent[a] > eps) Nin = clip_slab<false>( vin, vout, Nin, a, bmin[a], bmax[a], eps );
+		}
+		for (uint32_t i = 0; i < Nin; i++)
+		{
+			#pragma unroll
+			for (int k = 0; k < 3; k++) mn[k] = tmin( mn[k], vin[i][k] ), mx[k] = tmax( mx[k], vin[i][k] );
+		}
+		has = Nin > 0;
+	}
+	else
+	{
+		// fragment never clipped before: only the two planes on the split axis matter (:8665-8724)
+		has = false;
+		if (extent[axis] > minDim[axis])
+		{
+			const float l = bmin[axis], r = bmax[axis];
+			float vout[4][3], t[3][3], C[3];
+			uint32_t Nout = 0;
+			load_tri( A, orig.prim, t );
+			const bool in0 = t[0][axis] >= l, in1 = t[1][axis] >= l, in2 = t[2][axis] >= l;
+			#pragma unroll
+			for (int e = 0; e < 3; e++)
+			{
+				const float* v0 = t[e], * v1 = t[(e + 1) % 3];
+				const bool v0in = e == 0 ? in0 : e == 1 ? in1 : in2, v1in = e == 0 ? in1 : e == 1 ? in2 : in0;
+				if (v0in || v1in)
+				{
+					if (v0in ^ v1in)
+					{
+						const float f = clampf( __fdiv_rn( __fsub_rn( l, v0[axis] ), __fsub_rn( v1[axis], v0[axis] ) ), 0.0f, 1.0f );
+						lerp3( C, v0, v1, f ), C[axis] = l, cp3( vout[Nout++], C );
+					}
+					if (v1in) cp3( vout[Nout++], v1 );
+				}
+			}
+			for (uint32_t v = 0; v < Nout; v++)
+			{
+				const float* v0 = vout[v], * v1 = vout[(v + 1) % Nout];
+				const bool v0in = v0[axis] <= r, v1in = v1[axis] <= r;
+				if (!(v0in || v1in)) continue; else if (v0in ^ v1in)
+				{
+					const float f = clampf( __fdiv_rn( __fsub_rn( r, v0[axis] ), __fsub_rn( v1[axis], v0[axis] ) ), 0.0f, 1.0f );
+					lerp3( C, v0, v1, f ), C[axis] = r, has = true;
+					#pragma unroll
+					for (int k = 0; k < 3; k++) mn[k] = tmin( mn[k], C[k] ), mx[k] = tmax( mx[k], C[k] );
+				}
+				if (v1in)
+				{
+					has = true;
+					#pragma unroll
+					for (int k = 0; k < 3; k++) mn[k] = tmin( mn[k], v1[k] ), mx[k] = tmax( mx[k], v1[k] );
+				}
+			}
+		}
+	}
+	#pragma unroll
+	for (int k = 0; k < 3; k++) nb_min[k] = tmax( mn[k], bmin[k] ), nb_max[k] = tmin( mx[k], bmax[k] );
+	return has;
+}
+
+// BVH::SplitFrag :8731-8793: the fragment's polygon cut at splitPos; only the two halves' boxes are kept.
+__device__ void split_frag( const HQArgs& A, const Frag& orig, float* lmin, float* lmax, float* rmin, float* rmax, const float* minDim,
+	const uint32_t splitAxis, const float splitPos, bool& leftOK, bool& rightOK )
+{
+	float vin[16][3], vout[16][3];
+	{
+		float t[3][3];
+		load_tri( A, orig.prim, t );
+		cp3( vin[0], t[0] ), cp3( vin[1], t[1] ), cp3( vin[2], t[2] );
+	}
+	uint32_t Nin = 3, Nleft = 0, Nright = 0;
+	if (orig.clipped) for (uint32_t a = 0; a < 3; a++) if (__fsub_rn( orig.bmax[a], orig.bmin[a] ) > minDim[a])
+		Nin = clip_slab<true>( vin, vout, Nin, a, orig.bmin[a], orig.bmax[a], 0.0f );
+	#pragma unroll
+	for (int k = 0; k < 3; k++) lmin[k] = rmin[k] = BVH_FAR, lmax[k] = rmax[k] = -BVH_FAR;
+	#define ADD_L( p ) { Nleft++; for (int k_ = 0; k_ < 3; k_++) lmin[k_] = tmin( lmin[k_], (p)[k_] ), lmax[k_] = tmax( lmax[k_], (p)[k_] ); }
+	#define ADD_R( p ) { Nright++; for (int k_ = 0; k_ < 3; k_++) rmin[k_] = tmin( rmin[k_], (p)[k_] ), rmax[k_] = tmax( rmax[k_], (p)[k_] ); }
+	for (uint32_t v = 0; v < Nin; v++)
+	{
+		const float* v0 = vin[v], * v1 = vin[(v + 1) % Nin];
+		const bool v0left = v0[splitAxis] < splitPos, v1left = v1[splitAxis] < splitPos;
+		if (v0left && v1left) ADD_L( v1 ) else if (!v0left && !v1left) ADD_R( v1 ) else
+		{
+			const float f = clampf( __fdiv_rn( __fsub_rn( splitPos, v0[splitAxis] ), __fsub_rn( v1[splitAxis], v0[splitAxis] ) ), 0.0f, 1.0f );
+			float C[3];
+			lerp3( C, v0, v1, f ), C[splitAxis] = splitPos;
+			ADD_L( C ) ADD_R( C )
+			if (v0left) ADD_R( v1 ) else ADD_L( v1 )
+		}
+	}
+	#undef ADD_L
+	#undef ADD_R
+	leftOK = Nleft > 0, rightOK = Nright > 0;
+}
+
+// ---------------------------------------------------------------------------------------------- group helpers
+template <int G> __device__ __forceinline__ void gsync() { if (G == 32) __syncwarp(); else __syncthreads(); }
+
+// exclusive scan of v over the G threads of the group; every thread gets the group total.  Callers pack two 16-bit
+// counters into v (a tile holds at most 256 of each).
+template <int G> __device__ __forceinline__ uint32_t gscan( GroupSmem& S, const uint32_t v, uint32_t& total, const int tid )
+{
+	const int lane = tid & 31;
+	uint32_t x = v;
+	#pragma unroll
+	for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync( 0xffffffffu, x, o ); if (lane >= o) x += y; }
+	if (G == 32) { total = __shfl_sync( 0xffffffffu, x, 31 ); return x - v; }
+	const int w = tid >> 5;
+	if (lane == 31) S.wtot[w] = x;
+	__syncthreads();
+	uint32_t base = 0, tot = 0;
+	#pragma unroll
+	for (int i = 0; i < G / 32; i++) { const uint32_t t = S.wtot[i]; if (i < w) base += t; tot += t; }
+	__syncthreads();
+	total = tot;
+	return base + x - v;
+}
+
+__device__ __forceinline__ void bins_reset( GroupSmem& S, const int tid, const int G )
+{
+	for (int k = tid; k < 3 * HQBINS * 3; k += G) (&S.kmin[0][0][0])[k] = f2key( BVH_FAR ), (&S.kmax[0][0][0])[k] = f2key( -BVH_FAR );
+	for (int k = tid; k < 3 * HQBINS; k += G) (&S.cntA[0][0])[k] = 0, (&S.cntB[0][0])[k] = 0;
+}
+__device__ __forceinline__ void bin_grow( GroupSmem& S, const uint32_t a, const uint32_t b, const float* mn, const float* mx )
+{
+	#pragma unroll
+	for (int k = 0; k < 3; k++) atomicMin( &S.kmin[a][b][k], f2key( mn[k] ) ), atomicMax( &S.kmax[a][b][k], f2key( mx[k] ) );
+}
+
+// 21 threads: candidate plane (a, i) from the bin tables: prefix / suffix unions, areas, counts, SAH cost
+// (object split :2779-2803 with countL = countR = cntA; spatial split :2847-2862 with countIn / countOut).
+__device__ __forceinline__ void sweep_candidate( GroupSmem& S, const int c, const bool spatial, const float rSAV, const float c_trav, const float c_int )
+{
+	const uint32_t a = c / 7, i = c % 7;
+	float l1[3] = { BVH_FAR, BVH_FAR, BVH_FAR }, l2[3] = { -BVH_FAR, -BVH_FAR, -BVH_FAR }, r1[3] = { BVH_FAR, BVH_FAR, BVH_FAR }, r2[3] = { -BVH_FAR, -BVH_FAR, -BVH_FAR };
+	uint32_t lN = 0, rN = 0;
+	for (uint32_t b = 0; b < HQBINS; b++)
+	{
+		if (b <= i)
+		{
+			lN += S.cntA[a][b];
+			#pragma unroll
+			for (int k = 0; k < 3; k++) l1[k] = tmin( l1[k], key2f( S.kmin[a][b][k] ) ), l2[k] = tmax( l2[k], key2f( S.kmax[a][b][k] ) );
+		}
+		else
+		{
+			rN += spatial ? S.cntB[a][b] : S.cntA[a][b];
+			#pragma unroll
+			for (int k = 0; k < 3; k++) r1[k] = tmin( r1[k], key2f( S.kmin[a][b][k] ) ), r2[k] = tmax( r2[k], key2f( S.kmax[a][b][k] ) );
+		}
+	}
+	const float AL = lN == 0 ? BVH_FAR : half_area3( __fsub_rn( l2[0], l1[0] ), __fsub_rn( l2[1], l1[1] ), __fsub_rn( l2[2], l1[2] ) );
+	const float AR = rN == 0 ? BVH_FAR : half_area3( __fsub_rn( r2[0], r1[0] ), __fsub_rn( r2[1], r1[1] ), __fsub_rn( r2[2], r1[2] ) );
+	S.cost[c] = split_cost( c_trav, c_int, rSAV, AL, (int)lN, AR, (int)rN );
+	S.cNL[c] = (int)lN, S.cNR[c] = (int)rN;
+	#pragma unroll
+	for (int k = 0; k < 3; k++) S.cb[c][k] = l1[k], S.cb[c][3 + k] = l2[k], S.cb[c][6 + k] = r1[k], S.cb[c][9 + k] = r2[k];
+}
+
+// One node, start to finish, by a group of G threads (G = 32: a warp, G = 256: a CTA).  Returns true and the two child
+// tasks when the node was split.
+template <int G> __device__ bool hq_node( const HQArgs& A, GroupSmem& S, const HQTask t, const int tid, HQTask& outL, HQTask& outR )
+{
+	const float4 n0 = A.tmp_nodes[(size_t)t.node * 2], n1 = A.tmp_nodes[(size_t)t.node * 2 + 1];
+	const float nmin3[3] = { n0.x, n0.y, n0.z }, nmax3[3] = { n1.x, n1.y, n1.z };
+	const uint32_t leftFirst = __float_as_uint( n0.w ), count = __float_as_uint( n1.w );
+	const float minDim[3] = { A.ctr->min_dim[0], A.ctr->min_dim[1], A.ctr->min_dim[2] };
+	const float ext[3] = { __fsub_rn( nmax3[0], nmin3[0] ), __fsub_rn( nmax3[1], nmin3[1] ), __fsub_rn( nmax3[2], nmin3[2] ) };
+	const bool axisOK[3] = { ext[0] > minDim[0], ext[1] > minDim[1], ext[2] > minDim[2] };
+	const float rpd3[3] = { __fdiv_rn( (float)HQBINS, ext[0] ), __fdiv_rn( (float)HQBINS, ext[1] ), __fdiv_rn( (float)HQBINS, ext[2] ) };
+	const float rSAV = __fdiv_rn( 1.0f, __fmaf_rn( ext[2], ext[0], __fmaf_rn( ext[1], ext[0], __fmul_rn( ext[1], ext[2] ) ) ) );
+	const float noSplitCost = __fmul_rn( __uint2float_rn( count ), A.c_int );
+	const int budget = (int)(t.sliceEnd - t.sliceStart);
+	const uint32_t* primIdx = A.prim_idx;
+
+	// ---- object split: bins :2758-2775
+	bins_reset( S, tid, G );
+	gsync<G>();
+	for (uint32_t i = tid; i < count; i += G)
+	{
+		const uint32_t fi = primIdx[leftFirst + i];
+		const float4 fa = A.frag_min[fi], fb = A.frag_max[fi];
+		const float mn[3] = { fa.x, fa.y, fa.z }, mx[3] = { fb.x, fb.y, fb.z };
+		#pragma unroll
+		for (int a = 0; a < 3; a++)
+		{
+			const int bi = clampi( cvtt( __fmul_rn( __fmaf_rn( __fadd_rn( mn[a], mx[a] ), 0.5f, -nmin3[a] ), rpd3[a] ) ), 0, HQBINS - 1 );
+			bin_grow( S, a, bi, mn, mx );
+			atomicAdd( &S.cntA[a][bi], 1u );
+		}
+	}
+	gsync<G>();
+	if (tid < 21) sweep_candidate( S, tid, false, rSAV, A.c_trav, A.c_int );
+	gsync<G>();
+	if (tid == 0)
+	{
+		float splitCost = noSplitCost;
+		int best = -1;
+		for (int c = 0; c < 21; c++)
+		{
+			if (!axisOK[c / 7]) continue;
+			const float C = S.cost[c];
+			if (C >= splitCost) continue;
+			splitCost = C, best = c;
+		}
+		S.hasObj = best >= 0, S.spatial = 0, S.bestNL = S.bestNR = 0;
+		bool trySpatial = false;
+		if (best >= 0)
+		{
+			S.bestAxis = best / 7, S.bestPos = best % 7, S.bestIdx = best;
+			for (int k = 0; k < 12; k++) S.best[k] = S.cb[best][k];
+			// spatialOverlap :2806-2807: half area of (bestLMax - bestRMin) over the root's
+			const float ov = __fdiv_rn( half_area3( __fsub_rn( S.best[3], S.best[6] ), __fsub_rn( S.best[4], S.best[7] ), __fsub_rn( S.best[5], S.best[8] ) ), A.ctr->root_area );
+			trySpatial = ov > 1e-4f;
+		}
+		// without an object candidate splitCost == noSplitCost and the reference's second disjunct holds whatever its stale bounds say
+		trySpatial = (budget > (int)count) && (trySpatial || splitCost >= noSplitCost);
+		S.splitCost = splitCost, S.trySpatial = trySpatial;
+	}
+	gsync<G>();
+
+	// ---- spatial split candidate :2808-2872
+	if (S.trySpatial)
+	{
+		bins_reset( S, tid, G );
+		gsync<G>();
+		for (uint32_t it = tid; it < count * 3; it += G)
+		{
+			const uint32_t i = it / 3, a = it - i * 3;
+			if (!axisOK[a]) continue;
+			const Frag f = load_frag( A, primIdx[leftFirst + i] );
+			const float planeDist = __fdiv_rn( ext[a], __fmul_rn( (float)HQBINS, 0.9999f ) );
+			const float rPlaneDist = __fdiv_rn( 1.0f, planeDist ), nodeMin = nmin3[a];
+			const int bin1 = clampi( cvtt( __fmul_rn( __fsub_rn( f.bmin[a], nodeMin ), rPlaneDist ) ), 0, HQBINS - 1 );
+			const int bin2 = clampi( cvtt( __fmul_rn( __fsub_rn( f.bmax[a], nodeMin ), rPlaneDist ) ), 0, HQBINS - 1 );
+			atomicAdd( &S.cntA[a][bin1], 1u ), atomicAdd( &S.cntB[a][bin2], 1u );
+			if (bin2 == bin1) bin_grow( S, a, bin1, f.bmin, f.bmax );
+			else for (int j = bin1; j <= bin2; j++)
+			{
+				float bmin[3] = { nmin3[0], nmin3[1], nmin3[2] }, bmax[3] = { nmax3[0], nmax3[1], nmax3[2] }, nbmin[3], nbmax[3];
+				bmin[a] = __fmaf_rn( __int2float_rn( j ), planeDist, nodeMin );
+				bmax[a] = j == HQBINS - 2 ? nmax3[a] : __fadd_rn( bmin[a], planeDist );
+				if (!clip_frag( A, f, nbmin, nbmax, bmin, bmax, minDim, a )) continue;
+				bin_grow( S, a, j, nbmin, nbmax );
+			}
+		}
+		gsync<G>();
+		if (tid < 21) sweep_candidate( S, tid, true, rSAV, A.c_trav, A.c_int );
+		gsync<G>();
+		if (tid == 0)
+		{
+			float splitCost = S.splitCost, minSplitCost = __fmul_rn( splitCost, 0.985f );
+			int best = -1;
+			for (int c = 0; c < 21; c++)
+			{
+				if (!axisOK[c / 7]) continue;
+				const float C = S.cost[c];
+				const int NL = S.cNL[c], NR = S.cNR[c];
+				// NL * NR > 0 is a wrapping 32-bit product in the reference build (imul)
+				if (C < minSplitCost && NL + NR < budget && (int)((uint32_t)NL * (uint32_t)NR) > 0) minSplitCost = splitCost = C, best = c;
+			}
+			if (best >= 0)
+			{
+				const uint32_t a = best / 7;
+				S.spatial = 1, S.bestAxis = a, S.bestPos = best % 7, S.bestIdx = best, S.splitCost = splitCost;
+				for (int k = 0; k < 12; k++) S.best[k] = S.cb[best][k];
+				S.bestNL = S.cNL[best], S.bestNR = S.cNR[best];
+				S.best[3 + a] = S.best[6 + a]; // bestLMax[a] = bestRMin[a], "accurate" :2868
+			}
+		}
+		gsync<G>();
+	}
+
+	// ---- leaf? :2874-2880
+	if (S.splitCost >= noSplitCost)
+	{
+		for (uint32_t i = tid; i < count; i += G) { const uint32_t p = leftFirst + i; A.prim_idx[p] = __float_as_uint( A.frag_min[A.prim_idx[p]].w ); }
+		if (tid == 0) atomicMax( &A.ctr->max_depth, t.depth );
+		return false;
+	}
+
+	// ---- partition into idxTmp :2882-2964
+	const uint32_t bestAxis = S.bestAxis, bestPos = S.bestPos;
+	uint32_t Apos = t.sliceStart, Bpos = t.sliceEnd;
+	if (!S.spatial)
+	{
+		const float rpd = rpd3[bestAxis], nmin = nmin3[bestAxis];
+		for (uint32_t base = 0; base < count; base += G)
+		{
+			const uint32_t i = base + tid;
+			uint32_t fr = 0, flag = 0;
+			if (i < count)
+			{
+				fr = primIdx[leftFirst + i];
+				const float mn = comp( A.frag_min[fr], bestAxis ), mx = comp( A.frag_max[fr], bestAxis );
+				const int bi = clampi( cvtt( __fmul_rn( __fmaf_rn( __fadd_rn( mn, mx ), 0.5f, -nmin ), rpd ) ), 0, HQBINS - 1 );
+				flag = bi <= (int)bestPos ? 1u : 0x10000u;
+			}
+			uint32_t tot;
+			const uint32_t ex = gscan<G>( S, flag, tot, tid );
+			if (flag == 1u) A.idx_tmp[Apos + (ex & 0xffffu)] = fr;
+			else if (flag) A.idx_tmp[Bpos - 1 - (ex >> 16)] = fr;
+			Apos += tot & 0xffffu, Bpos -= tot >> 16;
+		}
+	}
+	else
+	{
+		const float planeDist = __fdiv_rn( ext[bestAxis], __fmul_rn( (float)HQBINS, 0.9999f ) );
+		const float rPlaneDist = __fdiv_rn( 1.0f, planeDist ), nodeMin = nmin3[bestAxis];
+		uint32_t* cls = A.cls + t.sliceStart, * strad = A.strad + t.sliceStart;
+		float* spos = A.spos + t.sliceStart;
+		// pass 1: left / right / straddler, straddlers listed in order
+		uint32_t nstrad = 0;
+		for (uint32_t base = 0; base < count; base += G)
+		{
+			const uint32_t i = base + tid;
+			uint32_t flag = 0;
+			if (i < count)
+			{
+				const uint32_t fr = primIdx[leftFirst + i];
+				const float mn = comp( A.frag_min[fr], bestAxis ), mx = comp( A.frag_max[fr], bestAxis );
+				const uint32_t bin1 = __float2uint_rz( tmax( __fmul_rn( __fsub_rn( mn, nodeMin ), rPlaneDist ), 0.0f ) );
+				const uint32_t bin2 = __float2uint_rz( tmax( __fmul_rn( __fsub_rn( mx, nodeMin ), rPlaneDist ), 0.0f ) );
+				const uint32_t c = bin2 <= bestPos ? 0u : bin1 > bestPos ? 1u : 2u;
+				cls[i] = c, flag = c == 2u;
+			}
+			uint32_t tot;
+			const uint32_t ex = gscan<G>( S, flag, tot, tid );
+			if (flag) strad[nstrad + ex] = i;
+			nstrad += tot;
+		}
+		gsync<G>();
+		// pass 2: the unsplitting chain :2895-2926, one warp, in order
+		if (tid < 32)
+		{
+			int NL = S.bestNL, NR = S.bestNR;
+			float cost = S.splitCost, LMin[3], LMax[3], RMin[3], RMax[3];
+			#pragma unroll
+			for (int k = 0; k < 3; k++) LMin[k] = S.best[k], LMax[k] = S.best[3 + k], RMin[k] = S.best[6 + k], RMax[k] = S.best[9 + k];
+			for (uint32_t base = 0; base < nstrad; base += 32)
+			{
+				const uint32_t k = base + tid, m = min( 32u, nstrad - base );
+				float4 fa = make_float4( 0, 0, 0, 0 ), fb = fa;
+				uint32_t i = 0;
+				if (k < nstrad) { i = strad[k]; const uint32_t fr = primIdx[leftFirst + i]; fa = A.frag_min[fr], fb = A.frag_max[fr]; }
+				uint32_t mydec = 2; float mypos = 0;
+				for (uint32_t s = 0; s < m; s++)
+				{
+					const float fmn[3] = { __shfl_sync( 0xffffffffu, fa.x, s ), __shfl_sync( 0xffffffffu, fa.y, s ), __shfl_sync( 0xffffffffu, fa.z, s ) };
+					const float fmx[3] = { __shfl_sync( 0xffffffffu, fb.x, s ), __shfl_sync( 0xffffffffu, fb.y, s ), __shfl_sync( 0xffffffffu, fb.z, s ) };
+					uint32_t dec = 2;
+					if (NR > 1)
+					{
+						float uMin[3], uMax[3];
+						#pragma unroll
+						for (int q = 0; q < 3; q++) uMin[q] = tmin( LMin[q], fmn[q] ), uMax[q] = tmax( LMax[q], fmx[q] );
+						const float AL = half_area3( __fsub_rn( uMax[0], uMin[0] ), __fsub_rn( uMax[1], uMin[1] ), __fsub_rn( uMax[2], uMin[2] ) );
+						const float AR = half_area3( __fsub_rn( RMax[0], RMin[0] ), __fsub_rn( RMax[1], RMin[1] ), __fsub_rn( RMax[2], RMin[2] ) );
+						const float C = split_cost( A.c_trav, A.c_int, rSAV, AL, NL, AR, NR - 1 );
+						if (C <= cost)
+						{
+							NR--, cost = C, dec = 0;
+							#pragma unroll
+							for (int q = 0; q < 3; q++) LMin[q] = uMin[q], LMax[q] = uMax[q];
+						}
+					}
+					if (dec == 2 && NL > 1)
+					{
+						float uMin[3], uMax[3];
+						#pragma unroll
+						for (int q = 0; q < 3; q++) uMin[q] = tmin( RMin[q], fmn[q] ), uMax[q] = tmax( RMax[q], fmx[q] );
+						const float AL = half_area3( __fsub_rn( LMax[0], LMin[0] ), __fsub_rn( LMax[1], LMin[1] ), __fsub_rn( LMax[2], LMin[2] ) );
+						const float AR = half_area3( __fsub_rn( uMax[0], uMin[0] ), __fsub_rn( uMax[1], uMin[1] ), __fsub_rn( uMax[2], uMin[2] ) );
+						const float C = split_cost( A.c_trav, A.c_int, rSAV, AL, NL - 1, AR, NR );
+						if (C <= cost)
+						{
+							NL--, cost = C, dec = 1;
+							#pragma unroll
+							for (int q = 0; q < 3; q++) RMin[q] = uMin[q], RMax[q] = uMax[q];
+						}
+					}
+					if ((uint32_t)tid == s) mydec = dec, mypos = bestAxis == 0 ? LMax[0] : bestAxis == 1 ? LMax[1] : LMax[2];
+				}
+				if (k < nstrad) cls[i] = mydec, spos[k] = mypos;
+			}
+		}
+		gsync<G>();
+		// pass 3: clip the fragments the chain decided to split :2927-2941
+		for (uint32_t k = tid; k < nstrad; k += G)
+		{
+			const uint32_t i = strad[k];
+			if (cls[i] != 2u) continue;
+			const uint32_t fragIdx = primIdx[leftFirst + i];
+			const Frag f = load_frag( A, fragIdx );
+			float lmin[3], lmax[3], rmin[3], rmax[3];
+			bool leftOK, rightOK;
+			split_frag( A, f, lmin, lmax, rmin, rmax, minDim, bestAxis, spos[k], leftOK, rightOK );
+			if (leftOK && rightOK)
+			{
+				const uint32_t nf = atomicAdd( &A.ctr->frag_ptr, 1u );
+				if (nf >= A.idx_cap) { atomicAdd( &A.ctr->overflow, 1u ); cls[i] = 0u; continue; }
+				store_frag( A, fragIdx, lmin, lmax, f.prim ), store_frag( A, nf, rmin, rmax, f.prim );
+				cls[i] = 0x80000000u | nf;
+			}
+			else cls[i] = leftOK ? 0u : 1u;
+		}
+		gsync<G>();
+		// pass 4: left part upward from sliceStart, right part downward from sliceEnd, in fragment order
+		for (uint32_t base = 0; base < count; base += G)
+		{
+			const uint32_t i = base + tid;
+			uint32_t fr = 0, c = 0, flag = 0;
+			if (i < count)
+			{
+				fr = primIdx[leftFirst + i], c = cls[i];
+				flag = (c & 0x80000000u) ? 0x10001u : c == 0u ? 1u : 0x10000u;
+			}
+			uint32_t tot;
+			const uint32_t ex = gscan<G>( S, flag, tot, tid );
+			if (flag & 1u) A.idx_tmp[Apos + (ex & 0xffffu)] = fr;
+			if (flag >> 16) A.idx_tmp[Bpos - 1 - (ex >> 16)] = (c & 0x80000000u) ? (c & 0x7fffffffu) : fr;
+			Apos += tot & 0xffffu, Bpos -= tot >> 16;
+		}
+		// child bounds are refreshed from the fragments :2943-2950
+		for (int k = tid; k < 12; k += G) S.ckey[k] = ((k / 3) & 1) ? f2key( -BVH_FAR ) : f2key( BVH_FAR );
+		gsync<G>();
+		const uint32_t nl = Apos - t.sliceStart, nr = t.sliceEnd - Bpos;
+		for (uint32_t i = tid; i < nl + nr; i += G)
+		{
+			const bool right = i >= nl;
+			const uint32_t fr = A.idx_tmp[right ? Bpos + (i - nl) : t.sliceStart + i];
+			const float4 fa = A.frag_min[fr], fb = A.frag_max[fr];
+			uint32_t* kk = S.ckey + (right ? 6 : 0);
+			atomicMin( kk + 0, f2key( fa.x ) ), atomicMin( kk + 1, f2key( fa.y ) ), atomicMin( kk + 2, f2key( fa.z ) );
+			atomicMax( kk + 3, f2key( fb.x ) ), atomicMax( kk + 4, f2key( fb.y ) ), atomicMax( kk + 5, f2key( fb.z ) );
+		}
+		gsync<G>();
+		if (tid < 12) S.best[tid] = key2f( S.ckey[tid] );
+	}
+	gsync<G>();
+	// copy back :2965 (the parts that hold fragments; the rest of the slice is never read through primIdx)
+	const uint32_t leftCount = Apos - t.sliceStart, rightCount = t.sliceEnd - Bpos;
+	for (uint32_t i = tid; i < leftCount + rightCount; i += G)
+	{
+		const uint32_t p = i < leftCount ? t.sliceStart + i : Bpos + (i - leftCount);
+		A.prim_idx[p] = A.idx_tmp[p];
+	}
+	gsync<G>();
+	if (leftCount == 0 || rightCount == 0)
+	{
+		// ":2939 spatial split failed": the reference reads the node's OLD range out of the refreshed primIdx, i.e. whatever
+		// idxTmp holds there (this node's own output where the ranges overlap, an ancestor's words or zeros elsewhere)
+		for (uint32_t i = tid; i < count; i += G) { const uint32_t p = leftFirst + i; A.prim_idx[p] = __float_as_uint( A.frag_min[A.idx_tmp[p]].w ); }
+		if (tid == 0)
+		{
+			const float* b = S.best;
+			A.tmp_nodes[(size_t)t.node * 2] = make_float4( tmin( b[0], b[6] ), tmin( b[1], b[7] ), tmin( b[2], b[8] ), n0.w );
+			A.tmp_nodes[(size_t)t.node * 2 + 1] = make_float4( tmax( b[3], b[9] ), tmax( b[4], b[10] ), tmax( b[5], b[11] ), n1.w );
+			atomicAdd( &A.ctr->failed_splits, 1u ), atomicMax( &A.ctr->max_depth, t.depth );
+		}
+		return false;
+	}
+	// ---- emit :2966-2984
+	if (tid == 0)
+	{
+		const uint32_t lc = atomicAdd( &A.ctr->node_ptr, 2u );
+		S.lc = lc;
+		if (lc + 2 <= A.node_cap)
+		{
+			const float* b = S.best;
+			A.tmp_nodes[(size_t)lc * 2] = make_float4( b[0], b[1], b[2], __uint_as_float( t.sliceStart ) );
+			A.tmp_nodes[(size_t)lc * 2 + 1] = make_float4( b[3], b[4], b[5], __uint_as_float( leftCount ) );
+			A.tmp_nodes[(size_t)lc * 2 + 2] = make_float4( b[6], b[7], b[8], __uint_as_float( Bpos ) );
+			A.tmp_nodes[(size_t)lc * 2 + 3] = make_float4( b[9], b[10], b[11], __uint_as_float( rightCount ) );
+			A.tmp_nodes[(size_t)t.node * 2] = make_float4( n0.x, n0.y, n0.z, __uint_as_float( lc ) );
+			A.tmp_nodes[(size_t)t.node * 2 + 1] = make_float4( n1.x, n1.y, n1.z, __uint_as_float( 0u ) );
+			A.parent[lc] = A.parent[lc + 1] = t.node;
+		}
+		else atomicAdd( &A.ctr->overflow, 1u );
+	}
+	gsync<G>();
+	const uint32_t lc = S.lc;
+	if (lc + 2 > A.node_cap) return false;
+	const uint32_t mid = (Apos + Bpos) >> 1;
+	outL.node = lc, outL.sliceStart = t.sliceStart, outL.sliceEnd = mid, outL.depth = t.depth + 1;
+	outR.node = lc + 1, outR.sliceStart = mid, outR.sliceEnd = t.sliceEnd, outR.depth = t.depth + 1;
+	gsync<G>();
+	return true;
+}
+
+// ---------------------------------------------------------------------------------------------- kernels
+__global__ void k_hq_init( HQArgs A )
+{
+	HQCounters* c = A.ctr;
+	c->node_ptr = 2, c->frag_ptr = A.n, c->next_big = 0, c->small_roots = 0, c->max_depth = 0, c->failed_splits = 0, c->overflow = 0;
+	for (int k = 0; k < 3; k++) c->root_key[k] = f2key( BVH_FAR ), c->root_key[3 + k] = f2key( -BVH_FAR );
+}
+
+// PrepareHQBuild :2677-2686: fragment boxes, identity primIdx, root bounds
+__global__ void k_hq_fragments( HQArgs A )
+{
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	float mn[3] = { BVH_FAR, BVH_FAR, BVH_FAR }, mx[3] = { -BVH_FAR, -BVH_FAR, -BVH_FAR };
+	if (i < A.n)
+	{
+		const float4 v0 = A.verts[(size_t)i * 3], v1 = A.verts[(size_t)i * 3 + 1], v2 = A.verts[(size_t)i * 3 + 2];
+		mn[0] = tmin( v0.x, tmin( v1.x, v2.x ) ), mn[1] = tmin( v0.y, tmin( v1.y, v2.y ) ), mn[2] = tmin( v0.z, tmin( v1.z, v2.z ) );
+		mx[0] = tmax( v0.x, tmax( v1.x, v2.x ) ), mx[1] = tmax( v0.y, tmax( v1.y, v2.y ) ), mx[2] = tmax( v0.z, tmax( v1.z, v2.z ) );
+		A.frag_min[i] = make_float4( mn[0], mn[1], mn[2], __uint_as_float( i ) );
+		A.frag_max[i] = make_float4( mx[0], mx[1], mx[2], __uint_as_float( 0u ) );
+		A.prim_idx[i] = i;
+	}
+	#pragma unroll
+	for (int k = 0; k < 3; k++)
+	{
+		uint32_t a = f2key( mn[k] ), b = f2key( mx[k] );
+		a = __reduce_min_sync( 0xffffffffu, a ), b = __reduce_max_sync( 0xffffffffu, b );
+		if ((threadIdx.x & 31) == 0) atomicMin( &A.ctr->root_key[k], a ), atomicMax( &A.ctr->root_key[3 + k], b );
+	}
+}
+
+__global__ void k_hq_root( HQArgs A )
+{
+	HQCounters* c = A.ctr;
+	float mn[3], mx[3];
+	for (int k = 0; k < 3; k++) mn[k] = key2f( c->root_key[k] ), mx[k] = key2f( c->root_key[3 + k] );
+	A.tmp_nodes[0] = make_float4( mn[0], mn[1], mn[2], __uint_as_float( 0u ) );
+	A.tmp_nodes[1] = make_float4( mx[0], mx[1], mx[2], __uint_as_float( A.n ) );
+	A.tmp_nodes[2] = A.tmp_nodes[3] = make_float4( 0, 0, 0, 0 );
+	A.parent[0] = A.parent[1] = 0xffffffffu;
+	const float ex = __fsub_rn( mx[0], mn[0] ), ey = __fsub_rn( mx[1], mn[1] ), ez = __fsub_rn( mx[2], mn[2] );
+	c->root_area = half_area3( ex, ey, ez );
+	c->min_dim[0] = __fmul_rn( ex, 1e-7f ), c->min_dim[1] = __fmul_rn( ey, 1e-7f ), c->min_dim[2] = __fmul_rn( ez, 1e-7f );
+	HQTask t = { 0u, 0u, A.idx_cap, 0u };
+	if (A.n > HQ_SMALL) A.lvl[0][0] = t, c->next_big = 1; else A.small[0] = t, c->small_roots = 1;
+}
+
+__device__ __forceinline__ void hq_enqueue( const HQArgs& A, HQTask* next, const HQTask c )
+{
+	const uint32_t cnt = __float_as_uint( A.tmp_nodes[(size_t)c.node * 2 + 1].w );
+	if (cnt > HQ_SMALL)
+	{
+		const uint32_t k = atomicAdd( &A.ctr->next_big, 1u );
+		if (k < A.lvl_cap) next[k] = c; else atomicAdd( &A.ctr->overflow, 1u );
+	}
+	else A.small[atomicAdd( &A.ctr->small_roots, 1u )] = c;
+}
+
+__global__ void __launch_bounds__( HQ_BIG_THREADS ) k_hq_level( HQArgs A, const HQTask* cur, HQTask* next )
+{
+	__shared__ GroupSmem S;
+	HQTask l, r;
+	const bool split = hq_node<HQ_BIG_THREADS>( A, S, cur[blockIdx.x], threadIdx.x, l, r );
+	if (split && threadIdx.x == 0) hq_enqueue( A, next, l ), hq_enqueue( A, next, r );
+}
+
+__global__ void __launch_bounds__( HQ_SMALL_WARPS * 32 ) k_hq_subtrees( HQArgs A, const uint32_t roots )
+{
+	__shared__ GroupSmem Ss[HQ_SMALL_WARPS];
+	__shared__ HQTask stack[HQ_SMALL_WARPS][HQ_STACK];
+	const uint32_t w = threadIdx.x >> 5, lane = threadIdx.x & 31, id = blockIdx.x * HQ_SMALL_WARPS + w;
+	if (id >= roots) return;
+	GroupSmem& S = Ss[w];
+	HQTask t = A.small[id];
+	uint32_t sp = 0;
+	for (;;)
+	{
+		HQTask l, r;
+		if (hq_node<32>( A, S, t, (int)lane, l, r ))
+		{
+			// continue with the child that holds fewer fragments, park the other: the stack stays logarithmic
+			const uint32_t cl = __float_as_uint( A.tmp_nodes[(size_t)l.node * 2 + 1].w ), cr = __float_as_uint( A.tmp_nodes[(size_t)r.node * 2 + 1].w );
+			const HQTask park = cl <= cr ? r : l;
+			t = cl <= cr ? l : r;
+			if (sp < HQ_STACK) { if (lane == 0) stack[w][sp] = park; sp++; }
+			else if (lane == 0) atomicAdd( &A.ctr->overflow, 1u );
+			__syncwarp();
+			continue;
+		}
+		if (!sp) break;
+		t = stack[w][--sp];
+		__syncwarp();
+	}
+}
+
+// ---- Compact() :3733-3770 as a parallel relayout
+// bottom-up: number of interior nodes / of leaf index entries per subtree (second arrival at a parent carries on)
+__global__ void k_hq_up( HQArgs A, const uint32_t tmp_count )
+{
+	uint32_t x = blockIdx.x * blockDim.x + threadIdx.x;
+	if (x >= tmp_count || x == 1) return;
+	const uint32_t cnt = __float_as_uint( A.tmp_nodes[(size_t)x * 2 + 1].w );
+	if (cnt == 0) return; // interior
+	A.sub_int[x] = 0, A.sub_prims[x] = cnt;
+	for (;;)
+	{
+		const uint32_t p = A.parent[x];
+		if (p == 0xffffffffu) break;
+		__threadfence();
+		if (atomicAdd( &A.arrive[p], 1u ) == 0) break;
+		__threadfence();
+		const uint32_t lc = __float_as_uint( A.tmp_nodes[(size_t)p * 2].w );
+		const volatile uint32_t* si = A.sub_int; const volatile uint32_t* sp = A.sub_prims;
+		A.sub_int[p] = si[lc] + si[lc + 1] + 1, A.sub_prims[p] = sp[lc] + sp[lc + 1];
+		x = p;
+	}
+}
+// top-down by walking to the root: K = interior nodes before x in DFS preorder, O = leaf index entries before x
+__global__ void k_hq_down( HQArgs A, const uint32_t tmp_count, float4* out_nodes, uint32_t* out_idx )
+{
+	const uint32_t x = blockIdx.x * blockDim.x + threadIdx.x;
+	if (x >= tmp_count) return;
+	if (x == 1) { out_nodes[2] = out_nodes[3] = make_float4( 0, 0, 0, 0 ); return; }
+	uint32_t K = 0, O = 0, c = x, Kparent = 0;
+	while (c != 0)
+	{
+		const uint32_t p = A.parent[c], lc = __float_as_uint( A.tmp_nodes[(size_t)p * 2].w );
+		uint32_t add = 1;
+		if (c == lc + 1) add += A.sub_int[lc], O += A.sub_prims[lc];
+		if (c == x) Kparent = add; // K(parent) = K(x) - add, fixed up below
+		K += add, c = p;
+	}
+	const uint32_t dst = x == 0 ? 0u : 2u + 2u * (K - Kparent) + ((x & 1u) ? 1u : 0u); // pairs start at even temp indices: odd = right child
+	const float4 a = A.tmp_nodes[(size_t)x * 2], b = A.tmp_nodes[(size_t)x * 2 + 1];
+	const uint32_t cnt = __float_as_uint( b.w );
+	if (cnt == 0) out_nodes[(size_t)dst * 2] = make_float4( a.x, a.y, a.z, __uint_as_float( 2u + 2u * K ) ), out_nodes[(size_t)dst * 2 + 1] = b;
+	else
+	{
+		out_nodes[(size_t)dst * 2] = make_float4( a.x, a.y, a.z, __uint_as_float( O ) ), out_nodes[(size_t)dst * 2 + 1] = b;
+		const uint32_t first = __float_as_uint( a.w );
+		for (uint32_t i = 0; i < cnt; i++) out_idx[O + i] = A.prim_idx[first + i];
+	}
+}
+} // namespace
+
+#define DEV_ALLOC( p, bytes ) do { void* q_ = 0; CUDA_TRY( cudaMalloc( &q_, (bytes) ) ); scratch.push_back( q_ ); (p) = (decltype( p ))q_; } while (0)
+
+int build_hq_launch( tbvh_bvh b, float c_trav, float c_int )
+{
+	const uint32_t n = b->info.prim_count, slack = n >> 1;
+	cudaStream_t s = b->ctx->stream;
+	std::vector<void*> scratch;
+	HQArgs A = {};
+	A.verts = b->d_verts, A.n = n, A.c_trav = c_trav, A.c_int = c_int;
+	A.idx_cap = n + slack, A.node_cap = 3 * n + 2;
+	A.lvl_cap = A.idx_cap / HQ_SMALL + 2;
+	HQCounters* h_ctr = 0;
+	cudaEvent_t e0 = 0, e1 = 0;
+	CUDA_TRY( cudaMalloc( &b->d_nodes, (size_t)A.node_cap * 32 ) );
+	CUDA_TRY( cudaMalloc( &b->d_prim_idx, (size_t)A.idx_cap * 4 ) );
+	auto body = [&]() -> int
+	{
+		DEV_ALLOC( A.frag_min, (size_t)A.idx_cap * 16 ); DEV_ALLOC( A.frag_max, (size_t)A.idx_cap * 16 );
+		DEV_ALLOC( A.prim_idx, (size_t)A.idx_cap * 4 ); DEV_ALLOC( A.idx_tmp, (size_t)A.idx_cap * 4 );
+		DEV_ALLOC( A.cls, (size_t)A.idx_cap * 4 ); DEV_ALLOC( A.strad, (size_t)A.idx_cap * 4 ); DEV_ALLOC( A.spos, (size_t)A.idx_cap * 4 );
+		DEV_ALLOC( A.tmp_nodes, (size_t)A.node_cap * 32 ); DEV_ALLOC( A.parent, (size_t)A.node_cap * 4 );
+		DEV_ALLOC( A.sub_int, (size_t)A.node_cap * 4 ); DEV_ALLOC( A.sub_prims, (size_t)A.node_cap * 4 ); DEV_ALLOC( A.arrive, (size_t)A.node_cap * 4 );
+		DEV_ALLOC( A.lvl[0], (size_t)A.lvl_cap * sizeof( HQTask ) ); DEV_ALLOC( A.lvl[1], (size_t)A.lvl_cap * sizeof( HQTask ) );
+		DEV_ALLOC( A.small, ((size_t)A.idx_cap + 1) * sizeof( HQTask ) );
+		DEV_ALLOC( A.ctr, sizeof( HQCounters ) );
+		CUDA_TRY( cudaMallocHost( &h_ctr, sizeof( HQCounters ) ) );
+		CUDA_TRY( cudaEventCreate( &e0 ) ); CUDA_TRY( cudaEventCreate( &e1 ) );
+		CUDA_TRY( cudaEventRecord( e0, s ) );
+		// the reference clears primIdx beyond triCount (:2700) and all of idxTmp (:3008)
+		CUDA_TRY( cudaMemsetAsync( A.prim_idx, 0, (size_t)A.idx_cap * 4, s ) );
+		CUDA_TRY( cudaMemsetAsync( A.idx_tmp, 0, (size_t)A.idx_cap * 4, s ) );
+		CUDA_TRY( cudaMemsetAsync( A.arrive, 0, (size_t)A.node_cap * 4, s ) );
+		k_hq_init<<<1, 1, 0, s>>>( A ); LAUNCHED();
+		k_hq_fragments<<<(n + 255) / 256, 256, 0, s>>>( A ); LAUNCHED();
+		k_hq_root<<<1, 1, 0, s>>>( A ); LAUNCHED();
+		uint32_t num = n > HQ_SMALL ? 1 : 0, level = 0;
+		while (num)
+		{
+			CUDA_TRY( cudaMemsetAsync( &A.ctr->next_big, 0, 4, s ) );
+			k_hq_level<<<num, HQ_BIG_THREADS, 0, s>>>( A, A.lvl[level & 1], A.lvl[(level + 1) & 1] ); LAUNCHED();
+			CUDA_TRY( cudaMemcpyAsync( h_ctr, A.ctr, sizeof( HQCounters ), cudaMemcpyDeviceToHost, s ) );
+			CUDA_TRY( cudaStreamSynchronize( s ) );
+			num = h_ctr->next_big;
+			if (h_ctr->overflow) { tbvh_set_error( "BuildHQ: pool overflow in the level phase" ); return TBVH_E_LIMIT; }
+			if (++level > 4096) { tbvh_set_error( "BuildHQ: runaway level count" ); return TBVH_E_LIMIT; }
+		}
+		CUDA_TRY( cudaMemcpyAsync( h_ctr, A.ctr, sizeof( HQCounters ), cudaMemcpyDeviceToHost, s ) );
+		CUDA_TRY( cudaStreamSynchronize( s ) );
+		const uint32_t roots = h_ctr->small_roots;
+		if (roots) { k_hq_subtrees<<<(roots + HQ_SMALL_WARPS - 1) / HQ_SMALL_WARPS, HQ_SMALL_WARPS * 32, 0, s>>>( A, roots ); LAUNCHED(); }
+		CUDA_TRY( cudaMemcpyAsync( h_ctr, A.ctr, sizeof( HQCounters ), cudaMemcpyDeviceToHost, s ) );
+		CUDA_TRY( cudaStreamSynchronize( s ) );
+		if (h_ctr->overflow) { tbvh_set_error( "BuildHQ: pool overflow in the subtree phase" ); return TBVH_E_LIMIT; }
+		const uint32_t tmp_count = h_ctr->node_ptr;
+		// Compact(): DFS-preorder numbering, leaf index ranges packed in DFS order; the tail of the index array is zeroed
+		CUDA_TRY( cudaMemsetAsync( b->d_prim_idx, 0, (size_t)A.idx_cap * 4, s ) );
+		if (tmp_count > 2)
+		{
+			k_hq_up<<<(tmp_count + 255) / 256, 256, 0, s>>>( A, tmp_count ); LAUNCHED();
+			k_hq_down<<<(tmp_count + 255) / 256, 256, 0, s>>>( A, tmp_count, b->d_nodes, b->d_prim_idx ); LAUNCHED();
+		}
+		else
+		{
+			CUDA_TRY( cudaMemcpyAsync( b->d_nodes, A.tmp_nodes, 64, cudaMemcpyDeviceToDevice, s ) );
+			CUDA_TRY( cudaMemcpyAsync( b->d_prim_idx, A.prim_idx, (size_t)A.idx_cap * 4, cudaMemcpyDeviceToDevice, s ) );
+		}
+		CUDA_TRY( cudaEventRecord( e1, s ) );
+		CUDA_TRY( cudaStreamSynchronize( s ) );
+		float ms = 0;
+		CUDA_TRY( cudaEventElapsedTime( &ms, e0, e1 ) );
+		b->info.build_ms = ms;
+		b->info.used_nodes = tmp_count, b->info.idx_count = A.idx_cap, b->info.max_depth = h_ctr->max_depth;
+		uint32_t rootw[8];
+		CUDA_TRY( cudaMemcpy( rootw, b->d_nodes, 32, cudaMemcpyDeviceToHost ) );
+		memcpy( b->info.aabb_min, rootw, 12 ), memcpy( b->info.aabb_max, rootw + 4, 12 );
+		b->root_ref = rootw[3], b->root_count = rootw[7];
+		b->d_trav = b->d_nodes;
+		return make_leaf_tris( b, s );
+	};
+	const int rc = body();
+	cudaStreamSynchronize( s );
+	for (void* p : scratch) cudaFree( p );
+	if (h_ctr) cudaFreeHost( h_ctr );
+	if (e0) cudaEventDestroy( e0 );
+	if (e1) cudaEventDestroy( e1 );
+	return rc;
+}
