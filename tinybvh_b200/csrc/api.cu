@@ -63,6 +63,10 @@ int tbvh_ctx_create( int device, tbvh_ctx* out )
 	c->trace_variant = tv ? atoi( tv ) : 3; // octant switch: +5 % on camera / shadow rays, -3 % on diffuse (profiles/README.md)
 	const char* st = getenv( "TBVH_SMALL_T" );
 	c->small_t = st ? atoi( st ) : 128;
+	const char* hs = getenv( "TBVH_HQ_SMALL" );
+	if (hs) c->hq_small = atoi( hs );
+	const char* hc = getenv( "TBVH_HQ_CLUSTER" );
+	if (hc) c->hq_cluster = atoi( hc );
 	const char* dm = getenv( "TBVH_D2H_MODE" );
 	c->d2h_mode = dm ? atoi( dm ) : 0;
 	const char* sp = getenv( "TBVH_H2D_SPLIT" );
@@ -89,6 +93,8 @@ int tbvh_set_option( tbvh_ctx c, const char* key, int value )
 	if (!strcmp( key, "trace_variant" )) c->trace_variant = value;
 	else if (!strcmp( key, "small_t" )) c->small_t = value;
 	else if (!strcmp( key, "small_mode" )) c->small_mode = value & 3;
+	else if (!strcmp( key, "hq_small" )) c->hq_small = value;
+	else if (!strcmp( key, "hq_cluster" )) c->hq_cluster = value;
 	else if (!strcmp( key, "d2h_mode" )) c->d2h_mode = value;
 	else if (!strcmp( key, "h2d_split" )) c->h2d_split = value < 1 ? 1 : value > 4 ? 4 : value;
 	else if (!strcmp( key, "host_path" )) c->host_path = value;

@@ -25,14 +25,17 @@
 //   k_hq_level     level-synchronous, one 256-thread CTA per node with more than HQ_SMALL fragments
 //   k_hq_subtrees  one warp per subtree of at most HQ_SMALL fragments, depth-first with a shared-memory task stack
 #include "common.cuh"
+#include <cooperative_groups.h>
 #include <stdlib.h>
 #include <string.h>
 #include <vector>
 
+namespace cg = cooperative_groups;
 namespace
 {
 #define HQBINS 8
-#define HQ_SMALL 256          // nodes with at most this many fragments go to the warp kernel
+#define HQ_SMALL_MAX 256      // switch point CTA/cluster per node -> warp per subtree (run-time value hq_small <= this)
+#define HQ_MAX_CLUSTER 16
 #define HQ_BIG_THREADS 256
 #define HQ_SMALL_WARPS 4
 #define HQ_STACK 64
@@ -43,6 +46,7 @@ struct HQCounters
 	uint32_t node_ptr;       // temp node records allocated (pairs from 2)
 	uint32_t frag_ptr;       // nextFrag
 	uint32_t next_big;       // tasks appended to the next level's list
+	uint32_t next_max;       // largest fragment count among them (sizes the clusters); cleared together with next_big
 	uint32_t small_roots;    // subtree roots for k_hq_subtrees
 	uint32_t max_depth;
 	uint32_t failed_splits;  // ":2939 spatial split failed" leaves
@@ -61,7 +65,7 @@ struct HQArgs
 	float4* tmp_nodes; uint32_t* parent; uint32_t* sub_int; uint32_t* sub_prims; uint32_t* arrive;
 	HQTask* lvl[2]; HQTask* small;
 	HQCounters* ctr;
-	uint32_t n, idx_cap, node_cap, lvl_cap;
+	uint32_t n, idx_cap, node_cap, lvl_cap, small_t;
 	float c_trav, c_int;
 };
 
@@ -76,6 +80,7 @@ struct GroupSmem
 	uint32_t bestAxis, bestPos, bestIdx;
 	int spatial, bestNL, bestNR, hasObj, trySpatial, leaf;
 	uint32_t wtot[8];
+	uint32_t ctot[HQ_MAX_CLUSTER];
 	uint32_t nstrad;
 	uint32_t ckey[12];                               // child bounds of a spatial partition: lmin, lmax, rmin, rmax keys
 	uint32_t lc;
@@ -135,7 +140,7 @@ template <bool CLAMP> __device__ __forceinline__ uint32_t clip_slab( float vin[1
 	const float le = __fsub_rn( l, eps ), re = __fadd_rn( r, eps );
 	for (uint32_t v = 0; v < Nin; v++)
 	{
-		const float* v0 = vin[v], * v1 = vin[(v + 1) % Nin];
+		const float* v0 = vin[v], * v1 = vin[v + 1 == Nin ? 0 : v + 1];
 		const bool v0in = v0[a] >= le, v1in = v1[a] >= le;
 		if (!(v0in || v1in)) continue; else if (v0in ^ v1in)
 		{
@@ -149,7 +154,7 @@ template <bool CLAMP> __device__ __forceinline__ uint32_t clip_slab( float vin[1
 	Nin = 0;
 	for (uint32_t v = 0; v < Nout; v++)
 	{
-		const float* v0 = vout[v], * v1 = vout[(v + 1) % Nout];
+		const float* v0 = vout[v], * v1 = vout[v + 1 == Nout ? 0 : v + 1];
 		const bool v0in = v0[a] <= re, v1in = v1[a] <= re;
 		if (!(v0in || v1in)) continue; else if (v0in ^ v1in)
 		{
@@ -221,7 +226,7 @@ __device__ bool clip_frag( const HQArgs& A, const Frag& orig, float* nb_min, flo
 			}
 			for (uint32_t v = 0; v < Nout; v++)
 			{
-				const float* v0 = vout[v], * v1 = vout[(v + 1) % Nout];
+				const float* v0 = vout[v], * v1 = vout[v + 1 == Nout ? 0 : v + 1];
 				const bool v0in = v0[axis] <= r, v1in = v1[axis] <= r;
 				if (!(v0in || v1in)) continue; else if (v0in ^ v1in)
 				{
@@ -263,7 +268,7 @@ __device__ void split_frag( const HQArgs& A, const Frag& orig, float* lmin, floa
 	#define ADD_R( p ) { Nright++; for (int k_ = 0; k_ < 3; k_++) rmin[k_] = tmin( rmin[k_], (p)[k_] ), rmax[k_] = tmax( rmax[k_], (p)[k_] ); }
 	for (uint32_t v = 0; v < Nin; v++)
 	{
-		const float* v0 = vin[v], * v1 = vin[(v + 1) % Nin];
+		const float* v0 = vin[v], * v1 = vin[v + 1 == Nin ? 0 : v + 1];
 		const bool v0left = v0[splitAxis] < splitPos, v1left = v1[splitAxis] < splitPos;
 		if (v0left && v1left) ADD_L( v1 ) else if (!v0left && !v1left) ADD_R( v1 ) else
 		{
@@ -280,24 +285,47 @@ __device__ void split_frag( const HQArgs& A, const Frag& orig, float* lmin, floa
 }
 
 // ---------------------------------------------------------------------------------------------- group helpers
-template <int G> __device__ __forceinline__ void gsync() { if (G == 32) __syncwarp(); else __syncthreads(); }
-
-// exclusive scan of v over the G threads of the group; every thread gets the group total.  Callers pack two 16-bit
-// counters into v (a tile holds at most 256 of each).
-template <int G> __device__ __forceinline__ uint32_t gscan( GroupSmem& S, const uint32_t v, uint32_t& total, const int tid )
+// A node is owned by a "group": one warp (G = 32), one CTA (G = 256, nct = 1) or a thread-block cluster of nct CTAs.  In a
+// cluster every CTA keeps its own GroupSmem (bins, scan scratch); the leader's copy S0 - reached through distributed shared
+// memory - holds the merged tables and every decision.
+struct Grp
 {
-	const int lane = tid & 31;
+	int tid, gtid, GT;        // thread in its CTA (lane for warps), thread in the group, threads in the group
+	uint32_t rank, nct;       // CTA rank in the cluster, cluster size
+	GroupSmem* S; GroupSmem* S0;
+};
+template <int G> __device__ __forceinline__ void lsync() { if (G == 32) __syncwarp(); else __syncthreads(); }
+template <int G> __device__ __forceinline__ void gsync( const Grp& g )
+{
+	if (G == 32) __syncwarp(); else if (g.nct == 1) __syncthreads(); else cg::this_cluster().sync();
+}
+
+// exclusive scan of v over the threads of the group; every thread gets the group total.  Callers pack two 16-bit
+// counters into v (a tile holds at most 4096 of each).
+template <int G> __device__ __forceinline__ uint32_t gscan( const Grp& g, const uint32_t v, uint32_t& total )
+{
+	const int lane = g.tid & 31;
 	uint32_t x = v;
 	#pragma unroll
 	for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync( 0xffffffffu, x, o ); if (lane >= o) x += y; }
 	if (G == 32) { total = __shfl_sync( 0xffffffffu, x, 31 ); return x - v; }
-	const int w = tid >> 5;
+	GroupSmem& S = *g.S;
+	const int w = g.tid >> 5;
 	if (lane == 31) S.wtot[w] = x;
 	__syncthreads();
 	uint32_t base = 0, tot = 0;
 	#pragma unroll
 	for (int i = 0; i < G / 32; i++) { const uint32_t t = S.wtot[i]; if (i < w) base += t; tot += t; }
 	__syncthreads();
+	if (g.nct > 1)
+	{
+		if (g.tid == 0) g.S0->ctot[g.rank] = tot;
+		cg::this_cluster().sync();
+		uint32_t cb = 0, ct = 0;
+		for (uint32_t r = 0; r < g.nct; r++) { const uint32_t t = g.S0->ctot[r]; if (r < g.rank) cb += t; ct += t; }
+		cg::this_cluster().sync();
+		base += cb, tot = ct;
+	}
 	total = tot;
 	return base + x - v;
 }
@@ -306,6 +334,20 @@ __device__ __forceinline__ void bins_reset( GroupSmem& S, const int tid, const i
 {
 	for (int k = tid; k < 3 * HQBINS * 3; k += G) (&S.kmin[0][0][0])[k] = f2key( BVH_FAR ), (&S.kmax[0][0][0])[k] = f2key( -BVH_FAR );
 	for (int k = tid; k < 3 * HQBINS; k += G) (&S.cntA[0][0])[k] = 0, (&S.cntB[0][0])[k] = 0;
+}
+// cluster: fold this CTA's tables into the leader's (distributed shared memory atomics)
+template <int G> __device__ __forceinline__ void bins_merge( const Grp& g )
+{
+	if (G == 32 || g.nct == 1) return;
+	__syncthreads();
+	if (g.rank != 0)
+	{
+		GroupSmem& S = *g.S; GroupSmem& D = *g.S0;
+		for (int k = g.tid; k < 3 * HQBINS * 3; k += G)
+			atomicMin( &(&D.kmin[0][0][0])[k], (&S.kmin[0][0][0])[k] ), atomicMax( &(&D.kmax[0][0][0])[k], (&S.kmax[0][0][0])[k] );
+		for (int k = g.tid; k < 3 * HQBINS; k += G)
+			atomicAdd( &(&D.cntA[0][0])[k], (&S.cntA[0][0])[k] ), atomicAdd( &(&D.cntB[0][0])[k], (&S.cntB[0][0])[k] );
+	}
 }
 __device__ __forceinline__ void bin_grow( GroupSmem& S, const uint32_t a, const uint32_t b, const float* mn, const float* mx )
 {
@@ -345,8 +387,12 @@ __device__ __forceinline__ void sweep_candidate( GroupSmem& S, const int c, cons
 
 // One node, start to finish, by a group of G threads (G = 32: a warp, G = 256: a CTA).  Returns true and the two child
 // tasks when the node was split.
-template <int G> __device__ bool hq_node( const HQArgs& A, GroupSmem& S, const HQTask t, const int tid, HQTask& outL, HQTask& outR )
+template <int G> __device__ bool hq_node( const HQArgs& A, const Grp& g, const HQTask t, HQTask& outL, HQTask& outR )
 {
+	GroupSmem& S = *g.S;            // this CTA's (warp's) tables
+	GroupSmem& S0 = *g.S0;          // the leader's: merged tables, decisions
+	const int tid = g.tid, gtid = g.gtid, GT = g.GT;
+	const bool lead = g.rank == 0;
 	const float4 n0 = A.tmp_nodes[(size_t)t.node * 2], n1 = A.tmp_nodes[(size_t)t.node * 2 + 1];
 	const float nmin3[3] = { n0.x, n0.y, n0.z }, nmax3[3] = { n1.x, n1.y, n1.z };
 	const uint32_t leftFirst = __float_as_uint( n0.w ), count = __float_as_uint( n1.w );
@@ -361,8 +407,8 @@ template <int G> __device__ bool hq_node( const HQArgs& A, GroupSmem& S, const H
 
 	// ---- object split: bins :2758-2775
 	bins_reset( S, tid, G );
-	gsync<G>();
-	for (uint32_t i = tid; i < count; i += G)
+	gsync<G>( g );
+	for (uint32_t i = gtid; i < count; i += GT)
 	{
 		const uint32_t fi = primIdx[leftFirst + i];
 		const float4 fa = A.frag_min[fi], fb = A.frag_max[fi];
@@ -375,10 +421,11 @@ template <int G> __device__ bool hq_node( const HQArgs& A, GroupSmem& S, const H
 			atomicAdd( &S.cntA[a][bi], 1u );
 		}
 	}
-	gsync<G>();
-	if (tid < 21) sweep_candidate( S, tid, false, rSAV, A.c_trav, A.c_int );
-	gsync<G>();
-	if (tid == 0)
+	bins_merge<G>( g );
+	gsync<G>( g );
+	if (lead && tid < 21) sweep_candidate( S, tid, false, rSAV, A.c_trav, A.c_int );
+	lsync<G>();
+	if (lead && tid == 0)
 	{
 		float splitCost = noSplitCost;
 		int best = -1;
@@ -403,14 +450,14 @@ template <int G> __device__ bool hq_node( const HQArgs& A, GroupSmem& S, const H
 		trySpatial = (budget > (int)count) && (trySpatial || splitCost >= noSplitCost);
 		S.splitCost = splitCost, S.trySpatial = trySpatial;
 	}
-	gsync<G>();
+	gsync<G>( g );
 
 	// ---- spatial split candidate :2808-2872
-	if (S.trySpatial)
+	if (S0.trySpatial)
 	{
 		bins_reset( S, tid, G );
-		gsync<G>();
-		for (uint32_t it = tid; it < count * 3; it += G)
+		gsync<G>( g );
+		for (uint32_t it = gtid; it < count * 3; it += GT)
 		{
 			const uint32_t i = it / 3, a = it - i * 3;
 			if (!axisOK[a]) continue;
@@ -430,10 +477,11 @@ template <int G> __device__ bool hq_node( const HQArgs& A, GroupSmem& S, const H
 				bin_grow( S, a, j, nbmin, nbmax );
 			}
 		}
-		gsync<G>();
-		if (tid < 21) sweep_candidate( S, tid, true, rSAV, A.c_trav, A.c_int );
-		gsync<G>();
-		if (tid == 0)
+		bins_merge<G>( g );
+		gsync<G>( g );
+		if (lead && tid < 21) sweep_candidate( S, tid, true, rSAV, A.c_trav, A.c_int );
+		lsync<G>();
+		if (lead && tid == 0)
 		{
 			float splitCost = S.splitCost, minSplitCost = __fmul_rn( splitCost, 0.985f );
 			int best = -1;
@@ -454,26 +502,28 @@ template <int G> __device__ bool hq_node( const HQArgs& A, GroupSmem& S, const H
 				S.best[3 + a] = S.best[6 + a]; // bestLMax[a] = bestRMin[a], "accurate" :2868
 			}
 		}
-		gsync<G>();
+		gsync<G>( g );
 	}
 
 	// ---- leaf? :2874-2880
-	if (S.splitCost >= noSplitCost)
+	if (S0.splitCost >= noSplitCost)
 	{
-		for (uint32_t i = tid; i < count; i += G) { const uint32_t p = leftFirst + i; A.prim_idx[p] = __float_as_uint( A.frag_min[A.prim_idx[p]].w ); }
-		if (tid == 0) atomicMax( &A.ctr->max_depth, t.depth );
+		for (uint32_t i = gtid; i < count; i += GT) { const uint32_t p = leftFirst + i; A.prim_idx[p] = __float_as_uint( A.frag_min[A.prim_idx[p]].w ); }
+		if (lead && tid == 0) atomicMax( &A.ctr->max_depth, t.depth );
+		gsync<G>( g ); // nobody reads the leader's tables after it has moved on
 		return false;
 	}
 
 	// ---- partition into idxTmp :2882-2964
-	const uint32_t bestAxis = S.bestAxis, bestPos = S.bestPos;
+	const uint32_t bestAxis = S0.bestAxis, bestPos = S0.bestPos;
+	const bool spatial = S0.spatial != 0;
 	uint32_t Apos = t.sliceStart, Bpos = t.sliceEnd;
-	if (!S.spatial)
+	if (!spatial)
 	{
 		const float rpd = rpd3[bestAxis], nmin = nmin3[bestAxis];
-		for (uint32_t base = 0; base < count; base += G)
+		for (uint32_t base = 0; base < count; base += GT)
 		{
-			const uint32_t i = base + tid;
+			const uint32_t i = base + gtid;
 			uint32_t fr = 0, flag = 0;
 			if (i < count)
 			{
@@ -483,7 +533,7 @@ template <int G> __device__ bool hq_node( const HQArgs& A, GroupSmem& S, const H
 				flag = bi <= (int)bestPos ? 1u : 0x10000u;
 			}
 			uint32_t tot;
-			const uint32_t ex = gscan<G>( S, flag, tot, tid );
+			const uint32_t ex = gscan<G>( g, flag, tot );
 			if (flag == 1u) A.idx_tmp[Apos + (ex & 0xffffu)] = fr;
 			else if (flag) A.idx_tmp[Bpos - 1 - (ex >> 16)] = fr;
 			Apos += tot & 0xffffu, Bpos -= tot >> 16;
@@ -497,9 +547,9 @@ template <int G> __device__ bool hq_node( const HQArgs& A, GroupSmem& S, const H
 		float* spos = A.spos + t.sliceStart;
 		// pass 1: left / right / straddler, straddlers listed in order
 		uint32_t nstrad = 0;
-		for (uint32_t base = 0; base < count; base += G)
+		for (uint32_t base = 0; base < count; base += GT)
 		{
-			const uint32_t i = base + tid;
+			const uint32_t i = base + gtid;
 			uint32_t flag = 0;
 			if (i < count)
 			{
@@ -511,13 +561,13 @@ template <int G> __device__ bool hq_node( const HQArgs& A, GroupSmem& S, const H
 				cls[i] = c, flag = c == 2u;
 			}
 			uint32_t tot;
-			const uint32_t ex = gscan<G>( S, flag, tot, tid );
+			const uint32_t ex = gscan<G>( g, flag, tot );
 			if (flag) strad[nstrad + ex] = i;
 			nstrad += tot;
 		}
-		gsync<G>();
+		gsync<G>( g );
 		// pass 2: the unsplitting chain :2895-2926, one warp, in order
-		if (tid < 32)
+		if (lead && tid < 32)
 		{
 			int NL = S.bestNL, NR = S.bestNR;
 			float cost = S.splitCost, LMin[3], LMax[3], RMin[3], RMax[3];
@@ -570,9 +620,9 @@ template <int G> __device__ bool hq_node( const HQArgs& A, GroupSmem& S, const H
 				if (k < nstrad) cls[i] = mydec, spos[k] = mypos;
 			}
 		}
-		gsync<G>();
+		gsync<G>( g );
 		// pass 3: clip the fragments the chain decided to split :2927-2941
-		for (uint32_t k = tid; k < nstrad; k += G)
+		for (uint32_t k = gtid; k < nstrad; k += GT)
 		{
 			const uint32_t i = strad[k];
 			if (cls[i] != 2u) continue;
@@ -590,11 +640,11 @@ template <int G> __device__ bool hq_node( const HQArgs& A, GroupSmem& S, const H
 			}
 			else cls[i] = leftOK ? 0u : 1u;
 		}
-		gsync<G>();
+		gsync<G>( g );
 		// pass 4: left part upward from sliceStart, right part downward from sliceEnd, in fragment order
-		for (uint32_t base = 0; base < count; base += G)
+		for (uint32_t base = 0; base < count; base += GT)
 		{
-			const uint32_t i = base + tid;
+			const uint32_t i = base + gtid;
 			uint32_t fr = 0, c = 0, flag = 0;
 			if (i < count)
 			{
@@ -602,16 +652,16 @@ template <int G> __device__ bool hq_node( const HQArgs& A, GroupSmem& S, const H
 				flag = (c & 0x80000000u) ? 0x10001u : c == 0u ? 1u : 0x10000u;
 			}
 			uint32_t tot;
-			const uint32_t ex = gscan<G>( S, flag, tot, tid );
+			const uint32_t ex = gscan<G>( g, flag, tot );
 			if (flag & 1u) A.idx_tmp[Apos + (ex & 0xffffu)] = fr;
 			if (flag >> 16) A.idx_tmp[Bpos - 1 - (ex >> 16)] = (c & 0x80000000u) ? (c & 0x7fffffffu) : fr;
 			Apos += tot & 0xffffu, Bpos -= tot >> 16;
 		}
 		// child bounds are refreshed from the fragments :2943-2950
 		for (int k = tid; k < 12; k += G) S.ckey[k] = ((k / 3) & 1) ? f2key( -BVH_FAR ) : f2key( BVH_FAR );
-		gsync<G>();
+		gsync<G>( g );
 		const uint32_t nl = Apos - t.sliceStart, nr = t.sliceEnd - Bpos;
-		for (uint32_t i = tid; i < nl + nr; i += G)
+		for (uint32_t i = gtid; i < nl + nr; i += GT)
 		{
 			const bool right = i >= nl;
 			const uint32_t fr = A.idx_tmp[right ? Bpos + (i - nl) : t.sliceStart + i];
@@ -620,34 +670,40 @@ template <int G> __device__ bool hq_node( const HQArgs& A, GroupSmem& S, const H
 			atomicMin( kk + 0, f2key( fa.x ) ), atomicMin( kk + 1, f2key( fa.y ) ), atomicMin( kk + 2, f2key( fa.z ) );
 			atomicMax( kk + 3, f2key( fb.x ) ), atomicMax( kk + 4, f2key( fb.y ) ), atomicMax( kk + 5, f2key( fb.z ) );
 		}
-		gsync<G>();
-		if (tid < 12) S.best[tid] = key2f( S.ckey[tid] );
+		if (G != 32 && g.nct > 1)
+		{
+			__syncthreads();
+			if (!lead && tid < 12) { if ((tid / 3) & 1) atomicMax( &S0.ckey[tid], S.ckey[tid] ); else atomicMin( &S0.ckey[tid], S.ckey[tid] ); }
+		}
+		gsync<G>( g );
+		if (lead && tid < 12) S.best[tid] = key2f( S.ckey[tid] );
 	}
-	gsync<G>();
+	gsync<G>( g );
 	// copy back :2965 (the parts that hold fragments; the rest of the slice is never read through primIdx)
 	const uint32_t leftCount = Apos - t.sliceStart, rightCount = t.sliceEnd - Bpos;
-	for (uint32_t i = tid; i < leftCount + rightCount; i += G)
+	for (uint32_t i = gtid; i < leftCount + rightCount; i += GT)
 	{
 		const uint32_t p = i < leftCount ? t.sliceStart + i : Bpos + (i - leftCount);
 		A.prim_idx[p] = A.idx_tmp[p];
 	}
-	gsync<G>();
+	gsync<G>( g );
 	if (leftCount == 0 || rightCount == 0)
 	{
 		// ":2939 spatial split failed": the reference reads the node's OLD range out of the refreshed primIdx, i.e. whatever
 		// idxTmp holds there (this node's own output where the ranges overlap, an ancestor's words or zeros elsewhere)
-		for (uint32_t i = tid; i < count; i += G) { const uint32_t p = leftFirst + i; A.prim_idx[p] = __float_as_uint( A.frag_min[A.idx_tmp[p]].w ); }
-		if (tid == 0)
+		for (uint32_t i = gtid; i < count; i += GT) { const uint32_t p = leftFirst + i; A.prim_idx[p] = __float_as_uint( A.frag_min[A.idx_tmp[p]].w ); }
+		if (lead && tid == 0)
 		{
 			const float* b = S.best;
 			A.tmp_nodes[(size_t)t.node * 2] = make_float4( tmin( b[0], b[6] ), tmin( b[1], b[7] ), tmin( b[2], b[8] ), n0.w );
 			A.tmp_nodes[(size_t)t.node * 2 + 1] = make_float4( tmax( b[3], b[9] ), tmax( b[4], b[10] ), tmax( b[5], b[11] ), n1.w );
 			atomicAdd( &A.ctr->failed_splits, 1u ), atomicMax( &A.ctr->max_depth, t.depth );
 		}
+		gsync<G>( g );
 		return false;
 	}
 	// ---- emit :2966-2984
-	if (tid == 0)
+	if (lead && tid == 0)
 	{
 		const uint32_t lc = atomicAdd( &A.ctr->node_ptr, 2u );
 		S.lc = lc;
@@ -664,21 +720,20 @@ template <int G> __device__ bool hq_node( const HQArgs& A, GroupSmem& S, const H
 		}
 		else atomicAdd( &A.ctr->overflow, 1u );
 	}
-	gsync<G>();
-	const uint32_t lc = S.lc;
-	if (lc + 2 > A.node_cap) return false;
+	gsync<G>( g );
+	const uint32_t lc = S0.lc;
 	const uint32_t mid = (Apos + Bpos) >> 1;
 	outL.node = lc, outL.sliceStart = t.sliceStart, outL.sliceEnd = mid, outL.depth = t.depth + 1;
 	outR.node = lc + 1, outR.sliceStart = mid, outR.sliceEnd = t.sliceEnd, outR.depth = t.depth + 1;
-	gsync<G>();
-	return true;
+	gsync<G>( g );
+	return lc + 2 <= A.node_cap;
 }
 
 // ---------------------------------------------------------------------------------------------- kernels
 __global__ void k_hq_init( HQArgs A )
 {
 	HQCounters* c = A.ctr;
-	c->node_ptr = 2, c->frag_ptr = A.n, c->next_big = 0, c->small_roots = 0, c->max_depth = 0, c->failed_splits = 0, c->overflow = 0;
+	c->node_ptr = 2, c->frag_ptr = A.n, c->next_big = 0, c->small_roots = 0, c->max_depth = 0, c->next_max = 0, c->failed_splits = 0, c->overflow = 0;
 	for (int k = 0; k < 3; k++) c->root_key[k] = f2key( BVH_FAR ), c->root_key[3 + k] = f2key( -BVH_FAR );
 }
 
@@ -718,26 +773,36 @@ __global__ void k_hq_root( HQArgs A )
 	c->root_area = half_area3( ex, ey, ez );
 	c->min_dim[0] = __fmul_rn( ex, 1e-7f ), c->min_dim[1] = __fmul_rn( ey, 1e-7f ), c->min_dim[2] = __fmul_rn( ez, 1e-7f );
 	HQTask t = { 0u, 0u, A.idx_cap, 0u };
-	if (A.n > HQ_SMALL) A.lvl[0][0] = t, c->next_big = 1; else A.small[0] = t, c->small_roots = 1;
+	if (A.n > A.small_t) A.lvl[0][0] = t, c->next_big = 1, c->next_max = A.n; else A.small[0] = t, c->small_roots = 1;
 }
 
 __device__ __forceinline__ void hq_enqueue( const HQArgs& A, HQTask* next, const HQTask c )
 {
 	const uint32_t cnt = __float_as_uint( A.tmp_nodes[(size_t)c.node * 2 + 1].w );
-	if (cnt > HQ_SMALL)
+	if (cnt > A.small_t)
 	{
+		atomicMax( &A.ctr->next_max, cnt );
 		const uint32_t k = atomicAdd( &A.ctr->next_big, 1u );
 		if (k < A.lvl_cap) next[k] = c; else atomicAdd( &A.ctr->overflow, 1u );
 	}
 	else A.small[atomicAdd( &A.ctr->small_roots, 1u )] = c;
 }
 
-__global__ void __launch_bounds__( HQ_BIG_THREADS ) k_hq_level( HQArgs A, const HQTask* cur, HQTask* next )
+// level-synchronous phase: one cluster of nct CTAs (run-time cluster dimension, 1..16) per node
+__global__ void __launch_bounds__( HQ_BIG_THREADS ) k_hq_level( HQArgs A, const HQTask* cur, HQTask* next, const uint32_t nct )
 {
 	__shared__ GroupSmem S;
+	Grp g;
+	g.tid = (int)threadIdx.x, g.nct = nct, g.rank = 0, g.S = g.S0 = &S;
+	if (nct > 1)
+	{
+		cg::cluster_group cl = cg::this_cluster();
+		g.rank = cl.block_rank(), g.S0 = cl.map_shared_rank( &S, 0 );
+	}
+	g.gtid = (int)(g.rank * HQ_BIG_THREADS + threadIdx.x), g.GT = (int)(nct * HQ_BIG_THREADS);
 	HQTask l, r;
-	const bool split = hq_node<HQ_BIG_THREADS>( A, S, cur[blockIdx.x], threadIdx.x, l, r );
-	if (split && threadIdx.x == 0) hq_enqueue( A, next, l ), hq_enqueue( A, next, r );
+	const bool split = hq_node<HQ_BIG_THREADS>( A, g, cur[blockIdx.x / nct], l, r );
+	if (split && g.rank == 0 && threadIdx.x == 0) hq_enqueue( A, next, l ), hq_enqueue( A, next, r );
 }
 
 __global__ void __launch_bounds__( HQ_SMALL_WARPS * 32 ) k_hq_subtrees( HQArgs A, const uint32_t roots )
@@ -746,13 +811,14 @@ __global__ void __launch_bounds__( HQ_SMALL_WARPS * 32 ) k_hq_subtrees( HQArgs A
 	__shared__ HQTask stack[HQ_SMALL_WARPS][HQ_STACK];
 	const uint32_t w = threadIdx.x >> 5, lane = threadIdx.x & 31, id = blockIdx.x * HQ_SMALL_WARPS + w;
 	if (id >= roots) return;
-	GroupSmem& S = Ss[w];
+	Grp g;
+	g.tid = g.gtid = (int)lane, g.GT = 32, g.rank = 0, g.nct = 1, g.S = g.S0 = &Ss[w];
 	HQTask t = A.small[id];
 	uint32_t sp = 0;
 	for (;;)
 	{
 		HQTask l, r;
-		if (hq_node<32>( A, S, t, (int)lane, l, r ))
+		if (hq_node<32>( A, g, t, l, r ))
 		{
 			// continue with the child that holds fewer fragments, park the other: the stack stays logarithmic
 			const uint32_t cl = __float_as_uint( A.tmp_nodes[(size_t)l.node * 2 + 1].w ), cr = __float_as_uint( A.tmp_nodes[(size_t)r.node * 2 + 1].w );
@@ -829,7 +895,11 @@ int build_hq_launch( tbvh_bvh b, float c_trav, float c_int )
 	HQArgs A = {};
 	A.verts = b->d_verts, A.n = n, A.c_trav = c_trav, A.c_int = c_int;
 	A.idx_cap = n + slack, A.node_cap = 3 * n + 2;
-	A.lvl_cap = A.idx_cap / HQ_SMALL + 2;
+	{
+		const int t = b->ctx->hq_small;
+		A.small_t = (uint32_t)(t < 8 ? 8 : t > HQ_SMALL_MAX ? HQ_SMALL_MAX : t);
+	}
+	A.lvl_cap = A.idx_cap / A.small_t + 2;
 	HQCounters* h_ctr = 0;
 	cudaEvent_t e0 = 0, e1 = 0;
 	CUDA_TRY( cudaMalloc( &b->d_nodes, (size_t)A.node_cap * 32 ) );
@@ -854,14 +924,24 @@ int build_hq_launch( tbvh_bvh b, float c_trav, float c_int )
 		k_hq_init<<<1, 1, 0, s>>>( A ); LAUNCHED();
 		k_hq_fragments<<<(n + 255) / 256, 256, 0, s>>>( A ); LAUNCHED();
 		k_hq_root<<<1, 1, 0, s>>>( A ); LAUNCHED();
-		uint32_t num = n > HQ_SMALL ? 1 : 0, level = 0;
+		uint32_t num = n > A.small_t ? 1 : 0, level = 0, max_count = n;
+		const uint32_t max_cluster = (uint32_t)(b->ctx->hq_cluster < 1 ? 1 : b->ctx->hq_cluster > HQ_MAX_CLUSTER ? HQ_MAX_CLUSTER : b->ctx->hq_cluster);
+		if (max_cluster > 8) CUDA_TRY( cudaFuncSetAttribute( k_hq_level, cudaFuncAttributeNonPortableClusterSizeAllowed, 1 ) );
 		while (num)
 		{
-			CUDA_TRY( cudaMemsetAsync( &A.ctr->next_big, 0, 4, s ) );
-			k_hq_level<<<num, HQ_BIG_THREADS, 0, s>>>( A, A.lvl[level & 1], A.lvl[(level + 1) & 1] ); LAUNCHED();
+			CUDA_TRY( cudaMemsetAsync( &A.ctr->next_big, 0, 8, s ) ); // next_big + next_max
+			// cluster size: enough CTAs for the largest node of the level (about 2048 fragments per CTA), no more than fills the GPU
+			uint32_t nct = 1;
+			while (nct < max_cluster && (size_t)nct * 2048 < max_count && (size_t)num * nct * 2 <= (size_t)b->ctx->sm_count * 4) nct <<= 1;
+			cudaLaunchConfig_t cfg = {};
+			cudaLaunchAttribute attr[1];
+			cfg.gridDim = dim3( num * nct ), cfg.blockDim = dim3( HQ_BIG_THREADS ), cfg.dynamicSmemBytes = 0, cfg.stream = s;
+			attr[0].id = cudaLaunchAttributeClusterDimension, attr[0].val.clusterDim.x = nct, attr[0].val.clusterDim.y = 1, attr[0].val.clusterDim.z = 1;
+			cfg.attrs = attr, cfg.numAttrs = 1;
+			CUDA_TRY( cudaLaunchKernelEx( &cfg, k_hq_level, A, (const HQTask*)A.lvl[level & 1], A.lvl[(level + 1) & 1], nct ) ); LAUNCHED();
 			CUDA_TRY( cudaMemcpyAsync( h_ctr, A.ctr, sizeof( HQCounters ), cudaMemcpyDeviceToHost, s ) );
 			CUDA_TRY( cudaStreamSynchronize( s ) );
-			num = h_ctr->next_big;
+			num = h_ctr->next_big, max_count = h_ctr->next_max;
 			if (h_ctr->overflow) { tbvh_set_error( "BuildHQ: pool overflow in the level phase" ); return TBVH_E_LIMIT; }
 			if (++level > 4096) { tbvh_set_error( "BuildHQ: runaway level count" ); return TBVH_E_LIMIT; }
 		}
