@@ -36,6 +36,7 @@ namespace
 #define HQBINS 8
 #define HQ_SMALL_MAX 256      // switch point CTA/cluster per node -> warp per subtree (run-time value hq_small <= this)
 #define HQ_MAX_CLUSTER 16
+#define HQ_E 8                 // consecutive fragments per thread and scan tile of the partition passes (8 * 4096 fits the 16-bit packed counters)
 #define HQ_BIG_THREADS 256
 #define HQ_SMALL_WARPS 4
 #define HQ_STACK 64
@@ -54,6 +55,7 @@ struct HQCounters
 	uint32_t root_key[6];
 	float root_area;
 	float min_dim[3];
+	unsigned long long prof[32]; // TBVH_HQ_PROFILE=1: leader-thread cycles per phase, [0..15] level phase, [16..31] subtree phase
 };
 
 struct HQArgs
@@ -65,7 +67,7 @@ struct HQArgs
 	float4* tmp_nodes; uint32_t* parent; uint32_t* sub_int; uint32_t* sub_prims; uint32_t* arrive;
 	HQTask* lvl[2]; HQTask* small;
 	HQCounters* ctr;
-	uint32_t n, idx_cap, node_cap, lvl_cap, small_t;
+	uint32_t n, idx_cap, node_cap, lvl_cap, small_t, profile;
 	float c_trav, c_int;
 };
 
@@ -393,6 +395,10 @@ template <int G> __device__ bool hq_node( const HQArgs& A, const Grp& g, const H
 	GroupSmem& S0 = *g.S0;          // the leader's: merged tables, decisions
 	const int tid = g.tid, gtid = g.gtid, GT = g.GT;
 	const bool lead = g.rank == 0;
+	// TBVH_HQ_PROFILE=1: cycles of the leader thread per phase, summed over nodes (the host prints them)
+	const bool prof = A.profile && lead && tid == 0;
+	unsigned long long pt0 = prof ? clock64() : 0;
+	#define PH( k ) do { if (prof) { const unsigned long long t1_ = clock64(); atomicAdd( &A.ctr->prof[(G == 32 ? 16 : 0) + (k)], t1_ - pt0 ); pt0 = t1_; } } while (0)
 	const float4 n0 = A.tmp_nodes[(size_t)t.node * 2], n1 = A.tmp_nodes[(size_t)t.node * 2 + 1];
 	const float nmin3[3] = { n0.x, n0.y, n0.z }, nmax3[3] = { n1.x, n1.y, n1.z };
 	const uint32_t leftFirst = __float_as_uint( n0.w ), count = __float_as_uint( n1.w );
@@ -423,6 +429,7 @@ template <int G> __device__ bool hq_node( const HQArgs& A, const Grp& g, const H
 	}
 	bins_merge<G>( g );
 	gsync<G>( g );
+	PH( 0 );
 	if (lead && tid < 21) sweep_candidate( S, tid, false, rSAV, A.c_trav, A.c_int );
 	lsync<G>();
 	if (lead && tid == 0)
@@ -451,6 +458,7 @@ template <int G> __device__ bool hq_node( const HQArgs& A, const Grp& g, const H
 		S.splitCost = splitCost, S.trySpatial = trySpatial;
 	}
 	gsync<G>( g );
+	PH( 1 );
 
 	// ---- spatial split candidate :2808-2872
 	if (S0.trySpatial)
@@ -479,6 +487,7 @@ template <int G> __device__ bool hq_node( const HQArgs& A, const Grp& g, const H
 		}
 		bins_merge<G>( g );
 		gsync<G>( g );
+		PH( 2 );
 		if (lead && tid < 21) sweep_candidate( S, tid, true, rSAV, A.c_trav, A.c_int );
 		lsync<G>();
 		if (lead && tid == 0)
@@ -503,6 +512,7 @@ template <int G> __device__ bool hq_node( const HQArgs& A, const Grp& g, const H
 			}
 		}
 		gsync<G>( g );
+		PH( 3 );
 	}
 
 	// ---- leaf? :2874-2880
@@ -511,6 +521,7 @@ template <int G> __device__ bool hq_node( const HQArgs& A, const Grp& g, const H
 		for (uint32_t i = gtid; i < count; i += GT) { const uint32_t p = leftFirst + i; A.prim_idx[p] = __float_as_uint( A.frag_min[A.prim_idx[p]].w ); }
 		if (lead && tid == 0) atomicMax( &A.ctr->max_depth, t.depth );
 		gsync<G>( g ); // nobody reads the leader's tables after it has moved on
+		PH( 9 );
 		return false;
 	}
 
@@ -521,23 +532,34 @@ template <int G> __device__ bool hq_node( const HQArgs& A, const Grp& g, const H
 	if (!spatial)
 	{
 		const float rpd = rpd3[bestAxis], nmin = nmin3[bestAxis];
-		for (uint32_t base = 0; base < count; base += GT)
+		for (uint32_t base = 0; base < count; base += GT * HQ_E)
 		{
-			const uint32_t i = base + gtid;
-			uint32_t fr = 0, flag = 0;
-			if (i < count)
+			uint32_t fr[HQ_E], flag[HQ_E], sum = 0;
+			#pragma unroll
+			for (int e = 0; e < HQ_E; e++)
 			{
-				fr = primIdx[leftFirst + i];
-				const float mn = comp( A.frag_min[fr], bestAxis ), mx = comp( A.frag_max[fr], bestAxis );
-				const int bi = clampi( cvtt( __fmul_rn( __fmaf_rn( __fadd_rn( mn, mx ), 0.5f, -nmin ), rpd ) ), 0, HQBINS - 1 );
-				flag = bi <= (int)bestPos ? 1u : 0x10000u;
+				const uint32_t i = base + gtid * HQ_E + e;
+				fr[e] = flag[e] = 0;
+				if (i < count)
+				{
+					fr[e] = primIdx[leftFirst + i];
+					const float mn = comp( A.frag_min[fr[e]], bestAxis ), mx = comp( A.frag_max[fr[e]], bestAxis );
+					const int bi = clampi( cvtt( __fmul_rn( __fmaf_rn( __fadd_rn( mn, mx ), 0.5f, -nmin ), rpd ) ), 0, HQBINS - 1 );
+					flag[e] = bi <= (int)bestPos ? 1u : 0x10000u;
+				}
+				sum += flag[e];
 			}
-			uint32_t tot;
-			const uint32_t ex = gscan<G>( g, flag, tot );
-			if (flag == 1u) A.idx_tmp[Apos + (ex & 0xffffu)] = fr;
-			else if (flag) A.idx_tmp[Bpos - 1 - (ex >> 16)] = fr;
+			uint32_t tot, run = gscan<G>( g, sum, tot );
+			#pragma unroll
+			for (int e = 0; e < HQ_E; e++)
+			{
+				if (flag[e] == 1u) A.idx_tmp[Apos + (run & 0xffffu)] = fr[e];
+				else if (flag[e]) A.idx_tmp[Bpos - 1 - (run >> 16)] = fr[e];
+				run += flag[e];
+			}
 			Apos += tot & 0xffffu, Bpos -= tot >> 16;
 		}
+		PH( 4 );
 	}
 	else
 	{
@@ -547,26 +569,35 @@ template <int G> __device__ bool hq_node( const HQArgs& A, const Grp& g, const H
 		float* spos = A.spos + t.sliceStart;
 		// pass 1: left / right / straddler, straddlers listed in order
 		uint32_t nstrad = 0;
-		for (uint32_t base = 0; base < count; base += GT)
+		for (uint32_t base = 0; base < count; base += GT * HQ_E)
 		{
-			const uint32_t i = base + gtid;
-			uint32_t flag = 0;
-			if (i < count)
+			uint32_t flags = 0;
+			#pragma unroll
+			for (int e = 0; e < HQ_E; e++)
 			{
-				const uint32_t fr = primIdx[leftFirst + i];
-				const float mn = comp( A.frag_min[fr], bestAxis ), mx = comp( A.frag_max[fr], bestAxis );
-				const uint32_t bin1 = __float2uint_rz( tmax( __fmul_rn( __fsub_rn( mn, nodeMin ), rPlaneDist ), 0.0f ) );
-				const uint32_t bin2 = __float2uint_rz( tmax( __fmul_rn( __fsub_rn( mx, nodeMin ), rPlaneDist ), 0.0f ) );
-				const uint32_t c = bin2 <= bestPos ? 0u : bin1 > bestPos ? 1u : 2u;
-				cls[i] = c, flag = c == 2u;
+				const uint32_t i = base + gtid * HQ_E + e;
+				if (i < count)
+				{
+					const uint32_t fr = primIdx[leftFirst + i];
+					const float mn = comp( A.frag_min[fr], bestAxis ), mx = comp( A.frag_max[fr], bestAxis );
+					const uint32_t bin1 = __float2uint_rz( tmax( __fmul_rn( __fsub_rn( mn, nodeMin ), rPlaneDist ), 0.0f ) );
+					const uint32_t bin2 = __float2uint_rz( tmax( __fmul_rn( __fsub_rn( mx, nodeMin ), rPlaneDist ), 0.0f ) );
+					const uint32_t c = bin2 <= bestPos ? 0u : bin1 > bestPos ? 1u : 2u;
+					cls[i] = c;
+					if (c == 2u) flags |= 1u << e;
+				}
 			}
-			uint32_t tot;
-			const uint32_t ex = gscan<G>( g, flag, tot );
-			if (flag) strad[nstrad + ex] = i;
+			uint32_t tot, run = gscan<G>( g, (uint32_t)__popc( flags ), tot );
+			#pragma unroll
+			for (int e = 0; e < HQ_E; e++) if (flags & (1u << e)) strad[nstrad + run++] = base + gtid * HQ_E + e;
 			nstrad += tot;
 		}
 		gsync<G>( g );
-		// pass 2: the unsplitting chain :2895-2926, one warp, in order
+		PH( 5 );
+		// pass 2: the unsplitting chain :2895-2926, one warp, in order.  A straddler that ends up split leaves the running
+		// state (child boxes, counts, cost) untouched, and most do: the 32 straddlers of a batch are judged in parallel
+		// against the current state, everything up to the first one that unsplits is final, that one commits and
+		// broadcasts its new state, the lanes behind it are judged again.
 		if (lead && tid < 32)
 		{
 			int NL = S.bestNL, NR = S.bestNR;
@@ -575,52 +606,68 @@ template <int G> __device__ bool hq_node( const HQArgs& A, const Grp& g, const H
 			for (int k = 0; k < 3; k++) LMin[k] = S.best[k], LMax[k] = S.best[3 + k], RMin[k] = S.best[6 + k], RMax[k] = S.best[9 + k];
 			for (uint32_t base = 0; base < nstrad; base += 32)
 			{
-				const uint32_t k = base + tid, m = min( 32u, nstrad - base );
+				const uint32_t k = base + tid;
+				const bool valid = k < nstrad;
 				float4 fa = make_float4( 0, 0, 0, 0 ), fb = fa;
 				uint32_t i = 0;
-				if (k < nstrad) { i = strad[k]; const uint32_t fr = primIdx[leftFirst + i]; fa = A.frag_min[fr], fb = A.frag_max[fr]; }
-				uint32_t mydec = 2; float mypos = 0;
-				for (uint32_t s = 0; s < m; s++)
+				if (valid) { i = strad[k]; const uint32_t fr = primIdx[leftFirst + i]; fa = A.frag_min[fr], fb = A.frag_max[fr]; }
+				const float fmn[3] = { fa.x, fa.y, fa.z }, fmx[3] = { fb.x, fb.y, fb.z };
+				uint32_t mydec = 2, start = 0;
+				float mypos = 0;
+				for (;;)
 				{
-					const float fmn[3] = { __shfl_sync( 0xffffffffu, fa.x, s ), __shfl_sync( 0xffffffffu, fa.y, s ), __shfl_sync( 0xffffffffu, fa.z, s ) };
-					const float fmx[3] = { __shfl_sync( 0xffffffffu, fb.x, s ), __shfl_sync( 0xffffffffu, fb.y, s ), __shfl_sync( 0xffffffffu, fb.z, s ) };
 					uint32_t dec = 2;
-					if (NR > 1)
+					float uMin[3], uMax[3], C = 0;
+					if (valid && (uint32_t)tid >= start)
 					{
-						float uMin[3], uMax[3];
-						#pragma unroll
-						for (int q = 0; q < 3; q++) uMin[q] = tmin( LMin[q], fmn[q] ), uMax[q] = tmax( LMax[q], fmx[q] );
-						const float AL = half_area3( __fsub_rn( uMax[0], uMin[0] ), __fsub_rn( uMax[1], uMin[1] ), __fsub_rn( uMax[2], uMin[2] ) );
-						const float AR = half_area3( __fsub_rn( RMax[0], RMin[0] ), __fsub_rn( RMax[1], RMin[1] ), __fsub_rn( RMax[2], RMin[2] ) );
-						const float C = split_cost( A.c_trav, A.c_int, rSAV, AL, NL, AR, NR - 1 );
-						if (C <= cost)
+						if (NR > 1)
 						{
-							NR--, cost = C, dec = 0;
 							#pragma unroll
-							for (int q = 0; q < 3; q++) LMin[q] = uMin[q], LMax[q] = uMax[q];
+							for (int q = 0; q < 3; q++) uMin[q] = tmin( LMin[q], fmn[q] ), uMax[q] = tmax( LMax[q], fmx[q] );
+							const float AL = half_area3( __fsub_rn( uMax[0], uMin[0] ), __fsub_rn( uMax[1], uMin[1] ), __fsub_rn( uMax[2], uMin[2] ) );
+							const float AR = half_area3( __fsub_rn( RMax[0], RMin[0] ), __fsub_rn( RMax[1], RMin[1] ), __fsub_rn( RMax[2], RMin[2] ) );
+							C = split_cost( A.c_trav, A.c_int, rSAV, AL, NL, AR, NR - 1 );
+							if (C <= cost) dec = 0;
+						}
+						if (dec == 2 && NL > 1)
+						{
+							#pragma unroll
+							for (int q = 0; q < 3; q++) uMin[q] = tmin( RMin[q], fmn[q] ), uMax[q] = tmax( RMax[q], fmx[q] );
+							const float AL = half_area3( __fsub_rn( LMax[0], LMin[0] ), __fsub_rn( LMax[1], LMin[1] ), __fsub_rn( LMax[2], LMin[2] ) );
+							const float AR = half_area3( __fsub_rn( uMax[0], uMin[0] ), __fsub_rn( uMax[1], uMin[1] ), __fsub_rn( uMax[2], uMin[2] ) );
+							C = split_cost( A.c_trav, A.c_int, rSAV, AL, NL - 1, AR, NR );
+							if (C <= cost) dec = 1;
 						}
 					}
-					if (dec == 2 && NL > 1)
+					const uint32_t changed = __ballot_sync( 0xffffffffu, dec != 2 );
+					const uint32_t first = changed ? (uint32_t)__ffs( changed ) - 1u : 32u;
+					if ((uint32_t)tid >= start && (uint32_t)tid < first) mydec = 2, mypos = bestAxis == 0 ? LMax[0] : bestAxis == 1 ? LMax[1] : LMax[2];
+					if (first == 32u) break;
+					if ((uint32_t)tid == first) mydec = dec;
+					const uint32_t d = __shfl_sync( 0xffffffffu, dec, first );
+					cost = __shfl_sync( 0xffffffffu, C, first );
+					float bMin[3], bMax[3];
+					#pragma unroll
+					for (int q = 0; q < 3; q++) bMin[q] = __shfl_sync( 0xffffffffu, uMin[q], first ), bMax[q] = __shfl_sync( 0xffffffffu, uMax[q], first );
+					if (d == 0)
 					{
-						float uMin[3], uMax[3];
+						NR--;
 						#pragma unroll
-						for (int q = 0; q < 3; q++) uMin[q] = tmin( RMin[q], fmn[q] ), uMax[q] = tmax( RMax[q], fmx[q] );
-						const float AL = half_area3( __fsub_rn( LMax[0], LMin[0] ), __fsub_rn( LMax[1], LMin[1] ), __fsub_rn( LMax[2], LMin[2] ) );
-						const float AR = half_area3( __fsub_rn( uMax[0], uMin[0] ), __fsub_rn( uMax[1], uMin[1] ), __fsub_rn( uMax[2], uMin[2] ) );
-						const float C = split_cost( A.c_trav, A.c_int, rSAV, AL, NL - 1, AR, NR );
-						if (C <= cost)
-						{
-							NL--, cost = C, dec = 1;
-							#pragma unroll
-							for (int q = 0; q < 3; q++) RMin[q] = uMin[q], RMax[q] = uMax[q];
-						}
+						for (int q = 0; q < 3; q++) LMin[q] = bMin[q], LMax[q] = bMax[q];
 					}
-					if ((uint32_t)tid == s) mydec = dec, mypos = bestAxis == 0 ? LMax[0] : bestAxis == 1 ? LMax[1] : LMax[2];
+					else
+					{
+						NL--;
+						#pragma unroll
+						for (int q = 0; q < 3; q++) RMin[q] = bMin[q], RMax[q] = bMax[q];
+					}
+					start = first + 1;
 				}
-				if (k < nstrad) cls[i] = mydec, spos[k] = mypos;
+				if (valid) cls[i] = mydec, spos[k] = mypos;
 			}
 		}
 		gsync<G>( g );
+		PH( 6 );
 		// pass 3: clip the fragments the chain decided to split :2927-2941
 		for (uint32_t k = gtid; k < nstrad; k += GT)
 		{
@@ -641,20 +688,31 @@ template <int G> __device__ bool hq_node( const HQArgs& A, const Grp& g, const H
 			else cls[i] = leftOK ? 0u : 1u;
 		}
 		gsync<G>( g );
+		PH( 7 );
 		// pass 4: left part upward from sliceStart, right part downward from sliceEnd, in fragment order
-		for (uint32_t base = 0; base < count; base += GT)
+		for (uint32_t base = 0; base < count; base += GT * HQ_E)
 		{
-			const uint32_t i = base + gtid;
-			uint32_t fr = 0, c = 0, flag = 0;
-			if (i < count)
+			uint32_t fr[HQ_E], c[HQ_E], flag[HQ_E], sum = 0;
+			#pragma unroll
+			for (int e = 0; e < HQ_E; e++)
 			{
-				fr = primIdx[leftFirst + i], c = cls[i];
-				flag = (c & 0x80000000u) ? 0x10001u : c == 0u ? 1u : 0x10000u;
+				const uint32_t i = base + gtid * HQ_E + e;
+				fr[e] = c[e] = flag[e] = 0;
+				if (i < count)
+				{
+					fr[e] = primIdx[leftFirst + i], c[e] = cls[i];
+					flag[e] = (c[e] & 0x80000000u) ? 0x10001u : c[e] == 0u ? 1u : 0x10000u;
+				}
+				sum += flag[e];
 			}
-			uint32_t tot;
-			const uint32_t ex = gscan<G>( g, flag, tot );
-			if (flag & 1u) A.idx_tmp[Apos + (ex & 0xffffu)] = fr;
-			if (flag >> 16) A.idx_tmp[Bpos - 1 - (ex >> 16)] = (c & 0x80000000u) ? (c & 0x7fffffffu) : fr;
+			uint32_t tot, run = gscan<G>( g, sum, tot );
+			#pragma unroll
+			for (int e = 0; e < HQ_E; e++)
+			{
+				if (flag[e] & 1u) A.idx_tmp[Apos + (run & 0xffffu)] = fr[e];
+				if (flag[e] >> 16) A.idx_tmp[Bpos - 1 - (run >> 16)] = (c[e] & 0x80000000u) ? (c[e] & 0x7fffffffu) : fr[e];
+				run += flag[e];
+			}
 			Apos += tot & 0xffffu, Bpos -= tot >> 16;
 		}
 		// child bounds are refreshed from the fragments :2943-2950
@@ -677,6 +735,7 @@ template <int G> __device__ bool hq_node( const HQArgs& A, const Grp& g, const H
 		}
 		gsync<G>( g );
 		if (lead && tid < 12) S.best[tid] = key2f( S.ckey[tid] );
+		PH( 8 );
 	}
 	gsync<G>( g );
 	// copy back :2965 (the parts that hold fragments; the rest of the slice is never read through primIdx)
@@ -687,6 +746,7 @@ template <int G> __device__ bool hq_node( const HQArgs& A, const Grp& g, const H
 		A.prim_idx[p] = A.idx_tmp[p];
 	}
 	gsync<G>( g );
+	PH( 10 );
 	if (leftCount == 0 || rightCount == 0)
 	{
 		// ":2939 spatial split failed": the reference reads the node's OLD range out of the refreshed primIdx, i.e. whatever
@@ -726,6 +786,8 @@ template <int G> __device__ bool hq_node( const HQArgs& A, const Grp& g, const H
 	outL.node = lc, outL.sliceStart = t.sliceStart, outL.sliceEnd = mid, outL.depth = t.depth + 1;
 	outR.node = lc + 1, outR.sliceStart = mid, outR.sliceEnd = t.sliceEnd, outR.depth = t.depth + 1;
 	gsync<G>( g );
+	PH( 11 );
+	#undef PH
 	return lc + 2 <= A.node_cap;
 }
 
@@ -735,6 +797,7 @@ __global__ void k_hq_init( HQArgs A )
 	HQCounters* c = A.ctr;
 	c->node_ptr = 2, c->frag_ptr = A.n, c->next_big = 0, c->small_roots = 0, c->max_depth = 0, c->next_max = 0, c->failed_splits = 0, c->overflow = 0;
 	for (int k = 0; k < 3; k++) c->root_key[k] = f2key( BVH_FAR ), c->root_key[3 + k] = f2key( -BVH_FAR );
+	for (int k = 0; k < 32; k++) c->prof[k] = 0;
 }
 
 // PrepareHQBuild :2677-2686: fragment boxes, identity primIdx, root bounds
@@ -900,6 +963,7 @@ int build_hq_launch( tbvh_bvh b, float c_trav, float c_int )
 		A.small_t = (uint32_t)(t < 8 ? 8 : t > HQ_SMALL_MAX ? HQ_SMALL_MAX : t);
 	}
 	A.lvl_cap = A.idx_cap / A.small_t + 2;
+	{ const char* e = getenv( "TBVH_HQ_PROFILE" ); A.profile = e && atoi( e ) ? 1u : 0u; }
 	HQCounters* h_ctr = 0;
 	cudaEvent_t e0 = 0, e1 = 0;
 	CUDA_TRY( cudaMalloc( &b->d_nodes, (size_t)A.node_cap * 32 ) );
@@ -953,6 +1017,12 @@ int build_hq_launch( tbvh_bvh b, float c_trav, float c_int )
 		CUDA_TRY( cudaStreamSynchronize( s ) );
 		if (h_ctr->overflow) { tbvh_set_error( "BuildHQ: pool overflow in the subtree phase" ); return TBVH_E_LIMIT; }
 		const uint32_t tmp_count = h_ctr->node_ptr;
+		if (A.profile)
+		{
+			static const char* nm[12] = { "obj-bin", "obj-sweep", "spat-bin", "spat-sweep", "part-obj", "part-p1", "chain", "split", "p4+bounds", "leaf", "copyback", "emit" };
+			for (int k = 0; k < 12; k++) fprintf( stderr, "hq-profile %-10s level %10.3f Mcyc   subtree %10.3f Mcyc\n", nm[k], h_ctr->prof[k] * 1e-6, h_ctr->prof[16 + k] * 1e-6 );
+			fprintf( stderr, "hq-profile failed_splits %u small_roots %u\n", h_ctr->failed_splits, h_ctr->small_roots );
+		}
 		// Compact(): DFS-preorder numbering, leaf index ranges packed in DFS order; the tail of the index array is zeroed
 		CUDA_TRY( cudaMemsetAsync( b->d_prim_idx, 0, (size_t)A.idx_cap * 4, s ) );
 		if (tmp_count > 2)
