@@ -75,9 +75,7 @@ struct GroupSmem
 {
 	uint32_t kmin[3][HQBINS][3], kmax[3][HQBINS][3]; // bin bounds as ordered keys
 	uint32_t cntA[3][HQBINS], cntB[3][HQBINS];       // object: count / spatial: countIn, countOut
-	float cost[24]; int cNL[24], cNR[24];
-	float cb[21][12];                                // candidate child bounds: lmin, lmax, rmin, rmax
-	float best[12];
+	float best[12];                                  // child bounds of the chosen split: lmin, lmax, rmin, rmax
 	float splitCost;
 	uint32_t bestAxis, bestPos, bestIdx;
 	int spatial, bestNL, bestNR, hasObj, trySpatial, leaf;
@@ -295,6 +293,7 @@ struct Grp
 	int tid, gtid, GT;        // thread in its CTA (lane for warps), thread in the group, threads in the group
 	uint32_t rank, nct;       // CTA rank in the cluster, cluster size
 	GroupSmem* S; GroupSmem* S0;
+	uint32_t* job;            // 3 * G words of this CTA's (warp's) shared memory: clip jobs of one item tile (spatial binning)
 };
 template <int G> __device__ __forceinline__ void lsync() { if (G == 32) __syncwarp(); else __syncthreads(); }
 template <int G> __device__ __forceinline__ void gsync( const Grp& g )
@@ -304,7 +303,7 @@ template <int G> __device__ __forceinline__ void gsync( const Grp& g )
 
 // exclusive scan of v over the threads of the group; every thread gets the group total.  Callers pack two 16-bit
 // counters into v (a tile holds at most 4096 of each).
-template <int G> __device__ __forceinline__ uint32_t gscan( const Grp& g, const uint32_t v, uint32_t& total )
+template <int G> __device__ __forceinline__ uint32_t lscan( const Grp& g, const uint32_t v, uint32_t& total )
 {
 	const int lane = g.tid & 31;
 	uint32_t x = v;
@@ -319,7 +318,13 @@ template <int G> __device__ __forceinline__ uint32_t gscan( const Grp& g, const 
 	#pragma unroll
 	for (int i = 0; i < G / 32; i++) { const uint32_t t = S.wtot[i]; if (i < w) base += t; tot += t; }
 	__syncthreads();
-	if (g.nct > 1)
+	total = tot;
+	return base + x - v;
+}
+template <int G> __device__ __forceinline__ uint32_t gscan( const Grp& g, const uint32_t v, uint32_t& total )
+{
+	uint32_t tot, base = lscan<G>( g, v, tot );
+	if (G != 32 && g.nct > 1)
 	{
 		if (g.tid == 0) g.S0->ctot[g.rank] = tot;
 		cg::this_cluster().sync();
@@ -329,7 +334,7 @@ template <int G> __device__ __forceinline__ uint32_t gscan( const Grp& g, const 
 		base += cb, tot = ct;
 	}
 	total = tot;
-	return base + x - v;
+	return base;
 }
 
 __device__ __forceinline__ void bins_reset( GroupSmem& S, const int tid, const int G )
@@ -357,34 +362,85 @@ __device__ __forceinline__ void bin_grow( GroupSmem& S, const uint32_t a, const 
 	for (int k = 0; k < 3; k++) atomicMin( &S.kmin[a][b][k], f2key( mn[k] ) ), atomicMax( &S.kmax[a][b][k], f2key( mx[k] ) );
 }
 
-// 21 threads: candidate plane (a, i) from the bin tables: prefix / suffix unions, areas, counts, SAH cost
-// (object split :2779-2803 with countL = countR = cntA; spatial split :2847-2862 with countIn / countOut).
-__device__ __forceinline__ void sweep_candidate( GroupSmem& S, const int c, const bool spatial, const float rSAV, const float c_trav, const float c_int )
+// One warp (all 32 lanes): the 21 candidate planes (a, i) of a node from its bin tables - prefix / suffix unions, areas,
+// counts, SAH cost on lanes 0..20 - and the choice among them.
+//   object split  (:2779-2803, countL = countR = cntA): first candidate in (axis, plane) order with C < splitCost, splitCost
+//                 starting at noSplitCost and lowered by every accepted candidate = the first strict minimum below it;
+//   spatial split (:2847-2870, countIn / countOut): the same among candidates with NL + NR < budget, NL * NR > 0 and
+//                 C < 0.985 * splitCost.
+// The winner lane stores the child boxes in S.best.  Returns the candidate index (-1: none) and its cost, on every lane.
+__device__ __forceinline__ int sweep_select( GroupSmem& S, const bool spatial, const float rSAV, const float c_trav, const float c_int,
+	const bool ok0, const bool ok1, const bool ok2, const float limit, const int budget, float& bestCost, int& bestNL, int& bestNR )
 {
-	const uint32_t a = c / 7, i = c % 7;
+	const int c = (int)(threadIdx.x & 31);
+	const uint32_t a = c < 21 ? c / 7 : 0, i = c % 7;
 	float l1[3] = { BVH_FAR, BVH_FAR, BVH_FAR }, l2[3] = { -BVH_FAR, -BVH_FAR, -BVH_FAR }, r1[3] = { BVH_FAR, BVH_FAR, BVH_FAR }, r2[3] = { -BVH_FAR, -BVH_FAR, -BVH_FAR };
 	uint32_t lN = 0, rN = 0;
+	#pragma unroll
 	for (uint32_t b = 0; b < HQBINS; b++)
 	{
+		const uint32_t ca = S.cntA[a][b], cb = spatial ? S.cntB[a][b] : ca;
+		float mn[3], mx[3];
+		#pragma unroll
+		for (int k = 0; k < 3; k++) mn[k] = key2f( S.kmin[a][b][k] ), mx[k] = key2f( S.kmax[a][b][k] );
 		if (b <= i)
 		{
-			lN += S.cntA[a][b];
+			lN += ca;
 			#pragma unroll
-			for (int k = 0; k < 3; k++) l1[k] = tmin( l1[k], key2f( S.kmin[a][b][k] ) ), l2[k] = tmax( l2[k], key2f( S.kmax[a][b][k] ) );
+			for (int k = 0; k < 3; k++) l1[k] = tmin( l1[k], mn[k] ), l2[k] = tmax( l2[k], mx[k] );
 		}
 		else
 		{
-			rN += spatial ? S.cntB[a][b] : S.cntA[a][b];
+			rN += cb;
 			#pragma unroll
-			for (int k = 0; k < 3; k++) r1[k] = tmin( r1[k], key2f( S.kmin[a][b][k] ) ), r2[k] = tmax( r2[k], key2f( S.kmax[a][b][k] ) );
+			for (int k = 0; k < 3; k++) r1[k] = tmin( r1[k], mn[k] ), r2[k] = tmax( r2[k], mx[k] );
 		}
 	}
 	const float AL = lN == 0 ? BVH_FAR : half_area3( __fsub_rn( l2[0], l1[0] ), __fsub_rn( l2[1], l1[1] ), __fsub_rn( l2[2], l1[2] ) );
 	const float AR = rN == 0 ? BVH_FAR : half_area3( __fsub_rn( r2[0], r1[0] ), __fsub_rn( r2[1], r1[1] ), __fsub_rn( r2[2], r1[2] ) );
-	S.cost[c] = split_cost( c_trav, c_int, rSAV, AL, (int)lN, AR, (int)rN );
-	S.cNL[c] = (int)lN, S.cNR[c] = (int)rN;
-	#pragma unroll
-	for (int k = 0; k < 3; k++) S.cb[c][k] = l1[k], S.cb[c][3 + k] = l2[k], S.cb[c][6 + k] = r1[k], S.cb[c][9 + k] = r2[k];
+	const float C = split_cost( c_trav, c_int, rSAV, AL, (int)lN, AR, (int)rN );
+	const bool cand = c < 21 && (a == 0 ? ok0 : a == 1 ? ok1 : ok2);
+	int best = -1;
+	if (spatial)
+	{
+		// NL * NR > 0 is a wrapping 32-bit product in the reference build (imul).  C < NaN and NaN < limit are both false, as in the loop.
+		const bool el = cand && C < limit && (int)(lN + rN) < budget && (int)(lN * rN) > 0;
+		const uint32_t m = __reduce_min_sync( 0xffffffffu, el ? f2key( C ) : 0xffffffffu );
+		const uint32_t win = __ballot_sync( 0xffffffffu, el && f2key( C ) == m );
+		if (win) best = __ffs( win ) - 1;
+	}
+	else if (__ballot_sync( 0xffffffffu, cand && C != C ) || limit != limit)
+	{
+		// a NaN cost (0 * inf on degenerate boxes) is "not >= splitCost" and so accepted by the reference's loop, and poisons every
+		// later comparison: replay the loop literally
+		float sc = limit;
+		for (int k = 0; k < 21; k++)
+		{
+			const float Ck = __shfl_sync( 0xffffffffu, C, k );
+			const bool ck = __shfl_sync( 0xffffffffu, (int)cand, k ) != 0;
+			if (!ck || Ck >= sc) continue;
+			sc = Ck, best = k;
+		}
+	}
+	else
+	{
+		const bool el = cand && C < limit;
+		const uint32_t m = __reduce_min_sync( 0xffffffffu, el ? f2key( C ) : 0xffffffffu );
+		const uint32_t win = __ballot_sync( 0xffffffffu, el && f2key( C ) == m );
+		if (win) best = __ffs( win ) - 1;
+	}
+	if (best >= 0)
+	{
+		if (c == best)
+		{
+			#pragma unroll
+			for (int k = 0; k < 3; k++) S.best[k] = l1[k], S.best[3 + k] = l2[k], S.best[6 + k] = r1[k], S.best[9 + k] = r2[k];
+		}
+		bestCost = __shfl_sync( 0xffffffffu, C, best );
+		bestNL = (int)__shfl_sync( 0xffffffffu, lN, best ), bestNR = (int)__shfl_sync( 0xffffffffu, rN, best );
+		__syncwarp();
+	}
+	return best;
 }
 
 // One node, start to finish, by a group of G threads (G = 32: a warp, G = 256: a CTA).  Returns true and the two child
@@ -430,32 +486,26 @@ template <int G> __device__ bool hq_node( const HQArgs& A, const Grp& g, const H
 	bins_merge<G>( g );
 	gsync<G>( g );
 	PH( 0 );
-	if (lead && tid < 21) sweep_candidate( S, tid, false, rSAV, A.c_trav, A.c_int );
-	lsync<G>();
-	if (lead && tid == 0)
+	if (lead && tid < 32)
 	{
 		float splitCost = noSplitCost;
-		int best = -1;
-		for (int c = 0; c < 21; c++)
+		int nl = 0, nr = 0;
+		const int best = sweep_select( S, false, rSAV, A.c_trav, A.c_int, axisOK[0], axisOK[1], axisOK[2], noSplitCost, budget, splitCost, nl, nr );
+		if (tid == 0)
 		{
-			if (!axisOK[c / 7]) continue;
-			const float C = S.cost[c];
-			if (C >= splitCost) continue;
-			splitCost = C, best = c;
+			S.hasObj = best >= 0, S.spatial = 0, S.bestNL = S.bestNR = 0;
+			bool trySpatial = false;
+			if (best >= 0)
+			{
+				S.bestAxis = best / 7, S.bestPos = best % 7, S.bestIdx = best;
+				// spatialOverlap :2806-2807: half area of (bestLMax - bestRMin) over the root's
+				const float ov = __fdiv_rn( half_area3( __fsub_rn( S.best[3], S.best[6] ), __fsub_rn( S.best[4], S.best[7] ), __fsub_rn( S.best[5], S.best[8] ) ), A.ctr->root_area );
+				trySpatial = ov > 1e-4f;
+			}
+			// without an object candidate splitCost == noSplitCost and the reference's second disjunct holds whatever its stale bounds say
+			trySpatial = (budget > (int)count) && (trySpatial || splitCost >= noSplitCost);
+			S.splitCost = splitCost, S.trySpatial = trySpatial;
 		}
-		S.hasObj = best >= 0, S.spatial = 0, S.bestNL = S.bestNR = 0;
-		bool trySpatial = false;
-		if (best >= 0)
-		{
-			S.bestAxis = best / 7, S.bestPos = best % 7, S.bestIdx = best;
-			for (int k = 0; k < 12; k++) S.best[k] = S.cb[best][k];
-			// spatialOverlap :2806-2807: half area of (bestLMax - bestRMin) over the root's
-			const float ov = __fdiv_rn( half_area3( __fsub_rn( S.best[3], S.best[6] ), __fsub_rn( S.best[4], S.best[7] ), __fsub_rn( S.best[5], S.best[8] ) ), A.ctr->root_area );
-			trySpatial = ov > 1e-4f;
-		}
-		// without an object candidate splitCost == noSplitCost and the reference's second disjunct holds whatever its stale bounds say
-		trySpatial = (budget > (int)count) && (trySpatial || splitCost >= noSplitCost);
-		S.splitCost = splitCost, S.trySpatial = trySpatial;
 	}
 	gsync<G>( g );
 	PH( 1 );
@@ -465,49 +515,70 @@ template <int G> __device__ bool hq_node( const HQArgs& A, const Grp& g, const H
 	{
 		bins_reset( S, tid, G );
 		gsync<G>( g );
-		for (uint32_t it = gtid; it < count * 3; it += GT)
+		const float planeDist3[3] = { __fdiv_rn( ext[0], __fmul_rn( (float)HQBINS, 0.9999f ) ), __fdiv_rn( ext[1], __fmul_rn( (float)HQBINS, 0.9999f ) ), __fdiv_rn( ext[2], __fmul_rn( (float)HQBINS, 0.9999f ) ) };
+		// items are (fragment, axis) pairs; an item that spans several bins becomes one clip job per bin (:2831-2845).  The
+		// jobs of a tile of items are spread over all threads of the CTA (warp), whichever thread owned the item.
+		for (uint32_t base = 0; base < count * 3; base += GT)
 		{
-			const uint32_t i = it / 3, a = it - i * 3;
-			if (!axisOK[a]) continue;
-			const Frag f = load_frag( A, primIdx[leftFirst + i] );
-			const float planeDist = __fdiv_rn( ext[a], __fmul_rn( (float)HQBINS, 0.9999f ) );
-			const float rPlaneDist = __fdiv_rn( 1.0f, planeDist ), nodeMin = nmin3[a];
-			const int bin1 = clampi( cvtt( __fmul_rn( __fsub_rn( f.bmin[a], nodeMin ), rPlaneDist ) ), 0, HQBINS - 1 );
-			const int bin2 = clampi( cvtt( __fmul_rn( __fsub_rn( f.bmax[a], nodeMin ), rPlaneDist ) ), 0, HQBINS - 1 );
-			atomicAdd( &S.cntA[a][bin1], 1u ), atomicAdd( &S.cntB[a][bin2], 1u );
-			if (bin2 == bin1) bin_grow( S, a, bin1, f.bmin, f.bmax );
-			else for (int j = bin1; j <= bin2; j++)
+			const uint32_t it = base + gtid;
+			uint32_t nb = 0, fi = 0, ab = 0;
+			if (it < count * 3)
 			{
-				float bmin[3] = { nmin3[0], nmin3[1], nmin3[2] }, bmax[3] = { nmax3[0], nmax3[1], nmax3[2] }, nbmin[3], nbmax[3];
-				bmin[a] = __fmaf_rn( __int2float_rn( j ), planeDist, nodeMin );
-				bmax[a] = j == HQBINS - 2 ? nmax3[a] : __fadd_rn( bmin[a], planeDist );
-				if (!clip_frag( A, f, nbmin, nbmax, bmin, bmax, minDim, a )) continue;
-				bin_grow( S, a, j, nbmin, nbmax );
+				const uint32_t i = it / 3, a = it - i * 3;
+				if (a == 0 ? axisOK[0] : a == 1 ? axisOK[1] : axisOK[2])
+				{
+					fi = primIdx[leftFirst + i];
+					const float4 fa = A.frag_min[fi], fb = A.frag_max[fi];
+					const float planeDist = a == 0 ? planeDist3[0] : a == 1 ? planeDist3[1] : planeDist3[2];
+					const float rPlaneDist = __fdiv_rn( 1.0f, planeDist ), nodeMin = a == 0 ? nmin3[0] : a == 1 ? nmin3[1] : nmin3[2];
+					const int bin1 = clampi( cvtt( __fmul_rn( __fsub_rn( comp( fa, a ), nodeMin ), rPlaneDist ) ), 0, HQBINS - 1 );
+					const int bin2 = clampi( cvtt( __fmul_rn( __fsub_rn( comp( fb, a ), nodeMin ), rPlaneDist ) ), 0, HQBINS - 1 );
+					atomicAdd( &S.cntA[a][bin1], 1u ), atomicAdd( &S.cntB[a][bin2], 1u );
+					if (bin2 == bin1)
+					{
+						const float mn[3] = { fa.x, fa.y, fa.z }, mx[3] = { fb.x, fb.y, fb.z };
+						bin_grow( S, a, bin1, mn, mx );
+					}
+					else nb = (uint32_t)(bin2 - bin1 + 1), ab = a | ((uint32_t)bin1 << 2);
+				}
 			}
+			uint32_t T;
+			const uint32_t off = lscan<G>( g, nb, T );
+			if (T == 0) continue; // uniform within the CTA (warp)
+			uint32_t* job_off = g.job, * job_fi = g.job + G, * job_ab = g.job + 2 * G;
+			job_off[tid] = off, job_fi[tid] = fi, job_ab[tid] = ab;
+			lsync<G>();
+			for (uint32_t q = tid; q < T; q += G)
+			{
+				// owner = last item whose first job is <= q (items without jobs share their successor's offset and are skipped by this)
+				uint32_t lo = 0, hi = G;
+				while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if (job_off[mid] <= q) lo = mid; else hi = mid; }
+				const uint32_t a = job_ab[lo] & 3u;
+				const int j = (int)(job_ab[lo] >> 2) + (int)(q - job_off[lo]);
+				const Frag f = load_frag( A, job_fi[lo] );
+				const float planeDist = a == 0 ? planeDist3[0] : a == 1 ? planeDist3[1] : planeDist3[2];
+				float bmin[3] = { nmin3[0], nmin3[1], nmin3[2] }, bmax[3] = { nmax3[0], nmax3[1], nmax3[2] }, nbmin[3], nbmax[3];
+				const float lo_a = __fmaf_rn( __int2float_rn( j ), planeDist, a == 0 ? nmin3[0] : a == 1 ? nmin3[1] : nmin3[2] );
+				const float hi_a = j == HQBINS - 2 ? (a == 0 ? nmax3[0] : a == 1 ? nmax3[1] : nmax3[2]) : __fadd_rn( lo_a, planeDist );
+				if (a == 0) bmin[0] = lo_a, bmax[0] = hi_a; else if (a == 1) bmin[1] = lo_a, bmax[1] = hi_a; else bmin[2] = lo_a, bmax[2] = hi_a;
+				if (!clip_frag( A, f, nbmin, nbmax, bmin, bmax, minDim, a )) continue;
+				bin_grow( S, a, (uint32_t)j, nbmin, nbmax );
+			}
+			lsync<G>();
 		}
 		bins_merge<G>( g );
 		gsync<G>( g );
 		PH( 2 );
-		if (lead && tid < 21) sweep_candidate( S, tid, true, rSAV, A.c_trav, A.c_int );
-		lsync<G>();
-		if (lead && tid == 0)
+		if (lead && tid < 32)
 		{
-			float splitCost = S.splitCost, minSplitCost = __fmul_rn( splitCost, 0.985f );
-			int best = -1;
-			for (int c = 0; c < 21; c++)
-			{
-				if (!axisOK[c / 7]) continue;
-				const float C = S.cost[c];
-				const int NL = S.cNL[c], NR = S.cNR[c];
-				// NL * NR > 0 is a wrapping 32-bit product in the reference build (imul)
-				if (C < minSplitCost && NL + NR < budget && (int)((uint32_t)NL * (uint32_t)NR) > 0) minSplitCost = splitCost = C, best = c;
-			}
-			if (best >= 0)
+			float splitCost = S.splitCost;
+			int nl = 0, nr = 0;
+			const int best = sweep_select( S, true, rSAV, A.c_trav, A.c_int, axisOK[0], axisOK[1], axisOK[2], __fmul_rn( splitCost, 0.985f ), budget, splitCost, nl, nr );
+			if (best >= 0 && tid == 0)
 			{
 				const uint32_t a = best / 7;
 				S.spatial = 1, S.bestAxis = a, S.bestPos = best % 7, S.bestIdx = best, S.splitCost = splitCost;
-				for (int k = 0; k < 12; k++) S.best[k] = S.cb[best][k];
-				S.bestNL = S.cNL[best], S.bestNR = S.cNR[best];
+				S.bestNL = nl, S.bestNR = nr;
 				S.best[3 + a] = S.best[6 + a]; // bestLMax[a] = bestRMin[a], "accurate" :2868
 			}
 		}
@@ -529,18 +600,21 @@ template <int G> __device__ bool hq_node( const HQArgs& A, const Grp& g, const H
 	const uint32_t bestAxis = S0.bestAxis, bestPos = S0.bestPos;
 	const bool spatial = S0.spatial != 0;
 	uint32_t Apos = t.sliceStart, Bpos = t.sliceEnd;
+	// consecutive fragments per thread in the scan tiles of the partition passes: HQ_E for big nodes (fewer group-wide scans),
+	// down to 1 when the node has no more fragments than the group has threads
+	const uint32_t epp = min( (uint32_t)HQ_E, (count + (uint32_t)GT - 1) / (uint32_t)GT );
 	if (!spatial)
 	{
 		const float rpd = rpd3[bestAxis], nmin = nmin3[bestAxis];
-		for (uint32_t base = 0; base < count; base += GT * HQ_E)
+		for (uint32_t base = 0; base < count; base += GT * epp)
 		{
 			uint32_t fr[HQ_E], flag[HQ_E], sum = 0;
 			#pragma unroll
 			for (int e = 0; e < HQ_E; e++)
 			{
-				const uint32_t i = base + gtid * HQ_E + e;
+				const uint32_t i = base + gtid * epp + e;
 				fr[e] = flag[e] = 0;
-				if (i < count)
+				if (e < (int)epp && i < count)
 				{
 					fr[e] = primIdx[leftFirst + i];
 					const float mn = comp( A.frag_min[fr[e]], bestAxis ), mx = comp( A.frag_max[fr[e]], bestAxis );
@@ -569,14 +643,14 @@ template <int G> __device__ bool hq_node( const HQArgs& A, const Grp& g, const H
 		float* spos = A.spos + t.sliceStart;
 		// pass 1: left / right / straddler, straddlers listed in order
 		uint32_t nstrad = 0;
-		for (uint32_t base = 0; base < count; base += GT * HQ_E)
+		for (uint32_t base = 0; base < count; base += GT * epp)
 		{
 			uint32_t flags = 0;
 			#pragma unroll
 			for (int e = 0; e < HQ_E; e++)
 			{
-				const uint32_t i = base + gtid * HQ_E + e;
-				if (i < count)
+				const uint32_t i = base + gtid * epp + e;
+				if (e < (int)epp && i < count)
 				{
 					const uint32_t fr = primIdx[leftFirst + i];
 					const float mn = comp( A.frag_min[fr], bestAxis ), mx = comp( A.frag_max[fr], bestAxis );
@@ -589,7 +663,7 @@ template <int G> __device__ bool hq_node( const HQArgs& A, const Grp& g, const H
 			}
 			uint32_t tot, run = gscan<G>( g, (uint32_t)__popc( flags ), tot );
 			#pragma unroll
-			for (int e = 0; e < HQ_E; e++) if (flags & (1u << e)) strad[nstrad + run++] = base + gtid * HQ_E + e;
+			for (int e = 0; e < HQ_E; e++) if (flags & (1u << e)) strad[nstrad + run++] = base + gtid * epp + e;
 			nstrad += tot;
 		}
 		gsync<G>( g );
@@ -690,15 +764,15 @@ template <int G> __device__ bool hq_node( const HQArgs& A, const Grp& g, const H
 		gsync<G>( g );
 		PH( 7 );
 		// pass 4: left part upward from sliceStart, right part downward from sliceEnd, in fragment order
-		for (uint32_t base = 0; base < count; base += GT * HQ_E)
+		for (uint32_t base = 0; base < count; base += GT * epp)
 		{
 			uint32_t fr[HQ_E], c[HQ_E], flag[HQ_E], sum = 0;
 			#pragma unroll
 			for (int e = 0; e < HQ_E; e++)
 			{
-				const uint32_t i = base + gtid * HQ_E + e;
+				const uint32_t i = base + gtid * epp + e;
 				fr[e] = c[e] = flag[e] = 0;
-				if (i < count)
+				if (e < (int)epp && i < count)
 				{
 					fr[e] = primIdx[leftFirst + i], c[e] = cls[i];
 					flag[e] = (c[e] & 0x80000000u) ? 0x10001u : c[e] == 0u ? 1u : 0x10000u;
@@ -855,8 +929,9 @@ __device__ __forceinline__ void hq_enqueue( const HQArgs& A, HQTask* next, const
 __global__ void __launch_bounds__( HQ_BIG_THREADS ) k_hq_level( HQArgs A, const HQTask* cur, HQTask* next, const uint32_t nct )
 {
 	__shared__ GroupSmem S;
+	__shared__ uint32_t job[3 * HQ_BIG_THREADS];
 	Grp g;
-	g.tid = (int)threadIdx.x, g.nct = nct, g.rank = 0, g.S = g.S0 = &S;
+	g.tid = (int)threadIdx.x, g.nct = nct, g.rank = 0, g.S = g.S0 = &S, g.job = job;
 	if (nct > 1)
 	{
 		cg::cluster_group cl = cg::this_cluster();
@@ -872,10 +947,11 @@ __global__ void __launch_bounds__( HQ_SMALL_WARPS * 32 ) k_hq_subtrees( HQArgs A
 {
 	__shared__ GroupSmem Ss[HQ_SMALL_WARPS];
 	__shared__ HQTask stack[HQ_SMALL_WARPS][HQ_STACK];
+	__shared__ uint32_t job[HQ_SMALL_WARPS][3 * 32];
 	const uint32_t w = threadIdx.x >> 5, lane = threadIdx.x & 31, id = blockIdx.x * HQ_SMALL_WARPS + w;
 	if (id >= roots) return;
 	Grp g;
-	g.tid = g.gtid = (int)lane, g.GT = 32, g.rank = 0, g.nct = 1, g.S = g.S0 = &Ss[w];
+	g.tid = g.gtid = (int)lane, g.GT = 32, g.rank = 0, g.nct = 1, g.S = g.S0 = &Ss[w], g.job = job[w];
 	HQTask t = A.small[id];
 	uint32_t sp = 0;
 	for (;;)
