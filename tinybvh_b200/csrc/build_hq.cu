@@ -372,34 +372,40 @@ __device__ __forceinline__ void bin_grow( GroupSmem& S, const uint32_t a, const 
 __device__ __forceinline__ int sweep_select( GroupSmem& S, const bool spatial, const float rSAV, const float c_trav, const float c_int,
 	const bool ok0, const bool ok1, const bool ok2, const float limit, const int budget, float& bestCost, int& bestNL, int& bestNR )
 {
-	const int c = (int)(threadIdx.x & 31);
-	const uint32_t a = c < 21 ? c / 7 : 0, i = c % 7;
-	float l1[3] = { BVH_FAR, BVH_FAR, BVH_FAR }, l2[3] = { -BVH_FAR, -BVH_FAR, -BVH_FAR }, r1[3] = { BVH_FAR, BVH_FAR, BVH_FAR }, r2[3] = { -BVH_FAR, -BVH_FAR, -BVH_FAR };
-	uint32_t lN = 0, rN = 0;
+	// lane = axis * 8 + bin: each lane decodes its own bin, then segmented (width 8) prefix and suffix unions by shuffles;
+	// candidate plane i of axis a sits on lane a * 8 + i (i < 7): left = prefix of that lane, right = suffix of the next lane.
+	// Lane order is candidate order.
+	const int lane = (int)(threadIdx.x & 31);
+	const uint32_t a = lane < 24 ? lane >> 3 : 0, i = lane & 7;
+	float l1[3], l2[3], r1[3], r2[3];
 	#pragma unroll
-	for (uint32_t b = 0; b < HQBINS; b++)
+	for (int k = 0; k < 3; k++) l1[k] = r1[k] = key2f( S.kmin[a][i][k] ), l2[k] = r2[k] = key2f( S.kmax[a][i][k] );
+	uint32_t lN = S.cntA[a][i], rN = spatial ? S.cntB[a][i] : lN;
+	#pragma unroll
+	for (int d = 1; d < 8; d <<= 1)
 	{
-		const uint32_t ca = S.cntA[a][b], cb = spatial ? S.cntB[a][b] : ca;
-		float mn[3], mx[3];
+		const bool up = (int)i >= d, dn = (int)i + d < 8;
 		#pragma unroll
-		for (int k = 0; k < 3; k++) mn[k] = key2f( S.kmin[a][b][k] ), mx[k] = key2f( S.kmax[a][b][k] );
-		if (b <= i)
+		for (int k = 0; k < 3; k++)
 		{
-			lN += ca;
-			#pragma unroll
-			for (int k = 0; k < 3; k++) l1[k] = tmin( l1[k], mn[k] ), l2[k] = tmax( l2[k], mx[k] );
+			const float a1 = __shfl_up_sync( 0xffffffffu, l1[k], d, 8 ), a2 = __shfl_up_sync( 0xffffffffu, l2[k], d, 8 );
+			const float b1 = __shfl_down_sync( 0xffffffffu, r1[k], d, 8 ), b2 = __shfl_down_sync( 0xffffffffu, r2[k], d, 8 );
+			if (up) l1[k] = tmin( l1[k], a1 ), l2[k] = tmax( l2[k], a2 );
+			if (dn) r1[k] = tmin( r1[k], b1 ), r2[k] = tmax( r2[k], b2 );
 		}
-		else
-		{
-			rN += cb;
-			#pragma unroll
-			for (int k = 0; k < 3; k++) r1[k] = tmin( r1[k], mn[k] ), r2[k] = tmax( r2[k], mx[k] );
-		}
+		const uint32_t an = __shfl_up_sync( 0xffffffffu, lN, d, 8 ), bn = __shfl_down_sync( 0xffffffffu, rN, d, 8 );
+		if (up) lN += an;
+		if (dn) rN += bn;
 	}
+	// right side of plane i = suffix starting at bin i + 1
+	#pragma unroll
+	for (int k = 0; k < 3; k++) r1[k] = __shfl_down_sync( 0xffffffffu, r1[k], 1, 8 ), r2[k] = __shfl_down_sync( 0xffffffffu, r2[k], 1, 8 );
+	rN = __shfl_down_sync( 0xffffffffu, rN, 1, 8 );
 	const float AL = lN == 0 ? BVH_FAR : half_area3( __fsub_rn( l2[0], l1[0] ), __fsub_rn( l2[1], l1[1] ), __fsub_rn( l2[2], l1[2] ) );
 	const float AR = rN == 0 ? BVH_FAR : half_area3( __fsub_rn( r2[0], r1[0] ), __fsub_rn( r2[1], r1[1] ), __fsub_rn( r2[2], r1[2] ) );
 	const float C = split_cost( c_trav, c_int, rSAV, AL, (int)lN, AR, (int)rN );
-	const bool cand = c < 21 && (a == 0 ? ok0 : a == 1 ? ok1 : ok2);
+	const int c = lane; // candidate id in lane space; converted to axis * 7 + plane on return
+	const bool cand = lane < 24 && i < 7 && (a == 0 ? ok0 : a == 1 ? ok1 : ok2);
 	int best = -1;
 	if (spatial)
 	{
@@ -414,7 +420,7 @@ __device__ __forceinline__ int sweep_select( GroupSmem& S, const bool spatial, c
 		// a NaN cost (0 * inf on degenerate boxes) is "not >= splitCost" and so accepted by the reference's loop, and poisons every
 		// later comparison: replay the loop literally
 		float sc = limit;
-		for (int k = 0; k < 21; k++)
+		for (int k = 0; k < 24; k++)
 		{
 			const float Ck = __shfl_sync( 0xffffffffu, C, k );
 			const bool ck = __shfl_sync( 0xffffffffu, (int)cand, k ) != 0;
@@ -439,6 +445,7 @@ __device__ __forceinline__ int sweep_select( GroupSmem& S, const bool spatial, c
 		bestCost = __shfl_sync( 0xffffffffu, C, best );
 		bestNL = (int)__shfl_sync( 0xffffffffu, lN, best ), bestNR = (int)__shfl_sync( 0xffffffffu, rN, best );
 		__syncwarp();
+		best = (best >> 3) * 7 + (best & 7);
 	}
 	return best;
 }
@@ -1066,13 +1073,16 @@ int build_hq_launch( tbvh_bvh b, float c_trav, float c_int )
 		k_hq_root<<<1, 1, 0, s>>>( A ); LAUNCHED();
 		uint32_t num = n > A.small_t ? 1 : 0, level = 0, max_count = n;
 		const uint32_t max_cluster = (uint32_t)(b->ctx->hq_cluster < 1 ? 1 : b->ctx->hq_cluster > HQ_MAX_CLUSTER ? HQ_MAX_CLUSTER : b->ctx->hq_cluster);
+		// tuning knobs of the cluster sizing rule (defaults measured on B200, profiles/README.md)
+		const char* env_cf = getenv( "TBVH_HQ_CTA_FRAGS" ); const char* env_cc = getenv( "TBVH_HQ_CTA_CAP" );
+		const size_t cta_frags = env_cf && atoi( env_cf ) > 0 ? (size_t)atoi( env_cf ) : 512, cta_cap = env_cc && atoi( env_cc ) > 0 ? (size_t)atoi( env_cc ) : 16;
 		if (max_cluster > 8) CUDA_TRY( cudaFuncSetAttribute( k_hq_level, cudaFuncAttributeNonPortableClusterSizeAllowed, 1 ) );
 		while (num)
 		{
 			CUDA_TRY( cudaMemsetAsync( &A.ctr->next_big, 0, 8, s ) ); // next_big + next_max
-			// cluster size: enough CTAs for the largest node of the level (about 2048 fragments per CTA), no more than fills the GPU
+			// cluster size: enough CTAs for the largest node of the level (about 512 fragments per CTA), at most 8 CTAs per SM in flight
 			uint32_t nct = 1;
-			while (nct < max_cluster && (size_t)nct * 2048 < max_count && (size_t)num * nct * 2 <= (size_t)b->ctx->sm_count * 4) nct <<= 1;
+			while (nct < max_cluster && (size_t)nct * cta_frags < max_count && (size_t)num * nct * 2 <= (size_t)b->ctx->sm_count * cta_cap) nct <<= 1;
 			cudaLaunchConfig_t cfg = {};
 			cudaLaunchAttribute attr[1];
 			cfg.gridDim = dim3( num * nct ), cfg.blockDim = dim3( HQ_BIG_THREADS ), cfg.dynamicSmemBytes = 0, cfg.stream = s;

@@ -30,7 +30,7 @@ struct tbvh_ctx_t
 	int h2d_split = 1;
 	int trace_variant = 3;           // BVH2 traversal kernel: 0 generic, 3 octant switch, 4 persistent warps (see trace_bvh2.cu)
 	int small_mode = 0;              // warp-subtree kernel: bit 0 = fragments staged in shared memory, bit 1 = aggregated bin updates
-	int hq_small = 64;               // BuildHQ: nodes of at most this many fragments go to the warp-per-subtree kernel (<= 256)
+	int hq_small = 16;               // BuildHQ: nodes of at most this many fragments go to the warp-per-subtree kernel (<= 256)
 	int hq_cluster = 16;             // BuildHQ: largest thread-block cluster a node of the level phase may get (1..16)
 	int small_t = 128;               // builder: subtrees of at most this many primitives go to the warp kernel (<= 256)
 	int d2h_mode = 0;                // hits back to the host: 0 = 2D copy of 16-byte rows, 1 = 2D copy of the whole 64-byte rows,
