@@ -36,6 +36,7 @@ namespace
 #define HQBINS 8
 #define HQ_SMALL_MAX 256      // switch point CTA/cluster per node -> warp per subtree (run-time value hq_small <= this)
 #define HQ_MAX_CLUSTER 16
+#define HQ_MLP 4               // independent index -> fragment load chains per thread in the binning loops
 #define HQ_E 8                 // consecutive fragments per thread and scan tile of the partition passes (8 * 4096 fits the 16-bit packed counters)
 #define HQ_BIG_THREADS 256
 #define HQ_SMALL_WARPS 4
@@ -293,7 +294,7 @@ struct Grp
 	int tid, gtid, GT;        // thread in its CTA (lane for warps), thread in the group, threads in the group
 	uint32_t rank, nct;       // CTA rank in the cluster, cluster size
 	GroupSmem* S; GroupSmem* S0;
-	uint32_t* job;            // 3 * G words of this CTA's (warp's) shared memory: clip jobs of one item tile (spatial binning)
+	uint32_t* job;            // 3 * HQ_MLP * G words of this CTA's (warp's) shared memory: clip jobs of one item tile (spatial binning)
 };
 template <int G> __device__ __forceinline__ void lsync() { if (G == 32) __syncwarp(); else __syncthreads(); }
 template <int G> __device__ __forceinline__ void gsync( const Grp& g )
@@ -477,17 +478,26 @@ template <int G> __device__ bool hq_node( const HQArgs& A, const Grp& g, const H
 	// ---- object split: bins :2758-2775
 	bins_reset( S, tid, G );
 	gsync<G>( g );
-	for (uint32_t i = gtid; i < count; i += GT)
+	// HQ_MLP fragments per thread and trip: the index -> fragment loads of a trip are issued together
+	for (uint32_t i0 = gtid; i0 < count; i0 += GT * HQ_MLP)
 	{
-		const uint32_t fi = primIdx[leftFirst + i];
-		const float4 fa = A.frag_min[fi], fb = A.frag_max[fi];
-		const float mn[3] = { fa.x, fa.y, fa.z }, mx[3] = { fb.x, fb.y, fb.z };
+		uint32_t fi[HQ_MLP];
+		float4 fa[HQ_MLP], fb[HQ_MLP];
 		#pragma unroll
-		for (int a = 0; a < 3; a++)
+		for (int u = 0; u < HQ_MLP; u++) { const uint32_t i = i0 + u * GT; fi[u] = i < count ? primIdx[leftFirst + i] : 0xffffffffu; }
+		#pragma unroll
+		for (int u = 0; u < HQ_MLP; u++) if (fi[u] != 0xffffffffu) fa[u] = A.frag_min[fi[u]], fb[u] = A.frag_max[fi[u]];
+		#pragma unroll
+		for (int u = 0; u < HQ_MLP; u++) if (fi[u] != 0xffffffffu)
 		{
-			const int bi = clampi( cvtt( __fmul_rn( __fmaf_rn( __fadd_rn( mn[a], mx[a] ), 0.5f, -nmin3[a] ), rpd3[a] ) ), 0, HQBINS - 1 );
-			bin_grow( S, a, bi, mn, mx );
-			atomicAdd( &S.cntA[a][bi], 1u );
+			const float mn[3] = { fa[u].x, fa[u].y, fa[u].z }, mx[3] = { fb[u].x, fb[u].y, fb[u].z };
+			#pragma unroll
+			for (int a = 0; a < 3; a++)
+			{
+				const int bi = clampi( cvtt( __fmul_rn( __fmaf_rn( __fadd_rn( mn[a], mx[a] ), 0.5f, -nmin3[a] ), rpd3[a] ) ), 0, HQBINS - 1 );
+				bin_grow( S, a, bi, mn, mx );
+				atomicAdd( &S.cntA[a][bi], 1u );
+			}
 		}
 	}
 	bins_merge<G>( g );
@@ -525,40 +535,53 @@ template <int G> __device__ bool hq_node( const HQArgs& A, const Grp& g, const H
 		const float planeDist3[3] = { __fdiv_rn( ext[0], __fmul_rn( (float)HQBINS, 0.9999f ) ), __fdiv_rn( ext[1], __fmul_rn( (float)HQBINS, 0.9999f ) ), __fdiv_rn( ext[2], __fmul_rn( (float)HQBINS, 0.9999f ) ) };
 		// items are (fragment, axis) pairs; an item that spans several bins becomes one clip job per bin (:2831-2845).  The
 		// jobs of a tile of items are spread over all threads of the CTA (warp), whichever thread owned the item.
-		for (uint32_t base = 0; base < count * 3; base += GT)
+		// kpp items per thread and tile (HQ_MLP for big nodes, 1 when the node has no more items than the group has threads)
+		const uint32_t items = count * 3, kpp = min( (uint32_t)HQ_MLP, (items + (uint32_t)GT - 1) / (uint32_t)GT );
+		uint32_t* job_off = g.job, * job_fi = g.job + HQ_MLP * G, * job_ab = g.job + 2 * HQ_MLP * G;
+		for (uint32_t base = 0; base < items; base += GT * kpp)
 		{
-			const uint32_t it = base + gtid;
-			uint32_t nb = 0, fi = 0, ab = 0;
-			if (it < count * 3)
+			uint32_t nb[HQ_MLP], fi[HQ_MLP], ab[HQ_MLP], nbsum = 0;
+			float4 fa[HQ_MLP], fb[HQ_MLP];
+			#pragma unroll
+			for (int u = 0; u < HQ_MLP; u++)
 			{
-				const uint32_t i = it / 3, a = it - i * 3;
-				if (a == 0 ? axisOK[0] : a == 1 ? axisOK[1] : axisOK[2])
-				{
-					fi = primIdx[leftFirst + i];
-					const float4 fa = A.frag_min[fi], fb = A.frag_max[fi];
-					const float planeDist = a == 0 ? planeDist3[0] : a == 1 ? planeDist3[1] : planeDist3[2];
-					const float rPlaneDist = __fdiv_rn( 1.0f, planeDist ), nodeMin = a == 0 ? nmin3[0] : a == 1 ? nmin3[1] : nmin3[2];
-					const int bin1 = clampi( cvtt( __fmul_rn( __fsub_rn( comp( fa, a ), nodeMin ), rPlaneDist ) ), 0, HQBINS - 1 );
-					const int bin2 = clampi( cvtt( __fmul_rn( __fsub_rn( comp( fb, a ), nodeMin ), rPlaneDist ) ), 0, HQBINS - 1 );
-					atomicAdd( &S.cntA[a][bin1], 1u ), atomicAdd( &S.cntB[a][bin2], 1u );
-					if (bin2 == bin1)
-					{
-						const float mn[3] = { fa.x, fa.y, fa.z }, mx[3] = { fb.x, fb.y, fb.z };
-						bin_grow( S, a, bin1, mn, mx );
-					}
-					else nb = (uint32_t)(bin2 - bin1 + 1), ab = a | ((uint32_t)bin1 << 2);
-				}
+				const uint32_t it = base + gtid * kpp + u, i = it / 3, a = it - i * 3;
+				nb[u] = 0, ab[u] = a, fi[u] = 0xffffffffu;
+				if (u < (int)kpp && it < items && (a == 0 ? axisOK[0] : a == 1 ? axisOK[1] : axisOK[2])) fi[u] = primIdx[leftFirst + i];
 			}
-			uint32_t T;
-			const uint32_t off = lscan<G>( g, nb, T );
+			#pragma unroll
+			for (int u = 0; u < HQ_MLP; u++) if (fi[u] != 0xffffffffu) fa[u] = A.frag_min[fi[u]], fb[u] = A.frag_max[fi[u]];
+			#pragma unroll
+			for (int u = 0; u < HQ_MLP; u++) if (fi[u] != 0xffffffffu)
+			{
+				const uint32_t a = ab[u];
+				const float planeDist = a == 0 ? planeDist3[0] : a == 1 ? planeDist3[1] : planeDist3[2];
+				const float rPlaneDist = __fdiv_rn( 1.0f, planeDist ), nodeMin = a == 0 ? nmin3[0] : a == 1 ? nmin3[1] : nmin3[2];
+				const int bin1 = clampi( cvtt( __fmul_rn( __fsub_rn( comp( fa[u], a ), nodeMin ), rPlaneDist ) ), 0, HQBINS - 1 );
+				const int bin2 = clampi( cvtt( __fmul_rn( __fsub_rn( comp( fb[u], a ), nodeMin ), rPlaneDist ) ), 0, HQBINS - 1 );
+				atomicAdd( &S.cntA[a][bin1], 1u ), atomicAdd( &S.cntB[a][bin2], 1u );
+				if (bin2 == bin1)
+				{
+					const float mn[3] = { fa[u].x, fa[u].y, fa[u].z }, mx[3] = { fb[u].x, fb[u].y, fb[u].z };
+					bin_grow( S, a, bin1, mn, mx );
+				}
+				else nb[u] = (uint32_t)(bin2 - bin1 + 1), ab[u] = a | ((uint32_t)bin1 << 2);
+				nbsum += nb[u];
+			}
+			uint32_t T, off = lscan<G>( g, nbsum, T );
 			if (T == 0) continue; // uniform within the CTA (warp)
-			uint32_t* job_off = g.job, * job_fi = g.job + G, * job_ab = g.job + 2 * G;
-			job_off[tid] = off, job_fi[tid] = fi, job_ab[tid] = ab;
+			#pragma unroll
+			for (int u = 0; u < HQ_MLP; u++)
+			{
+				const uint32_t e = (uint32_t)tid * HQ_MLP + u;
+				job_off[e] = off, job_fi[e] = fi[u], job_ab[e] = ab[u];
+				off += nb[u];
+			}
 			lsync<G>();
 			for (uint32_t q = tid; q < T; q += G)
 			{
 				// owner = last item whose first job is <= q (items without jobs share their successor's offset and are skipped by this)
-				uint32_t lo = 0, hi = G;
+				uint32_t lo = 0, hi = G * HQ_MLP;
 				while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if (job_off[mid] <= q) lo = mid; else hi = mid; }
 				const uint32_t a = job_ab[lo] & 3u;
 				const int j = (int)(job_ab[lo] >> 2) + (int)(q - job_off[lo]);
@@ -936,7 +959,7 @@ __device__ __forceinline__ void hq_enqueue( const HQArgs& A, HQTask* next, const
 __global__ void __launch_bounds__( HQ_BIG_THREADS ) k_hq_level( HQArgs A, const HQTask* cur, HQTask* next, const uint32_t nct )
 {
 	__shared__ GroupSmem S;
-	__shared__ uint32_t job[3 * HQ_BIG_THREADS];
+	__shared__ uint32_t job[3 * HQ_MLP * HQ_BIG_THREADS];
 	Grp g;
 	g.tid = (int)threadIdx.x, g.nct = nct, g.rank = 0, g.S = g.S0 = &S, g.job = job;
 	if (nct > 1)
@@ -954,7 +977,7 @@ __global__ void __launch_bounds__( HQ_SMALL_WARPS * 32 ) k_hq_subtrees( HQArgs A
 {
 	__shared__ GroupSmem Ss[HQ_SMALL_WARPS];
 	__shared__ HQTask stack[HQ_SMALL_WARPS][HQ_STACK];
-	__shared__ uint32_t job[HQ_SMALL_WARPS][3 * 32];
+	__shared__ uint32_t job[HQ_SMALL_WARPS][3 * HQ_MLP * 32];
 	const uint32_t w = threadIdx.x >> 5, lane = threadIdx.x & 31, id = blockIdx.x * HQ_SMALL_WARPS + w;
 	if (id >= roots) return;
 	Grp g;
