@@ -147,6 +147,13 @@ public:
 		TBVH_FATAL_IF( tbvh_convert( h, TBVH_LAYOUT_BVH_GPU ), "BVH_GPU::Build" );
 		sync_info();
 	}
+	// BVH_GPU::BuildHQ tiny_bvh.h:4588: bvh.BuildHQ, then ConvertFrom
+	template <class Vec4> void BuildHQ( const Vec4* vertices, const uint32_t primCount )
+	{
+		TBVH_FATAL_IF( tbvh_build_flavour( h, vertices, (uint32_t)sizeof( Vec4 ), primCount, TBVH_HOST, c_trav, c_int, TBVH_BUILD_HQ ), "BVH_GPU::BuildHQ" );
+		TBVH_FATAL_IF( tbvh_convert( h, TBVH_LAYOUT_BVH_GPU ), "BVH_GPU::BuildHQ" );
+		sync_info();
+	}
 	// BVH_GPU::ConvertFrom( const BVH& ) tiny_bvh.h:4612 - shares the source's device data, like the reference
 	void ConvertFrom( const BVH& original )
 	{
@@ -167,6 +174,13 @@ public:
 		// BVH8_CWBVH::Build -> bvh8.bvh.BuildDefault = BuildAVX on x86 (tiny_bvh.h:5830)
 		TBVH_FATAL_IF( tbvh_build_flavour( h, vertices, (uint32_t)sizeof( Vec4 ), primCount, TBVH_HOST, c_trav, c_int, TBVH_BUILD_AVX ), "BVH8_CWBVH::Build" );
 		TBVH_FATAL_IF( tbvh_convert( h, TBVH_LAYOUT_CWBVH ), "BVH8_CWBVH::Build" );
+		sync_info(), usedBlocks = Info().used_blocks;
+	}
+	// BVH8_CWBVH::BuildHQ tiny_bvh.h:5859: bvh.BuildHQ, SplitLeafs(3), MBVH<8> collapse, CWBVH encode
+	template <class Vec4> void BuildHQ( const Vec4* vertices, const uint32_t primCount )
+	{
+		TBVH_FATAL_IF( tbvh_build_flavour( h, vertices, (uint32_t)sizeof( Vec4 ), primCount, TBVH_HOST, c_trav, c_int, TBVH_BUILD_HQ ), "BVH8_CWBVH::BuildHQ" );
+		TBVH_FATAL_IF( tbvh_convert( h, TBVH_LAYOUT_CWBVH ), "BVH8_CWBVH::BuildHQ" );
 		sync_info(), usedBlocks = Info().used_blocks;
 	}
 	void ConvertFrom( const BVH& original )

@@ -89,3 +89,29 @@ def test_build_hq_is_deterministic(gpu):
     a = api.BVH().BuildHQ(v).download()
     b = api.BVH().BuildHQ(v).download()
     assert np.array_equal(a[0].view(np.uint8), b[0].view(np.uint8)) and np.array_equal(a[1], b[1])
+
+
+@pytest.mark.parametrize("scene", ["synthetic:5000", "bunny", "sponza"])
+def test_derived_layouts_build_hq(gpu, scene):
+    """BVH_GPU::BuildHQ (:4588) and BVH8_CWBVH::BuildHQ (:5859): the SBVH pushed through the same converters."""
+    from oracle import refpy
+    if not refpy.available():
+        pytest.skip("needs oracle/_ref")
+    v, label = scenes.load_scene(scene)
+    ref = refpy.RefBVH(v, mode=2, threaded=False)
+    want = refpy.RefBVHGPU(ref).nodes
+    got = api.BVH_GPU().BuildHQ(v).download()
+    assert got.shape == want.shape and np.array_equal(got.view(np.uint32), want.view(np.uint32)), f"{label}: BVH_GPU nodes differ"
+    cw = refpy.RefCWBVH(v, mode=1)
+    e = api.BVH8_CWBVH().BuildHQ(v)
+    nodes, tris = e.download()
+    assert nodes.shape == cw.nodes.shape and np.array_equal(nodes.view(np.uint32), cw.nodes.view(np.uint32)), f"{label}: bvh8Data differs"
+    used = int(cw.source_bvh().nodes["triCount"].sum()) * 3   # the reference leaves the records beyond the referenced ones uninitialised
+    assert tris.shape[0] >= used and np.array_equal(tris[:used].view(np.uint32), cw.tris[:used].view(np.uint32)), f"{label}: bvh8Tris differs"
+    # traversal of the SBVH-derived CWBVH: bit-identical to the reference's own CPU walk of the same data
+    lo, hi = scenes.scene_bounds(v)
+    eye, view = (R.SPONZA_EYES[0], R.SPONZA_VIEWS[0]) if scene == "sponza" else R.bounds_camera(lo, hi, "outside")
+    a = R.primary_rays(eye, view, 96, 96, 4)
+    b = a.copy()
+    cw.intersect(a), e.Intersect(b)
+    assert util.compare_hits(b, a) == {"prim": 0, "t": 0, "u": 0, "v": 0}

@@ -197,6 +197,13 @@ class BVH_GPU(_Base):
         check(_lib.lib().tbvh_convert(self.h, LAYOUT_BVH_GPU))
         return self
 
+    def BuildHQ(self, vertices, primCount: int = 0):
+        """BVH_GPU::BuildHQ (tiny_bvh.h:4588): bvh.BuildHQ, then ConvertFrom."""
+        p, stride, nv, space, keep = _verts_arg(vertices)
+        check(_lib.lib().tbvh_build_flavour(self.h, p, stride, primCount or nv // 3, space, self.c_trav, self.c_int, _lib.BUILD_HQ))
+        check(_lib.lib().tbvh_convert(self.h, LAYOUT_BVH_GPU))
+        return self
+
     def upload(self, nodes, primIdx, vertices):
         p, stride, nv, space, keep = _verts_arg(vertices)
         nodes = np.ascontiguousarray(nodes)
@@ -220,6 +227,13 @@ class BVH8_CWBVH(_Base):
         p, stride, nv, space, keep = _verts_arg(vertices)
         # BVH8_CWBVH::Build -> bvh8.bvh.BuildDefault (tiny_bvh.h:5830) = BuildAVX on x86, then the conversion chain
         check(_lib.lib().tbvh_build_flavour(self.h, p, stride, primCount or nv // 3, space, self.c_trav, self.c_int, self.build_flavour))
+        check(_lib.lib().tbvh_convert(self.h, LAYOUT_CWBVH))
+        return self
+
+    def BuildHQ(self, vertices, primCount: int = 0):
+        """BVH8_CWBVH::BuildHQ (tiny_bvh.h:5859): bvh.BuildHQ, SplitLeafs(3), 8-wide collapse, CWBVH encode."""
+        p, stride, nv, space, keep = _verts_arg(vertices)
+        check(_lib.lib().tbvh_build_flavour(self.h, p, stride, primCount or nv // 3, space, self.c_trav, self.c_int, _lib.BUILD_HQ))
         check(_lib.lib().tbvh_convert(self.h, LAYOUT_CWBVH))
         return self
 
