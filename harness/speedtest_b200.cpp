@@ -137,5 +137,27 @@ int main( int argc, char** argv )
 		}
 	}
 	printf( "validation: speedtest tolerance %s; exact: %zu prim mismatches, %zu t-bit mismatches over %zu rays\n", ok ? "passed" : "FAILED", primDiff, tDiff, 3 * Nfull );
-	return ok && primDiff == 0 && tDiff == 0 ? 0 : 1;
+
+	// ---- SBVH (the speedtest's BuildHQ line, :678): reference BVH::BuildHQ on the host, the same builder on the GPU
+	bool hqSame = false;
+	{
+		BVH ref_hq;
+		t.reset();
+		ref_hq.BuildHQ( triangles, verts / 3 );
+		const float refHQ = t.elapsed();
+		printf( "reference BVH::BuildHQ        : %7.2f ms, %u nodes, SAH %.2f\n", refHQ * 1000, ref_hq.usedNodes, ref_hq.SAHCost() );
+		tinybvh_b200::BVH gpu_hq;
+		gpu_hq.BuildHQ( triangles, verts / 3 );
+		gpu_hq.BuildHQ( triangles, verts / 3 );
+		printf( "tinybvh_b200 BVH::BuildHQ     : %7.3f ms (device), %u nodes, idxCount %u  -> %.1fx\n", gpu_hq.buildMs, gpu_hq.usedNodes, gpu_hq.idxCount, refHQ * 1000 / gpu_hq.buildMs );
+		std::vector<uint8_t> nodes( (size_t)gpu_hq.usedNodes * 32 );
+		std::vector<uint32_t> idx( gpu_hq.idxCount );
+		gpu_hq.Download( nodes.data(), idx.data() );
+		uint32_t refs = 0;
+		for (uint32_t n = 0; n < ref_hq.usedNodes; n++) if (n != 1) refs += ref_hq.bvhNode[n].triCount;
+		hqSame = gpu_hq.usedNodes == ref_hq.usedNodes && gpu_hq.idxCount == ref_hq.idxCount && memcmp( nodes.data(), ref_hq.bvhNode, nodes.size() ) == 0 &&
+			memcmp( idx.data(), ref_hq.primIdx, (size_t)refs * 4 ) == 0;
+		printf( "  SBVH node array and the %u referenced primIdx entries %s BVH::BuildHQ's\n", refs, hqSame ? "are identical to" : "DIFFER from" );
+	}
+	return ok && primDiff == 0 && tDiff == 0 && hqSame ? 0 : 1;
 }

@@ -135,7 +135,7 @@ __device__ __forceinline__ void cp3( float* d, const float* s ) { d[0] = s[0], d
 
 // Sutherland-Hodgman of polygon vin[0..Nin) against the slab l <= x[a] <= r, in place (result back in vin); the generic
 // loops of ClipFrag (:8630-8658, tolerance eps, unclamped f) and SplitFrag (:8744-8770, eps = 0, f clamped to [0,1]).
-template <bool CLAMP> __device__ __forceinline__ uint32_t clip_slab( float vin[16][3], float vout[16][3], uint32_t Nin, const uint32_t a, const float l, const float r, const float eps )
+template <bool CLAMP> __device__ __noinline__ uint32_t clip_slab( float vin[16][3], float vout[16][3], uint32_t Nin, const uint32_t a, const float l, const float r, const float eps )
 {
 	uint32_t Nout = 0;
 	const float le = __fsub_rn( l, eps ), re = __fadd_rn( r, eps );
@@ -171,7 +171,7 @@ template <bool CLAMP> __device__ __forceinline__ uint32_t clip_slab( float vin[1
 
 // BVH::ClipFrag :8614-8729: bounds of (fragment's triangle) clipped to box [bmin_in, bmax_in] ^ fragment box.
 // Returns false when nothing is left; nb_min / nb_max receive the new fragment's box either way (as the reference does).
-__device__ bool clip_frag( const HQArgs& A, const Frag& orig, float* nb_min, float* nb_max, const float* bmin_in, const float* bmax_in, const float* minDim, const uint32_t axis )
+__device__ __noinline__ bool clip_frag( const HQArgs& A, const Frag& orig, float* nb_min, float* nb_max, const float* bmin_in, const float* bmax_in, const float* minDim, const uint32_t axis )
 {
 	float bmin[3], bmax[3], extent[3];
 	#pragma unroll
@@ -187,6 +187,7 @@ __device__ bool clip_frag( const HQArgs& A, const Frag& orig, float* nb_min, flo
 			cp3( vin[0], t[0] ), cp3( vin[1], t[1] ), cp3( vin[2], t[2] );
 		}
 		uint32_t Nin = 3;
+		#pragma unroll 1
 		for (uint32_t a = 0; a < 3; a++)
 		{
 			const float eps = minDim[a];
@@ -251,7 +252,7 @@ __device__ bool clip_frag( const HQArgs& A, const Frag& orig, float* nb_min, flo
 }
 
 // BVH::SplitFrag :8731-8793: the fragment's polygon cut at splitPos; only the two halves' boxes are kept.
-__device__ void split_frag( const HQArgs& A, const Frag& orig, float* lmin, float* lmax, float* rmin, float* rmax, const float* minDim,
+__device__ __noinline__ void split_frag( const HQArgs& A, const Frag& orig, float* lmin, float* lmax, float* rmin, float* rmax, const float* minDim,
 	const uint32_t splitAxis, const float splitPos, bool& leftOK, bool& rightOK )
 {
 	float vin[16][3], vout[16][3];
@@ -261,7 +262,9 @@ __device__ void split_frag( const HQArgs& A, const Frag& orig, float* lmin, floa
 		cp3( vin[0], t[0] ), cp3( vin[1], t[1] ), cp3( vin[2], t[2] );
 	}
 	uint32_t Nin = 3, Nleft = 0, Nright = 0;
-	if (orig.clipped) for (uint32_t a = 0; a < 3; a++) if (__fsub_rn( orig.bmax[a], orig.bmin[a] ) > minDim[a])
+	if (orig.clipped)
+		#pragma unroll 1
+		for (uint32_t a = 0; a < 3; a++) if (__fsub_rn( orig.bmax[a], orig.bmin[a] ) > minDim[a])
 		Nin = clip_slab<true>( vin, vout, Nin, a, orig.bmin[a], orig.bmax[a], 0.0f );
 	#pragma unroll
 	for (int k = 0; k < 3; k++) lmin[k] = rmin[k] = BVH_FAR, lmax[k] = rmax[k] = -BVH_FAR;
@@ -370,7 +373,7 @@ __device__ __forceinline__ void bin_grow( GroupSmem& S, const uint32_t a, const 
 //   spatial split (:2847-2870, countIn / countOut): the same among candidates with NL + NR < budget, NL * NR > 0 and
 //                 C < 0.985 * splitCost.
 // The winner lane stores the child boxes in S.best.  Returns the candidate index (-1: none) and its cost, on every lane.
-__device__ __forceinline__ int sweep_select( GroupSmem& S, const bool spatial, const float rSAV, const float c_trav, const float c_int,
+__device__ __noinline__ int sweep_select( GroupSmem& S, const bool spatial, const float rSAV, const float c_trav, const float c_int,
 	const bool ok0, const bool ok1, const bool ok2, const float limit, const int budget, float& bestCost, int& bestNL, int& bestNR )
 {
 	// lane = axis * 8 + bin: each lane decodes its own bin, then segmented (width 8) prefix and suffix unions by shuffles;
@@ -956,7 +959,7 @@ __device__ __forceinline__ void hq_enqueue( const HQArgs& A, HQTask* next, const
 }
 
 // level-synchronous phase: one cluster of nct CTAs (run-time cluster dimension, 1..16) per node
-__global__ void __launch_bounds__( HQ_BIG_THREADS ) k_hq_level( HQArgs A, const HQTask* cur, HQTask* next, const uint32_t nct )
+__global__ void __launch_bounds__( HQ_BIG_THREADS, 3 ) k_hq_level( HQArgs A, const HQTask* cur, HQTask* next, const uint32_t nct )
 {
 	__shared__ GroupSmem S;
 	__shared__ uint32_t job[3 * HQ_MLP * HQ_BIG_THREADS];
@@ -973,7 +976,7 @@ __global__ void __launch_bounds__( HQ_BIG_THREADS ) k_hq_level( HQArgs A, const 
 	if (split && g.rank == 0 && threadIdx.x == 0) hq_enqueue( A, next, l ), hq_enqueue( A, next, r );
 }
 
-__global__ void __launch_bounds__( HQ_SMALL_WARPS * 32 ) k_hq_subtrees( HQArgs A, const uint32_t roots )
+__global__ void __launch_bounds__( HQ_SMALL_WARPS * 32, 6 ) k_hq_subtrees( HQArgs A, const uint32_t roots )
 {
 	__shared__ GroupSmem Ss[HQ_SMALL_WARPS];
 	__shared__ HQTask stack[HQ_SMALL_WARPS][HQ_STACK];
