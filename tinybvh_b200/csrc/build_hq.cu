@@ -360,10 +360,17 @@ template <int G> __device__ __forceinline__ void bins_merge( const Grp& g )
 			atomicAdd( &(&D.cntA[0][0])[k], (&S.cntA[0][0])[k] ), atomicAdd( &(&D.cntB[0][0])[k], (&S.cntB[0][0])[k] );
 	}
 }
+// Shared atomics are the scarce resource of the binning loops (8192 of them per 256-thread trip), and after the first few
+// fragments of a bin almost none of them changes anything: look first (a stale value only errs towards doing the atomic).
 __device__ __forceinline__ void bin_grow( GroupSmem& S, const uint32_t a, const uint32_t b, const float* mn, const float* mx )
 {
 	#pragma unroll
-	for (int k = 0; k < 3; k++) atomicMin( &S.kmin[a][b][k], f2key( mn[k] ) ), atomicMax( &S.kmax[a][b][k], f2key( mx[k] ) );
+	for (int k = 0; k < 3; k++)
+	{
+		const uint32_t lo = f2key( mn[k] ), hi = f2key( mx[k] );
+		if (lo < *(volatile uint32_t*)&S.kmin[a][b][k]) atomicMin( &S.kmin[a][b][k], lo );
+		if (hi > *(volatile uint32_t*)&S.kmax[a][b][k]) atomicMax( &S.kmax[a][b][k], hi );
+	}
 }
 
 // One warp (all 32 lanes): the 21 candidate planes (a, i) of a node from its bin tables - prefix / suffix unions, areas,
@@ -826,14 +833,44 @@ template <int G> __device__ bool hq_node( const HQArgs& A, const Grp& g, const H
 		for (int k = tid; k < 12; k += G) S.ckey[k] = ((k / 3) & 1) ? f2key( -BVH_FAR ) : f2key( BVH_FAR );
 		gsync<G>( g );
 		const uint32_t nl = Apos - t.sliceStart, nr = t.sliceEnd - Bpos;
-		for (uint32_t i = gtid; i < nl + nr; i += GT)
 		{
-			const bool right = i >= nl;
-			const uint32_t fr = A.idx_tmp[right ? Bpos + (i - nl) : t.sliceStart + i];
-			const float4 fa = A.frag_min[fr], fb = A.frag_max[fr];
-			uint32_t* kk = S.ckey + (right ? 6 : 0);
-			atomicMin( kk + 0, f2key( fa.x ) ), atomicMin( kk + 1, f2key( fa.y ) ), atomicMin( kk + 2, f2key( fa.z ) );
-			atomicMax( kk + 3, f2key( fb.x ) ), atomicMax( kk + 4, f2key( fb.y ) ), atomicMax( kk + 5, f2key( fb.z ) );
+			// per-thread boxes over its fragments, one redux per word and warp, one shared atomic per word and warp
+			uint32_t bk[12];
+			#pragma unroll
+			for (int k = 0; k < 12; k++) bk[k] = ((k / 3) & 1) ? f2key( -BVH_FAR ) : f2key( BVH_FAR );
+			for (uint32_t base = 0; base < nl + nr; base += GT * HQ_MLP)
+			{
+				uint32_t fr[HQ_MLP];
+				#pragma unroll
+				for (int u = 0; u < HQ_MLP; u++)
+				{
+					const uint32_t i = base + gtid + u * GT;
+					fr[u] = i < nl + nr ? A.idx_tmp[i >= nl ? Bpos + (i - nl) : t.sliceStart + i] : 0xffffffffu;
+				}
+				#pragma unroll
+				for (int u = 0; u < HQ_MLP; u++) if (fr[u] != 0xffffffffu)
+				{
+					const float4 fa = A.frag_min[fr[u]], fb = A.frag_max[fr[u]];
+					const uint32_t ka[6] = { f2key( fa.x ), f2key( fa.y ), f2key( fa.z ), f2key( fb.x ), f2key( fb.y ), f2key( fb.z ) };
+					if (base + gtid + u * GT >= nl)
+					{
+						#pragma unroll
+						for (int q = 0; q < 3; q++) bk[6 + q] = min( bk[6 + q], ka[q] ), bk[9 + q] = max( bk[9 + q], ka[3 + q] );
+					}
+					else
+					{
+						#pragma unroll
+						for (int q = 0; q < 3; q++) bk[q] = min( bk[q], ka[q] ), bk[3 + q] = max( bk[3 + q], ka[3 + q] );
+					}
+				}
+			}
+			__syncwarp();
+			#pragma unroll
+			for (int k = 0; k < 12; k++)
+			{
+				const uint32_t r = ((k / 3) & 1) ? __reduce_max_sync( 0xffffffffu, bk[k] ) : __reduce_min_sync( 0xffffffffu, bk[k] );
+				if ((tid & 31) == 0) { if ((k / 3) & 1) atomicMax( &S.ckey[k], r ); else atomicMin( &S.ckey[k], r ); }
+			}
 		}
 		if (G != 32 && g.nct > 1)
 		{
@@ -1072,7 +1109,7 @@ int build_hq_launch( tbvh_bvh b, float c_trav, float c_int )
 		A.small_t = (uint32_t)(t < 8 ? 8 : t > HQ_SMALL_MAX ? HQ_SMALL_MAX : t);
 	}
 	A.lvl_cap = A.idx_cap / A.small_t + 2;
-	{ const char* e = getenv( "TBVH_HQ_PROFILE" ); A.profile = e && atoi( e ) ? 1u : 0u; }
+	{ const char* e = getenv( "TBVH_HQ_PROFILE" ); A.profile = e ? (uint32_t)atoi( e ) : 0u; }
 	HQCounters* h_ctr = 0;
 	cudaEvent_t e0 = 0, e1 = 0;
 	CUDA_TRY( cudaMalloc( &b->d_nodes, (size_t)A.node_cap * 32 ) );
@@ -1117,6 +1154,14 @@ int build_hq_launch( tbvh_bvh b, float c_trav, float c_int )
 			CUDA_TRY( cudaLaunchKernelEx( &cfg, k_hq_level, A, (const HQTask*)A.lvl[level & 1], A.lvl[(level + 1) & 1], nct ) ); LAUNCHED();
 			CUDA_TRY( cudaMemcpyAsync( h_ctr, A.ctr, sizeof( HQCounters ), cudaMemcpyDeviceToHost, s ) );
 			CUDA_TRY( cudaStreamSynchronize( s ) );
+			if (A.profile > 1)
+			{
+				static unsigned long long prev[12];
+				if (level == 0) memset( prev, 0, sizeof( prev ) );
+				fprintf( stderr, "hq-level %2u nodes %5u nct %2u max %7u:", level, num, nct, max_count );
+				for (int k = 0; k < 12; k++) { fprintf( stderr, " %7.1f", (h_ctr->prof[k] - prev[k]) * 1e-3 / num ); prev[k] = h_ctr->prof[k]; }
+				fprintf( stderr, "  kcyc/node\n" );
+			}
 			num = h_ctr->next_big, max_count = h_ctr->next_max;
 			if (h_ctr->overflow) { tbvh_set_error( "BuildHQ: pool overflow in the level phase" ); return TBVH_E_LIMIT; }
 			if (++level > 4096) { tbvh_set_error( "BuildHQ: runaway level count" ); return TBVH_E_LIMIT; }
