@@ -97,6 +97,14 @@ protected:
 		usedNodes = layout == TBVH_LAYOUT_BVH_GPU ? i.used_nodes_gpu : i.used_nodes, triCount = i.prim_count, idxCount = i.idx_count, buildMs = i.build_ms;
 		memcpy( aabbMin, i.aabb_min, 12 ), memcpy( aabbMax, i.aabb_max, 12 );
 	}
+	// the ( vertices, indices, primCount ) overloads (tiny_bvh.h:889-900, 1111-1117, 1145-1150): the reference takes no vertex
+	// count there, so it is derived from the largest index
+	template <class Vec4> void build_indexed( const Vec4* vertices, const uint32_t* indices, const uint32_t primCount, const int flavour, const char* what )
+	{
+		uint32_t vmax = 0;
+		for (size_t i = 0; i < (size_t)primCount * 3; i++) vmax = indices[i] > vmax ? indices[i] : vmax;
+		TBVH_FATAL_IF( tbvh_build_indexed( h, vertices, (uint32_t)sizeof( Vec4 ), vmax + 1, indices, primCount, TBVH_HOST, c_trav, c_int, flavour ), what );
+	}
 	void adopt( const BVHBase& o ) { if (own) tbvh_bvh_destroy( h ); h = o.h, own = false; } // "both must be kept alive" (README.md:99)
 	tbvh_bvh h = 0;
 	int layout;
@@ -127,6 +135,10 @@ public:
 		TBVH_FATAL_IF( tbvh_build_flavour( h, vertices, (uint32_t)sizeof( Vec4 ), primCount, TBVH_HOST, c_trav, c_int, TBVH_BUILD_HQ ), "BVH::BuildHQ" );
 		sync_info();
 	}
+	// indexed geometry: BVH::Build / BuildAVX / BuildHQ( vertices, indices, primCount ) tiny_bvh.h:889-900
+	template <class Vec4> void Build( const Vec4* vertices, const uint32_t* indices, const uint32_t primCount ) { build_indexed( vertices, indices, primCount, TBVH_BUILD_REFERENCE, "BVH::Build" ); sync_info(); }
+	template <class Vec4> void BuildAVX( const Vec4* vertices, const uint32_t* indices, const uint32_t primCount ) { build_indexed( vertices, indices, primCount, TBVH_BUILD_AVX, "BVH::BuildAVX" ); sync_info(); }
+	template <class Vec4> void BuildHQ( const Vec4* vertices, const uint32_t* indices, const uint32_t primCount ) { build_indexed( vertices, indices, primCount, TBVH_BUILD_HQ, "BVH::BuildHQ" ); sync_info(); }
 	// consume / produce the reference's public arrays (bvhNode, primIdx: tiny_bvh.h:952-964)
 	template <class Vec4> void Upload( const void* bvhNode, uint32_t used, const uint32_t* primIdx, uint32_t idxCnt, const Vec4* vertices, uint32_t primCount )
 	{
@@ -145,6 +157,18 @@ public:
 		// BVH_GPU::Build -> bvh.BuildDefault = BuildAVX on x86 (tiny_bvh.h:1817-1832)
 		TBVH_FATAL_IF( tbvh_build_flavour( h, vertices, (uint32_t)sizeof( Vec4 ), primCount, TBVH_HOST, c_trav, c_int, TBVH_BUILD_AVX ), "BVH_GPU::Build" );
 		TBVH_FATAL_IF( tbvh_convert( h, TBVH_LAYOUT_BVH_GPU ), "BVH_GPU::Build" );
+		sync_info();
+	}
+	template <class Vec4> void Build( const Vec4* vertices, const uint32_t* indices, const uint32_t primCount ) // :4560
+	{
+		build_indexed( vertices, indices, primCount, TBVH_BUILD_AVX, "BVH_GPU::Build" );
+		TBVH_FATAL_IF( tbvh_convert( h, TBVH_LAYOUT_BVH_GPU ), "BVH_GPU::Build" );
+		sync_info();
+	}
+	template <class Vec4> void BuildHQ( const Vec4* vertices, const uint32_t* indices, const uint32_t primCount ) // :4594
+	{
+		build_indexed( vertices, indices, primCount, TBVH_BUILD_HQ, "BVH_GPU::BuildHQ" );
+		TBVH_FATAL_IF( tbvh_convert( h, TBVH_LAYOUT_BVH_GPU ), "BVH_GPU::BuildHQ" );
 		sync_info();
 	}
 	// BVH_GPU::BuildHQ tiny_bvh.h:4588: bvh.BuildHQ, then ConvertFrom
@@ -173,6 +197,12 @@ public:
 	{
 		// BVH8_CWBVH::Build -> bvh8.bvh.BuildDefault = BuildAVX on x86 (tiny_bvh.h:5830)
 		TBVH_FATAL_IF( tbvh_build_flavour( h, vertices, (uint32_t)sizeof( Vec4 ), primCount, TBVH_HOST, c_trav, c_int, TBVH_BUILD_AVX ), "BVH8_CWBVH::Build" );
+		TBVH_FATAL_IF( tbvh_convert( h, TBVH_LAYOUT_CWBVH ), "BVH8_CWBVH::Build" );
+		sync_info(), usedBlocks = Info().used_blocks;
+	}
+	template <class Vec4> void Build( const Vec4* vertices, const uint32_t* indices, const uint32_t primCount ) // :5836
+	{
+		build_indexed( vertices, indices, primCount, TBVH_BUILD_AVX, "BVH8_CWBVH::Build" );
 		TBVH_FATAL_IF( tbvh_convert( h, TBVH_LAYOUT_CWBVH ), "BVH8_CWBVH::Build" );
 		sync_info(), usedBlocks = Info().used_blocks;
 	}

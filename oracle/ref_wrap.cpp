@@ -60,6 +60,17 @@ void* ref_bvh_build( const float* verts, uint32_t primCount, int mode, int threa
 	else b->BuildHQ( v, primCount );
 	return b;
 }
+// the ( vertices, indices, primCount ) overloads (:2139, :6410, :2641): verts holds vertCount vertices, indices 3 * primCount entries
+void* ref_bvh_build_indexed( const float* verts, uint32_t vertCount, const uint32_t* indices, uint32_t primCount, int mode, int threaded )
+{
+	BVH* b = new BVH();
+	b->threadedBuild = threaded != 0;
+	const bvhvec4slice v( (const bvhvec4*)verts, vertCount, sizeof( bvhvec4 ) );
+	if (mode == 0) b->Build( v, indices, primCount );
+	else if (mode == 1) b->BuildAVX( v, indices, primCount );
+	else b->BuildHQ( v, indices, primCount );
+	return b;
+}
 void ref_bvh_destroy( void* h ) { delete (BVH*)h; }
 uint32_t ref_bvh_used_nodes( void* h ) { return ((BVH*)h)->usedNodes; }
 uint32_t ref_bvh_idx_count( void* h ) { return ((BVH*)h)->idxCount; }

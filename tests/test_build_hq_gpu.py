@@ -115,3 +115,35 @@ def test_derived_layouts_build_hq(gpu, scene):
     b = a.copy()
     cw.intersect(a), e.Intersect(b)
     assert util.compare_hits(b, a) == {"prim": 0, "t": 0, "u": 0, "v": 0}
+
+
+@pytest.mark.parametrize("mode,method", [(0, "Build"), (1, "BuildAVX"), (2, "BuildHQ")])
+def test_indexed_geometry_builds(gpu, mode, method):
+    """The ( vertices, indices, primCount ) overloads (tiny_bvh.h:889-900) through tbvh_build_indexed: same tree as the
+    reference builds from the shared-vertex mesh, same hits."""
+    from oracle import refpy
+    from tests.test_oracle_pin import indexed_mesh
+    if not refpy.available():
+        pytest.skip("needs oracle/_ref")
+    flat, verts, idx = indexed_mesh(20000, 43)
+    ref = refpy.RefBVH(verts, mode=mode, threaded=False, indices=idx)
+    e = getattr(api.BVH(), method)(verts, indices=idx)
+    nodes, pidx = e.download()
+    assert e.info().prim_count == 20000
+    assert np.array_equal(nodes.view(np.uint32), ref.nodes.view(np.uint32)), f"{method}( vertices, indices ): node array differs"
+    used = int(ref.nodes["triCount"].sum())
+    assert np.array_equal(pidx[:used], ref.prim_idx[:used])
+    lo, hi = scenes.scene_bounds(flat)
+    want = R.primary_rays(*R.bounds_camera(lo, hi, "outside"), 64, 64, 4)
+    got = want.copy()
+    ref.intersect(want), e.Intersect(got)
+    assert util.compare_hits(got, want) == {"prim": 0, "t": 0, "u": 0, "v": 0}
+
+
+def test_indexed_build_rejects_bad_index(gpu):
+    verts = np.zeros((4, 4), np.float32)
+    verts[1, 0] = verts[2, 1] = verts[3, 2] = 1
+    with pytest.raises(api.TbvhError):
+        api.BVH().Build(verts, indices=np.array([0, 1, 2, 1, 2, 7], np.uint32))
+    e = api.BVH().Build(verts, indices=np.array([0, 1, 2, 1, 2, 3], np.uint32))
+    assert e.info().prim_count == 2 and e.info().used_nodes == 2

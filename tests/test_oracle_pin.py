@@ -144,3 +144,32 @@ def test_port_clip_and_split_frag_match_reference():
         pos = np.float32(fr["bmin"][0][axis] + ext[axis] * rng.random())
         sr, sp = ref.split_frag(fr, min_dim, axis, pos), portpy.split_frag(v, fr, min_dim, axis, pos)
         assert sr[:2] == sp[:2] and sr[2].tobytes() == sp[2].tobytes() and sr[3].tobytes() == sp[3].tobytes()
+
+
+def indexed_mesh(ntris, seed):
+    """A shared-vertex version of a procedural soup: unique vertices + an index list (with a shuffled vertex order)."""
+    v = scenes.procedural_scene(ntris, seed=seed)
+    uniq, inv = np.unique(v.view(np.uint32).reshape(-1, 4), axis=0, return_inverse=True)
+    perm = np.random.default_rng(seed).permutation(uniq.shape[0])
+    rank = np.empty_like(perm)
+    rank[perm] = np.arange(perm.shape[0])
+    return v, uniq[perm].view(np.float32), rank[inv.reshape(-1)].astype(np.uint32)
+
+
+@pytest.mark.skipif(not refpy.available(), reason="oracle/_ref not built (needs /root/reference)")
+@pytest.mark.parametrize("mode", [0, 1, 2])
+def test_reference_indexed_build_equals_flat_build(mode):
+    """What tbvh_build_indexed relies on: Build / BuildAVX / BuildHQ( vertices, indices, n ) (tiny_bvh.h:889-900) produce the
+    tree of the flat soup verts[indices] - PrepareBuild only differs in where it reads the three vertices (:2290-2308)."""
+    flat, verts, idx = indexed_mesh(3000, 41)
+    assert np.array_equal(verts[idx].view(np.uint32), flat.view(np.uint32))
+    a = refpy.RefBVH(flat, mode=mode, threaded=False)
+    b = refpy.RefBVH(verts, mode=mode, threaded=False, indices=idx)
+    assert np.array_equal(a.nodes.view(np.uint32), b.nodes.view(np.uint32))
+    used = int(a.nodes["triCount"].sum())
+    assert np.array_equal(a.prim_idx[:used], b.prim_idx[:used])
+    r = R.make_rays(np.tile(np.array([[0.1, 0.2, -30.0]], np.float32), (64, 1)),
+                    np.random.default_rng(3).normal(size=(64, 3)).astype(np.float32) * 0.1 + np.array([0, 0, 1], np.float32))
+    ra, rb = r.copy(), r.copy()
+    a.intersect(ra, threads=1), b.intersect(rb, threads=1)
+    assert np.array_equal(G.hits_as_u32(ra), G.hits_as_u32(rb))

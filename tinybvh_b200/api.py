@@ -72,6 +72,21 @@ class _Base:
         check(_lib.lib().tbvh_bvh_create(self.ctx, C.byref(self.h)))
         self.c_trav, self.c_int = 1.0, 1.0  # BVHBase::c_trav / c_int (:819-820)
 
+    def _build(self, vertices, primCount, flavour, indices=None):
+        """tbvh_build_flavour, or tbvh_build_indexed for the (vertices, indices, primCount) overloads (tiny_bvh.h:889-900)."""
+        p, stride, nv, space, keep = _verts_arg(vertices)
+        if indices is None:
+            check(_lib.lib().tbvh_build_flavour(self.h, p, stride, primCount or nv // 3, space, self.c_trav, self.c_int, flavour))
+            return
+        if _is_torch(indices):
+            assert space == DEVICE and indices.is_cuda and indices.is_contiguous() and indices.element_size() == 4
+            ip, ni = C.c_void_p(indices.data_ptr()), indices.numel()
+        else:
+            assert space == HOST, "device vertices need device indices"
+            indices = np.ascontiguousarray(indices, np.uint32).reshape(-1)
+            ip, ni = _np_ptr(indices), indices.shape[0]
+        check(_lib.lib().tbvh_build_indexed(self.h, p, stride, nv, ip, primCount or ni // 3, space, self.c_trav, self.c_int, flavour))
+
     def __del__(self):
         try:
             if getattr(self, "h", None) and self.h.value:
@@ -150,22 +165,19 @@ class BVH(_Base):
     """tinybvh::BVH (tiny_bvh.h:846-985): Wald 32-byte nodes; binned-SAH Build on the GPU."""
     layout = LAYOUT_BVH
 
-    def Build(self, vertices, primCount: int = 0):
-        p, stride, nv, space, keep = _verts_arg(vertices)
-        n = primCount or nv // 3
-        check(_lib.lib().tbvh_build(self.h, p, stride, n, space, self.c_trav, self.c_int))
+    def Build(self, vertices, primCount: int = 0, indices=None):
+        """BVH::Build( vertices, primCount ) :2124 / ( vertices, indices, primCount ) :2139."""
+        self._build(vertices, primCount, _lib.BUILD_REFERENCE, indices)
         return self
 
-    def BuildAVX(self, vertices, primCount: int = 0):
+    def BuildAVX(self, vertices, primCount: int = 0, indices=None):
         """BVH::BuildAVX (tiny_bvh.h:6400) - the flavour BuildDefault uses on x86."""
-        p, stride, nv, space, keep = _verts_arg(vertices)
-        check(_lib.lib().tbvh_build_flavour(self.h, p, stride, primCount or nv // 3, space, self.c_trav, self.c_int, _lib.BUILD_AVX))
+        self._build(vertices, primCount, _lib.BUILD_AVX, indices)
         return self
 
-    def BuildHQ(self, vertices, primCount: int = 0):
+    def BuildHQ(self, vertices, primCount: int = 0, indices=None):
         """BVH::BuildHQ (tiny_bvh.h:2623): SBVH with spatial splits; idxCount becomes primCount + primCount/2."""
-        p, stride, nv, space, keep = _verts_arg(vertices)
-        check(_lib.lib().tbvh_build_flavour(self.h, p, stride, primCount or nv // 3, space, self.c_trav, self.c_int, _lib.BUILD_HQ))
+        self._build(vertices, primCount, _lib.BUILD_HQ, indices)
         return self
 
     def upload(self, nodes, primIdx, vertices):
@@ -190,17 +202,15 @@ class BVH_GPU(_Base):
     """tinybvh::BVH_GPU (tiny_bvh.h:1092-1127): Aila-Laine 64-byte nodes."""
     layout = LAYOUT_BVH_GPU
 
-    def Build(self, vertices, primCount: int = 0):
-        p, stride, nv, space, keep = _verts_arg(vertices)
+    def Build(self, vertices, primCount: int = 0, indices=None):
         # BVH_GPU::Build -> bvh.BuildDefault (tiny_bvh.h:4580-4590) = BuildAVX on x86, then ConvertFrom
-        check(_lib.lib().tbvh_build_flavour(self.h, p, stride, primCount or nv // 3, space, self.c_trav, self.c_int, self.build_flavour))
+        self._build(vertices, primCount, self.build_flavour, indices)
         check(_lib.lib().tbvh_convert(self.h, LAYOUT_BVH_GPU))
         return self
 
-    def BuildHQ(self, vertices, primCount: int = 0):
+    def BuildHQ(self, vertices, primCount: int = 0, indices=None):
         """BVH_GPU::BuildHQ (tiny_bvh.h:4588): bvh.BuildHQ, then ConvertFrom."""
-        p, stride, nv, space, keep = _verts_arg(vertices)
-        check(_lib.lib().tbvh_build_flavour(self.h, p, stride, primCount or nv // 3, space, self.c_trav, self.c_int, _lib.BUILD_HQ))
+        self._build(vertices, primCount, _lib.BUILD_HQ, indices)
         check(_lib.lib().tbvh_convert(self.h, LAYOUT_BVH_GPU))
         return self
 
@@ -223,17 +233,15 @@ class BVH8_CWBVH(_Base):
     """tinybvh::BVH8_CWBVH (tiny_bvh.h:1334-1362): 80-byte compressed wide nodes + 48-byte triangles."""
     layout = LAYOUT_CWBVH
 
-    def Build(self, vertices, primCount: int = 0):
-        p, stride, nv, space, keep = _verts_arg(vertices)
+    def Build(self, vertices, primCount: int = 0, indices=None):
         # BVH8_CWBVH::Build -> bvh8.bvh.BuildDefault (tiny_bvh.h:5830) = BuildAVX on x86, then the conversion chain
-        check(_lib.lib().tbvh_build_flavour(self.h, p, stride, primCount or nv // 3, space, self.c_trav, self.c_int, self.build_flavour))
+        self._build(vertices, primCount, self.build_flavour, indices)
         check(_lib.lib().tbvh_convert(self.h, LAYOUT_CWBVH))
         return self
 
-    def BuildHQ(self, vertices, primCount: int = 0):
+    def BuildHQ(self, vertices, primCount: int = 0, indices=None):
         """BVH8_CWBVH::BuildHQ (tiny_bvh.h:5859): bvh.BuildHQ, SplitLeafs(3), 8-wide collapse, CWBVH encode."""
-        p, stride, nv, space, keep = _verts_arg(vertices)
-        check(_lib.lib().tbvh_build_flavour(self.h, p, stride, primCount or nv // 3, space, self.c_trav, self.c_int, _lib.BUILD_HQ))
+        self._build(vertices, primCount, _lib.BUILD_HQ, indices)
         check(_lib.lib().tbvh_convert(self.h, LAYOUT_CWBVH))
         return self
 

@@ -174,6 +174,51 @@ static int upload_verts( tbvh_bvh b, const void* verts, uint32_t stride, uint32_
 	return TBVH_OK;
 }
 
+// indexed geometry (the `vertices, indices, primCount` overloads, tiny_bvh.h:889-900): the engine keeps its own copy of
+// the vertices anyway, so the indices are resolved once, on the device, into the flat 3-vertices-per-triangle array the
+// kernels read.  The tree is the one the reference builds with vertIdx set (same fragments, same primIdx numbering).
+__global__ void k_gather_verts( const float4* __restrict__ src, const uint32_t* __restrict__ indices, float4* __restrict__ dst, const uint32_t n, const uint32_t vert_count, uint32_t* bad )
+{
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	const uint32_t v = indices[i];
+	if (v >= vert_count) { atomicAdd( bad, 1u ); dst[i] = make_float4( 0, 0, 0, 0 ); return; }
+	dst[i] = src[v];
+}
+static int upload_verts_indexed( tbvh_bvh b, const void* verts, uint32_t stride, uint32_t vert_count, const uint32_t* indices, uint32_t prim_count, int space, cudaStream_t s )
+{
+	ARG_CHECK( verts && indices && stride >= 12 && (stride & 3) == 0 && prim_count > 0 && vert_count > 0, "bad indexed vertex slice" );
+	const size_t nv = (size_t)prim_count * 3;
+	const cudaMemcpyKind kind = space == TBVH_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+	float4* d_src = 0; uint32_t* d_idx = 0; uint32_t* d_bad = 0;
+	int rc = TBVH_OK;
+	auto body = [&]() -> int
+	{
+		CUDA_TRY( cudaMalloc( &d_src, (size_t)vert_count * 16 ) );
+		CUDA_TRY( cudaMalloc( &d_idx, nv * 4 ) );
+		CUDA_TRY( cudaMalloc( &d_bad, 4 ) );
+		CUDA_TRY( cudaMalloc( &b->d_verts, nv * 16 ) );
+		CUDA_TRY( cudaMemsetAsync( d_bad, 0, 4, s ) );
+		if (stride == 16) CUDA_TRY( cudaMemcpyAsync( d_src, verts, (size_t)vert_count * 16, kind, s ) );
+		else
+		{
+			CUDA_TRY( cudaMemsetAsync( d_src, 0, (size_t)vert_count * 16, s ) );
+			CUDA_TRY( cudaMemcpy2DAsync( d_src, 16, verts, stride, stride < 16 ? stride : 16, vert_count, kind, s ) );
+		}
+		CUDA_TRY( cudaMemcpyAsync( d_idx, indices, nv * 4, kind, s ) );
+		k_gather_verts<<<(unsigned)((nv + 255) / 256), 256, 0, s>>>( d_src, d_idx, b->d_verts, (uint32_t)nv, vert_count, d_bad ); LAUNCHED();
+		uint32_t bad = 0;
+		CUDA_TRY( cudaMemcpyAsync( &bad, d_bad, 4, cudaMemcpyDeviceToHost, s ) );
+		CUDA_TRY( cudaStreamSynchronize( s ) );
+		if (bad) { tbvh_set_error( "indexed build: %u indices point past the %u vertices", bad, vert_count ); return TBVH_E_ARG; }
+		return TBVH_OK;
+	};
+	rc = body();
+	cudaFree( d_src ), cudaFree( d_idx ), cudaFree( d_bad );
+	b->info.prim_count = prim_count;
+	return rc;
+}
+
 static uint32_t depth_of_bvh( const uint32_t* nodes /* 8 words per node */, uint32_t used_nodes )
 {
 	// iterative DFS over Wald nodes; returns the depth of the deepest node (root = 0)
@@ -302,6 +347,19 @@ int tbvh_build_flavour( tbvh_bvh b, const void* verts, uint32_t stride, uint32_t
 	CUDA_TRY( cudaSetDevice( b->ctx->device ) );
 	free_layouts( b );
 	TRY( upload_verts( b, verts, stride, prim_count, space, b->ctx->stream ) );
+	if (flavour == TBVH_BUILD_HQ) TRY( build_hq_launch( b, c_trav, c_int ) ); else TRY( build_sah_launch( b, c_trav, c_int, flavour ) );
+	b->info.layouts = 1u << TBVH_LAYOUT_BVH;
+	return TBVH_OK;
+}
+
+int tbvh_build_indexed( tbvh_bvh b, const void* verts, uint32_t stride, uint32_t vert_count, const uint32_t* indices, uint32_t prim_count, int space,
+	float c_trav, float c_int, int flavour )
+{
+	ARG_CHECK( b, "NULL handle" );
+	ARG_CHECK( flavour == TBVH_BUILD_REFERENCE || flavour == TBVH_BUILD_AVX || flavour == TBVH_BUILD_HQ, "unknown builder flavour" );
+	CUDA_TRY( cudaSetDevice( b->ctx->device ) );
+	free_layouts( b );
+	TRY( upload_verts_indexed( b, verts, stride, vert_count, indices, prim_count, space, b->ctx->stream ) );
 	if (flavour == TBVH_BUILD_HQ) TRY( build_hq_launch( b, c_trav, c_int ) ); else TRY( build_sah_launch( b, c_trav, c_int, flavour ) );
 	b->info.layouts = 1u << TBVH_LAYOUT_BVH;
 	return TBVH_OK;
