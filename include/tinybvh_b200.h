@@ -102,6 +102,11 @@ int tbvh_build_flavour( tbvh_bvh bvh, const void* verts, uint32_t stride, uint32
 int tbvh_build_indexed( tbvh_bvh bvh, const void* verts, uint32_t stride, uint32_t vert_count, const uint32_t* indices, uint32_t prim_count, int space,
 	float c_trav, float c_int, int flavour );
 
+/* BVH::Refit (tiny_bvh.h:3055-3093): the triangles moved, the topology stays - leaf boxes from the new vertices, interior
+ * boxes bottom-up.  verts as for tbvh_build, same prim_count.  TBVH_E_STATE for an SBVH (the reference's fatal "refitting an
+ * SBVH") or when no BVH-layout tree is resident.  Derived layouts on the handle are dropped; tbvh_convert again. */
+int tbvh_refit( tbvh_bvh bvh, const void* verts, uint32_t stride, uint32_t prim_count, int space );
+
 /* consume a tree built elsewhere, in the reference's own layouts (the public members bvhNode / primIdx /
  * verts of tiny_bvh.h:952-964, BVH_GPU::bvhNode :1124, BVH8_CWBVH::bvh8Data / bvh8Tris :1356-1357) */
 int tbvh_upload_bvh( tbvh_bvh bvh, const void* nodes32, uint32_t used_nodes, const uint32_t* prim_idx, uint32_t idx_count,

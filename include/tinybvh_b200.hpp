@@ -121,12 +121,29 @@ public:
 	template <class Vec4> void Build( const Vec4* vertices, const uint32_t primCount )
 	{
 		TBVH_FATAL_IF( tbvh_build( h, vertices, (uint32_t)sizeof( Vec4 ), primCount, TBVH_HOST, c_trav, c_int ), "BVH::Build" );
-		sync_info();
+		remember( vertices, (uint32_t)sizeof( Vec4 ), 0, primCount ), sync_info();
 	}
 	// BVH::BuildAVX( const bvhvec4*, uint32_t ) tiny_bvh.h:6400 - the flavour BuildDefault picks on x86
 	template <class Vec4> void BuildAVX( const Vec4* vertices, const uint32_t primCount )
 	{
 		TBVH_FATAL_IF( tbvh_build_flavour( h, vertices, (uint32_t)sizeof( Vec4 ), primCount, TBVH_HOST, c_trav, c_int, TBVH_BUILD_AVX ), "BVH::BuildAVX" );
+		remember( vertices, (uint32_t)sizeof( Vec4 ), 0, primCount ), sync_info();
+	}
+	// BVH::Refit( nodeIdx = 0 ) tiny_bvh.h:3055 - the caller moved the vertices in the array it built from; like the reference the
+	// shim kept the pointer (BVHBase::verts, "we're not copying this data" :2055), the engine receives the new positions
+	void Refit( const uint32_t = 0 )
+	{
+		if (!vertsPtr) { fprintf( stderr, "Fatal error in tinybvh_b200 BVH::Refit: nothing was built from a host vertex array.\n" ); exit( 1 ); }
+		if (!vertIdx) TBVH_FATAL_IF( tbvh_refit( h, vertsPtr, vertsStride, vertsPrims, TBVH_HOST ), "BVH::Refit" );
+		else
+		{
+			// indexed geometry: resolve the indices on the host into the flat order the engine keeps
+			float* flat = (float*)malloc( (size_t)vertsPrims * 3 * 16 );
+			for (size_t i = 0; i < (size_t)vertsPrims * 3; i++) memcpy( flat + i * 4, (const char*)vertsPtr + (size_t)vertIdx[i] * vertsStride, vertsStride < 16 ? vertsStride : 16 );
+			const int rc = tbvh_refit( h, flat, 16, vertsPrims, TBVH_HOST );
+			free( flat );
+			TBVH_FATAL_IF( rc, "BVH::Refit" );
+		}
 		sync_info();
 	}
 	// BVH::BuildHQ( const bvhvec4*, uint32_t ) tiny_bvh.h:2623 - SBVH (spatial splits), ends with Compact()
@@ -136,8 +153,8 @@ public:
 		sync_info();
 	}
 	// indexed geometry: BVH::Build / BuildAVX / BuildHQ( vertices, indices, primCount ) tiny_bvh.h:889-900
-	template <class Vec4> void Build( const Vec4* vertices, const uint32_t* indices, const uint32_t primCount ) { build_indexed( vertices, indices, primCount, TBVH_BUILD_REFERENCE, "BVH::Build" ); sync_info(); }
-	template <class Vec4> void BuildAVX( const Vec4* vertices, const uint32_t* indices, const uint32_t primCount ) { build_indexed( vertices, indices, primCount, TBVH_BUILD_AVX, "BVH::BuildAVX" ); sync_info(); }
+	template <class Vec4> void Build( const Vec4* vertices, const uint32_t* indices, const uint32_t primCount ) { build_indexed( vertices, indices, primCount, TBVH_BUILD_REFERENCE, "BVH::Build" ); remember( vertices, (uint32_t)sizeof( Vec4 ), indices, primCount ), sync_info(); }
+	template <class Vec4> void BuildAVX( const Vec4* vertices, const uint32_t* indices, const uint32_t primCount ) { build_indexed( vertices, indices, primCount, TBVH_BUILD_AVX, "BVH::BuildAVX" ); remember( vertices, (uint32_t)sizeof( Vec4 ), indices, primCount ), sync_info(); }
 	template <class Vec4> void BuildHQ( const Vec4* vertices, const uint32_t* indices, const uint32_t primCount ) { build_indexed( vertices, indices, primCount, TBVH_BUILD_HQ, "BVH::BuildHQ" ); sync_info(); }
 	// consume / produce the reference's public arrays (bvhNode, primIdx: tiny_bvh.h:952-964)
 	template <class Vec4> void Upload( const void* bvhNode, uint32_t used, const uint32_t* primIdx, uint32_t idxCnt, const Vec4* vertices, uint32_t primCount )
@@ -146,6 +163,10 @@ public:
 		sync_info();
 	}
 	void Download( void* bvhNode, uint32_t* primIdx ) const { TBVH_FATAL_IF( tbvh_download_bvh( h, bvhNode, primIdx, TBVH_HOST ), "BVH::Download" ); }
+private:
+	void remember( const void* v, uint32_t stride, const uint32_t* idx, uint32_t prims ) { vertsPtr = v, vertsStride = stride, vertIdx = idx, vertsPrims = prims; }
+	const void* vertsPtr = 0; const uint32_t* vertIdx = 0; // BVHBase::verts / vertIdx (:806-807): pointers to the caller's arrays, for Refit
+	uint32_t vertsStride = 16, vertsPrims = 0;
 };
 
 class BVH_GPU : public BVHBase

@@ -40,6 +40,7 @@ def lib():
         L.orc_occluded.restype, L.orc_occluded.argtypes = None, [vp, vp, vp, vp, u64, vp, i32]
         L.orc_tri_test.restype, L.orc_tri_test.argtypes = i32, [vp] * 5 + [f32] + [vp] * 3
         L.orc_to_bvh_gpu.restype, L.orc_to_bvh_gpu.argtypes = u32, [vp, vp]
+        L.orc_refit.restype, L.orc_refit.argtypes = None, [vp, u32, vp, vp]
         L.orc_sah_cost.restype, L.orc_sah_cost.argtypes = f32, [vp, u32, f32, f32]
         _lib = L
     return _lib
@@ -77,6 +78,12 @@ class PortBVH:
         bits = np.zeros((rays.shape[0] + 31) // 32, np.uint32)
         lib().orc_occluded(_ptr(self.nodes), _ptr(self.prim_idx), _ptr(self.verts), _ptr(rays), rays.shape[0], _ptr(bits), threads)
         return bits
+
+    def refit(self, new_verts):
+        """orc_refit: BVH::Refit with the vertex array replaced by new_verts (same topology)."""
+        self.verts = np.ascontiguousarray(new_verts, np.float32).reshape(-1, 4)
+        self.nodes = self.nodes.copy()
+        lib().orc_refit(_ptr(self.nodes), self.nodes.shape[0], _ptr(self.prim_idx), _ptr(self.verts))
 
     def to_bvh_gpu(self):
         out = np.zeros(self.nodes.shape[0], NODE64)

@@ -79,6 +79,7 @@ const void* ref_bvh_nodes( void* h ) { return ((BVH*)h)->bvhNode; }
 const uint32_t* ref_bvh_prim_idx( void* h ) { return ((BVH*)h)->primIdx; }
 float ref_bvh_sah_cost( void* h ) { return ((BVH*)h)->SAHCost(); }
 void ref_bvh_compact( void* h ) { ((BVH*)h)->Compact(); }
+void ref_bvh_refit( void* h ) { ((BVH*)h)->Refit(); } // the caller has already moved the vertices in the array the BVH points at
 void ref_bvh_split_leafs( void* h, uint32_t maxPrims ) { ((BVH*)h)->SplitLeafs( maxPrims ); }
 // wrap externally produced arrays (e.g. a GPU-built tree) so the reference can traverse / score them.
 void* ref_bvh_from_arrays( const void* nodes, uint32_t usedNodes, const uint32_t* primIdx, uint32_t idxCount, const float* verts, uint32_t primCount )

@@ -37,7 +37,7 @@ def lib():
             "ref_bvh_used_nodes": (u32, [vp]), "ref_bvh_idx_count": (u32, [vp]), "ref_bvh_tri_count": (u32, [vp]),
             "ref_bvh_nodes": (vp, [vp]), "ref_bvh_prim_idx": (vp, [vp]),
             "ref_bvh_sah_cost": (C.c_float, [vp]),
-            "ref_bvh_compact": (None, [vp]), "ref_bvh_split_leafs": (None, [vp, u32]),
+            "ref_bvh_compact": (None, [vp]), "ref_bvh_refit": (None, [vp]), "ref_bvh_split_leafs": (None, [vp, u32]),
             "ref_bvh_from_arrays": (vp, [vp, u32, vp, u32, vp, u32]),
             "ref_bvh_intersect": (None, [vp, vp, u64, i32]),
             "ref_bvh_occluded": (None, [vp, vp, u64, vp, i32]),
@@ -98,7 +98,7 @@ class RefBVH(_Traceable):
         if _handle is not None:
             self.h, self._own = _handle, False
             return
-        self.verts = np.ascontiguousarray(verts, np.float32).reshape(-1, 4)
+        self.verts = np.array(verts, np.float32, copy=True).reshape(-1, 4)   # own copy: refit() overwrites it in place
         if indices is None:
             self.h = lib().ref_bvh_build(_ptr(self.verts), self.verts.shape[0] // 3, mode, int(threaded))
         else:  # the ( vertices, indices, primCount ) overloads; the object keeps both arrays alive (the reference keeps pointers)
@@ -146,6 +146,11 @@ class RefBVH(_Traceable):
 
     def sah_cost(self):
         return float(lib().ref_bvh_sah_cost(self.h))
+
+    def refit(self, new_verts):
+        """BVH::Refit (:3055): the reference reads the vertex array it was built from - overwrite it in place, then refit."""
+        self.verts[...] = np.asarray(new_verts, np.float32).reshape(self.verts.shape)
+        lib().ref_bvh_refit(self.h)
 
     def compact(self):
         lib().ref_bvh_compact(self.h)

@@ -398,6 +398,35 @@ static float sah_rec( const orc_node* nodes, uint32_t i, float c_trav, float c_i
 	if (n->triCount > 0) return c_int * sa * n->triCount;
 	return c_trav * sa + sah_rec( nodes, n->leftFirst, c_trav, c_int ) + sah_rec( nodes, n->leftFirst + 1, c_trav, c_int );
 }
+/* BVH::Refit :3055-3093 (no vertIdx): nodes backwards, leaves from their triangles' current vertices, interior nodes from
+ * their children; node 1 is skipped. */
+void orc_refit( orc_node* nodes, uint32_t usedNodes, const uint32_t* primIdx, const float* verts )
+{
+	for (int32_t i = (int32_t)usedNodes - 1; i >= 0; i--) if (i != 1)
+	{
+		orc_node* n = &nodes[i];
+		if (n->triCount)
+		{
+			float bmin[3] = { BVH_FAR, BVH_FAR, BVH_FAR }, bmax[3] = { -BVH_FAR, -BVH_FAR, -BVH_FAR };
+			for (uint32_t j = 0; j < n->triCount; j++)
+			{
+				const float* v0 = verts + (size_t)primIdx[n->leftFirst + j] * 12, * v1 = v0 + 4, * v2 = v0 + 8;
+				for (int a = 0; a < 3; a++)
+				{
+					const float t1 = v0[a] < bmin[a] ? v0[a] : bmin[a], t2 = v0[a] > bmax[a] ? v0[a] : bmax[a];
+					const float t3 = v1[a] < v2[a] ? v1[a] : v2[a], t4 = v1[a] > v2[a] ? v1[a] : v2[a];
+					bmin[a] = t1 < t3 ? t1 : t3, bmax[a] = t2 > t4 ? t2 : t4;
+				}
+			}
+			n->minx = bmin[0], n->miny = bmin[1], n->minz = bmin[2], n->maxx = bmax[0], n->maxy = bmax[1], n->maxz = bmax[2];
+			continue;
+		}
+		const orc_node* l = &nodes[n->leftFirst], * r = l + 1;
+		n->minx = l->minx < r->minx ? l->minx : r->minx, n->miny = l->miny < r->miny ? l->miny : r->miny, n->minz = l->minz < r->minz ? l->minz : r->minz;
+		n->maxx = l->maxx > r->maxx ? l->maxx : r->maxx, n->maxy = l->maxy > r->maxy ? l->maxy : r->maxy, n->maxz = l->maxz > r->maxz ? l->maxz : r->maxz;
+	}
+}
+
 float orc_sah_cost( const orc_node* nodes, uint32_t nodeIdx, float c_trav, float c_int )
 {
 	const orc_node* n = &nodes[nodeIdx];

@@ -47,6 +47,9 @@ int orc_tri_test( const float* O, const float* D, const float* v0, const float* 
 /* BVH_GPU::ConvertFrom (:4612): DFS re-layout into 64-byte Aila-Laine nodes. Returns usedNodes. */
 uint32_t orc_to_bvh_gpu( const orc_node* nodes, orc_node_gpu* out );
 
+/* BVH::Refit (:3055-3093), flat (non-indexed) geometry: boxes recomputed in place from verts (primCount*3 float4) */
+void orc_refit( orc_node* nodes, uint32_t usedNodes, const uint32_t* primIdx, const float* verts );
+
 /* BVH::SAHCost (:1889) */
 float orc_sah_cost( const orc_node* nodes, uint32_t nodeIdx, float c_trav, float c_int );
 

@@ -173,3 +173,24 @@ def test_reference_indexed_build_equals_flat_build(mode):
     ra, rb = r.copy(), r.copy()
     a.intersect(ra, threads=1), b.intersect(rb, threads=1)
     assert np.array_equal(G.hits_as_u32(ra), G.hits_as_u32(rb))
+
+
+def moved(v, seed, amp=0.02):
+    """The same triangles, every vertex displaced a little (an animation frame)."""
+    rng = np.random.default_rng(seed)
+    w = v.copy()
+    ext = float((v[:, :3].max(0) - v[:, :3].min(0)).max())
+    w[:, :3] += (rng.random((v.shape[0], 3), np.float32) - 0.5) * np.float32(amp * ext)
+    return w
+
+
+@pytest.mark.skipif(not refpy.available(), reason="oracle/_ref not built (needs /root/reference)")
+@pytest.mark.parametrize("ntris,seed", [(20000, 51), (300, 52), (1, 53)])
+def test_port_refit_matches_reference(ntris, seed):
+    v = scenes.procedural_scene(ntris, seed=seed)
+    ref, port = refpy.RefBVH(v, mode=0, threaded=False), portpy.PortBVH(v)
+    before = port.nodes.copy()
+    w = moved(v, seed)
+    ref.refit(w), port.refit(w)
+    assert np.array_equal(port.nodes.view(np.uint32), ref.nodes.view(np.uint32))
+    assert not np.array_equal(port.nodes.view(np.uint32), before.view(np.uint32))

@@ -180,6 +180,13 @@ class BVH(_Base):
         self._build(vertices, primCount, _lib.BUILD_HQ, indices)
         return self
 
+    def Refit(self, vertices):
+        """BVH::Refit (tiny_bvh.h:3055): same triangles, new positions.  The reference re-reads the caller's vertex array through
+        the pointer it kept; the engine holds its own copy, so the array is passed again."""
+        p, stride, nv, space, keep = _verts_arg(vertices)
+        check(_lib.lib().tbvh_refit(self.h, p, stride, nv // 3, space))
+        return self
+
     def upload(self, nodes, primIdx, vertices):
         """Consume a tree built elsewhere in the reference's BVH layout (bvhNode / primIdx / verts, :952-964)."""
         p, stride, nv, space, keep = _verts_arg(vertices)

@@ -127,6 +127,7 @@ static void free_layouts( tbvh_bvh b )
 	for (void* q : p) if (q) cudaFree( q );
 	b->d_verts = 0, b->d_nodes = 0, b->d_prim_idx = 0, b->d_leaf_tris = 0, b->d_nodes_gpu = 0, b->d_cw_nodes = 0, b->d_cw_tris = 0, b->d_trav = 0;
 	memset( &b->info, 0, sizeof( b->info ) );
+	b->refittable = true;
 }
 
 int tbvh_bvh_destroy( tbvh_bvh b )
@@ -348,7 +349,31 @@ int tbvh_build_flavour( tbvh_bvh b, const void* verts, uint32_t stride, uint32_t
 	free_layouts( b );
 	TRY( upload_verts( b, verts, stride, prim_count, space, b->ctx->stream ) );
 	if (flavour == TBVH_BUILD_HQ) TRY( build_hq_launch( b, c_trav, c_int ) ); else TRY( build_sah_launch( b, c_trav, c_int, flavour ) );
-	b->info.layouts = 1u << TBVH_LAYOUT_BVH;
+	b->info.layouts = 1u << TBVH_LAYOUT_BVH, b->refittable = flavour != TBVH_BUILD_HQ;
+	return TBVH_OK;
+}
+
+// BVH::Refit (tiny_bvh.h:3055): same topology, new vertex positions
+int tbvh_refit( tbvh_bvh b, const void* verts, uint32_t stride, uint32_t prim_count, int space )
+{
+	ARG_CHECK( b && verts, "NULL argument" );
+	CUDA_TRY( cudaSetDevice( b->ctx->device ) );
+	if (!(b->info.layouts & (1u << TBVH_LAYOUT_BVH)) || !b->d_nodes || b->d_trav != b->d_nodes) { tbvh_set_error( "tbvh_refit: no BVH-layout tree on this handle" ); return TBVH_E_STATE; }
+	if (!b->refittable) { tbvh_set_error( "tbvh_refit: refitting an SBVH (BVH::Refit, tiny_bvh.h:3057)" ); return TBVH_E_STATE; }
+	ARG_CHECK( prim_count == b->info.prim_count && stride >= 12 && (stride & 3) == 0, "tbvh_refit: the vertex slice must describe the same triangles" );
+	cudaStream_t s = b->ctx->stream;
+	const size_t nv = (size_t)prim_count * 3;
+	const cudaMemcpyKind kind = space == TBVH_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+	if (stride == 16) CUDA_TRY( cudaMemcpyAsync( b->d_verts, verts, nv * 16, kind, s ) );
+	else CUDA_TRY( cudaMemcpy2DAsync( b->d_verts, 16, verts, stride, stride < 16 ? stride : 16, nv, kind, s ) );
+	TRY( refit_launch( b, s ) );
+	// derived layouts describe the old boxes: drop them (the reference's BVH_GPU / BVH8_CWBVH are re-converted after a refit too)
+	if (b->d_nodes_gpu) cudaFree( b->d_nodes_gpu ), b->d_nodes_gpu = 0;
+	if (b->d_cw_nodes) cudaFree( b->d_cw_nodes ), b->d_cw_nodes = 0;
+	if (b->d_cw_tris) cudaFree( b->d_cw_tris ), b->d_cw_tris = 0;
+	b->info.layouts = 1u << TBVH_LAYOUT_BVH, b->info.used_nodes_gpu = 0, b->info.used_blocks = 0, b->info.cwbvh_tri_count = 0;
+	TRY( make_leaf_tris( b, s ) );
+	CUDA_TRY( cudaStreamSynchronize( s ) );
 	return TBVH_OK;
 }
 
@@ -361,7 +386,7 @@ int tbvh_build_indexed( tbvh_bvh b, const void* verts, uint32_t stride, uint32_t
 	free_layouts( b );
 	TRY( upload_verts_indexed( b, verts, stride, vert_count, indices, prim_count, space, b->ctx->stream ) );
 	if (flavour == TBVH_BUILD_HQ) TRY( build_hq_launch( b, c_trav, c_int ) ); else TRY( build_sah_launch( b, c_trav, c_int, flavour ) );
-	b->info.layouts = 1u << TBVH_LAYOUT_BVH;
+	b->info.layouts = 1u << TBVH_LAYOUT_BVH, b->refittable = flavour != TBVH_BUILD_HQ;
 	return TBVH_OK;
 }
 

@@ -62,6 +62,7 @@ struct tbvh_bvh_t
 	// LAYOUT_CWBVH
 	float4* d_cw_nodes = 0;    // 5 float4 per node
 	float4* d_cw_tris = 0;     // 3 float4 per triangle
+	bool refittable = true;    // BVHBase::refittable (:811): false after BuildHQ ("can't refit an SBVH", :3027)
 	// statistics
 	int stats = 0;
 	unsigned long long* d_stats = 0; // [0]=steps [1]=tris
@@ -102,6 +103,7 @@ int bvh2_trace_launch( tbvh_bvh b, const void* d_rays, uint32_t stride, void* d_
 int cwbvh_trace_launch( tbvh_bvh b, const void* d_rays, uint32_t stride, void* d_hits, uint32_t hit_stride, uint32_t* d_bits, uint64_t n, bool anyhit, cudaStream_t s );
 int build_sah_launch( tbvh_bvh b, float c_trav, float c_int, int flavour );
 int build_hq_launch( tbvh_bvh b, float c_trav, float c_int );
+int refit_launch( tbvh_bvh b, cudaStream_t s );
 int make_leaf_tris( tbvh_bvh b, cudaStream_t s );
 int bvh_gpu_to_bvh( tbvh_bvh b, uint32_t used_nodes_gpu, cudaStream_t s );
 int bvh_to_bvh_gpu( tbvh_bvh b, cudaStream_t s );
