@@ -60,6 +60,15 @@ void* ref_bvh_build( const float* verts, uint32_t primCount, int mode, int threa
 	else b->BuildHQ( v, primCount );
 	return b;
 }
+// non-default SAH constants (BVHBase::c_trav / c_int, :819-820)
+void* ref_bvh_build_costs( const float* verts, uint32_t primCount, int mode, int threaded, float c_trav, float c_int )
+{
+	BVH* b = new BVH();
+	b->threadedBuild = threaded != 0, b->c_trav = c_trav, b->c_int = c_int;
+	const bvhvec4* v = (const bvhvec4*)verts;
+	if (mode == 0) b->Build( v, primCount ); else if (mode == 1) b->BuildAVX( v, primCount ); else b->BuildHQ( v, primCount );
+	return b;
+}
 // the ( vertices, indices, primCount ) overloads (:2139, :6410, :2641): verts holds vertCount vertices, indices 3 * primCount entries
 void* ref_bvh_build_indexed( const float* verts, uint32_t vertCount, const uint32_t* indices, uint32_t primCount, int mode, int threaded )
 {

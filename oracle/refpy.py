@@ -32,6 +32,7 @@ def lib():
         sig = {
             "ref_hardware_threads": (i32, []),
             "ref_bvh_build": (vp, [vp, u32, i32, i32]),
+            "ref_bvh_build_costs": (vp, [vp, u32, i32, i32, C.c_float, C.c_float]),
             "ref_bvh_build_indexed": (vp, [vp, u32, vp, u32, i32, i32]),
             "ref_bvh_destroy": (None, [vp]),
             "ref_bvh_used_nodes": (u32, [vp]), "ref_bvh_idx_count": (u32, [vp]), "ref_bvh_tri_count": (u32, [vp]),
@@ -93,13 +94,15 @@ class RefBVH(_Traceable):
     """BVH::Build / BuildAVX / BuildHQ + BVH::Intersect / IsOccluded - THE parity oracle (mode 0)."""
     _intersect, _occluded = "ref_bvh_intersect", "ref_bvh_occluded"
 
-    def __init__(self, verts: np.ndarray = None, mode: int = 0, threaded: bool = False, _handle=None, _owner=None, indices=None):
+    def __init__(self, verts: np.ndarray = None, mode: int = 0, threaded: bool = False, _handle=None, _owner=None, indices=None, costs=None):
         self._owner = _owner
         if _handle is not None:
             self.h, self._own = _handle, False
             return
         self.verts = np.array(verts, np.float32, copy=True).reshape(-1, 4)   # own copy: refit() overwrites it in place
-        if indices is None:
+        if costs is not None:   # (c_trav, c_int)
+            self.h = lib().ref_bvh_build_costs(_ptr(self.verts), self.verts.shape[0] // 3, mode, int(threaded), float(costs[0]), float(costs[1]))
+        elif indices is None:
             self.h = lib().ref_bvh_build(_ptr(self.verts), self.verts.shape[0] // 3, mode, int(threaded))
         else:  # the ( vertices, indices, primCount ) overloads; the object keeps both arrays alive (the reference keeps pointers)
             self.indices = np.ascontiguousarray(indices, np.uint32).reshape(-1)

@@ -70,3 +70,15 @@ def test_bistro_build_hq_identical(gpu):
     assert np.array_equal(nodes.view(np.uint32), nodes_want.view(np.uint32)), "GPU-built Bistro SBVH differs from BVH::BuildHQ"
     assert np.array_equal(idx[: idx_want.shape[0]], idx_want) and not idx[idx_want.shape[0]:].any()
     print("bistro: BuildHQ", e.info().build_ms, "ms, nodes", nodes.shape[0], "refs", idx_want.shape[0], "depth", e.info().max_depth)
+
+
+@pytest.mark.skipif(not refpy.available(), reason="needs oracle/_ref")
+def test_bistro_cwbvh_build_hq(gpu):
+    """BVH8_CWBVH::BuildHQ (:5859) at Bistro's size: SBVH -> SplitLeafs(3) -> 8-wide collapse -> CWBVH, all on the GPU."""
+    v = bistro()
+    cw = refpy.RefCWBVH(v, mode=1)
+    e = api.BVH8_CWBVH().BuildHQ(v)
+    nodes, tris = e.download()
+    assert nodes.shape == cw.nodes.shape and np.array_equal(nodes.view(np.uint32), cw.nodes.view(np.uint32)), "bvh8Data differs"
+    used = int(cw.source_bvh().nodes["triCount"].sum()) * 3
+    assert np.array_equal(tris[:used].view(np.uint32), cw.tris[:used].view(np.uint32)), "bvh8Tris differs"

@@ -147,3 +147,20 @@ def test_indexed_build_rejects_bad_index(gpu):
         api.BVH().Build(verts, indices=np.array([0, 1, 2, 1, 2, 7], np.uint32))
     e = api.BVH().Build(verts, indices=np.array([0, 1, 2, 1, 2, 3], np.uint32))
     assert e.info().prim_count == 2 and e.info().used_nodes == 2
+
+
+@pytest.mark.parametrize("costs", [(1.0, 2.0), (3.0, 0.5)])
+def test_builders_with_other_sah_constants(gpu, costs):
+    """c_trav / c_int reach all three GPU builders through the C-ABI (BVHBase::c_trav / c_int, tiny_bvh.h:819-820)."""
+    from oracle import portpy
+    v = scenes.procedural_scene(40000, 62)
+    for method, avx in (("Build", False), ("BuildAVX", True)):
+        e = api.BVH()
+        e.c_trav, e.c_int = costs
+        nodes, idx = getattr(e, method)(v).download()
+        o = portpy.PortBVH(v, c_trav=costs[0], c_int=costs[1], avx=avx)
+        assert np.array_equal(nodes.view(np.uint32), o.nodes.view(np.uint32)) and np.array_equal(idx, o.prim_idx), method
+    e = api.BVH()
+    e.c_trav, e.c_int = costs
+    hn, hi, ic = portpy.build_hq(v, *costs)
+    assert_same_hq_tree(e.BuildHQ(v), hn, hi, ic, f"BuildHQ costs {costs}")

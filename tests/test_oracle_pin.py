@@ -194,3 +194,20 @@ def test_port_refit_matches_reference(ntris, seed):
     ref.refit(w), port.refit(w)
     assert np.array_equal(port.nodes.view(np.uint32), ref.nodes.view(np.uint32))
     assert not np.array_equal(port.nodes.view(np.uint32), before.view(np.uint32))
+
+
+@pytest.mark.skipif(not refpy.available(), reason="oracle/_ref not built (needs /root/reference)")
+@pytest.mark.parametrize("costs", [(1.0, 2.0), (3.0, 0.5), (0.25, 1.0)])
+def test_port_matches_reference_with_other_sah_constants(costs):
+    """BVHBase::c_trav / c_int (:819-820) enter the termination test of all three builders."""
+    v = scenes.procedural_scene(6000, seed=61)
+    for mode in (0, 1, 2):
+        ref = refpy.RefBVH(v, mode=mode, threaded=False, costs=costs)
+        if mode == 2:
+            nodes, idx, _ = portpy.build_hq(v, *costs)
+            assert np.array_equal(nodes.view(np.uint32), ref.nodes.view(np.uint32)) and np.array_equal(idx, ref.prim_idx[: idx.shape[0]])
+        else:
+            port = portpy.PortBVH(v, c_trav=costs[0], c_int=costs[1], avx=mode == 1)
+            assert np.array_equal(port.nodes.view(np.uint32), ref.nodes.view(np.uint32)) and np.array_equal(port.prim_idx, ref.prim_idx)
+    # the constants matter: the default tree is a different one
+    assert refpy.RefBVH(v, mode=0, threaded=False).used_nodes != refpy.RefBVH(v, mode=0, threaded=False, costs=costs).used_nodes
