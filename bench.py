@@ -209,12 +209,19 @@ def run_ours(args):
 
     # ---- build on rank 0 (timed separately: build Mtris/s), then ONE broadcast of the BVH over NVLink
     bvh = api.BVH(device=local)
-    build_ms, bcast_ms = None, None
+    build_ms, bcast_ms, build_hq = None, None, None
     if rank == 0:
         bvh.Build(verts)              # warm-up build (allocations, first-launch costs)
         bvh = api.BVH(device=local)
         bvh.Build(verts)
         build_ms = bvh.info().build_ms
+        # the other builder of the path, reported beside it (not part of the timed steps): BVH::BuildHQ (SBVH)
+        hq = api.BVH(device=local)
+        hq.BuildHQ(verts)
+        hq = api.BVH(device=local)
+        hq.BuildHQ(verts)
+        build_hq = {"ms": hq.info().build_ms, "mtris_per_s": ntris / hq.info().build_ms / 1e3, "nodes": hq.info().used_nodes, "idx_count": hq.info().idx_count}
+        del hq
     if world > 1:
         from tinybvh_b200 import multi
         arrays = None
@@ -361,7 +368,7 @@ def run_ours(args):
                        "bvh_built_on": "GPU (tbvh_build, binned SAH)"},
             "primary_mrays": n * world / prim_ms / 1e3, "shadow_mrays": n * world / shad_ms / 1e3,
             "build": {"ms": build_ms, "mtris_per_s": (ntris / build_ms / 1e3) if build_ms else None, "bcast_ms": bcast_ms,
-                      "bvh_bytes": bvh_bytes},
+                      "bvh_bytes": bvh_bytes, "build_hq": build_hq},
             "roofline": {"bound": "hbm", "kernel": "k_trace_cwbvh<closest>" if args.layout == "cwbvh" else "k_trace_bvh2<closest>",
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                          "peak_source": which, "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_ms": prim_ms,

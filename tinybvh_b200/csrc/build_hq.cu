@@ -1135,7 +1135,7 @@ int build_hq_launch( tbvh_bvh b, float c_trav, float c_int )
 		k_hq_fragments<<<(n + 255) / 256, 256, 0, s>>>( A ); LAUNCHED();
 		k_hq_root<<<1, 1, 0, s>>>( A ); LAUNCHED();
 		uint32_t num = n > A.small_t ? 1 : 0, level = 0, max_count = n;
-		const uint32_t max_cluster = (uint32_t)(b->ctx->hq_cluster < 1 ? 1 : b->ctx->hq_cluster > HQ_MAX_CLUSTER ? HQ_MAX_CLUSTER : b->ctx->hq_cluster);
+		uint32_t max_cluster = (uint32_t)(b->ctx->hq_cluster < 1 ? 1 : b->ctx->hq_cluster > HQ_MAX_CLUSTER ? HQ_MAX_CLUSTER : b->ctx->hq_cluster);
 		// tuning knobs of the cluster sizing rule (defaults measured on B200, profiles/README.md)
 		const char* env_cf = getenv( "TBVH_HQ_CTA_FRAGS" ); const char* env_cc = getenv( "TBVH_HQ_CTA_CAP" );
 		const size_t cta_frags = env_cf && atoi( env_cf ) > 0 ? (size_t)atoi( env_cf ) : 512, cta_cap = env_cc && atoi( env_cc ) > 0 ? (size_t)atoi( env_cc ) : 16;
@@ -1151,7 +1151,13 @@ int build_hq_launch( tbvh_bvh b, float c_trav, float c_int )
 			cfg.gridDim = dim3( num * nct ), cfg.blockDim = dim3( HQ_BIG_THREADS ), cfg.dynamicSmemBytes = 0, cfg.stream = s;
 			attr[0].id = cudaLaunchAttributeClusterDimension, attr[0].val.clusterDim.x = nct, attr[0].val.clusterDim.y = 1, attr[0].val.clusterDim.z = 1;
 			cfg.attrs = attr, cfg.numAttrs = 1;
-			CUDA_TRY( cudaLaunchKernelEx( &cfg, k_hq_level, A, (const HQTask*)A.lvl[level & 1], A.lvl[(level + 1) & 1], nct ) ); LAUNCHED();
+			{
+				// a cluster shape the device cannot co-schedule (MIG slices, fewer SMs per GPC) fails at launch: nothing has run, so
+				// fall back to the next smaller shape
+				const cudaError_t le = cudaLaunchKernelEx( &cfg, k_hq_level, A, (const HQTask*)A.lvl[level & 1], A.lvl[(level + 1) & 1], nct );
+				if (le != cudaSuccess && nct > 1) { cudaGetLastError(); max_cluster = nct >> 1; continue; }
+				CUDA_TRY( le ); LAUNCHED();
+			}
 			CUDA_TRY( cudaMemcpyAsync( h_ctr, A.ctr, sizeof( HQCounters ), cudaMemcpyDeviceToHost, s ) );
 			CUDA_TRY( cudaStreamSynchronize( s ) );
 			if (A.profile > 1)
