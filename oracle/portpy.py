@@ -40,6 +40,8 @@ def lib():
         L.orc_occluded.restype, L.orc_occluded.argtypes = None, [vp, vp, vp, vp, u64, vp, i32]
         L.orc_tri_test.restype, L.orc_tri_test.argtypes = i32, [vp] * 5 + [f32] + [vp] * 3
         L.orc_to_bvh_gpu.restype, L.orc_to_bvh_gpu.argtypes = u32, [vp, vp]
+        L.orc_intersect_tlas.restype, L.orc_intersect_tlas.argtypes = None, [vp, vp, vp, vp, vp, u64]
+        L.orc_occluded_tlas.restype, L.orc_occluded_tlas.argtypes = None, [vp, vp, vp, vp, vp, u64, vp]
         L.orc_refit.restype, L.orc_refit.argtypes = None, [vp, u32, vp, vp]
         L.orc_sah_cost.restype, L.orc_sah_cost.argtypes = f32, [vp, u32, f32, f32]
         _lib = L
@@ -92,6 +94,32 @@ class PortBVH:
 
     def sah_cost(self, c_trav=1.0, c_int=1.0):
         return float(lib().orc_sah_cost(_ptr(self.nodes), 0, c_trav, c_int))
+
+
+class PortTLAS:
+    """orc_intersect_tlas / orc_occluded_tlas: a TLAS (nodes + primIdx over instance boxes) walked with PortBVH BLASses.
+    instances: the reference's 192-byte BLASInstance records, already updated (invTransform, box)."""
+
+    def __init__(self, nodes, prim_idx, instances, blasses):
+        self.nodes = np.ascontiguousarray(nodes).view(NODE32).reshape(-1)
+        self.prim_idx = np.ascontiguousarray(prim_idx, np.uint32)
+        self.instances = np.ascontiguousarray(instances)
+        assert self.instances.dtype.itemsize == 192
+        self.blasses = list(blasses)
+        class _B(C.Structure):
+            _fields_ = [("nodes", C.c_void_p), ("primIdx", C.c_void_p), ("verts", C.c_void_p)]
+        self._table = (_B * len(self.blasses))(*[_B(b.nodes.ctypes.data, b.prim_idx.ctypes.data, b.verts.ctypes.data) for b in self.blasses])
+
+    def intersect(self, rays):
+        assert rays.dtype.itemsize == 128 and rays.flags.c_contiguous
+        lib().orc_intersect_tlas(_ptr(self.nodes), _ptr(self.prim_idx), _ptr(self.instances), C.cast(self._table, C.c_void_p), _ptr(rays), rays.shape[0])
+        return rays
+
+    def occluded(self, rays):
+        assert rays.dtype.itemsize == 128 and rays.flags.c_contiguous
+        bits = np.zeros((rays.shape[0] + 31) // 32, np.uint32)
+        lib().orc_occluded_tlas(_ptr(self.nodes), _ptr(self.prim_idx), _ptr(self.instances), C.cast(self._table, C.c_void_p), _ptr(rays), rays.shape[0], _ptr(bits))
+        return bits
 
 
 def build_hq(verts, c_trav: float = 1.0, c_int: float = 1.0):

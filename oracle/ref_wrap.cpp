@@ -135,6 +135,32 @@ void ref_split_frag( void* h, const void* orig, void* left, void* right, const f
 	*lok = l, *rok = r;
 }
 
+// ---------------------------------------------------------------- TLAS over BVH-layout BLASses
+// BVH::Build( BLASInstance*, instCount, BVHBase**, blasCount ) :2221 + IntersectTLAS :3306 / IsOccludedTLAS :3455.
+// instances: instCount records of the reference's 192-byte BLASInstance (:1443) with transform / blasIdx / mask filled in;
+// Update() (:8386) writes invTransform and the world-space box into them, as the reference's own Build does.
+static_assert( sizeof( BLASInstance ) == 192, "BLASInstance is 192 bytes" );
+struct RefTLAS { BVH tlas; std::vector<BVHBase*> blas; };
+void* ref_tlas_build( void* instances, uint32_t instCount, void** blasHandles, uint32_t blasCount )
+{
+	RefTLAS* t = new RefTLAS();
+	for (uint32_t i = 0; i < blasCount; i++) t->blas.push_back( (BVH*)blasHandles[i] );
+	t->tlas.threadedBuild = false;
+	t->tlas.Build( (BLASInstance*)instances, instCount, t->blas.data(), blasCount );
+	return t;
+}
+void ref_tlas_destroy( void* h ) { delete (RefTLAS*)h; }
+void* ref_tlas_bvh( void* h ) { return &((RefTLAS*)h)->tlas; }
+int ref_sizeof_blas_instance() { return (int)sizeof( BLASInstance ); }
+int ref_inst_idx_bits() { return INST_IDX_BITS; }
+int ref_offsetof_hit_inst() {
+#if INST_IDX_BITS == 32
+	return (int)(offsetof( Ray, hit ) + offsetof( Intersection, inst ));
+#else
+	return -1;
+#endif
+}
+
 // ---------------------------------------------------------------- BVH_GPU (Aila-Laine 64-byte nodes)
 void* ref_bvhgpu_from_bvh( void* bvh, int compact )
 {

@@ -44,6 +44,8 @@ def lib():
             "ref_bvh_occluded": (None, [vp, vp, u64, vp, i32]),
             "ref_clip_frag": (i32, [vp, vp, vp, vp, vp, vp, u32]),
             "ref_split_frag": (None, [vp, vp, vp, vp, vp, u32, C.c_float, vp, vp]),
+            "ref_tlas_build": (vp, [vp, u32, vp, u32]), "ref_tlas_destroy": (None, [vp]), "ref_tlas_bvh": (vp, [vp]),
+            "ref_sizeof_blas_instance": (i32, []), "ref_inst_idx_bits": (i32, []), "ref_offsetof_hit_inst": (i32, []),
             "ref_bvhgpu_from_bvh": (vp, [vp, i32]), "ref_bvhgpu_destroy": (None, [vp]),
             "ref_bvhgpu_used_nodes": (u32, [vp]), "ref_bvhgpu_nodes": (vp, [vp]),
             "ref_bvhgpu_intersect": (None, [vp, vp, u64, i32]),
@@ -160,6 +162,44 @@ class RefBVH(_Traceable):
 
     def split_leafs(self, n):
         lib().ref_bvh_split_leafs(self.h, n)
+
+
+# BLASInstance :1443 - 192 bytes: row-major 4x4 transform / inverse, world box, BLAS number, ray mask
+BLAS_INSTANCE = np.dtype([("transform", "16f4"), ("invTransform", "16f4"), ("aabbMin", "3f4"), ("blasIdx", "u4"),
+                          ("aabbMax", "3f4"), ("mask", "u4"), ("dummy", "8u4")])
+
+
+def make_instances(transforms, blas_idx, masks=None):
+    """BLASInstance records with transform / blasIdx / mask set and the rest at the class defaults (identity inverse, empty box)."""
+    t = np.asarray(transforms, np.float32).reshape(-1, 16)
+    inst = np.zeros(t.shape[0], BLAS_INSTANCE)
+    inst["transform"] = t
+    inst["invTransform"] = np.eye(4, dtype=np.float32).reshape(-1)
+    inst["aabbMin"], inst["aabbMax"] = 1e30, -1e30
+    inst["blasIdx"] = np.asarray(blas_idx, np.uint32)
+    inst["mask"] = 0xFFFF if masks is None else np.asarray(masks, np.uint32)
+    return inst
+
+
+class RefTLAS(_Traceable):
+    """BVH::Build( BLASInstance*, n, BVHBase**, m ) + IntersectTLAS / IsOccludedTLAS through BVH::Intersect / IsOccluded.
+    `instances` (BLAS_INSTANCE array) is updated in place by BLASInstance::Update, exactly as the reference does."""
+    _intersect, _occluded = "ref_bvh_intersect", "ref_bvh_occluded"
+
+    def __init__(self, instances: np.ndarray, blasses):
+        assert instances.dtype == BLAS_INSTANCE and instances.flags.c_contiguous
+        self.instances, self.blasses = instances, list(blasses)
+        hs = (C.c_void_p * len(self.blasses))(*[b.h for b in self.blasses])
+        self.t = lib().ref_tlas_build(_ptr(instances), instances.shape[0], hs, len(self.blasses))
+        self.h = lib().ref_tlas_bvh(self.t)
+
+    def __del__(self):
+        if getattr(self, "t", None):
+            lib().ref_tlas_destroy(self.t)
+            self.t = None
+
+    def bvh(self) -> RefBVH:
+        return RefBVH(_handle=self.h, _owner=self)
 
 
 class RefBVHGPU(_Traceable):

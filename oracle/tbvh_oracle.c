@@ -299,6 +299,7 @@ static int intersect1( const orc_node* nodes, const uint32_t* primIdx, const flo
 				{
 					if (anyhit) return 1;
 					ray->t = t, ray->u = u, ray->v = v, ray->prim = pi;
+					ray->pad = ray->instIdx; /* hit.inst = ray.instIdx (IntersectTri :8525, INST_IDX_BITS == 32): byte 44 of the record */
 				}
 			}
 			if (stackPtr == 0) break; else node = stack[--stackPtr];
@@ -361,6 +362,76 @@ void orc_occluded( const orc_node* nodes, const uint32_t* primIdx, const float* 
 }
 
 /* BVH_GPU::ConvertFrom :4612-4655 */
+/* -------------------------------------------------------------------------------------------- TLAS / BLAS
+ * BVH::IntersectTLAS :3306-3380 and IsOccludedTLAS :3455-3519 over BVH-layout BLASses (INST_IDX_BITS == 32: the instance
+ * number travels in hit.inst, byte 44 of the Ray record).  Per instance of a TLAS leaf: skip unless inst.mask & ray.mask,
+ * O' = transform_point( O, invTransform ), D' = transform_vector( D, invTransform ) (:513-527; the frozen build computes a
+ * row as fma( Tz, z, fma( Tx, x, Ty*y ) ) + Tw and divides by w only when w != 1), rD' = safercp( D' ) (:442), then the
+ * BLAS is traversed by BVH::Intersect / IsOccluded with the running hit. */
+static inline float safercp( float x ) { if (x > 1e-12f || x < -1e-12f) return 1.0f / x; else return x >= 0 ? BVH_FAR : -BVH_FAR; }
+static void transform_ray( const float* T, const orc_ray* ray, orc_ray* temp )
+{
+	const float* O = ray->O, * D = ray->D;
+	float r[3];
+	for (int k = 0; k < 3; k++) r[k] = fmaf( T[k * 4 + 2], O[2], fmaf( T[k * 4], O[0], T[k * 4 + 1] * O[1] ) ) + T[k * 4 + 3];
+	const float w = fmaf( O[2], T[14], fmaf( O[0], T[12], O[1] * T[13] ) ) + T[15];
+	if (!(w == 1)) { const float rw = 1.0f / w; for (int k = 0; k < 3; k++) r[k] = r[k] * rw; }
+	for (int k = 0; k < 3; k++)
+	{
+		temp->O[k] = r[k];
+		temp->D[k] = fmaf( T[k * 4 + 2], D[2], fmaf( T[k * 4], D[0], T[k * 4 + 1] * D[1] ) );
+		temp->rD[k] = safercp( temp->D[k] );
+	}
+}
+static int intersect_tlas1( const orc_node* nodes, const uint32_t* primIdx, const orc_instance* inst, const orc_blas* blas, orc_ray* ray, int anyhit )
+{
+	const orc_node* node = &nodes[0], * stack[64];
+	uint32_t stackPtr = 0;
+	const int pos[3] = { ray->D[0] >= 0, ray->D[1] >= 0, ray->D[2] >= 0 };
+	const float ro[3] = { ray->O[0] * ray->rD[0], ray->O[1] * ray->rD[1], ray->O[2] * ray->rD[2] };
+	while (1)
+	{
+		if (node->triCount > 0)
+		{
+			for (uint32_t i = 0; i < node->triCount; i++)
+			{
+				const uint32_t instIdx = primIdx[node->leftFirst + i];
+				const orc_instance* in = &inst[instIdx];
+				if (!(in->mask & ray->mask)) continue;
+				const orc_blas* b = &blas[in->blasIdx];
+				orc_ray temp;
+				memset( &temp, 0, sizeof( temp ) );
+				temp.mask = 0xFFFF; /* Ray() = default: mask = RAY_MASK_INTERSECT_ALL */
+				transform_ray( in->invTransform, ray, &temp );
+				temp.instIdx = instIdx; /* << (32 - INST_IDX_BITS) = << 0 */
+				temp.pad = ray->pad, temp.t = ray->t, temp.u = ray->u, temp.v = ray->v, temp.prim = ray->prim; /* temp.hit = ray.hit */
+				if (intersect1( b->nodes, b->primIdx, b->verts, &temp, anyhit )) return 1;
+				if (!anyhit) ray->pad = temp.pad, ray->t = temp.t, ray->u = temp.u, ray->v = temp.v, ray->prim = temp.prim; /* ray.hit = temp.hit */
+			}
+			if (stackPtr == 0) break; else node = stack[--stackPtr];
+			continue;
+		}
+		const orc_node* child1 = &nodes[node->leftFirst], * child2 = &nodes[node->leftFirst + 1];
+		float dist1 = slab( child1, ray->rD, ro, pos, ray->t ), dist2 = slab( child2, ray->rD, ro, pos, ray->t );
+		if (dist1 > dist2) { float t = dist1; dist1 = dist2, dist2 = t; const orc_node* c = child1; child1 = child2, child2 = c; }
+		if (dist1 == BVH_FAR) { if (stackPtr == 0) break; else node = stack[--stackPtr]; }
+		else { node = child1; if (dist2 != BVH_FAR) stack[stackPtr++] = child2; }
+	}
+	return 0;
+}
+void orc_intersect_tlas( const orc_node* nodes, const uint32_t* primIdx, const orc_instance* inst, const orc_blas* blas, void* rays, uint64_t n )
+{
+	for (uint64_t i = 0; i < n; i++) intersect_tlas1( nodes, primIdx, inst, blas, (orc_ray*)rays + i, 0 );
+}
+void orc_occluded_tlas( const orc_node* nodes, const uint32_t* primIdx, const orc_instance* inst, const orc_blas* blas, const void* rays, uint64_t n, uint32_t* bits )
+{
+	for (uint64_t i = 0; i < n; i++)
+	{
+		orc_ray tmp = ((const orc_ray*)rays)[i];
+		if (intersect_tlas1( nodes, primIdx, inst, blas, &tmp, 1 )) bits[i >> 5] |= 1u << (i & 31);
+	}
+}
+
 uint32_t orc_to_bvh_gpu( const orc_node* nodes, orc_node_gpu* out )
 {
 	uint32_t newNodePtr = 0, nodeIdx = 0, stack[512], stackPtr = 0;

@@ -40,6 +40,14 @@ void orc_split_frag( const float* verts, const void* orig, void* left, void* rig
 void orc_intersect( const orc_node* nodes, const uint32_t* primIdx, const float* verts, void* rays, uint64_t n, int threads );
 void orc_occluded( const orc_node* nodes, const uint32_t* primIdx, const float* verts, const void* rays, uint64_t n, uint32_t* bits, int threads );
 
+/* TLAS / BLAS: BVH::IntersectTLAS (:3306) / IsOccludedTLAS (:3455) with BVH-layout BLASses and INST_IDX_BITS == 32 (hit.inst
+ * at byte 44 of the Ray record).  inst: the reference's 192-byte BLASInstance records (:1443), already Update()d;
+ * blas[k]: the k-th BLAS (its node array, primIdx and vertices).  bits must be zeroed by the caller. */
+typedef struct { float transform[16], invTransform[16]; float aabbMin[3]; uint32_t blasIdx; float aabbMax[3]; uint32_t mask; uint32_t dummy[8]; } orc_instance;
+typedef struct { const orc_node* nodes; const uint32_t* primIdx; const float* verts; } orc_blas;
+void orc_intersect_tlas( const orc_node* nodes, const uint32_t* primIdx, const orc_instance* inst, const orc_blas* blas, void* rays, uint64_t n );
+void orc_occluded_tlas( const orc_node* nodes, const uint32_t* primIdx, const orc_instance* inst, const orc_blas* blas, const void* rays, uint64_t n, uint32_t* bits );
+
 /* One Moeller-Trumbore test in the oracle's arithmetic (MOLLER_TRUMBORE_TEST :1644-1656).
  * Returns 1 and writes t,u,v when the triangle is accepted for a ray with the given tmax. */
 int orc_tri_test( const float* O, const float* D, const float* v0, const float* v1, const float* v2, float tmax, float* t, float* u, float* v );

@@ -211,3 +211,39 @@ def test_port_matches_reference_with_other_sah_constants(costs):
             assert np.array_equal(port.nodes.view(np.uint32), ref.nodes.view(np.uint32)) and np.array_equal(port.prim_idx, ref.prim_idx)
     # the constants matter: the default tree is a different one
     assert refpy.RefBVH(v, mode=0, threaded=False).used_nodes != refpy.RefBVH(v, mode=0, threaded=False, costs=costs).used_nodes
+
+
+def tlas_case(seed, n_inst=40):
+    """Two BLASses, n_inst instances with random transforms, every fifth one masked out for ordinary rays."""
+    v = [scenes.procedural_scene(2000, seed), scenes.procedural_scene(500, seed + 1)]
+    inst = refpy.make_instances(util.random_transforms(n_inst, seed), [i % 2 for i in range(n_inst)],
+                                masks=[0xFFFF if i % 5 else 0x2 for i in range(n_inst)])
+    rng = np.random.default_rng(seed)
+    D = rng.normal(size=(20000, 3)).astype(np.float32) * 0.35 + np.array([0, 0, 1], np.float32)
+    O = np.tile(np.array([[0, 0, -120]], np.float32), (D.shape[0], 1))
+    return v, inst, O, D
+
+
+@pytest.mark.skipif(not refpy.available(), reason="oracle/_ref not built (needs /root/reference)")
+def test_port_tlas_matches_reference():
+    """BVH::IntersectTLAS / IsOccludedTLAS (:3306, :3455): instance transform, mask test, hit.inst, occlusion."""
+    assert refpy.lib().ref_inst_idx_bits() == 32 and refpy.lib().ref_offsetof_hit_inst() == 44
+    v, inst, O, D = tlas_case(91)
+    blas_ref = [refpy.RefBVH(x, mode=0) for x in v]
+    tl = refpy.RefTLAS(inst, blas_ref)          # Update()s inst in place: inverse transforms and world boxes
+    tb = tl.bvh()
+    port = portpy.PortTLAS(tb.nodes, tb.prim_idx, inst, [portpy.PortBVH(x) for x in v])
+    a, b = R.make_rays(O, D), R.make_rays(O, D)
+    tl.intersect(a, threads=1), port.intersect(b)
+    wa, wb = a.view(np.uint32).reshape(-1, 32)[:, 11:16], b.view(np.uint32).reshape(-1, 32)[:, 11:16]   # inst, t, u, v, prim
+    assert np.array_equal(wa, wb)
+    hit = a["t"] < 1e30
+    assert hit.sum() > 10000 and len(np.unique(wa[hit, 0])) > 20 and not np.isin(wa[hit, 0], np.arange(0, 40, 5)).any()
+    sh = R.make_rays(O, D, tmax=150.0)
+    assert np.array_equal(tl.occluded(sh, threads=1), port.occluded(sh))
+    masked = R.make_rays(O, D)
+    masked["mask"] = 0x2     # these rays see only the instances the others skip
+    a, b = masked.copy(), masked.copy()
+    tl.intersect(a, threads=1), port.intersect(b)
+    assert np.array_equal(a.view(np.uint32).reshape(-1, 32)[:, 11:16], b.view(np.uint32).reshape(-1, 32)[:, 11:16])
+    assert np.isin(a.view(np.uint32).reshape(-1, 32)[a["t"] < 1e30, 11], np.arange(0, 40, 5)).all()

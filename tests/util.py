@@ -64,3 +64,19 @@ def classify_mismatches(got, want, verts):
         else:
             real += 1
     return {"mismatch": int(bad.size), "tie_equivalent": ties, "real": real}
+
+
+def random_transforms(count, seed, spread=60.0):
+    """Row-major 4x4 instance transforms: rotation x (non-uniform) scale x translation, as tiny_bvh's bvhmat4 stores them."""
+    rng = np.random.default_rng(seed)
+    out = np.zeros((count, 16), np.float32)
+    for i in range(count):
+        a, b, c = rng.random(3) * 6.28
+        rx = np.array([[1, 0, 0], [0, np.cos(a), -np.sin(a)], [0, np.sin(a), np.cos(a)]])
+        ry = np.array([[np.cos(b), 0, np.sin(b)], [0, 1, 0], [-np.sin(b), 0, np.cos(b)]])
+        rz = np.array([[np.cos(c), -np.sin(c), 0], [np.sin(c), np.cos(c), 0], [0, 0, 1]])
+        m = np.eye(4)
+        m[:3, :3] = (rx @ ry @ rz) @ np.diag(0.4 + rng.random(3) * 1.2)
+        m[:3, 3] = (rng.random(3) - 0.5) * spread
+        out[i] = m.astype(np.float32).reshape(-1)
+    return out
