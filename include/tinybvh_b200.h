@@ -102,6 +102,17 @@ int tbvh_build_flavour( tbvh_bvh bvh, const void* verts, uint32_t stride, uint32
 int tbvh_build_indexed( tbvh_bvh bvh, const void* verts, uint32_t stride, uint32_t vert_count, const uint32_t* indices, uint32_t prim_count, int space,
 	float c_trav, float c_int, int flavour );
 
+/* TLAS: BVH::Build( BLASInstance* instances, instCount, BVHBase** blasses, blasCount ) tiny_bvh.h:2221, traversed by
+ * BVH::IntersectTLAS (:3306) / IsOccludedTLAS (:3455) whenever tbvh_intersect / tbvh_occluded (or the _device forms) are
+ * called on the handle.  instances: inst_count records of the reference's 192-byte BLASInstance (:1443), inst_stride bytes
+ * apart, ALREADY Update()d (invTransform and world box filled in: the reference's own "blasses == 0" mode, :2245);
+ * blasses: handles holding a BVH-layout triangle tree in the same context - they must outlive the TLAS ("both must be kept
+ * alive").  INST_IDX_BITS == 32 (the library default): a hit stores the instance number in hit.inst, byte 44 of the Ray
+ * record, so closest hits are always returned in place (tbvh_intersect_packed / a separate d_hits array: TBVH_E_UNSUPPORTED).
+ * Pass layout TBVH_LAYOUT_BVH to the traversal calls. */
+int tbvh_build_tlas( tbvh_bvh tlas, const void* instances, uint32_t inst_stride, uint32_t inst_count, const tbvh_bvh* blasses, uint32_t blas_count,
+	float c_trav, float c_int );
+
 /* BVH::Refit (tiny_bvh.h:3055-3093): the triangles moved, the topology stays - leaf boxes from the new vertices, interior
  * boxes bottom-up.  verts as for tbvh_build, same prim_count.  TBVH_E_STATE for an SBVH (the reference's fatal "refitting an
  * SBVH") or when no BVH-layout tree is resident.  Derived layouts on the handle are dropped; tbvh_convert again. */

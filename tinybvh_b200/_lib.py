@@ -42,6 +42,7 @@ SYMBOLS = {
     "tbvh_bvh_info": (i32, [vp, C.POINTER(Info)]),
     "tbvh_build": (i32, [vp, vp, u32, u32, i32, f32, f32]),
     "tbvh_build_flavour": (i32, [vp, vp, u32, u32, i32, f32, f32, i32]),
+    "tbvh_build_tlas": (i32, [vp, vp, u32, u32, vp, u32, f32, f32]),
     "tbvh_refit": (i32, [vp, vp, u32, u32, i32]),
     "tbvh_build_indexed": (i32, [vp, vp, u32, u32, vp, u32, i32, f32, f32, i32]),
     "tbvh_upload_bvh": (i32, [vp, vp, u32, vp, u32, vp, u32, u32, i32]),

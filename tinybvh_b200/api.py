@@ -205,6 +205,24 @@ class BVH(_Base):
         return nodes, idx
 
 
+BLAS_INSTANCE = np.dtype([("transform", "16f4"), ("invTransform", "16f4"), ("aabbMin", "3f4"), ("blasIdx", "u4"),
+                          ("aabbMax", "3f4"), ("mask", "u4"), ("dummy", "8u4")])   # tinybvh::BLASInstance, tiny_bvh.h:1443 (192 bytes)
+
+
+class TLAS(BVH):
+    """A tinybvh::BVH built with Build( BLASInstance*, instCount, BVHBase**, blasCount ) (tiny_bvh.h:2221): Intersect / IsOccluded on
+    it are IntersectTLAS / IsOccludedTLAS.  `instances`: BLAS_INSTANCE records already Update()d by the caller (inverse transform
+    and world box, as BLASInstance::Update :8386 computes them); `blasses`: BVH objects of this module, kept alive by this one."""
+
+    def Build(self, instances, blasses):
+        inst = np.ascontiguousarray(instances)
+        assert inst.dtype.itemsize == 192
+        self.blasses = list(blasses)
+        hs = (C.c_void_p * len(self.blasses))(*[b.h for b in self.blasses])
+        check(_lib.lib().tbvh_build_tlas(self.h, _np_ptr(inst), 192, inst.shape[0], hs, len(self.blasses), self.c_trav, self.c_int))
+        return self
+
+
 class BVH_GPU(_Base):
     """tinybvh::BVH_GPU (tiny_bvh.h:1092-1127): Aila-Laine 64-byte nodes."""
     layout = LAYOUT_BVH_GPU

@@ -123,9 +123,10 @@ int tbvh_bvh_create( tbvh_ctx ctx, tbvh_bvh* out )
 static void free_layouts( tbvh_bvh b )
 {
 	if (b->d_trav && b->d_trav != b->d_nodes) cudaFree( b->d_trav );
-	void* p[] = { b->d_verts, b->d_nodes, b->d_prim_idx, b->d_leaf_tris, b->d_nodes_gpu, b->d_cw_nodes, b->d_cw_tris };
+	void* p[] = { b->d_verts, b->d_nodes, b->d_prim_idx, b->d_leaf_tris, b->d_nodes_gpu, b->d_cw_nodes, b->d_cw_tris, b->d_aabbs, b->d_inst, b->d_blas };
 	for (void* q : p) if (q) cudaFree( q );
 	b->d_verts = 0, b->d_nodes = 0, b->d_prim_idx = 0, b->d_leaf_tris = 0, b->d_nodes_gpu = 0, b->d_cw_nodes = 0, b->d_cw_tris = 0, b->d_trav = 0;
+	b->d_aabbs = 0, b->d_inst = 0, b->d_blas = 0, b->inst_count = 0, b->blas_count = 0;
 	memset( &b->info, 0, sizeof( b->info ) );
 	b->refittable = true;
 }
@@ -353,6 +354,50 @@ int tbvh_build_flavour( tbvh_bvh b, const void* verts, uint32_t stride, uint32_t
 	return TBVH_OK;
 }
 
+// BVH::Build( BLASInstance*, instCount, BVHBase**, blasCount ) tiny_bvh.h:2221 in its "blasses == 0" mode (:2245): the instances
+// arrive Update()d - inverse transform and world-space box filled in - and the TLAS is the reference builder's tree over the boxes
+int tbvh_build_tlas( tbvh_bvh t, const void* instances, uint32_t inst_stride, uint32_t inst_count, const tbvh_bvh* blasses, uint32_t blas_count, float c_trav, float c_int )
+{
+	ARG_CHECK( t && instances && blasses && inst_count > 0 && blas_count > 0 && inst_stride >= 160, "bad TLAS arguments" );
+	CUDA_TRY( cudaSetDevice( t->ctx->device ) );
+	free_layouts( t );
+	std::vector<float4> boxes( (size_t)inst_count * 2 );
+	std::vector<TlasInst> inst( inst_count );
+	std::vector<BlasRef> refs( blas_count );
+	for (uint32_t k = 0; k < blas_count; k++)
+	{
+		const tbvh_bvh b = blasses[k];
+		ARG_CHECK( b && b != t && b->ctx == t->ctx, "TLAS: a BLAS handle is NULL or lives in another context" );
+		if (!(b->info.layouts & (1u << TBVH_LAYOUT_BVH)) || !b->d_trav || !b->d_leaf_tris || b->d_inst)
+		{ tbvh_set_error( "TLAS: BLAS %u holds no BVH-layout triangle tree (IntersectTLAS walks LAYOUT_BVH BLASses, tiny_bvh.h:3341)", k ); return TBVH_E_STATE; }
+		refs[k].trav = b->d_trav, refs[k].tris = b->d_leaf_tris, refs[k].root_ref = b->root_ref, refs[k].root_count = b->root_count, refs[k].pad0 = refs[k].pad1 = 0;
+	}
+	for (uint32_t i = 0; i < inst_count; i++)
+	{
+		// BLASInstance :1443: transform @0, invTransform @64, aabbMin @128, blasIdx @140, aabbMax @144, mask @156
+		const char* r = (const char*)instances + (size_t)i * inst_stride;
+		memcpy( inst[i].inv, r + 64, 64 );
+		memcpy( &inst[i].blasIdx, r + 140, 4 ), memcpy( &inst[i].mask, r + 156, 4 );
+		inst[i].pad0 = inst[i].pad1 = 0;
+		ARG_CHECK( inst[i].blasIdx < blas_count, "TLAS: an instance names a BLAS past blas_count" );
+		float mn[3], mx[3];
+		memcpy( mn, r + 128, 12 ), memcpy( mx, r + 144, 12 );
+		boxes[(size_t)i * 2] = make_float4( mn[0], mn[1], mn[2], 0 ), boxes[(size_t)i * 2 + 1] = make_float4( mx[0], mx[1], mx[2], 0 );
+	}
+	cudaStream_t s = t->ctx->stream;
+	CUDA_TRY( cudaMalloc( &t->d_aabbs, boxes.size() * 16 ) );
+	CUDA_TRY( cudaMalloc( &t->d_inst, inst.size() * sizeof( TlasInst ) ) );
+	CUDA_TRY( cudaMalloc( &t->d_blas, refs.size() * sizeof( BlasRef ) ) );
+	CUDA_TRY( cudaMemcpyAsync( t->d_aabbs, boxes.data(), boxes.size() * 16, cudaMemcpyHostToDevice, s ) );
+	CUDA_TRY( cudaMemcpyAsync( t->d_inst, inst.data(), inst.size() * sizeof( TlasInst ), cudaMemcpyHostToDevice, s ) );
+	CUDA_TRY( cudaMemcpyAsync( t->d_blas, refs.data(), refs.size() * sizeof( BlasRef ), cudaMemcpyHostToDevice, s ) );
+	CUDA_TRY( cudaStreamSynchronize( s ) ); // the host vectors go out of scope
+	t->info.prim_count = inst_count, t->inst_count = inst_count, t->blas_count = blas_count;
+	TRY( build_sah_launch( t, c_trav, c_int, TBVH_BUILD_REFERENCE ) ); // "Build(); // or BuildAVX, for large TLAS." :2258
+	t->info.layouts = 1u << TBVH_LAYOUT_BVH, t->refittable = false; // "do not refit a TLAS, use Build(..)" :3060
+	return TBVH_OK;
+}
+
 // BVH::Refit (tiny_bvh.h:3055): same topology, new vertex positions
 int tbvh_refit( tbvh_bvh b, const void* verts, uint32_t stride, uint32_t prim_count, int space )
 {
@@ -452,6 +497,12 @@ int tbvh_intersect_device( tbvh_bvh b, int layout, void* d_rays, uint32_t stride
 {
 	ARG_CHECK( b && d_rays && stride >= 64 && (stride & 15) == 0, "bad ray buffer" );
 	CUDA_TRY( cudaSetDevice( b->ctx->device ) );
+	if (b->d_inst)
+	{
+		// TLAS: hits carry the instance (hit.inst, byte 44) and are written into the ray records
+		if (d_hits) { tbvh_set_error( "TLAS hits are written in place (t,u,v,prim at byte 48, inst at byte 44): pass d_hits = NULL" ); return TBVH_E_UNSUPPORTED; }
+		return tlas_trace_launch( b, d_rays, stride, 0, n, false, (cudaStream_t)stream );
+	}
 	if (d_hits) return trace_dispatch( b, layout, d_rays, stride, d_hits, 16, 0, n, false, (cudaStream_t)stream );
 	return trace_dispatch( b, layout, d_rays, stride, (char*)d_rays + 48, stride, 0, n, false, (cudaStream_t)stream );
 }
@@ -460,6 +511,7 @@ int tbvh_occluded_device( tbvh_bvh b, int layout, const void* d_rays, uint32_t s
 {
 	ARG_CHECK( b && d_rays && d_bits && stride >= 64 && (stride & 15) == 0, "bad ray buffer" );
 	CUDA_TRY( cudaSetDevice( b->ctx->device ) );
+	if (b->d_inst) return tlas_trace_launch( b, d_rays, stride, d_bits, n, true, (cudaStream_t)stream );
 	return trace_dispatch( b, layout, d_rays, stride, 0, 0, d_bits, n, true, (cudaStream_t)stream );
 }
 
@@ -565,6 +617,23 @@ static int intersect_host( tbvh_bvh b, int layout, void* rays, uint32_t stride, 
 	tbvh_ctx c = b->ctx;
 	TRY( ensure_stage( c ) );
 	char* dev_alias = (char*)mapped_alias( rays );
+	if (b->d_inst)
+	{
+		// TLAS: staged 64-byte records, hits written into them by the kernel, bytes 44..63 (inst, t, u, v, prim) copied back
+		if (packed_hits) { tbvh_set_error( "tbvh_intersect_packed: TLAS hits carry the instance and are returned in the ray records" ); return TBVH_E_UNSUPPORTED; }
+		int k = 0;
+		for (uint64_t off = 0; off < n; off += c->stage_rays, k = (k + 1) % 3)
+		{
+			const uint64_t cnt = n - off < c->stage_rays ? n - off : c->stage_rays;
+			cudaStream_t s = c->copy_streams[k];
+			char* h = (char*)rays + off * stride;
+			TRY( stage_in( c, k, h, dev_alias ? dev_alias + off * stride : 0, stride, cnt, s ) );
+			TRY( tlas_trace_launch( b, c->d_stage[k], 64, 0, cnt, false, s ) );
+			CUDA_TRY( cudaMemcpy2DAsync( h + 44, stride, (char*)c->d_stage[k] + 44, 64, 20, cnt, cudaMemcpyDeviceToHost, s ) );
+		}
+		for (int i = 0; i < 3; i++) CUDA_TRY( cudaStreamSynchronize( c->copy_streams[i] ) );
+		return TBVH_OK;
+	}
 	const int mode = packed_hits ? 4 : (c->d2h_mode == 3 && !(dev_alias && (stride & 15) == 0)) ? 0 : c->d2h_mode;
 	if (mode == 2 || mode == 4)
 		for (int i = 0; i < 3; i++) if (!c->d_hits_pack[i]) CUDA_TRY( cudaMalloc( &c->d_hits_pack[i], c->stage_rays * 16 ) );
@@ -623,7 +692,8 @@ int tbvh_occluded( tbvh_bvh b, int layout, const void* rays, uint32_t stride, ui
 		cudaStream_t s = c->copy_streams[k];
 		const char* h = (const char*)rays + off * stride;
 		TRY( stage_in( c, k, h, dev_alias ? dev_alias + off * stride : 0, stride, cnt, s ) );
-		TRY( trace_dispatch( b, layout, c->d_stage[k], 64, 0, 0, (uint32_t*)c->d_stage_bits[k], cnt, true, s ) );
+		if (b->d_inst) TRY( tlas_trace_launch( b, c->d_stage[k], 64, (uint32_t*)c->d_stage_bits[k], cnt, true, s ) );
+		else TRY( trace_dispatch( b, layout, c->d_stage[k], 64, 0, 0, (uint32_t*)c->d_stage_bits[k], cnt, true, s ) );
 		CUDA_TRY( cudaMemcpyAsync( bits + off / 32, c->d_stage_bits[k], ((cnt + 31) / 32) * 4, cudaMemcpyDeviceToHost, s ) );
 	}
 	for (int i = 0; i < 3; i++) CUDA_TRY( cudaStreamSynchronize( c->copy_streams[i] ) );

@@ -46,6 +46,7 @@ struct Counters
 struct BuildArgs
 {
 	const float4* verts;
+	const float4* aabbs;     // TLAS build (BVH::Build( BLASInstance*, .. ) :2243-2255): fragment i = box (aabbs[2i], aabbs[2i+1]) instead of a triangle's
 	float4* frag_min; float4* frag_max;
 	uint32_t* idx[2]; uint32_t* idx_final;
 	uint16_t* bin_ids;
@@ -252,7 +253,14 @@ __global__ void __launch_bounds__( 256 ) k_fragments( BuildArgs A )
 	// PrepareBuild :2300-2308: bmin = min(v0, min(v1, v2)), bmax likewise; root box = union; primIdx[i] = i
 	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
 	float mn[3] = { BVH_FAR, BVH_FAR, BVH_FAR }, mx[3] = { -BVH_FAR, -BVH_FAR, -BVH_FAR };
-	if (i < A.n)
+	if (i < A.n && A.aabbs)
+	{
+		const float4 lo = __ldg( A.aabbs + (size_t)i * 2 ), hi = __ldg( A.aabbs + (size_t)i * 2 + 1 );
+		mn[0] = lo.x, mn[1] = lo.y, mn[2] = lo.z, mx[0] = hi.x, mx[1] = hi.y, mx[2] = hi.z;
+		A.frag_min[i] = make_float4( mn[0], mn[1], mn[2], 0 ), A.frag_max[i] = make_float4( mx[0], mx[1], mx[2], 0 );
+		A.idx[0][i] = i;
+	}
+	else if (i < A.n)
 	{
 		const float4 v0 = __ldg( A.verts + (size_t)i * 3 ), v1 = __ldg( A.verts + (size_t)i * 3 + 1 ), v2 = __ldg( A.verts + (size_t)i * 3 + 2 );
 		mn[0] = fminf( v0.x, fminf( v1.x, v2.x ) ), mn[1] = fminf( v0.y, fminf( v1.y, v2.y ) ), mn[2] = fminf( v0.z, fminf( v1.z, v2.z ) );
@@ -829,7 +837,7 @@ int build_sah_launch( tbvh_bvh b, float c_trav, float c_int, int flavour )
 	cudaStream_t s = b->ctx->stream;
 	std::vector<void*> scratch;
 	BuildArgs A = {};
-	A.verts = b->d_verts, A.n = n, A.c_trav = c_trav, A.c_int = c_int, A.flavour = (uint32_t)flavour;
+	A.verts = b->d_verts, A.aabbs = b->d_aabbs, A.n = n, A.c_trav = c_trav, A.c_int = c_int, A.flavour = (uint32_t)flavour;
 	{
 		const int t = b->ctx->small_t; // measured on B200: 128 beats 64 and 256 (profiles/README.md)
 		A.small_t = (uint32_t)(t < 8 ? 8 : t > SMALL_T ? SMALL_T : t);
@@ -922,7 +930,7 @@ int build_sah_launch( tbvh_bvh b, float c_trav, float c_int, int flavour )
 		memcpy( b->info.aabb_min, rootw, 12 ), memcpy( b->info.aabb_max, rootw + 4, 12 );
 		b->root_ref = rootw[3], b->root_count = rootw[7];
 		b->d_trav = b->d_nodes;
-		return make_leaf_tris( b, s );
+		return b->d_aabbs ? TBVH_OK : make_leaf_tris( b, s ); // a TLAS has no triangles of its own
 	};
 	rc = body();
 	cudaStreamSynchronize( s );

@@ -62,6 +62,11 @@ struct tbvh_bvh_t
 	// LAYOUT_CWBVH
 	float4* d_cw_nodes = 0;    // 5 float4 per node
 	float4* d_cw_tris = 0;     // 3 float4 per triangle
+	// TLAS (BVH::Build( BLASInstance*, instCount, BVHBase**, blasCount ) :2221): nodes / primIdx over instance boxes + device tables
+	float4* d_aabbs = 0;       // instance boxes the TLAS was built over (2 float4 per instance)
+	void* d_inst = 0;          // TlasInst records (inverse transform, BLAS number, mask)
+	void* d_blas = 0;          // BlasRef records (traversal arrays of every BLAS)
+	uint32_t inst_count = 0, blas_count = 0;
 	bool refittable = true;    // BVHBase::refittable (:811): false after BuildHQ ("can't refit an SBVH", :3027)
 	// statistics
 	int stats = 0;
@@ -104,6 +109,9 @@ int cwbvh_trace_launch( tbvh_bvh b, const void* d_rays, uint32_t stride, void* d
 int build_sah_launch( tbvh_bvh b, float c_trav, float c_int, int flavour );
 int build_hq_launch( tbvh_bvh b, float c_trav, float c_int );
 int refit_launch( tbvh_bvh b, cudaStream_t s );
+int tlas_trace_launch( tbvh_bvh b, const void* d_rays, uint32_t stride, uint32_t* d_bits, uint64_t n, bool anyhit, cudaStream_t s );
+struct TlasInst { float inv[16]; uint32_t blasIdx, mask, pad0, pad1; };                                  // 80 bytes
+struct BlasRef { const float4* trav; const float4* tris; uint32_t root_ref, root_count, pad0, pad1; };   // 32 bytes
 int make_leaf_tris( tbvh_bvh b, cudaStream_t s );
 int bvh_gpu_to_bvh( tbvh_bvh b, uint32_t used_nodes_gpu, cudaStream_t s );
 int bvh_to_bvh_gpu( tbvh_bvh b, cudaStream_t s );
