@@ -152,6 +152,21 @@ public:
 		TBVH_FATAL_IF( tbvh_build_flavour( h, vertices, (uint32_t)sizeof( Vec4 ), primCount, TBVH_HOST, c_trav, c_int, TBVH_BUILD_HQ ), "BVH::BuildHQ" );
 		sync_info();
 	}
+	// TLAS: BVH::Build( BLASInstance* instances, instCount, BVHBase** blasses, blasCount ) tiny_bvh.h:2221.  Inst is the
+	// reference's 192-byte tinybvh::BLASInstance; the instances must already be Update()d (inverse transform + world box,
+	// :8386 - run the reference's own inst.Update( &hostBVH ) with hostBVH.aabbMin / aabbMax copied from the BLAS's aabbMin /
+	// aabbMax here, or fill the fields directly): the engine implements the reference's "blasses == 0" contract (:2245).
+	// Intersect / IsOccluded on the TLAS are then IntersectTLAS / IsOccludedTLAS; a hit carries hit.inst (INST_IDX_BITS == 32).
+	template <class Inst> void Build( Inst* instances, const uint32_t instCount, BVHBase** blasses, const uint32_t blasCount )
+	{
+		static_assert( sizeof( Inst ) == 192, "tinybvh::BLASInstance is 192 bytes (tiny_bvh.h:1443)" );
+		tbvh_bvh* hs = (tbvh_bvh*)malloc( sizeof( tbvh_bvh ) * (blasCount ? blasCount : 1) );
+		for (uint32_t k = 0; k < blasCount; k++) hs[k] = blasses[k]->handle();
+		const int rc = tbvh_build_tlas( h, instances, (uint32_t)sizeof( Inst ), instCount, hs, blasCount, c_trav, c_int );
+		free( hs );
+		TBVH_FATAL_IF( rc, "BVH::Build( BLASInstance*, .. )" );
+		sync_info();
+	}
 	// indexed geometry: BVH::Build / BuildAVX / BuildHQ( vertices, indices, primCount ) tiny_bvh.h:889-900
 	template <class Vec4> void Build( const Vec4* vertices, const uint32_t* indices, const uint32_t primCount ) { build_indexed( vertices, indices, primCount, TBVH_BUILD_REFERENCE, "BVH::Build" ); remember( vertices, (uint32_t)sizeof( Vec4 ), indices, primCount ), sync_info(); }
 	template <class Vec4> void BuildAVX( const Vec4* vertices, const uint32_t* indices, const uint32_t primCount ) { build_indexed( vertices, indices, primCount, TBVH_BUILD_AVX, "BVH::BuildAVX" ); remember( vertices, (uint32_t)sizeof( Vec4 ), indices, primCount ), sync_info(); }
