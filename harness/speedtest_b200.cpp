@@ -159,5 +159,79 @@ int main( int argc, char** argv )
 			memcmp( idx.data(), ref_hq.primIdx, (size_t)refs * 4 ) == 0;
 		printf( "  SBVH node array and the %u referenced primIdx entries %s BVH::BuildHQ's\n", refs, hqSame ? "are identical to" : "DIFFER from" );
 	}
-	return ok && primDiff == 0 && tDiff == 0 && hqSame ? 0 : 1;
+
+	// ---- animation: move the vertices in place, Refit both trees (tiny_bvh_anim.cpp's pattern; BVH::Refit :3055)
+	bool refitSame = false;
+	{
+		BVH ref_anim;
+		ref_anim.threadedBuild = false;
+		ref_anim.Build( triangles, verts / 3 );
+		tinybvh_b200::BVH gpu_anim;
+		gpu_anim.Build( triangles, verts / 3 );
+		for (uint32_t i = 0; i < verts; i++) triangles[i].y += 0.05f * sinf( triangles[i].x * 0.37f ); // the caller edits its own array
+		t.reset();
+		ref_anim.Refit();
+		const float refRefit = t.elapsed();
+		gpu_anim.Refit();
+		std::vector<uint8_t> nodes( (size_t)gpu_anim.usedNodes * 32 );
+		std::vector<uint32_t> idx( gpu_anim.idxCount );
+		gpu_anim.Download( nodes.data(), idx.data() );
+		refitSame = gpu_anim.usedNodes == ref_anim.usedNodes && memcmp( nodes.data(), ref_anim.bvhNode, nodes.size() ) == 0;
+		printf( "BVH::Refit: reference %.2f ms, tinybvh_b200 %.3f ms (device); refitted node array %s\n", refRefit * 1000, gpu_anim.buildMs, refitSame ? "identical" : "DIFFERS" );
+	}
+
+	// ---- TLAS / BLAS (tiny_bvh_gpu2.cpp's pattern): 27 instances of the scene, reference IntersectTLAS vs the two-level kernel
+	bool tlasSame = false;
+	{
+		BVH ref_blas;
+		ref_blas.Build( triangles, verts / 3 );
+		tinybvh_b200::BVH gpu_blas;
+		gpu_blas.Build( triangles, verts / 3 );
+		const int N = 27;
+		BLASInstance* inst = (BLASInstance*)malloc64( N * sizeof( BLASInstance ) );
+		const float span = 2.2f * tinybvh_max( ref_blas.aabbMax.x - ref_blas.aabbMin.x, ref_blas.aabbMax.z - ref_blas.aabbMin.z );
+		for (int i = 0; i < N; i++)
+		{
+			inst[i] = BLASInstance( 0 );
+			const float a = 0.4f * i, sc = 0.5f + 0.04f * i;
+			float* T = (float*)&inst[i].transform;
+			T[0] = cosf( a ) * sc, T[2] = sinf( a ) * sc, T[5] = sc, T[8] = -sinf( a ) * sc, T[10] = cosf( a ) * sc, T[15] = 1;
+			T[1] = T[4] = T[6] = T[9] = T[12] = T[13] = T[14] = 0;
+			T[3] = (i % 3 - 1) * span, T[7] = (i / 9 - 1) * span * 0.6f, T[11] = ((i / 3) % 3 - 1) * span;
+		}
+		BVHBase* blasList[1] = { &ref_blas };
+		BVH ref_tlas;
+		ref_tlas.Build( inst, N, blasList, 1 ); // Update()s the instances: inverse transforms + world boxes
+		tinybvh_b200::BVHBase* gpuList[1] = { &gpu_blas };
+		tinybvh_b200::BVH gpu_tlas;
+		gpu_tlas.Build( inst, N, gpuList, 1 );
+		const size_t M = (size_t)W * H;
+		Ray* a = (Ray*)malloc64( M * sizeof( Ray ) ), * b = (Ray*)malloc64( M * sizeof( Ray ) );
+		const bvhvec3 eye( span * 0.2f, span * 1.1f, -span * 2.6f ), view = tinybvh_normalize( bvhvec3( -0.05f, -0.35f, 1 ) );
+		const bvhvec3 right = tinybvh_normalize( tinybvh_cross( bvhvec3( 0, 1, 0 ), view ) ), up = 0.75f * tinybvh_cross( view, right ), C = eye + 1.2f * view;
+		for (int y = 0; y < H; y++) for (int x = 0; x < W; x++)
+		{
+			const bvhvec3 P = C + ((x + 0.5f) / W * 2 - 1) * right + (1 - (y + 0.5f) / H * 2) * up;
+			a[(size_t)y * W + x] = Ray( eye, tinybvh_normalize( P - eye ) );
+		}
+		memcpy( b, a, M * sizeof( Ray ) );
+		t.reset();
+		parallel_batches( M, [&]( size_t s0, size_t s1 ) { for (size_t k = s0; k < s1; k++) ref_tlas.Intersect( a[k] ); } );
+		const float refT = t.elapsed();
+		gpu_tlas.Intersect( b, M ); // warm-up, then timed on fresh rays
+		for (size_t k = 0; k < M; k++) b[k].hit = Ray( eye, view ).hit;
+		t.reset();
+		gpu_tlas.Intersect( b, M );
+		const float gpuT = t.elapsed();
+		size_t diff = 0, hits = 0;
+		for (size_t k = 0; k < M; k++)
+		{
+			hits += a[k].hit.t < 1e30f;
+			diff += memcmp( &a[k].hit.t, &b[k].hit.t, 16 ) != 0 || (a[k].hit.t < 1e30f && a[k].hit.inst != b[k].hit.inst);
+		}
+		tlasSame = diff == 0 && gpu_tlas.usedNodes == ref_tlas.usedNodes;
+		printf( "TLAS of %d instances: reference IntersectTLAS %.2f ms (%u threads), tinybvh_b200 %.2f ms incl. PCIe; %zu of %zu rays hit, %zu differ (t,u,v,prim,inst)\n",
+			N, refT * 1000, std::thread::hardware_concurrency(), gpuT * 1000, hits, M, diff );
+	}
+	return ok && primDiff == 0 && tDiff == 0 && hqSame && refitSame && tlasSame ? 0 : 1;
 }
