@@ -160,6 +160,9 @@ public:
 	template <class Inst> void Build( Inst* instances, const uint32_t instCount, BVHBase** blasses, const uint32_t blasCount )
 	{
 		static_assert( sizeof( Inst ) == 192, "tinybvh::BLASInstance is 192 bytes (tiny_bvh.h:1443)" );
+#ifdef INST_IDX_BITS
+		TBVH_FATAL_IF( tbvh_set_option( context(), "inst_idx_bits", INST_IDX_BITS ), "inst_idx_bits" ); // where a hit stores its instance (:114-119)
+#endif
 		tbvh_bvh* hs = (tbvh_bvh*)malloc( sizeof( tbvh_bvh ) * (blasCount ? blasCount : 1) );
 		for (uint32_t k = 0; k < blasCount; k++) hs[k] = blasses[k]->handle();
 		const int rc = tbvh_build_tlas( h, instances, (uint32_t)sizeof( Inst ), instCount, hs, blasCount, c_trav, c_int );

@@ -62,3 +62,26 @@ def test_tlas_device_rays_and_errors(gpu):
         api.TLAS().Build(inst, [blas[0]])            # an instance names BLAS 1
     with pytest.raises(api.TbvhError):
         api.TLAS().Build(inst, [blas[0], t])         # a TLAS is not a BLAS
+
+
+def test_tlas_instance_bits_in_prim(gpu):
+    """A host program compiled with INST_IDX_BITS 10 (the speedtest's setting): the instance rides in the top bits of hit.prim."""
+    from oracle import refpy
+    if not refpy.available():
+        pytest.skip("needs oracle/_ref")
+    v, inst, O, D = tlas_case(95, 30)
+    ref = refpy.RefTLAS(inst, [refpy.RefBVH(x, mode=0, threaded=False) for x in v])
+    t = api.TLAS().Build(inst, [api.BVH().Build(x) for x in v])
+    rays = R.make_rays(O, D)
+    want, got = rays.copy(), rays.copy()
+    ref.intersect(want)                                   # reference built with INST_IDX_BITS 32: inst in its own field
+    api.set_option("inst_idx_bits", 10)
+    try:
+        t.Intersect(got)
+    finally:
+        api.set_option("inst_idx_bits", 32)
+    hit = want["t"] < 1e30
+    w, g = words(want), words(got)
+    assert np.array_equal(g[:, 1:4], w[:, 1:4])           # t, u, v
+    assert np.array_equal(g[hit, 4], w[hit, 4] + (w[hit, 0] << 22)) and np.array_equal(g[~hit, 4], w[~hit, 4])
+    assert np.array_equal(g[:, 0], words(rays)[:, 0])     # byte 44 untouched

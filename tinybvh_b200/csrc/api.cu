@@ -93,6 +93,7 @@ int tbvh_set_option( tbvh_ctx c, const char* key, int value )
 	if (!strcmp( key, "trace_variant" )) c->trace_variant = value;
 	else if (!strcmp( key, "small_t" )) c->small_t = value;
 	else if (!strcmp( key, "small_mode" )) c->small_mode = value & 3;
+	else if (!strcmp( key, "inst_idx_bits" )) c->inst_idx_bits = value;
 	else if (!strcmp( key, "hq_small" )) c->hq_small = value;
 	else if (!strcmp( key, "hq_cluster" )) c->hq_cluster = value;
 	else if (!strcmp( key, "d2h_mode" )) c->d2h_mode = value;

@@ -78,7 +78,7 @@ template <bool ANYHIT> __device__ bool trace_blas( const BlasRef B, const float 
 
 template <bool ANYHIT> __global__ void __launch_bounds__( 128 ) k_trace_tlas( const float4* __restrict__ nodes, const uint32_t* __restrict__ prim_idx,
 	const TlasInst* __restrict__ inst, const BlasRef* __restrict__ blas, char* rays, const uint32_t stride, uint32_t* __restrict__ bits, const uint64_t n,
-	const uint32_t root_ref, const uint32_t root_count )
+	const uint32_t root_ref, const uint32_t root_count, const uint32_t inst_shift /* 32 - INST_IDX_BITS; 0 = separate hit.inst field */ )
 {
 	const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
 	bool occluded = false;
@@ -138,7 +138,11 @@ template <bool ANYHIT> __global__ void __launch_bounds__( 128 ) k_trace_tlas( co
 						occluded = true;
 						break;
 					}
-					if (hit) hinst = instIdx; // hit.inst = ray.instIdx (IntersectTri :8525)
+					if (hit)
+					{
+						hinst = instIdx; // hit.inst = ray.instIdx (IntersectTri :8525)
+						if (inst_shift) hprim += instIdx << inst_shift; // INST_IDX_BITS != 32: hit.prim = triIdx + ( instIdx << INST_IDX_SHFT ) (:8527)
+					}
 				}
 				if (ANYHIT && occluded) break;
 			}
@@ -149,7 +153,7 @@ template <bool ANYHIT> __global__ void __launch_bounds__( 128 ) k_trace_tlas( co
 		if (!ANYHIT)
 		{
 			char* rec = rays + i * stride;
-			*(uint32_t*)(rec + 44) = hinst;
+			if (inst_shift == 0) *(uint32_t*)(rec + 44) = hinst; // INST_IDX_BITS == 32: hit.inst (:664)
 			*(float4*)(rec + 48) = make_float4( tmax, hu, hv, __uint_as_float( hprim ) );
 		}
 	}
@@ -167,8 +171,10 @@ int tlas_trace_launch( tbvh_bvh b, const void* d_rays, uint32_t stride, uint32_t
 	if (n == 0) return TBVH_OK;
 	const uint64_t grid = (n + 127) / 128;
 	if (grid > 0x7fffffffull) { tbvh_set_error( "ray batch too large for one launch" ); return TBVH_E_ARG; }
-	if (anyhit) k_trace_tlas<true><<<(uint32_t)grid, 128, 0, s>>>( b->d_nodes, b->d_prim_idx, (const TlasInst*)b->d_inst, (const BlasRef*)b->d_blas, (char*)d_rays, stride, d_bits, n, b->root_ref, b->root_count );
-	else k_trace_tlas<false><<<(uint32_t)grid, 128, 0, s>>>( b->d_nodes, b->d_prim_idx, (const TlasInst*)b->d_inst, (const BlasRef*)b->d_blas, (char*)d_rays, stride, d_bits, n, b->root_ref, b->root_count );
+	const int bits_opt = b->ctx->inst_idx_bits;
+	const uint32_t shift = bits_opt >= 4 && bits_opt < 32 ? (uint32_t)(32 - bits_opt) : 0u;
+	if (anyhit) k_trace_tlas<true><<<(uint32_t)grid, 128, 0, s>>>( b->d_nodes, b->d_prim_idx, (const TlasInst*)b->d_inst, (const BlasRef*)b->d_blas, (char*)d_rays, stride, d_bits, n, b->root_ref, b->root_count, shift );
+	else k_trace_tlas<false><<<(uint32_t)grid, 128, 0, s>>>( b->d_nodes, b->d_prim_idx, (const TlasInst*)b->d_inst, (const BlasRef*)b->d_blas, (char*)d_rays, stride, d_bits, n, b->root_ref, b->root_count, shift );
 	LAUNCHED();
 	return TBVH_OK;
 }
