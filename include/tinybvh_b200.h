@@ -65,7 +65,9 @@ int tbvh_device_count( void );
 /* tuning knobs (no reference counterpart; defaults are the measured best): "trace_variant" 0 = generic BVH2 kernel,
  * 3 = octant-switch, 4 = persistent warps; "small_t" builder switch point (8..256); "d2h_mode" / "h2d_split" / "host_path"
  * select how the host-buffer path moves ray records and hits across PCIe.  Environment variables TBVH_<KEY> set the
- * defaults at context creation. */
+ * defaults at context creation.  BuildHQ: "hq_small" (fragments below which a subtree goes to the warp kernel, default 16),
+ * "hq_cluster" (largest thread-block cluster per node, 1..16).  "inst_idx_bits": the host program's INST_IDX_BITS (see
+ * tbvh_build_tlas). */
 int tbvh_set_option( tbvh_ctx ctx, const char* key, int value );
 /* pinned host memory for ray buffers (replaces tinybvh::malloc64 / BVHContext::malloc for rays, tiny_bvh.h:261-292, 763-768) */
 int tbvh_host_alloc( size_t bytes, void** out );
