@@ -206,7 +206,7 @@ int main( int argc, char** argv )
 		tinybvh_b200::BVH gpu_tlas;
 		gpu_tlas.Build( inst, N, gpuList, 1 );
 		const size_t M = (size_t)W * H;
-		Ray* a = (Ray*)malloc64( M * sizeof( Ray ) ), * b = (Ray*)malloc64( M * sizeof( Ray ) );
+		Ray* a = (Ray*)malloc64( M * sizeof( Ray ) ), * b = (Ray*)tinybvh_b200::malloc_pinned( M * sizeof( Ray ) ); // rays that cross PCIe: page-locked
 		const bvhvec3 eye( span * 0.2f, span * 1.1f, -span * 2.6f ), view = tinybvh_normalize( bvhvec3( -0.05f, -0.35f, 1 ) );
 		const bvhvec3 right = tinybvh_normalize( tinybvh_cross( bvhvec3( 0, 1, 0 ), view ) ), up = 0.75f * tinybvh_cross( view, right ), C = eye + 1.2f * view;
 		for (int y = 0; y < H; y++) for (int x = 0; x < W; x++)
