@@ -105,7 +105,7 @@ class ClockSampler:
 
 
 # ---------------------------------------------------------------------------------------------- reference arm / cpu baseline
-def cpu_reference(scene, verts, prim, shadow, passes, threads=0):
+def cpu_reference(scene, verts, prim, shadow, passes, threads=0, hq=True):
     """The reference's own CPU implementation of the path on the host cores: BVH8_CPU::Build + Intersect / IsOccluded
     (tiny_bvh.h:7210-7472) from oracle/_ref; the pinned plain-C port of BVH::Intersect when _ref is absent."""
     from oracle import portpy, refpy
@@ -113,9 +113,9 @@ def cpu_reference(scene, verts, prim, shadow, passes, threads=0):
     if refpy.available():
         kind, cores = "reference", refpy.hardware_threads() if threads <= 0 else threads
         t0 = time.perf_counter()
-        bvh = refpy.RefBVH8CPU(verts)
+        bvh = refpy.RefBVH8CPU(verts, hq=hq)
         build_s = time.perf_counter() - t0
-        impl = "BVH8_CPU::Build + Intersect/IsOccluded (AVX2), 10k-ray batches off an atomic counter"
+        impl = f"BVH8_CPU::{'BuildHQ' if hq else 'Build'} + Intersect/IsOccluded (AVX2), 10k-ray batches off an atomic counter"
     else:
         kind, cores = "port", os.cpu_count() if threads <= 0 else threads
         t0 = time.perf_counter()
@@ -163,7 +163,7 @@ def run_reference(args):
     # bounded sample: the CPU gets a quarter-resolution slice of the workload per step unless --full-reference
     sres = res if args.full_reference else max(256, res // 2)
     prim, sh = host_primary_and_shadow(args.scene, verts, label, sres, 0)
-    cb = cpu_reference(args.scene, verts, prim, sh, passes=max(1, args.steps))
+    cb = cpu_reference(args.scene, verts, prim, sh, passes=max(1, args.steps), hq=args.tree == "hq")
     out = {"metric": METRIC, "value": cb["value"], "unit": "Mrays/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
            "ms_per_step": cb["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
            "data": data_label(label), "impl": "reference",
@@ -186,7 +186,7 @@ def data_label(label):
 
 
 def workload_name(args, label):
-    return f"{label}_{args.layout}_{args.res}x{args.res}x16_primary+shadow"
+    return f"{label}_{'sbvh' if args.tree == 'hq' else 'sah'}_{args.layout}_{args.res}x{args.res}x16_primary+shadow"
 
 
 # ---------------------------------------------------------------------------------------------- our arm
@@ -211,17 +211,20 @@ def run_ours(args):
     bvh = api.BVH(device=local)
     build_ms, bcast_ms, build_hq = None, None, None
     if rank == 0:
-        bvh.Build(verts)              # warm-up build (allocations, first-launch costs)
-        bvh = api.BVH(device=local)
-        bvh.Build(verts)
-        build_ms = bvh.info().build_ms
-        # the other builder of the path, reported beside it (not part of the timed steps): BVH::BuildHQ (SBVH)
+        # both builders of the path are timed (second call each: the first pays allocations and first-launch costs); the rays are
+        # traced through the tree --tree names - the SBVH by default, as in the reference's own traversal benchmarks
+        sah = api.BVH(device=local)
+        sah.Build(verts)
+        sah = api.BVH(device=local)
+        sah.Build(verts)
+        build_ms = sah.info().build_ms
         hq = api.BVH(device=local)
         hq.BuildHQ(verts)
         hq = api.BVH(device=local)
         hq.BuildHQ(verts)
         build_hq = {"ms": hq.info().build_ms, "mtris_per_s": ntris / hq.info().build_ms / 1e3, "nodes": hq.info().used_nodes, "idx_count": hq.info().idx_count}
-        del hq
+        bvh = hq if args.tree == "hq" else sah
+        del hq, sah
     if world > 1:
         from tinybvh_b200 import multi
         arrays = None
@@ -354,7 +357,7 @@ def run_ours(args):
         tp = os.path.join(REPO, "profiles", "traffic.json")
         if os.path.isfile(tp):
             try:
-                traffic = json.load(open(tp)).get(f"k_trace_{'cwbvh' if args.layout == 'cwbvh' else 'bvh2'}_closest_{label}")
+                traffic = json.load(open(tp)).get(f"k_trace_{'cwbvh' if args.layout == 'cwbvh' else 'bvh2'}_closest_{label}" + ("_sbvh" if args.tree == "hq" else ""))
             except Exception:
                 traffic = None
         out = {
@@ -365,7 +368,8 @@ def run_ours(args):
                        "rays_per_step_per_gpu": 2 * n, "primary_rays_per_gpu": n, "shadow_rays_per_gpu": n,
                        "parallelism": f"rays sharded by index over {world} GPU(s) (each shard = the same 16.8M-ray view), BVH built on rank 0 and broadcast once (NCCL), no collective during traversal" if world > 1 else "1 GPU",
                        "l2": "no flush: per-step inputs (2 x %.2f GB ray records) exceed the 126 MB L2" % (n * 64 / 1e9),
-                       "bvh_built_on": "GPU (tbvh_build, binned SAH)"},
+                       "tree": "BVH::BuildHQ (SBVH), as tiny_bvh_speedtest.cpp builds for its traversal runs" if args.tree == "hq" else "BVH::Build (binned SAH)",
+                       "bvh_built_on": "GPU (tbvh_build_flavour)"},
             "primary_mrays": n * world / prim_ms / 1e3, "shadow_mrays": n * world / shad_ms / 1e3,
             "build": {"ms": build_ms, "mtris_per_s": (ntris / build_ms / 1e3) if build_ms else None, "bcast_ms": bcast_ms,
                       "bvh_bytes": bvh_bytes, "build_hq": build_hq},
@@ -385,7 +389,7 @@ def run_ours(args):
             t0 = time.time()
             sres = max(256, args.res // 2)
             p2, s2 = host_primary_and_shadow(args.scene, verts, label, sres, 0)
-            cb = cpu_reference(args.scene, verts, p2, s2, passes=3)
+            cb = cpu_reference(args.scene, verts, p2, s2, passes=3, hq=args.tree == "hq")
             out["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample", "impl", "primary_mrays", "shadow_mrays", "build_mtris")}
             log(f"[bench] cpu baseline took {time.time() - t0:.1f}s")
         print(json.dumps(out), flush=True)
@@ -403,6 +407,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--scene", default="sponza")
     ap.add_argument("--layout", default="bvh", choices=["bvh", "cwbvh"])
+    ap.add_argument("--tree", default="hq", choices=["hq", "sah"],
+                    help="hq: BVH::BuildHQ (SBVH), the tree every traversal benchmark of tiny_bvh_speedtest.cpp builds (:894, 960, 1013, 1099, 1197); sah: BVH::Build")
     ap.add_argument("--res", type=int, default=1024, help="primary rays = res*res*16 (1024 -> 16,777,216)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--full-reference", action="store_true")

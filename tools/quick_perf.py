@@ -31,12 +31,13 @@ def main():
     scene = sys.argv[1] if len(sys.argv) > 1 else "sponza"
     res = int(sys.argv[2]) if len(sys.argv) > 2 else 512
     v, label = scenes.load_scene(scene)
-    e = api.BVH().Build(v)
-    e = api.BVH().Build(v)
+    builder = "BuildHQ" if "--hq" in sys.argv else "Build"   # --hq: trace the SBVH
+    e = getattr(api.BVH(), builder)(v)
+    e = getattr(api.BVH(), builder)(v)
     i = e.info()
     print(f"{label}: {v.shape[0] // 3} tris, GPU build {i.build_ms:.3f} ms ({v.shape[0] // 3 / i.build_ms / 1e3:.1f} Mtris/s), nodes {i.used_nodes}, depth {i.max_depth}, "
           f"variant {os.environ.get('TBVH_TRACE_VARIANT', '0')} small_t {os.environ.get('TBVH_SMALL_T', '256')}")
-    layout = sys.argv[3] if len(sys.argv) > 3 else "bvh"
+    layout = sys.argv[3] if len(sys.argv) > 3 and not sys.argv[3].startswith("--") else "bvh"
     if layout == "cwbvh":
         import ctypes as C
         t0 = time.time()
