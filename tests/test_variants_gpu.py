@@ -81,3 +81,38 @@ def test_builder_switch_point_does_not_change_the_tree(gpu, small_t):
         assert np.array_equal(nodes.view(np.uint32), np.ascontiguousarray(o.nodes).view(np.uint32)) and np.array_equal(idx, o.prim_idx)
     finally:
         api.set_option("small_t", 128)
+
+
+def test_packed_upload_host_path(gpu):
+    """host_path 2: host threads pack O, D, mask, t (u, v, prim) into 48 / 32 bytes per ray after checking rD == safercp( D ),
+    the device rebuilds rD.  Same bits as the default path; rays with a hand-set rD fall back to the 64-byte copy; a miss leaves
+    u, v, prim as they were."""
+    v = scenes.procedural_scene(60000, 77)
+    o = util.oracle_bvh(v)
+    lo, hi = scenes.scene_bounds(v)
+    rays = R.primary_rays(*R.bounds_camera(lo, hi, "outside"), 512, 512, 4)      # 1,048,576 rays: above the 65,536-ray threshold
+    rays["u"], rays["v"], rays["prim"] = 0.25, 0.5, 77                            # what a miss must leave behind
+    want = rays.copy()
+    o.intersect(want)
+    sh = util.derived_sets(want, v, (lo, hi))["shadow"]
+    want_bits = o.occluded(sh)
+    e = api.BVH().Build(v)
+    api.set_option("host_path", 2)
+    try:
+        got = rays.copy()
+        e.Intersect(got)
+        assert util.compare_hits(got, want) == ZERO
+        miss = want["t"] >= 1e30
+        assert miss.any() and np.all(got["prim"][miss] == 77) and np.all(got["u"][miss] == np.float32(0.25))
+        assert np.array_equal(e.IsOccluded(sh), want_bits)
+        hits = e.IntersectPacked(rays)
+        assert np.array_equal(hits["t"].view(np.uint32), want["t"].view(np.uint32)) and np.array_equal(hits["prim"], want["prim"])
+        # a chunk holding a ray whose rD is not safercp( D ) must take the 64-byte path and honour the stored rD
+        odd = rays.copy()
+        odd["rD"][123456] = odd["rD"][123456] * np.float32(1.5)
+        want_odd = odd.copy()
+        o.intersect(want_odd)
+        e.Intersect(odd)
+        assert util.compare_hits(odd, want_odd) == ZERO
+    finally:
+        api.set_option("host_path", 0)

@@ -6,6 +6,10 @@
 #include <string.h>
 #include <vector>
 #include <thread>
+#include <atomic>
+#include <mutex>
+#include <condition_variable>
+#include <memory>
 #include <new>
 
 static thread_local char g_err[512] = "";
@@ -58,7 +62,7 @@ int tbvh_ctx_create( int device, tbvh_ctx* out )
 		for (int p = 0; p < 4; p++) CUDA_TRY( cudaEventCreateWithFlags( &c->ev_part[i][p], cudaEventDisableTiming ) );
 	}
 	const char* hp = getenv( "TBVH_HOST_PATH" );
-	c->host_path = hp && !strcmp( hp, "zerocopy" ) ? 1 : 0;
+	c->host_path = hp && !strcmp( hp, "zerocopy" ) ? 1 : hp && !strcmp( hp, "packed" ) ? 2 : 0;
 	const char* tv = getenv( "TBVH_TRACE_VARIANT" );
 	c->trace_variant = tv ? atoi( tv ) : 3; // octant switch: +5 % on camera / shadow rays, -3 % on diffuse (profiles/README.md)
 	const char* st = getenv( "TBVH_SMALL_T" );
@@ -601,6 +605,116 @@ static void scatter_hits_host( const char* packed, char* rays, uint32_t stride, 
 	for (auto& t : pool) t.join();
 }
 
+// ---- host_path 2: packed upload ---------------------------------------------------------------------------------
+// The copy engine moves 64-byte rows out of 128-byte records at ~40 GB/s; a contiguous pinned copy runs at the link's ~54 GB/s
+// and needs fewer bytes: the stored rD of a ray built by Ray::Ray is safercp( D ) (tiny_bvh.h:698), which the device can
+// recompute bit for bit (IEEE division).  Host threads therefore pack O, D, mask, t (and u, v, prim for closest hits, so a miss
+// writes back what was there) into 48 / 32 bytes per ray while CHECKING that rD really is safercp( D ); a chunk with any ray
+// whose rD was set by other means falls back to the 64-byte path.  A device kernel expands the packed records into the staged
+// 64-byte layout the traversal kernels read.
+static inline float host_safercp( const float x ) { if (x > 1e-12f || x < -1e-12f) return 1.0f / x; else return x >= 0 ? BVH_FAR : -BVH_FAR; }
+struct PackJob { const char* src; uint32_t stride; uint64_t cnt; char* dst; int rec; };
+static void pack_slice( const PackJob& j, const unsigned t, const unsigned T, std::atomic<int>& bad )
+{
+	const uint64_t per = (j.cnt + T - 1) / T, a = per * t, e = a + per < j.cnt ? a + per : j.cnt;
+	int mismatch = 0;
+	for (uint64_t i = a; i < e; i++)
+	{
+		const float* r = (const float*)(j.src + i * j.stride);
+		float* o = (float*)(j.dst + i * j.rec);
+		const float c0 = host_safercp( r[4] ), c1 = host_safercp( r[5] ), c2 = host_safercp( r[6] );
+		mismatch |= memcmp( &c0, r + 8, 4 ) | memcmp( &c1, r + 9, 4 ) | memcmp( &c2, r + 10, 4 );
+		o[0] = r[0], o[1] = r[1], o[2] = r[2], o[3] = r[12];               // O, hit.t
+		o[4] = r[4], o[5] = r[5], o[6] = r[6], o[7] = r[3];                // D, mask
+		if (j.rec == 48) o[8] = r[13], o[9] = r[14], o[10] = r[15], o[11] = 0; // hit.u, v, prim
+	}
+	if (mismatch) bad = 1;
+}
+class PackPool
+{
+public:
+	explicit PackPool( unsigned threads ) : T( threads ) { for (unsigned t = 0; t < T; t++) th.emplace_back( [this, t]() { worker( t ); } ); }
+	~PackPool() { { std::lock_guard<std::mutex> lk( m ); quit = true; } cv_go.notify_all(); for (auto& t : th) t.join(); }
+	bool run( const PackJob& j ) // true when every ray of the chunk had a canonical rD
+	{
+		{ std::lock_guard<std::mutex> lk( m ); job = j, done = 0, bad = 0, gen++; }
+		cv_go.notify_all();
+		std::unique_lock<std::mutex> lk( m );
+		cv_done.wait( lk, [&]() { return done == T; } );
+		return bad == 0;
+	}
+private:
+	void worker( unsigned t )
+	{
+		uint64_t seen = 0;
+		for (;;)
+		{
+			std::unique_lock<std::mutex> lk( m );
+			cv_go.wait( lk, [&]() { return quit || gen != seen; } );
+			if (quit) return;
+			seen = gen;
+			const PackJob j = job;
+			lk.unlock();
+			pack_slice( j, t, T, bad );
+			lk.lock();
+			if (++done == T) cv_done.notify_one();
+		}
+	}
+	unsigned T;
+	std::vector<std::thread> th;
+	std::mutex m;
+	std::condition_variable cv_go, cv_done;
+	uint64_t gen = 0;
+	unsigned done = 0;
+	bool quit = false;
+	PackJob job = {};
+	std::atomic<int> bad{ 0 };
+};
+// packed record -> staged 64-byte ray record: rows (O, mask) (D, 0) (safercp( D ), 0) (t, u, v, prim)
+__global__ void __launch_bounds__( 256 ) k_unpack_rays( const float4* __restrict__ src, const int rows /* 3 or 2 */, float4* __restrict__ dst, const uint64_t n )
+{
+	const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	const float4 a = src[i * rows], d = src[i * rows + 1];
+	float4 h = make_float4( a.w, 0, 0, 0 );
+	if (rows == 3) { const float4 c = src[i * rows + 2]; h = make_float4( a.w, c.x, c.y, c.z ); }
+	const float rx = (d.x > 1e-12f || d.x < -1e-12f) ? __fdiv_rn( 1.0f, d.x ) : (d.x >= 0 ? BVH_FAR : -BVH_FAR);
+	const float ry = (d.y > 1e-12f || d.y < -1e-12f) ? __fdiv_rn( 1.0f, d.y ) : (d.y >= 0 ? BVH_FAR : -BVH_FAR);
+	const float rz = (d.z > 1e-12f || d.z < -1e-12f) ? __fdiv_rn( 1.0f, d.z ) : (d.z >= 0 ? BVH_FAR : -BVH_FAR);
+	dst[i * 4] = make_float4( a.x, a.y, a.z, d.w ), dst[i * 4 + 1] = make_float4( d.x, d.y, d.z, 0 );
+	dst[i * 4 + 2] = make_float4( rx, ry, rz, 0 ), dst[i * 4 + 3] = h;
+}
+static int ensure_pack( tbvh_ctx c )
+{
+	if (c->h_pack[0]) return TBVH_OK;
+	for (int i = 0; i < 3; i++)
+	{
+		CUDA_TRY( cudaHostAlloc( &c->h_pack[i], STAGE_RAYS * 48, cudaHostAllocDefault ) );
+		CUDA_TRY( cudaMalloc( &c->d_pack[i], STAGE_RAYS * 48 ) );
+		CUDA_TRY( cudaEventCreateWithFlags( &c->ev_pack[i], cudaEventDisableTiming ) );
+	}
+	return TBVH_OK;
+}
+static unsigned pack_threads()
+{
+	static int env = -1;
+	if (env < 0) { const char* e = getenv( "TBVH_PACK_THREADS" ); env = e ? atoi( e ) : 0; }
+	unsigned t = env > 0 ? (unsigned)env : std::thread::hardware_concurrency() / 8;
+	return t < 1 ? 1 : t > 64 ? 64 : t;
+}
+// one chunk through the packed path; returns 1 when it was taken, 0 when the chunk must use the 64-byte path (non-canonical rD)
+static int stage_in_packed( tbvh_ctx c, PackPool& pool, const int k, const uint64_t chunk, const char* h, const uint32_t stride, const uint64_t cnt, const int rec, cudaStream_t s )
+{
+	if (chunk >= 3) CUDA_TRY( cudaEventSynchronize( c->ev_pack[k] ) ); // the staging buffer's previous copy has left the host
+	const PackJob j = { h, stride, cnt, (char*)c->h_pack[k], rec };
+	if (!pool.run( j )) return 0;
+	CUDA_TRY( cudaMemcpyAsync( c->d_pack[k], c->h_pack[k], cnt * rec, cudaMemcpyHostToDevice, s ) );
+	CUDA_TRY( cudaEventRecord( c->ev_pack[k], s ) );
+	k_unpack_rays<<<(uint32_t)((cnt + 255) / 256), 256, 0, s>>>( (const float4*)c->d_pack[k], rec / 16, (float4*)c->d_stage[k], cnt );
+	LAUNCHED();
+	return 1;
+}
+
 static int intersect_host( tbvh_bvh b, int layout, void* rays, uint32_t stride, uint64_t n, void* packed_hits );
 
 int tbvh_intersect( tbvh_bvh b, int layout, void* rays, uint32_t stride, uint64_t n ) { return intersect_host( b, layout, rays, stride, n, 0 ); }
@@ -642,14 +756,19 @@ static int intersect_host( tbvh_bvh b, int layout, void* rays, uint32_t stride, 
 	{
 		if (c->h_hits_rays < n) { if (c->h_hits) cudaFreeHost( c->h_hits ); c->h_hits = 0; CUDA_TRY( cudaHostAlloc( &c->h_hits, n * 16, cudaHostAllocDefault ) ); c->h_hits_rays = n; }
 	}
+	std::unique_ptr<PackPool> pool;
+	if (c->host_path == 2 && n >= 65536) { TRY( ensure_pack( c ) ); pool.reset( new PackPool( pack_threads() ) ); }
 	int k = 0;
-	for (uint64_t off = 0; off < n; off += c->stage_rays, k = (k + 1) % 3)
+	uint64_t chunk = 0;
+	for (uint64_t off = 0; off < n; off += c->stage_rays, k = (k + 1) % 3, chunk++)
 	{
 		const uint64_t cnt = n - off < c->stage_rays ? n - off : c->stage_rays;
 		cudaStream_t s = c->copy_streams[k];
 		char* h = (char*)rays + off * stride;
 		char* hd = dev_alias ? dev_alias + off * stride : 0;
-		TRY( stage_in( c, k, h, hd, stride, cnt, s ) );
+		int took = 0;
+		if (pool) { took = stage_in_packed( c, *pool, k, chunk, h, stride, cnt, 48, s ); if (took < 0) return took; }
+		if (!took) TRY( stage_in( c, k, h, hd, stride, cnt, s ) );
 		if (mode == 2 || mode == 4)
 		{
 			// hits leave the device packed (16 B per ray, one contiguous copy per chunk): into the caller's packed array
@@ -686,13 +805,18 @@ int tbvh_occluded( tbvh_bvh b, int layout, const void* rays, uint32_t stride, ui
 	tbvh_ctx c = b->ctx;
 	TRY( ensure_stage( c ) );
 	const char* dev_alias = (const char*)mapped_alias( rays );
+	std::unique_ptr<PackPool> pool;
+	if (c->host_path == 2 && !b->d_inst && n >= 65536) { TRY( ensure_pack( c ) ); pool.reset( new PackPool( pack_threads() ) ); }
 	int k = 0;
-	for (uint64_t off = 0; off < n; off += c->stage_rays, k = (k + 1) % 3)
+	uint64_t chunk = 0;
+	for (uint64_t off = 0; off < n; off += c->stage_rays, k = (k + 1) % 3, chunk++)
 	{
 		const uint64_t cnt = n - off < c->stage_rays ? n - off : c->stage_rays;
 		cudaStream_t s = c->copy_streams[k];
 		const char* h = (const char*)rays + off * stride;
-		TRY( stage_in( c, k, h, dev_alias ? dev_alias + off * stride : 0, stride, cnt, s ) );
+		int took = 0;
+		if (pool) { took = stage_in_packed( c, *pool, k, chunk, h, stride, cnt, 32, s ); if (took < 0) return took; }
+		if (!took) TRY( stage_in( c, k, h, dev_alias ? dev_alias + off * stride : 0, stride, cnt, s ) );
 		if (b->d_inst) TRY( tlas_trace_launch( b, c->d_stage[k], 64, (uint32_t*)c->d_stage_bits[k], cnt, true, s ) );
 		else TRY( trace_dispatch( b, layout, c->d_stage[k], 64, 0, 0, (uint32_t*)c->d_stage_bits[k], cnt, true, s ) );
 		CUDA_TRY( cudaMemcpyAsync( bits + off / 32, c->d_stage_bits[k], ((cnt + 31) / 32) * 4, cudaMemcpyDeviceToHost, s ) );

@@ -37,6 +37,9 @@ struct tbvh_ctx_t
 	int d2h_mode = 0;                // hits back to the host: 0 = 2D copy of 16-byte rows, 1 = 2D copy of the whole 64-byte rows,
 	                                 // 2 = packed 1D copy to pinned staging + multi-threaded host scatter, 3 = scatter kernel (zero copy)
 	void* d_hits_pack[3] = { 0, 0, 0 };
+	// host_path 2: rays are packed by host threads into pinned staging (48 or 32 bytes per ray) and cross PCIe as ONE contiguous copy
+	void* h_pack[3] = { 0, 0, 0 }; void* d_pack[3] = { 0, 0, 0 };
+	cudaEvent_t ev_pack[3] = { 0, 0, 0 };
 	void* h_hits = 0; size_t h_hits_rays = 0; // pinned staging for d2h_mode 2
 	cudaStream_t aux_streams[4] = { 0, 0, 0, 0 };
 	cudaEvent_t ev_done[3] = { 0, 0, 0 };
