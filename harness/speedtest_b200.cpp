@@ -199,12 +199,16 @@ int main( int argc, char** argv )
 			T[1] = T[4] = T[6] = T[9] = T[12] = T[13] = T[14] = 0;
 			T[3] = (i % 3 - 1) * span, T[7] = (i / 9 - 1) * span * 0.6f, T[11] = ((i / 3) % 3 - 1) * span;
 		}
+		BLASInstance* inst2 = (BLASInstance*)malloc64( N * sizeof( BLASInstance ) );
+		memcpy( inst2, inst, N * sizeof( BLASInstance ) );
 		BVHBase* blasList[1] = { &ref_blas };
 		BVH ref_tlas;
 		ref_tlas.Build( inst, N, blasList, 1 ); // Update()s the instances: inverse transforms + world boxes
 		tinybvh_b200::BVHBase* gpuList[1] = { &gpu_blas };
 		tinybvh_b200::BVH gpu_tlas;
-		gpu_tlas.Build( inst, N, gpuList, 1 );
+		gpu_tlas.Build( inst2, N, gpuList, 1 ); // the shim Update()s its copy the same way
+		const bool updSame = memcmp( inst, inst2, N * sizeof( BLASInstance ) ) == 0;
+		printf( "BLASInstance::Update: %d records %s the reference's\n", N, updSame ? "identical to" : "DIFFER from" );
 		const size_t M = (size_t)W * H;
 		Ray* a = (Ray*)malloc64( M * sizeof( Ray ) ), * b = (Ray*)tinybvh_b200::malloc_pinned( M * sizeof( Ray ) ); // rays that cross PCIe: page-locked
 		const bvhvec3 eye( span * 0.2f, span * 1.1f, -span * 2.6f ), view = tinybvh_normalize( bvhvec3( -0.05f, -0.35f, 1 ) );
@@ -229,7 +233,7 @@ int main( int argc, char** argv )
 			hits += a[k].hit.t < 1e30f;
 			diff += memcmp( &a[k].hit.t, &b[k].hit.t, 16 ) != 0 || (a[k].hit.t < 1e30f && a[k].hit.inst != b[k].hit.inst);
 		}
-		tlasSame = diff == 0 && gpu_tlas.usedNodes == ref_tlas.usedNodes;
+		tlasSame = diff == 0 && gpu_tlas.usedNodes == ref_tlas.usedNodes && updSame;
 		printf( "TLAS of %d instances: reference IntersectTLAS %.2f ms (%u threads), tinybvh_b200 %.2f ms incl. PCIe; %zu of %zu rays hit, %zu differ (t,u,v,prim,inst)\n",
 			N, refT * 1000, std::thread::hardware_concurrency(), gpuT * 1000, hits, M, diff );
 	}

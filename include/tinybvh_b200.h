@@ -114,6 +114,12 @@ int tbvh_build_indexed( tbvh_bvh bvh, const void* verts, uint32_t stride, uint32
  * A host program compiled with another INST_IDX_BITS (4..31) sets tbvh_set_option( ctx, "inst_idx_bits", bits ): hits then
  * carry the instance in the top bits of hit.prim (prim = triIdx + (inst << (32 - bits)), :8527) and byte 44 is left alone.
  * Pass layout TBVH_LAYOUT_BVH to the traversal calls. */
+/* BLASInstance::Update( BVHBase* blas ) tiny_bvh.h:8386 on one 192-byte record: invTransform = inverse of transform
+ * (InvertTransform :8402), aabbMin / aabbMax = box of the eight transformed corners of the BLAS's root box.  Host arithmetic in
+ * the reference build's own operation order: the record comes out bit-identical to the reference's.  _box takes the root box
+ * directly (no device needed). */
+int tbvh_instance_update( void* instance, tbvh_bvh blas );
+int tbvh_instance_update_box( void* instance, const float* blas_aabb_min, const float* blas_aabb_max );
 int tbvh_build_tlas( tbvh_bvh tlas, const void* instances, uint32_t inst_stride, uint32_t inst_count, const tbvh_bvh* blasses, uint32_t blas_count,
 	float c_trav, float c_int );
 

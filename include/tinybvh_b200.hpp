@@ -153,9 +153,8 @@ public:
 		sync_info();
 	}
 	// TLAS: BVH::Build( BLASInstance* instances, instCount, BVHBase** blasses, blasCount ) tiny_bvh.h:2221.  Inst is the
-	// reference's 192-byte tinybvh::BLASInstance; the instances must already be Update()d (inverse transform + world box,
-	// :8386 - run the reference's own inst.Update( &hostBVH ) with hostBVH.aabbMin / aabbMax copied from the BLAS's aabbMin /
-	// aabbMax here, or fill the fields directly): the engine implements the reference's "blasses == 0" contract (:2245).
+	// reference's 192-byte tinybvh::BLASInstance.  As in the reference (:2245-2250) every instance is Update()d first - inverse
+	// transform and world box, computed on the host bit-identically to BLASInstance::Update (:8386) - and written back.
 	// Intersect / IsOccluded on the TLAS are then IntersectTLAS / IsOccludedTLAS; a hit carries hit.inst (INST_IDX_BITS == 32).
 	template <class Inst> void Build( Inst* instances, const uint32_t instCount, BVHBase** blasses, const uint32_t blasCount )
 	{
@@ -165,6 +164,12 @@ public:
 #endif
 		tbvh_bvh* hs = (tbvh_bvh*)malloc( sizeof( tbvh_bvh ) * (blasCount ? blasCount : 1) );
 		for (uint32_t k = 0; k < blasCount; k++) hs[k] = blasses[k]->handle();
+		for (uint32_t i = 0; i < instCount; i++) // instList[i].Update( blas ) :2247-2249, bit-identical to the reference's
+		{
+			uint32_t blasIdx;
+			memcpy( &blasIdx, (const char*)&instances[i] + 140, 4 );
+			TBVH_FATAL_IF( blasIdx >= blasCount || tbvh_instance_update( &instances[i], hs[blasIdx] ), "BLASInstance::Update" );
+		}
 		const int rc = tbvh_build_tlas( h, instances, (uint32_t)sizeof( Inst ), instCount, hs, blasCount, c_trav, c_int );
 		free( hs );
 		TBVH_FATAL_IF( rc, "BVH::Build( BLASInstance*, .. )" );

@@ -42,6 +42,7 @@ def lib():
         L.orc_to_bvh_gpu.restype, L.orc_to_bvh_gpu.argtypes = u32, [vp, vp]
         L.orc_intersect_tlas.restype, L.orc_intersect_tlas.argtypes = None, [vp, vp, vp, vp, vp, u64]
         L.orc_occluded_tlas.restype, L.orc_occluded_tlas.argtypes = None, [vp, vp, vp, vp, vp, u64, vp]
+        L.orc_instance_update.restype, L.orc_instance_update.argtypes = None, [vp, vp, vp]
         L.orc_refit.restype, L.orc_refit.argtypes = None, [vp, u32, vp, vp]
         L.orc_sah_cost.restype, L.orc_sah_cost.argtypes = f32, [vp, u32, f32, f32]
         _lib = L
@@ -120,6 +121,15 @@ class PortTLAS:
         bits = np.zeros((rays.shape[0] + 31) // 32, np.uint32)
         lib().orc_occluded_tlas(_ptr(self.nodes), _ptr(self.prim_idx), _ptr(self.instances), C.cast(self._table, C.c_void_p), _ptr(rays), rays.shape[0], _ptr(bits))
         return bits
+
+
+def instance_update(instances, bmin, bmax):
+    """orc_instance_update on every record of a BLASInstance array (in place), for BLAS root boxes bmin[i] / bmax[i] (or one box)."""
+    lo, hi = np.ascontiguousarray(bmin, np.float32).reshape(-1, 3), np.ascontiguousarray(bmax, np.float32).reshape(-1, 3)
+    for i in range(instances.shape[0]):
+        a, b = lo[i % lo.shape[0]].copy(), hi[i % hi.shape[0]].copy()
+        lib().orc_instance_update(instances[i:i + 1].ctypes.data, _ptr(a), _ptr(b))
+    return instances
 
 
 def build_hq(verts, c_trav: float = 1.0, c_int: float = 1.0):

@@ -149,6 +149,13 @@ void* ref_tlas_build( void* instances, uint32_t instCount, void** blasHandles, u
 	t->tlas.Build( (BLASInstance*)instances, instCount, t->blas.data(), blasCount );
 	return t;
 }
+// BLASInstance::Update (:8386) on one 192-byte record, for a BLAS whose root box is [bmin, bmax]
+void ref_instance_update( void* instance, const float* bmin, const float* bmax )
+{
+	BVH blas;
+	blas.aabbMin = bvhvec3( bmin[0], bmin[1], bmin[2] ), blas.aabbMax = bvhvec3( bmax[0], bmax[1], bmax[2] );
+	((BLASInstance*)instance)->Update( &blas );
+}
 void ref_tlas_destroy( void* h ) { delete (RefTLAS*)h; }
 void* ref_tlas_bvh( void* h ) { return &((RefTLAS*)h)->tlas; }
 int ref_sizeof_blas_instance() { return (int)sizeof( BLASInstance ); }

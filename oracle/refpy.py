@@ -44,6 +44,7 @@ def lib():
             "ref_bvh_occluded": (None, [vp, vp, u64, vp, i32]),
             "ref_clip_frag": (i32, [vp, vp, vp, vp, vp, vp, u32]),
             "ref_split_frag": (None, [vp, vp, vp, vp, vp, u32, C.c_float, vp, vp]),
+            "ref_instance_update": (None, [vp, vp, vp]),
             "ref_tlas_build": (vp, [vp, u32, vp, u32]), "ref_tlas_destroy": (None, [vp]), "ref_tlas_bvh": (vp, [vp]),
             "ref_sizeof_blas_instance": (i32, []), "ref_inst_idx_bits": (i32, []), "ref_offsetof_hit_inst": (i32, []),
             "ref_bvhgpu_from_bvh": (vp, [vp, i32]), "ref_bvhgpu_destroy": (None, [vp]),

@@ -45,6 +45,8 @@ void orc_occluded( const orc_node* nodes, const uint32_t* primIdx, const float* 
  * blas[k]: the k-th BLAS (its node array, primIdx and vertices).  bits must be zeroed by the caller. */
 typedef struct { float transform[16], invTransform[16]; float aabbMin[3]; uint32_t blasIdx; float aabbMax[3]; uint32_t mask; uint32_t dummy[8]; } orc_instance;
 typedef struct { const orc_node* nodes; const uint32_t* primIdx; const float* verts; } orc_blas;
+/* BLASInstance::Update (:8386): inverse transform + world box of a BLAS whose root box is [bmin, bmax] */
+void orc_instance_update( orc_instance* inst, const float* bmin, const float* bmax );
 void orc_intersect_tlas( const orc_node* nodes, const uint32_t* primIdx, const orc_instance* inst, const orc_blas* blas, void* rays, uint64_t n );
 void orc_occluded_tlas( const orc_node* nodes, const uint32_t* primIdx, const orc_instance* inst, const orc_blas* blas, const void* rays, uint64_t n, uint32_t* bits );
 

@@ -43,3 +43,24 @@ def test_no_cpu_fallback_without_device():
     rc = L.tbvh_ctx_create(0, ctypes.byref(h))
     assert rc != 0
     assert b"no CPU fallback" in L.tbvh_last_error() or b"cuda" in L.tbvh_last_error().lower()
+
+
+def test_instance_update_matches_the_oracle():
+    """tbvh_instance_update_box is host arithmetic (no device needed): BLASInstance::Update (tiny_bvh.h:8386), bit for bit."""
+    import ctypes as C
+    import numpy as np
+    from oracle import portpy
+    from tinybvh_b200 import api
+    rng = np.random.default_rng(3)
+    T = (rng.random((500, 16), np.float32) - 0.5) * 4
+    T[::2, 12:15], T[::2, 15] = 0, 1
+    a = np.zeros(500, api.BLAS_INSTANCE)
+    a["transform"] = T
+    a["mask"] = 0xFFFF
+    b = a.copy()
+    lo, hi = np.array([-1.5, -0.7, -2.2], np.float32), np.array([1.1, 2.3, 0.9], np.float32)
+    portpy.instance_update(a, lo, hi)
+    L = _lib.lib()
+    for i in range(500):
+        assert L.tbvh_instance_update_box(C.c_void_p(b[i:i + 1].ctypes.data), lo.ctypes.data_as(C.c_void_p), hi.ctypes.data_as(C.c_void_p)) == 0
+    assert a.tobytes() == b.tobytes()

@@ -249,3 +249,19 @@ def test_port_tlas_matches_reference():
     tl.intersect(a, threads=1), port.intersect(b)
     wa, wb = a.view(np.uint32).reshape(-1, 32)[:, 11:16], b.view(np.uint32).reshape(-1, 32)[:, 11:16]
     assert np.array_equal(wa, wb) and np.isin(wa[a["t"] < 1e30, 0], np.arange(0, 40, 5)).any()
+
+
+@pytest.mark.skipif(not refpy.available(), reason="oracle/_ref not built (needs /root/reference)")
+def test_port_instance_update_matches_reference():
+    """BLASInstance::Update / InvertTransform (:8386-8428): the vectorised reference build fuses different multiply-adds in
+    different rows of the cofactor matrix; the restatement reproduces all of them (affine and projective matrices)."""
+    rng = np.random.default_rng(5)
+    T = (rng.random((3000, 16), np.float32) - 0.5) * 4
+    T[::2, 12:15], T[::2, 15] = 0, 1
+    a = refpy.make_instances(T, np.zeros(3000, np.uint32))
+    b = a.copy()
+    lo, hi = np.array([-1.5, -0.7, -2.2], np.float32), np.array([1.1, 2.3, 0.9], np.float32)
+    for i in range(a.shape[0]):
+        refpy.lib().ref_instance_update(a[i:i + 1].ctypes.data, lo.ctypes.data, hi.ctypes.data)
+    portpy.instance_update(b, lo, hi)
+    assert a.tobytes() == b.tobytes()

@@ -21,9 +21,11 @@ def test_tlas_matches_reference(gpu, n_inst, builder):
         pytest.skip("needs oracle/_ref")
     v, inst, O, D = tlas_case(91, n_inst)
     mode = {"Build": 0, "BuildAVX": 1, "BuildHQ": 2}[builder]
-    ref = refpy.RefTLAS(inst, [refpy.RefBVH(x, mode=mode, threaded=False) for x in v])   # Update()s inst in place
+    inst_ref = inst.copy()
+    ref = refpy.RefTLAS(inst_ref, [refpy.RefBVH(x, mode=mode, threaded=False) for x in v])   # Update()s inst_ref in place
     blas = [getattr(api.BVH(), builder)(x) for x in v]
-    t = api.TLAS().Build(inst, blas)
+    t = api.TLAS().Build(inst, blas)                                                         # the engine Update()s inst in place
+    assert inst.tobytes() == inst_ref.tobytes(), "BLASInstance::Update differs"
     nodes, idx = t.download()
     rb = ref.bvh()
     assert np.array_equal(nodes.view(np.uint32), rb.nodes.view(np.uint32)) and np.array_equal(idx, rb.prim_idx), "TLAS tree differs"
@@ -48,7 +50,7 @@ def test_tlas_device_rays_and_errors(gpu):
     v, inst, O, D = tlas_case(93, 24)
     ref = refpy.RefTLAS(inst, [refpy.RefBVH(x, mode=0, threaded=False) for x in v])
     blas = [api.BVH().Build(x) for x in v]
-    t = api.TLAS().Build(inst, blas)
+    t = api.TLAS().Build(inst, blas, update=False)   # records already updated by the reference: the "blasses == 0" contract
     rays = R.make_rays(O, D)
     want = rays.copy()
     ref.intersect(want)

@@ -214,10 +214,15 @@ class TLAS(BVH):
     it are IntersectTLAS / IsOccludedTLAS.  `instances`: BLAS_INSTANCE records already Update()d by the caller (inverse transform
     and world box, as BLASInstance::Update :8386 computes them); `blasses`: BVH objects of this module, kept alive by this one."""
 
-    def Build(self, instances, blasses):
-        inst = np.ascontiguousarray(instances)
-        assert inst.dtype.itemsize == 192
+    def Build(self, instances, blasses, update: bool = True):
+        """update=True: BLASInstance::Update (:8386) is applied to every record first - in place, as the reference's Build does when it
+        is handed the BLAS list (:2245-2250); update=False: the records already carry inverse transform and world box."""
+        inst = instances
+        assert inst.dtype.itemsize == 192 and inst.flags.c_contiguous
         self.blasses = list(blasses)
+        if update:
+            for i in range(inst.shape[0]):
+                check(_lib.lib().tbvh_instance_update(C.c_void_p(inst[i:i + 1].ctypes.data), self.blasses[int(inst["blasIdx"][i])].h))
         hs = (C.c_void_p * len(self.blasses))(*[b.h for b in self.blasses])
         check(_lib.lib().tbvh_build_tlas(self.h, _np_ptr(inst), 192, inst.shape[0], hs, len(self.blasses), self.c_trav, self.c_int))
         return self

@@ -359,6 +359,81 @@ int tbvh_build_flavour( tbvh_bvh b, const void* verts, uint32_t stride, uint32_t
 	return TBVH_OK;
 }
 
+// ---- BLASInstance::Update on the host (the engine's own restatement; host code, so gcc's contraction is switched off for it)
+#define UPD_ATTR __attribute__( (optimize( "fp-contract=off" )) )
+
+/* BLASInstance::InvertTransform (:8402-8428) + Update (:8386-8399).  The frozen reference build vectorises the sixteen cofactor
+ * sums, and the lanes of different rows end up with different fused multiply-adds; the shapes below were identified by
+ * exhaustive search over every contraction gcc may legally form (3 x 2^4 per cofactor, 12 for the determinant, 6^4 for the
+ * corner transform) against BLASInstance::Update on 2,000 random matrices, and are pinned by the tests.  A cofactor is
+ * s0*(a0*b0)*c0 + ... + s5*(a5*b5)*c5 with p_k = round( a_k*b_k ):
+ *   rows 0,1 : t0 = round( p0*c0 ); acc = fma( +-p1, c1, t0 ); then fma( +-p_k, c_k, acc ) for k = 2..5
+ *   row 2    : acc = fma( p0, c0, +-round( p1*c1 ) ); k=2: acc +- round( p2*c2 ); k=3,4: fma; k=5: acc +- round( p5*c5 )
+ *   row 3    : acc = fma( p0, c0, +-round( p1*c1 ) ); k=2: fma; k=3,4: acc +- round(..); k=5: fma
+ *   det      = fma( T3, c12, fma( T2, c8, fma( T0, c0, round( T1*c4 ) ) ) ); every cell is then multiplied by 1/det
+ *   corner   : row = fma( Tz, z, fma( Tx, x, round( Ty*y ) ) ) + Tw, divided by w only when w != 1 */
+typedef struct { signed char s; unsigned char a, b, c; } UPD_TERM;
+static const UPD_TERM UPD_E[16][6] = {
+ {{+1,5,10,15},{-1,5,11,14},{-1,9,6,15},{+1,9,7,14},{+1,13,6,11},{-1,13,7,10}}, {{-1,1,10,15},{+1,1,11,14},{+1,9,2,15},{-1,9,3,14},{-1,13,2,11},{+1,13,3,10}},
+ {{+1,1,6,15},{-1,1,7,14},{-1,5,2,15},{+1,5,3,14},{+1,13,2,7},{-1,13,3,6}}, {{-1,1,6,11},{+1,1,7,10},{+1,5,2,11},{-1,5,3,10},{-1,9,2,7},{+1,9,3,6}},
+ {{-1,4,10,15},{+1,4,11,14},{+1,8,6,15},{-1,8,7,14},{-1,12,6,11},{+1,12,7,10}}, {{+1,0,10,15},{-1,0,11,14},{-1,8,2,15},{+1,8,3,14},{+1,12,2,11},{-1,12,3,10}},
+ {{-1,0,6,15},{+1,0,7,14},{+1,4,2,15},{-1,4,3,14},{-1,12,2,7},{+1,12,3,6}}, {{+1,0,6,11},{-1,0,7,10},{-1,4,2,11},{+1,4,3,10},{+1,8,2,7},{-1,8,3,6}},
+ {{+1,4,9,15},{-1,4,11,13},{-1,8,5,15},{+1,8,7,13},{+1,12,5,11},{-1,12,7,9}}, {{-1,0,9,15},{+1,0,11,13},{+1,8,1,15},{-1,8,3,13},{-1,12,1,11},{+1,12,3,9}},
+ {{+1,0,5,15},{-1,0,7,13},{-1,4,1,15},{+1,4,3,13},{+1,12,1,7},{-1,12,3,5}}, {{-1,0,5,11},{+1,0,7,9},{+1,4,1,11},{-1,4,3,9},{-1,8,1,7},{+1,8,3,5}},
+ {{-1,4,9,14},{+1,4,10,13},{+1,8,5,14},{-1,8,6,13},{-1,12,5,10},{+1,12,6,9}}, {{+1,0,9,14},{-1,0,10,13},{-1,8,1,14},{+1,8,2,13},{+1,12,1,10},{-1,12,2,9}},
+ {{-1,0,5,14},{+1,0,6,13},{+1,4,1,14},{-1,4,2,13},{-1,12,1,6},{+1,12,2,5}}, {{+1,0,5,10},{-1,0,6,9},{-1,4,1,10},{+1,4,2,9},{+1,8,1,6},{-1,8,2,5}} };
+UPD_ATTR static float upd_cofactor( const float* T, const UPD_TERM* e, const int first_fused_left, const unsigned fused_mask )
+{
+	float p[6];
+	for (int k = 0; k < 6; k++) p[k] = T[e[k].a] * T[e[k].b];
+	const float p0 = e[0].s < 0 ? -p[0] : p[0];
+	float acc;
+	if (first_fused_left) { const float t1 = p[1] * T[e[1].c]; acc = fmaf( p0, T[e[0].c], e[1].s > 0 ? t1 : -t1 ); }
+	else { const float t0 = p0 * T[e[0].c]; acc = fmaf( e[1].s > 0 ? p[1] : -p[1], T[e[1].c], t0 ); }
+	for (int k = 2; k < 6; k++)
+	{
+		if (fused_mask & (1u << (k - 2))) acc = fmaf( e[k].s > 0 ? p[k] : -p[k], T[e[k].c], acc );
+		else { const float t = p[k] * T[e[k].c]; acc = e[k].s > 0 ? acc + t : acc - t; }
+	}
+	return acc;
+}
+UPD_ATTR static void upd_instance( float* T /* transform, 16 */, float* iT /* invTransform, 16 */, float* aabbMin, float* aabbMax, const float* bmin, const float* bmax )
+{
+	float c[16];
+	for (int k = 0; k < 16; k++) c[k] = k < 8 ? upd_cofactor( T, UPD_E[k], 0, 15u ) : k < 12 ? upd_cofactor( T, UPD_E[k], 1, 6u ) : upd_cofactor( T, UPD_E[k], 1, 9u );
+	const float t14 = T[1] * c[4];
+	const float det = fmaf( T[3], c[12], fmaf( T[2], c[8], fmaf( T[0], c[0], t14 ) ) );
+	if (det == 0) { for (int k = 0; k < 16; k++) iT[k] = c[k]; } /* "invert failed": the reference returns with the cofactors stored */
+	else { const float invdet = 1.0f / det; for (int k = 0; k < 16; k++) iT[k] = c[k] * invdet; }
+	for (int k = 0; k < 3; k++) aabbMin[k] = 1e30f, aabbMax[k] = -1e30f;
+	for (int j = 0; j < 8; j++)
+	{
+		const float p[3] = { j & 1 ? bmax[0] : bmin[0], j & 2 ? bmax[1] : bmin[1], j & 4 ? bmax[2] : bmin[2] };
+		float r[3];
+		for (int k = 0; k < 3; k++) { const float ty = T[k * 4 + 1] * p[1]; r[k] = fmaf( T[k * 4 + 2], p[2], fmaf( T[k * 4], p[0], ty ) ) + T[k * 4 + 3]; }
+		const float wy = T[13] * p[1];
+		const float w = fmaf( T[14], p[2], fmaf( T[12], p[0], wy ) ) + T[15];
+		if (!(w == 1)) { const float rw = 1.0f / w; r[0] = r[0] * rw, r[1] = r[1] * rw, r[2] = r[2] * rw; }
+		for (int k = 0; k < 3; k++) aabbMin[k] = aabbMin[k] < r[k] ? aabbMin[k] : r[k], aabbMax[k] = aabbMax[k] > r[k] ? aabbMax[k] : r[k];
+	}
+}
+#undef UPD_ATTR
+int tbvh_instance_update_box( void* instance, const float* bmin, const float* bmax )
+{
+	ARG_CHECK( instance && bmin && bmax, "NULL argument" );
+	float T[16], iT[16], mn[3], mx[3];
+	memcpy( T, instance, 64 );
+	upd_instance( T, iT, mn, mx, bmin, bmax );
+	memcpy( (char*)instance + 64, iT, 64 ), memcpy( (char*)instance + 128, mn, 12 ), memcpy( (char*)instance + 144, mx, 12 );
+	return TBVH_OK;
+}
+int tbvh_instance_update( void* instance, tbvh_bvh blas )
+{
+	ARG_CHECK( instance && blas, "NULL argument" );
+	if (!(blas->info.layouts & (1u << TBVH_LAYOUT_BVH))) { tbvh_set_error( "tbvh_instance_update: the BLAS holds no tree" ); return TBVH_E_STATE; }
+	return tbvh_instance_update_box( instance, blas->info.aabb_min, blas->info.aabb_max );
+}
+
 // BVH::Build( BLASInstance*, instCount, BVHBase**, blasCount ) tiny_bvh.h:2221 in its "blasses == 0" mode (:2245): the instances
 // arrive Update()d - inverse transform and world-space box filled in - and the TLAS is the reference builder's tree over the boxes
 int tbvh_build_tlas( tbvh_bvh t, const void* instances, uint32_t inst_stride, uint32_t inst_count, const tbvh_bvh* blasses, uint32_t blas_count, float c_trav, float c_int )
