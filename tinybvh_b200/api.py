@@ -221,6 +221,8 @@ class TLAS(BVH):
         assert inst.dtype.itemsize == 192 and inst.flags.c_contiguous
         self.blasses = list(blasses)
         if update:
+            if int(inst["blasIdx"].max()) >= len(self.blasses):
+                raise TbvhError("TLAS: an instance names a BLAS past the list")
             for i in range(inst.shape[0]):
                 check(_lib.lib().tbvh_instance_update(C.c_void_p(inst[i:i + 1].ctypes.data), self.blasses[int(inst["blasIdx"][i])].h))
         hs = (C.c_void_p * len(self.blasses))(*[b.h for b in self.blasses])
