@@ -265,3 +265,31 @@ def test_port_instance_update_matches_reference():
         refpy.lib().ref_instance_update(a[i:i + 1].ctypes.data, lo.ctypes.data, hi.ctypes.data)
     portpy.instance_update(b, lo, hi)
     assert a.tobytes() == b.tobytes()
+
+
+def test_port_tlas_matches_golden_vectors():
+    """Committed outputs of the reference's TLAS path (tools/make_golden.py make_tlas): BLASInstance::Update, the TLAS tree over the
+    instance boxes, IntersectTLAS hits (inst, t, u, v, prim) and IsOccludedTLAS bits for two ray masks."""
+    import os
+    g = dict(np.load(os.path.join(G.GOLDEN, "tlas", "tlas_24.npz")))
+    v = [g["verts0"], g["verts1"]]
+    blas = [portpy.PortBVH(x) for x in v]
+    inst = g["instances_raw"].view(refpy.BLAS_INSTANCE).reshape(-1).copy()
+    lo = np.stack([b.nodes[0]["aabbMin"] for b in blas])[inst["blasIdx"]]
+    hi = np.stack([b.nodes[0]["aabbMax"] for b in blas])[inst["blasIdx"]]
+    portpy.instance_update(inst, lo, hi)
+    assert np.array_equal(inst.view(np.uint32).reshape(-1, 48), g["instances"])
+    # the TLAS is the reference builder's tree over the instance boxes: a "triangle" (min, max, min) has exactly that box
+    fake = np.zeros((inst.shape[0] * 3, 4), np.float32)
+    fake[0::3, :3], fake[1::3, :3], fake[2::3, :3] = inst["aabbMin"], inst["aabbMax"], inst["aabbMin"]
+    tl = portpy.PortBVH(fake)
+    assert np.array_equal(tl.nodes.view(np.uint32).reshape(-1, 8), g["tlas_nodes"]) and np.array_equal(tl.prim_idx, g["tlas_prim_idx"])
+    port = portpy.PortTLAS(tl.nodes, tl.prim_idx, inst, blas)
+    for mask in (1, 2):
+        r = np.zeros(g["rays_O"].shape[0], R.RAY_DTYPE)
+        r["O"], r["D"], r["rD"], r["t"], r["mask"] = g["rays_O"], g["rays_D"], g["rays_rD"], g["rays_tmax"], mask
+        sh = r.copy()
+        sh["t"] = 150.0
+        port.intersect(r)
+        assert np.array_equal(r.view(np.uint32).reshape(-1, 32)[:, 11:16], g[f"hit_mask{mask}"])
+        assert np.array_equal(port.occluded(sh), g[f"occluded_mask{mask}"])

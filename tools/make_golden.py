@@ -53,7 +53,36 @@ def make(name, verts, res):
           "hits", int((prim["t"] < 1e30).sum()), "occluded", int(np.unpackbits(d["shadow_bits"].view(np.uint8)).sum()))
 
 
+def make_tlas(name):
+    """TLAS / BLAS golden vectors: BLASInstance::Update, BVH::Build( BLASInstance*, .. ), IntersectTLAS / IsOccludedTLAS of the reference."""
+    from tests.util import random_transforms
+    v = [scenes.procedural_scene(600, 31), scenes.procedural_scene(200, 32)]
+    raw = refpy.make_instances(random_transforms(24, 33), [i % 2 for i in range(24)], masks=[0x3 if i % 5 else 0x2 for i in range(24)])
+    inst = raw.copy()
+    tl = refpy.RefTLAS(inst, [refpy.RefBVH(x, mode=0, threaded=False) for x in v])    # Update()s inst
+    tb = tl.bvh()
+    rng = np.random.default_rng(34)
+    D = rng.normal(size=(6000, 3)).astype(np.float32) * 0.35 + np.array([0, 0, 1], np.float32)
+    O = np.tile(np.array([[0, 0, -120]], np.float32), (D.shape[0], 1))
+    d = {"verts0": v[0], "verts1": v[1], "instances_raw": raw.view(np.uint32).reshape(-1, 48), "instances": inst.view(np.uint32).reshape(-1, 48),
+         "tlas_nodes": tb.nodes.copy().view(np.uint32).reshape(-1, 8), "tlas_prim_idx": tb.prim_idx.copy()}
+    for mask in (1, 2):
+        r = R.make_rays(O, D)
+        r["mask"] = mask
+        for k, x in ray_core(r).items():
+            d[f"rays_{k}"] = x
+        tl.intersect(r, threads=1)
+        d[f"hit_mask{mask}"] = r.view(np.uint32).reshape(-1, 32)[:, 11:16].copy()      # inst, t, u, v, prim
+        sh = R.make_rays(O, D, tmax=150.0)
+        sh["mask"] = mask
+        d[f"occluded_mask{mask}"] = tl.occluded(sh, threads=1)
+    os.makedirs(os.path.join(OUT, "tlas"), exist_ok=True)
+    np.savez_compressed(os.path.join(OUT, "tlas", name + ".npz"), **d)
+    print(name, "instances", inst.shape[0], "tlas nodes", tb.used_nodes, "hits", int((d["hit_mask2"][:, 1].view(np.float32) < 1e30).sum()))
+
+
 if __name__ == "__main__":
+    make_tlas("tlas_24")
     make("atrium_3k", scenes.procedural_scene(3000, seed=11), 32)
     # degenerate inputs: coincident triangles (exact t ties), a flat (zero-extent axis) soup, a single triangle
     rng = np.random.default_rng(5)
