@@ -293,3 +293,11 @@ def test_port_tlas_matches_golden_vectors():
         port.intersect(r)
         assert np.array_equal(r.view(np.uint32).reshape(-1, 32)[:, 11:16], g[f"hit_mask{mask}"])
         assert np.array_equal(port.occluded(sh), g[f"occluded_mask{mask}"])
+
+
+@pytest.mark.parametrize("path", G.golden_files(), ids=lambda p: p.split("/")[-1])
+def test_port_refit_matches_golden(path):
+    g = G.load(path)
+    port = portpy.PortBVH(g["verts"])
+    port.refit(g["refit_verts"])
+    assert np.array_equal(port.nodes.view(np.uint32).reshape(-1, 8), g["refit_nodes"])

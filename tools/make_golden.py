@@ -47,6 +47,13 @@ def make(name, verts, res):
     d["hq_nodes"] = hq.nodes.copy().view(np.uint32).reshape(-1, 8)
     d["hq_prim_idx"] = hq.prim_idx[: int(hq.nodes["triCount"].sum())].copy()
     d["hq_idx_count"] = np.array([hq.idx_count], np.uint32)
+    # BVH::Refit (:3055) after every vertex moved a little (same topology)
+    rng = np.random.default_rng(97)
+    w = verts.copy()
+    w[:, :3] += (rng.random((verts.shape[0], 3), np.float32) - 0.5) * np.float32(0.02 * float((hi - lo).max()))
+    rf = refpy.RefBVH(verts, mode=0, threaded=False)
+    rf.refit(w)
+    d["refit_verts"], d["refit_nodes"] = w, rf.nodes.copy().view(np.uint32).reshape(-1, 8)
     os.makedirs(OUT, exist_ok=True)
     np.savez_compressed(os.path.join(OUT, name + ".npz"), **d)
     print(name, "tris", verts.shape[0] // 3, "nodes", ref.used_nodes, "rays", prim.shape[0],
