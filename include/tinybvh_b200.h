@@ -114,6 +114,11 @@ int tbvh_build_indexed( tbvh_bvh bvh, const void* verts, uint32_t stride, uint32
  * A host program compiled with another INST_IDX_BITS (4..31) sets tbvh_set_option( ctx, "inst_idx_bits", bits ): hits then
  * carry the instance in the top bits of hit.prim (prim = triIdx + (inst << (32 - bits)), :8527) and byte 44 is left alone.
  * Pass layout TBVH_LAYOUT_BVH to the traversal calls. */
+/* BVH::SAHCost( 0 ) tiny_bvh.h:1889-1897: the tree's SAH cost, host recursion over the (downloaded) 32-byte node array in the
+ * reference's own order and rounding - the number the speedtest prints after every build.  _nodes works on a host array. */
+int tbvh_sah_cost( tbvh_bvh bvh, float c_trav, float c_int, float* out );
+int tbvh_sah_cost_nodes( const void* nodes32, uint32_t used_nodes, float c_trav, float c_int, float* out );
+
 /* BLASInstance::Update( BVHBase* blas ) tiny_bvh.h:8386 on one 192-byte record: invTransform = inverse of transform
  * (InvertTransform :8402), aabbMin / aabbMax = box of the eight transformed corners of the BLAS's root box.  Host arithmetic in
  * the reference build's own operation order: the record comes out bit-identical to the reference's.  _box takes the root box

@@ -64,3 +64,20 @@ def test_instance_update_matches_the_oracle():
     for i in range(500):
         assert L.tbvh_instance_update_box(C.c_void_p(b[i:i + 1].ctypes.data), lo.ctypes.data_as(C.c_void_p), hi.ctypes.data_as(C.c_void_p)) == 0
     assert a.tobytes() == b.tobytes()
+
+
+def test_sah_cost_of_a_host_node_array_matches_the_oracle():
+    """tbvh_sah_cost_nodes is host arithmetic: BVH::SAHCost (tiny_bvh.h:1889) bit for bit, on golden trees incl. the SBVH ones."""
+    import ctypes as C
+    import numpy as np
+    from oracle import portpy
+    from tests import golden_util as G
+    L = _lib.lib()
+    for path in G.golden_files():
+        g = G.load(path)
+        for key in ("nodes", "hq_nodes"):
+            nodes = np.ascontiguousarray(g[key])
+            want = np.float32(portpy.lib().orc_sah_cost(nodes.ctypes.data_as(C.c_void_p), 0, 1.0, 1.0))
+            out = C.c_float()
+            assert L.tbvh_sah_cost_nodes(nodes.ctypes.data_as(C.c_void_p), nodes.shape[0], 1.0, 1.0, C.byref(out)) == 0
+            assert np.float32(out.value).view(np.uint32) == want.view(np.uint32), (path, key)

@@ -301,3 +301,14 @@ def test_port_refit_matches_golden(path):
     port = portpy.PortBVH(g["verts"])
     port.refit(g["refit_verts"])
     assert np.array_equal(port.nodes.view(np.uint32).reshape(-1, 8), g["refit_nodes"])
+
+
+@pytest.mark.skipif(not refpy.available(), reason="oracle/_ref not built (needs /root/reference)")
+@pytest.mark.parametrize("mode", [0, 1, 2])
+def test_port_sah_cost_matches_reference(mode):
+    """BVH::SAHCost (:1889) of the Build / BuildAVX / BuildHQ trees, the number the speedtest prints."""
+    v = scenes.procedural_scene(20000, 71)
+    ref = refpy.RefBVH(v, mode=mode, threaded=False)
+    nodes = ref.nodes   # a copy: keep it alive while C reads it
+    got = np.float32(portpy.lib().orc_sah_cost(nodes.ctypes.data, 0, 1.0, 1.0))
+    assert got.view(np.uint32) == np.float32(ref.sah_cost()).view(np.uint32)

@@ -180,6 +180,12 @@ class BVH(_Base):
         self._build(vertices, primCount, _lib.BUILD_HQ, indices)
         return self
 
+    def SAHCost(self) -> float:
+        """BVH::SAHCost( 0 ) (tiny_bvh.h:1889): host recursion over the downloaded nodes, the reference's value bit for bit."""
+        out = C.c_float()
+        check(_lib.lib().tbvh_sah_cost(self.h, self.c_trav, self.c_int, C.byref(out)))
+        return float(out.value)
+
     def Refit(self, vertices):
         """BVH::Refit (tiny_bvh.h:3055): same triangles, new positions.  The reference re-reads the caller's vertex array through
         the pointer it kept; the engine holds its own copy, so the array is passed again."""

@@ -359,6 +359,36 @@ int tbvh_build_flavour( tbvh_bvh b, const void* verts, uint32_t stride, uint32_t
 	return TBVH_OK;
 }
 
+// ---- BVH::SAHCost (tiny_bvh.h:1889-1897) over a downloaded node array: host recursion in the reference's own order
+__attribute__( (optimize( "fp-contract=off" )) ) static float sah_rec( const float* nodes /* 8 words per node */, const uint32_t i, const float c_trav, const float c_int )
+{
+	const float* n = nodes + (size_t)i * 8;
+	uint32_t leftFirst, triCount;
+	memcpy( &leftFirst, n + 3, 4 ), memcpy( &triCount, n + 7, 4 );
+	const float ex = n[4] - n[0], ey = n[5] - n[1], ez = n[6] - n[2];
+	const float sa = fmaf( ez, ex, fmaf( ey, ex, ey * ez ) ); // BVHBase::SA :8477 in the reference build's pairing
+	if (triCount > 0) return c_int * sa * triCount;
+	return c_trav * sa + sah_rec( nodes, leftFirst, c_trav, c_int ) + sah_rec( nodes, leftFirst + 1, c_trav, c_int );
+}
+__attribute__( (optimize( "fp-contract=off" )) ) int tbvh_sah_cost_nodes( const void* nodes32, uint32_t used_nodes, float c_trav, float c_int, float* out )
+{
+	ARG_CHECK( nodes32 && used_nodes >= 1 && out, "bad arguments" );
+	const float* n = (const float*)nodes32;
+	const float cost = sah_rec( n, 0, c_trav, c_int );
+	const float ex = n[4] - n[0], ey = n[5] - n[1], ez = n[6] - n[2];
+	*out = cost / fmaf( ez, ex, fmaf( ey, ex, ey * ez ) ); // the root divides by its own area (:1896)
+	return TBVH_OK;
+}
+int tbvh_sah_cost( tbvh_bvh b, float c_trav, float c_int, float* out )
+{
+	ARG_CHECK( b && out, "NULL argument" );
+	if (!(b->info.layouts & (1u << TBVH_LAYOUT_BVH)) || !b->d_nodes) { tbvh_set_error( "tbvh_sah_cost: no BVH-layout tree on this handle" ); return TBVH_E_STATE; }
+	CUDA_TRY( cudaSetDevice( b->ctx->device ) );
+	std::vector<float> nodes( (size_t)b->info.used_nodes * 8 );
+	CUDA_TRY( cudaMemcpy( nodes.data(), b->d_nodes, nodes.size() * 4, cudaMemcpyDeviceToHost ) );
+	return tbvh_sah_cost_nodes( nodes.data(), b->info.used_nodes, c_trav, c_int, out );
+}
+
 // ---- BLASInstance::Update on the host (the engine's own restatement; host code, so gcc's contraction is switched off for it)
 #define UPD_ATTR __attribute__( (optimize( "fp-contract=off" )) )
 
