@@ -64,7 +64,8 @@ const char* tbvh_last_error( void );
 int tbvh_device_count( void );
 /* tuning knobs (no reference counterpart; defaults are the measured best): "trace_variant" 0 = generic BVH2 kernel,
  * 3 = octant-switch, 4 = persistent warps; "small_t" builder switch point (8..256); "d2h_mode" / "h2d_split" / "host_path"
- * select how the host-buffer path moves ray records and hits across PCIe.  Environment variables TBVH_<KEY> set the
+ * select how the host-buffer path moves ray records and hits across PCIe ("host_path" 0 = copy engine 2D copies, the default;
+ * 1 = gather kernels over the pinned mapping; 2 = host threads pack 48 / 32 bytes per ray after checking rD == safercp( D )).  Environment variables TBVH_<KEY> set the
  * defaults at context creation.  BuildHQ: "hq_small" (fragments below which a subtree goes to the warp kernel, default 16),
  * "hq_cluster" (largest thread-block cluster per node, 1..16).  "inst_idx_bits": the host program's INST_IDX_BITS (see
  * tbvh_build_tlas). */
