@@ -20,7 +20,7 @@ NODE64 = np.dtype([("lmin", "3f4"), ("left", "u4"), ("lmax", "3f4"), ("right", "
 
 
 def build_lib(force: bool = False):
-    srcs = [os.path.join(_HERE, f) for f in ("tbvh_oracle.c", "tbvh_oracle_hq.c", "tbvh_oracle.h")]
+    srcs = [os.path.join(_HERE, f) for f in ("tbvh_oracle.c", "tbvh_oracle_hq.c", "tbvh_oracle_cwbvh.c", "tbvh_oracle.h")]
     if force or not os.path.isfile(PORT_SO) or any(os.path.getmtime(PORT_SO) < os.path.getmtime(s) for s in srcs):
         subprocess.check_call(["make", "-C", _HERE, "port"], stdout=subprocess.DEVNULL)
 
@@ -43,6 +43,8 @@ def lib():
         L.orc_intersect_tlas.restype, L.orc_intersect_tlas.argtypes = None, [vp, vp, vp, vp, vp, u64]
         L.orc_occluded_tlas.restype, L.orc_occluded_tlas.argtypes = None, [vp, vp, vp, vp, vp, u64, vp]
         L.orc_instance_update.restype, L.orc_instance_update.argtypes = None, [vp, vp, vp]
+        L.orc_cwbvh_from_bvh.restype, L.orc_cwbvh_from_bvh.argtypes = u32, [vp, u32, vp, u32, vp, u32, vp, vp]
+        L.orc_cwbvh_intersect.restype, L.orc_cwbvh_intersect.argtypes = None, [vp, vp, vp, u64]
         L.orc_refit.restype, L.orc_refit.argtypes = None, [vp, u32, vp, vp]
         L.orc_sah_cost.restype, L.orc_sah_cost.argtypes = f32, [vp, u32, f32, f32]
         _lib = L
@@ -121,6 +123,29 @@ class PortTLAS:
         bits = np.zeros((rays.shape[0] + 31) // 32, np.uint32)
         lib().orc_occluded_tlas(_ptr(self.nodes), _ptr(self.prim_idx), _ptr(self.instances), C.cast(self._table, C.c_void_p), _ptr(rays), rays.shape[0], _ptr(bits))
         return bits
+
+
+class PortCWBVH:
+    """orc_cwbvh_from_bvh + orc_cwbvh_intersect: the CWBVH conversion chain over a BVH2 (nodes, primIdx[, idxCount]) and the
+    reference's CPU walk of the result."""
+
+    def __init__(self, nodes, prim_idx, verts, idx_count=None):
+        nodes = np.ascontiguousarray(nodes).view(NODE32).reshape(-1)
+        prim_idx = np.ascontiguousarray(prim_idx, np.uint32)
+        self.verts = np.ascontiguousarray(verts, np.float32).reshape(-1, 4)
+        n = self.verts.shape[0] // 3
+        ic = int(idx_count) if idx_count is not None else prim_idx.shape[0]
+        pidx = np.zeros(ic, np.uint32)
+        pidx[: prim_idx.shape[0]] = prim_idx
+        data = np.zeros((n * 5, 4), np.float32)
+        self.tris = np.zeros((ic * 3, 4), np.float32)
+        blocks = lib().orc_cwbvh_from_bvh(_ptr(nodes), nodes.shape[0], _ptr(pidx), ic, _ptr(self.verts), n, _ptr(data), _ptr(self.tris))
+        self.nodes = data[:blocks].copy()
+
+    def intersect(self, rays):
+        assert rays.dtype.itemsize == 128 and rays.flags.c_contiguous
+        lib().orc_cwbvh_intersect(_ptr(self.nodes), _ptr(self.tris), _ptr(rays), rays.shape[0])
+        return rays
 
 
 def instance_update(instances, bmin, bmax):

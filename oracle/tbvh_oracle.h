@@ -60,6 +60,13 @@ uint32_t orc_to_bvh_gpu( const orc_node* nodes, orc_node_gpu* out );
 /* BVH::Refit (:3055-3093), flat (non-indexed) geometry: boxes recomputed in place from verts (primCount*3 float4) */
 void orc_refit( orc_node* nodes, uint32_t usedNodes, const uint32_t* primIdx, const float* verts );
 
+/* The conversion chain of BVH8_CWBVH::Build / BuildHQ (:5822-5866) applied to a BVH2: SplitLeafs( 3 ) :1988, MBVH<8>::ConvertFrom
+ * :4975, BVH8_CWBVH::ConvertFrom :5884 (tbvh_oracle_cwbvh.c).  data: triCount * 5 float4 blocks, tris: idxCount * 3 float4; both are
+ * zeroed first, as the reference does.  Returns usedBlocks. */
+uint32_t orc_cwbvh_from_bvh( const orc_node* nodes, uint32_t usedNodes, const uint32_t* primIdx, uint32_t idxCount, const float* verts, uint32_t triCount, float* data, float* tris );
+/* BVH8_CWBVH::Intersect (:7046-7154), the reference's CPU walk of the compressed layout, over 128-byte Ray records in place */
+void orc_cwbvh_intersect( const float* bvh8Data, const float* bvh8Tris, void* rays, uint64_t n );
+
 /* BVH::SAHCost (:1889) */
 float orc_sah_cost( const orc_node* nodes, uint32_t nodeIdx, float c_trav, float c_int );
 

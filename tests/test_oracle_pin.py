@@ -312,3 +312,40 @@ def test_port_sah_cost_matches_reference(mode):
     nodes = ref.nodes   # a copy: keep it alive while C reads it
     got = np.float32(portpy.lib().orc_sah_cost(nodes.ctypes.data, 0, 1.0, 1.0))
     assert got.view(np.uint32) == np.float32(ref.sah_cost()).view(np.uint32)
+
+
+# ---------------------------------------------------------------- CWBVH chain + CPU walk restatement, oracle/tbvh_oracle_cwbvh.c
+@pytest.mark.parametrize("path", G.golden_files(), ids=lambda p: p.split("/")[-1])
+def test_port_cwbvh_matches_golden(path):
+    g = G.load(path)
+    if "cwbvh_nodes" not in g:
+        pytest.skip("single-node scene: the reference refuses to convert it (:5889)")
+    port = portpy.PortBVH(g["verts"])
+    cw = portpy.PortCWBVH(port.nodes, port.prim_idx, g["verts"])
+    assert np.array_equal(cw.nodes.view(np.uint32), g["cwbvh_nodes"])
+    assert np.array_equal(cw.tris.view(np.uint32), g["cwbvh_tris"])
+    lo, hi = scenes.scene_bounds(g["verts"])
+    res = int(round((g["cwbvh_primary_hit"].shape[0] // 4) ** 0.5))
+    r = R.primary_rays(*R.bounds_camera(lo, hi, "outside"), res, res, 4)
+    cw.intersect(r)
+    assert np.array_equal(G.hits_as_u32(r), g["cwbvh_primary_hit"])
+
+
+@pytest.mark.skipif(not refpy.available(), reason="oracle/_ref not built (needs /root/reference)")
+@pytest.mark.parametrize("ntris,cw_mode,bvh_mode", [(20000, 0, 1), (5000, 1, 2), (3000, 2, 0), (5, 2, 0)])
+def test_port_cwbvh_matches_reference(ntris, cw_mode, bvh_mode):
+    """BVH8_CWBVH::Build (BuildAVX tree) / BuildHQ (SBVH) / the scalar-Build chain: bvh8Data and the referenced bvh8Tris byte for
+    byte, BVH8_CWBVH::Intersect hits bit for bit."""
+    v = scenes.procedural_scene(ntris, seed=81)
+    ref = refpy.RefCWBVH(v, mode=cw_mode)
+    b = refpy.RefBVH(v, mode=bvh_mode, threaded=False)
+    nodes = b.nodes
+    used = int(nodes["triCount"].sum())
+    port = portpy.PortCWBVH(nodes, b.prim_idx[:used], v, idx_count=b.idx_count)
+    assert np.array_equal(port.nodes.view(np.uint32), ref.nodes.view(np.uint32))
+    assert np.array_equal(port.tris[: used * 3].view(np.uint32), ref.tris[: used * 3].view(np.uint32))
+    lo, hi = scenes.scene_bounds(v)
+    a = R.primary_rays(*R.bounds_camera(lo, hi, "inside"), 64, 64, 4)
+    c = a.copy()
+    ref.intersect(a, threads=1), port.intersect(c)
+    assert np.array_equal(G.hits_as_u32(a), G.hits_as_u32(c))

@@ -47,6 +47,14 @@ def make(name, verts, res):
     d["hq_nodes"] = hq.nodes.copy().view(np.uint32).reshape(-1, 8)
     d["hq_prim_idx"] = hq.prim_idx[: int(hq.nodes["triCount"].sum())].copy()
     d["hq_idx_count"] = np.array([hq.idx_count], np.uint32)
+    # BVH8_CWBVH: the conversion chain (SplitLeafs(3), MBVH<8>, CWBVH encode) over the BVH::Build tree, and the reference's CPU walk
+    if verts.shape[0] > 3:   # "converting a single-node bvh" is a fatal error in the reference (:5889)
+        cw = refpy.RefCWBVH(verts, mode=2)
+        d["cwbvh_nodes"] = cw.nodes.copy().view(np.uint32)
+        d["cwbvh_tris"] = cw.tris[: verts.shape[0]].copy().view(np.uint32)     # 3 records per triangle reference
+        cp = R.primary_rays(*R.bounds_camera(lo, hi, "outside"), res, res, 4)
+        cw.intersect(cp, threads=1)
+        d["cwbvh_primary_hit"] = np.stack([cp["t"].view(np.uint32), cp["u"].view(np.uint32), cp["v"].view(np.uint32), cp["prim"]], 1)
     # BVH::Refit (:3055) after every vertex moved a little (same topology)
     rng = np.random.default_rng(97)
     w = verts.copy()
