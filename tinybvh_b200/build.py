@@ -48,6 +48,24 @@ def build(force: bool = False, verbose: bool = False) -> str:
     return SO
 
 
+GEN_SO = os.path.join(HERE, "libtbvh_raygen.so")
+
+
+def build_raygen(force: bool = False) -> str:
+    """The host-side workload generator (hostgen/raygen.c): plain C + OpenMP, float32 with contraction off so the rays are the
+    ones tinybvh_b200/rays.py computes."""
+    src = os.path.join(HERE, "hostgen", "raygen.c")
+    if not force and os.path.isfile(GEN_SO) and os.path.getmtime(GEN_SO) >= os.path.getmtime(src):
+        return GEN_SO
+    cmd = ["gcc", "-O2", "-fopenmp", "-ffp-contract=off", "-fno-fast-math", "-fPIC", "-shared", src, "-lm", "-o", GEN_SO + ".tmp"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("gcc failed:\n" + r.stdout + r.stderr)
+    os.replace(GEN_SO + ".tmp", GEN_SO)
+    return GEN_SO
+
+
 if __name__ == "__main__":
     import sys
     print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    print(build_raygen(force="--force" in sys.argv))

@@ -164,3 +164,109 @@ def diffuse_rays(primary: np.ndarray, verts: np.ndarray, seed: int = 0x123456) -
 def gpu_records(rays: np.ndarray) -> np.ndarray:
     """First 64 bytes of every 128-byte host record, contiguous (what tiny_bvh_speedtest.cpp:1110-1115 uploads)."""
     return np.ascontiguousarray(rays.view(np.uint8).reshape(-1, 128)[:, :64]).view(GPU_RAY_DTYPE).reshape(-1)
+
+
+# ---------------------------------------------------------------------------------------------- fast generators (hostgen/raygen.c)
+_gen = None
+
+
+def _genlib():
+    """libtbvh_raygen.so: the same generators in C + OpenMP (bit-identical records, tests/test_raygen.py); None when not built."""
+    global _gen
+    if _gen is None:
+        import ctypes as C
+        import os
+        so = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libtbvh_raygen.so")
+        if not os.path.isfile(so):
+            _gen = False
+            return None
+        L = C.CDLL(so)
+        vp, u64, u32, f = C.c_void_p, C.c_uint64, C.c_uint32, C.c_float
+        L.tbvh_gen_primary.argtypes = [vp, u64, u64, vp, vp, vp, vp, u32, u32, u32]
+        L.tbvh_gen_shadow.argtypes = [vp, vp, vp, u64, vp, f]
+        L.tbvh_gen_diffuse.argtypes = [vp, vp, vp, u64, u64, vp, u32]
+        L.tbvh_gen_reset_hits.argtypes = [vp, u64, f]
+        L.tbvh_gen_store_hits.argtypes = [vp, vp, u64]
+        for fn in (L.tbvh_gen_primary, L.tbvh_gen_shadow, L.tbvh_gen_diffuse, L.tbvh_gen_reset_hits, L.tbvh_gen_store_hits):
+            fn.restype = None
+        _gen = L
+    return _gen or None
+
+
+def _p(a):
+    return a.ctypes.data
+
+
+def camera_plane(eye, view):
+    """eye, p1, p2-p1, p3-p1 of the speedtest's view plane (tiny_bvh_speedtest.cpp:499-520), float32."""
+    eye = np.asarray(eye, f32)
+    view = normalize(np.asarray(view, f32))
+    right = normalize(np.cross(np.array([0, 1, 0], f32), view).astype(f32))
+    up = (f32(0.8) * np.cross(view, right)).astype(f32)
+    C = (eye + f32(2) * view).astype(f32)
+    p1, p2, p3 = C - right + up, C + right + up, C - right - up
+    return eye, p1.astype(f32), (p2 - p1).astype(f32), (p3 - p1).astype(f32)
+
+
+def primary_rays_into(out: np.ndarray, eye, view, width: int, height: int, spp: int = 16, first: int = 0) -> np.ndarray:
+    """Fill `out` (RAY_DTYPE, e.g. page-locked) with rays [first, first+len(out)) of the camera set `primary_rays` defines."""
+    assert out.dtype.itemsize == 128 and out.flags.c_contiguous and width % 4 == 0 and height % 4 == 0 and 16 % spp == 0
+    n = out.shape[0]
+    assert first + n <= width * height * spp
+    L = _genlib()
+    if L is None:
+        out[:] = primary_rays(eye, view, width, height, spp)[first:first + n]
+        return out
+    e, p1, d21, d31 = [np.ascontiguousarray(x, f32) for x in camera_plane(eye, view)]
+    L.tbvh_gen_primary(_p(out), first, n, _p(e), _p(p1), _p(d21), _p(d31), width, height, spp)
+    return out
+
+
+def shadow_rays_into(out: np.ndarray, primary: np.ndarray, light, eps: float, hits: np.ndarray = None) -> np.ndarray:
+    """`shadow_rays` into `out`; `hits` (packed t,u,v,prim per ray) replaces the records' own hit.t when given."""
+    assert out.dtype.itemsize == 128 and primary.dtype.itemsize == 128 and out.shape[0] == primary.shape[0]
+    L = _genlib()
+    if L is None:
+        src = primary
+        if hits is not None:
+            src = primary.copy()
+            src["t"] = np.asarray(hits).reshape(-1, 4)[:, 0]
+        out[:] = shadow_rays(src, light, eps)
+        return out
+    light = np.ascontiguousarray(light, f32)
+    hp = None
+    if hits is not None:
+        hits = np.ascontiguousarray(hits).view(f32).reshape(-1, 4)
+        assert hits.shape[0] == primary.shape[0]
+        hp = _p(hits)
+    L.tbvh_gen_shadow(_p(out), _p(primary), hp, out.shape[0], _p(light), np.float32(eps))
+    return out
+
+
+def diffuse_rays_into(out: np.ndarray, primary: np.ndarray, verts: np.ndarray, hits: np.ndarray = None, seed: int = 0x123456, first: int = 0) -> np.ndarray:
+    """`diffuse_rays` into `out` for rays [first, first+len(out)) of the whole set (the per-ray seed is the global ray index)."""
+    assert out.dtype.itemsize == 128 and primary.dtype.itemsize == 128 and out.shape[0] == primary.shape[0]
+    L = _genlib()
+    if L is None:
+        assert first == 0
+        src = primary
+        if hits is not None:
+            src = primary.copy()
+            h = np.asarray(hits).view(f32).reshape(-1, 4)
+            src["t"], src["prim"] = h[:, 0], h[:, 3].view(np.uint32)
+        out[:] = diffuse_rays(src, verts, seed)
+        return out
+    verts = np.ascontiguousarray(verts, f32)
+    hp = None
+    if hits is not None:
+        hits = np.ascontiguousarray(hits).view(f32).reshape(-1, 4)
+        hp = _p(hits)
+    L.tbvh_gen_diffuse(_p(out), _p(primary), hp, first, out.shape[0], _p(verts), seed)
+    return out
+
+
+def reset_hits_fast(rays: np.ndarray, tmax=BVH_FAR) -> None:
+    L = _genlib()
+    if L is None or rays.dtype.itemsize != 128:
+        return reset_hits(rays, tmax)
+    L.tbvh_gen_reset_hits(_p(rays), rays.shape[0], np.float32(tmax))
