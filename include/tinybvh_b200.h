@@ -12,6 +12,12 @@
  *  - there is NO CPU fallback: without a CUDA device every call that touches data fails with TBVH_E_CUDA.
  *  - `space` says where a caller pointer lives: TBVH_HOST or TBVH_DEVICE (device pointers are plain
  *    CUdeviceptr values of the context's device, e.g. torch tensor data_ptr()).
+ *  - device-space INPUTS (vertices, indices, node arrays passed with TBVH_DEVICE) are read on the engine's own stream: the caller
+ *    makes sure the work that produces them has completed (synchronise the producing stream) before the call.  The *_device
+ *    traversal calls are the exception: they run on the stream the caller passes.
+ *  - host batch calls (tbvh_intersect / _packed / tbvh_occluded) may be issued from several threads on one handle, as the
+ *    reference's const Intersect / IsOccluded are (tiny_bvh_speedtest.cpp:392-401); they are serialised per context.  Builds,
+ *    uploads, conversions and refits are exclusive, like the reference's Build.
  *  - ray records are the reference's `Ray` (tiny_bvh.h:688-709): O at byte 0, D at 16, rD at 32, hit
  *    (t,u,v,prim) at 48..63; `stride` is 128 for the host struct, 64 for the packed GPU record
  *    (traverse.cl:11-17).  hit.t on entry is the ray's maximum distance.
@@ -42,6 +48,7 @@ extern "C" {
 
 typedef struct tbvh_ctx_t* tbvh_ctx;   /* one per CUDA device */
 typedef struct tbvh_bvh_t* tbvh_bvh;   /* one acceleration structure (any subset of the layouts) */
+typedef struct tbvh_group_t* tbvh_group; /* several devices of one process: BVH replicas + index-sharded ray batches */
 
 typedef struct tbvh_info
 {
@@ -62,16 +69,24 @@ int tbvh_ctx_create( int device, tbvh_ctx* out );
 int tbvh_ctx_destroy( tbvh_ctx ctx );
 const char* tbvh_last_error( void );
 int tbvh_device_count( void );
+/* host topology of a device: the NUMA node it hangs off (-1 when the system does not say), and a call that restricts the calling
+ * thread (and the threads it creates afterwards) to that node's CPUs - ray buffers first-touched or page-locked from such a thread
+ * are read by the device's DMA engine from local memory instead of across the socket interconnect. */
+int tbvh_device_numa_node( int device );
+int tbvh_bind_thread_to_device( int device );
 /* tuning knobs (no reference counterpart; defaults are the measured best): "trace_variant" 0 = generic BVH2 kernel,
  * 3 = octant-switch, 4 = persistent warps; "small_t" builder switch point (8..256); "d2h_mode" / "h2d_split" / "host_path"
  * select how the host-buffer path moves ray records and hits across PCIe ("host_path" 0 = copy engine 2D copies, the default;
- * 1 = gather kernels over the pinned mapping; 2 = host threads pack 48 / 32 bytes per ray after checking rD == safercp( D )).  Environment variables TBVH_<KEY> set the
- * defaults at context creation.  BuildHQ: "hq_small" (fragments below which a subtree goes to the warp kernel, default 16),
+ * 1 = gather kernel over the pinned mapping; "d2h_mode" 0 = 2D copy of the 16-byte hits into the records, 3 = scatter kernel over
+ * the pinned mapping; "h2d_split" 1..4 inbound streams per chunk; "chunk_rays" rays per pipeline chunk, default 524288).
+ * Environment variables TBVH_<KEY> set the defaults at context creation.  BuildHQ: "hq_small" (fragments below which a subtree goes to the warp kernel, default 16),
  * "hq_cluster" (largest thread-block cluster per node, 1..16).  "inst_idx_bits": the host program's INST_IDX_BITS (see
  * tbvh_build_tlas). */
 int tbvh_set_option( tbvh_ctx ctx, const char* key, int value );
-/* pinned host memory for ray buffers (replaces tinybvh::malloc64 / BVHContext::malloc for rays, tiny_bvh.h:261-292, 763-768) */
+/* pinned host memory for ray buffers (replaces tinybvh::malloc64 / BVHContext::malloc for rays, tiny_bvh.h:261-292, 763-768).
+ * The pages are taken from the NUMA node of the current CUDA device (tbvh_host_alloc) or of `device` (_near). */
 int tbvh_host_alloc( size_t bytes, void** out );
+int tbvh_host_alloc_near( int device, size_t bytes, void** out );
 int tbvh_host_free( void* p );
 int tbvh_host_register( void* p, size_t bytes );
 int tbvh_host_unregister( void* p );
@@ -174,6 +189,27 @@ int tbvh_occluded_device( tbvh_bvh bvh, int layout, const void* d_rays, uint32_t
  * returns the per-ray cost from Intersect, tiny_bvh.h:3303): steps = nodes visited, tris = triangle tests. */
 int tbvh_set_stats( tbvh_bvh bvh, int enable );
 int tbvh_get_stats( tbvh_bvh bvh, uint64_t* steps, uint64_t* tris );
+
+/* ---- several GPUs in one process (rays shard by index, the BVH is replicated once, no traffic between devices
+ * during traversal).  The reference has no counterpart: its GPU path drives one OpenCL device (tiny_bvh_speedtest.cpp:1092-1241).
+ *  tbvh_group_create     devices[count] (NULL / 0 = all devices), one engine context each, peer access enabled where possible
+ *  tbvh_group_replicate  copy the traversal arrays of a built / uploaded / converted BVH to every device of the group (peer copies
+ *                        over NVLink); ms_out = device time of the copies.  Call again after the source changed.
+ *  tbvh_group_intersect / _occluded  tbvh_intersect / tbvh_occluded on a HOST batch, rays [first, first+count) of
+ *                        tbvh_shard_range( n, g, size ) going to device g from a worker thread bound to that device's NUMA node
+ *  tbvh_group_host_alloc page-locked buffer of n records whose index ranges live on the NUMA node of the device that reads them
+ *  tbvh_shard_range      the partition itself: contiguous, boundaries on multiples of 32 rays (occlusion words are never shared) */
+int tbvh_group_create( const int* devices, int count, tbvh_group* out );
+int tbvh_group_destroy( tbvh_group group );
+int tbvh_group_size( tbvh_group group );
+tbvh_ctx tbvh_group_ctx( tbvh_group group, int i );
+tbvh_bvh tbvh_group_replica( tbvh_group group, int i );
+int tbvh_group_replicate( tbvh_group group, tbvh_bvh src, double* ms_out );
+int tbvh_group_intersect( tbvh_group group, int layout, void* rays, uint32_t stride, uint64_t n );
+int tbvh_group_occluded( tbvh_group group, int layout, const void* rays, uint32_t stride, uint64_t n, uint32_t* bits );
+int tbvh_group_host_alloc( tbvh_group group, uint32_t stride, uint64_t n, void** out );
+int tbvh_group_host_free( tbvh_group group, void* p );
+void tbvh_shard_range( uint64_t n, uint32_t part, uint32_t parts, uint64_t* first, uint64_t* count );
 
 /* number of kernels this library has launched since load (bench.py reports it as gpu_launches) */
 uint64_t tbvh_launch_count( void );

@@ -64,6 +64,20 @@ SYMBOLS = {
     "tbvh_set_stats": (i32, [vp, i32]),
     "tbvh_get_stats": (i32, [vp, C.POINTER(u64), C.POINTER(u64)]),
     "tbvh_launch_count": (u64, []),
+    "tbvh_device_numa_node": (i32, [i32]),
+    "tbvh_bind_thread_to_device": (i32, [i32]),
+    "tbvh_host_alloc_near": (i32, [i32, sz, C.POINTER(vp)]),
+    "tbvh_group_create": (i32, [vp, i32, C.POINTER(vp)]),
+    "tbvh_group_destroy": (i32, [vp]),
+    "tbvh_group_size": (i32, [vp]),
+    "tbvh_group_ctx": (vp, [vp, i32]),
+    "tbvh_group_replica": (vp, [vp, i32]),
+    "tbvh_group_replicate": (i32, [vp, vp, C.POINTER(C.c_double)]),
+    "tbvh_group_intersect": (i32, [vp, i32, vp, u32, u64]),
+    "tbvh_group_occluded": (i32, [vp, i32, vp, u32, u64, vp]),
+    "tbvh_group_host_alloc": (i32, [vp, u32, u64, C.POINTER(vp)]),
+    "tbvh_group_host_free": (i32, [vp, vp]),
+    "tbvh_shard_range": (None, [u64, u32, u32, C.POINTER(u64), C.POINTER(u64)]),
 }
 
 _lib = None

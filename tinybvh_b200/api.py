@@ -54,8 +54,12 @@ def _is_torch(x) -> bool:
 def _verts_arg(verts):
     """-> (pointer, stride, vertex count, space, keepalive)"""
     if _is_torch(verts):
+        import torch
         assert verts.is_cuda and verts.is_contiguous() and verts.dtype.is_floating_point and verts.element_size() == 4
         v = verts.reshape(-1, 4)
+        # device-space inputs are read on the engine's own stream (include/tinybvh_b200.h "device-space inputs"): whatever torch
+        # has queued to produce them must have finished
+        torch.cuda.current_stream(verts.device).synchronize()
         return C.c_void_p(v.data_ptr()), 16, v.shape[0], DEVICE, v
     v = np.ascontiguousarray(verts, np.float32).reshape(-1, 4)
     return _np_ptr(v), 16, v.shape[0], HOST, v
@@ -298,11 +302,15 @@ class BVH8_CWBVH(_Base):
         return d, t
 
 
-def pinned_empty(n: int, dtype) -> np.ndarray:
-    """numpy array in page-locked host memory (tbvh_host_alloc): full-speed DMA for the host path."""
+def pinned_empty(n: int, dtype, device: int = None) -> np.ndarray:
+    """numpy array in page-locked host memory on the NUMA node of `device` (default: the current CUDA device): full-speed DMA
+    for the host path (tbvh_host_alloc / tbvh_host_alloc_near)."""
     dtype = np.dtype(dtype)
     p = C.c_void_p()
-    check(_lib.lib().tbvh_host_alloc(n * dtype.itemsize, C.byref(p)))
+    if device is None:
+        check(_lib.lib().tbvh_host_alloc(n * dtype.itemsize, C.byref(p)))
+    else:
+        check(_lib.lib().tbvh_host_alloc_near(device, n * dtype.itemsize, C.byref(p)))
     buf = (C.c_char * (n * dtype.itemsize)).from_address(p.value)
     a = np.frombuffer(buf, dtype=dtype, count=n)
     a.flags.writeable = True
@@ -317,3 +325,74 @@ def pinned_free(a: np.ndarray):
     p = _pinned.pop(a.ctypes.data, None)
     if p is not None:
         check(_lib.lib().tbvh_host_free(p))
+
+
+def bind_to_device(device: int = 0) -> bool:
+    """Restrict the calling thread (and threads it starts later: OpenMP, the host pipeline) to the CPUs of the NUMA node `device`
+    hangs off.  False when the system exposes no topology."""
+    return _lib.lib().tbvh_bind_thread_to_device(device) == OK
+
+
+def shard_range(n: int, part: int, parts: int):
+    """tbvh_shard_range: contiguous [first, first+count) of n rays for `part`, boundaries on multiples of 32."""
+    a, c = C.c_uint64(), C.c_uint64()
+    _lib.lib().tbvh_shard_range(n, part, parts, C.byref(a), C.byref(c))
+    return a.value, c.value
+
+
+class Group:
+    """Several GPUs of one process (tbvh_group_*): `replicate(bvh)` copies a BVH to every device over NVLink, `Intersect` /
+    `IsOccluded` shard a host ray batch by index over the devices.  `layout` follows the replicated object."""
+
+    def __init__(self, devices=None):
+        self.h = C.c_void_p()
+        if devices is None:
+            check(_lib.lib().tbvh_group_create(None, 0, C.byref(self.h)))
+        else:
+            arr = (C.c_int * len(devices))(*devices)
+            check(_lib.lib().tbvh_group_create(arr, len(devices), C.byref(self.h)))
+        self.layout = LAYOUT_BVH
+        self.src = None
+
+    def __len__(self):
+        return _lib.lib().tbvh_group_size(self.h)
+
+    def replicate(self, bvh) -> float:
+        ms = C.c_double()
+        check(_lib.lib().tbvh_group_replicate(self.h, bvh.h, C.byref(ms)))
+        self.src, self.layout = bvh, bvh.layout
+        return ms.value
+
+    def empty_rays(self, n: int, dtype) -> np.ndarray:
+        """page-locked array whose index ranges sit on the NUMA node of the device that will read them (tbvh_group_host_alloc)"""
+        dtype = np.dtype(dtype)
+        p = C.c_void_p()
+        check(_lib.lib().tbvh_group_host_alloc(self.h, dtype.itemsize, n, C.byref(p)))
+        buf = (C.c_char * (n * dtype.itemsize)).from_address(p.value)
+        a = np.frombuffer(buf, dtype=dtype, count=n)
+        a.flags.writeable = True
+        return a
+
+    def Intersect(self, rays: np.ndarray) -> np.ndarray:
+        assert rays.dtype.itemsize in (64, 128) and rays.flags.c_contiguous
+        check(_lib.lib().tbvh_group_intersect(self.h, self.layout, _np_ptr(rays), rays.dtype.itemsize, rays.shape[0]))
+        return rays
+
+    def IsOccluded(self, rays: np.ndarray, bits: np.ndarray = None) -> np.ndarray:
+        assert rays.dtype.itemsize in (64, 128) and rays.flags.c_contiguous
+        n = rays.shape[0]
+        if bits is None:
+            bits = np.zeros((n + 31) // 32, np.uint32)
+        check(_lib.lib().tbvh_group_occluded(self.h, self.layout, _np_ptr(rays), rays.dtype.itemsize, n, _np_ptr(bits)))
+        return bits
+
+    def close(self):
+        if self.h is not None and self.h.value:
+            _lib.lib().tbvh_group_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

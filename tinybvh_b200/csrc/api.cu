@@ -26,7 +26,68 @@ void tbvh_set_error( const char* fmt, ... )
 #define ARG_CHECK( c, msg ) do { if (!(c)) { tbvh_set_error( "%s: %s", __func__, msg ); return TBVH_E_ARG; } } while (0)
 #define TRY( x ) do { int r_ = (x); if (r_ != TBVH_OK) return r_; } while (0)
 
-static const size_t STAGE_RAYS = 1u << 20; // rays per host-path chunk (64 MiB of device records)
+
+// ---- host topology: which NUMA node a device hangs off, and its CPUs (sysfs; no libnuma in the image) -----------------
+#include <sched.h>
+#include <unistd.h>
+#include <sys/mman.h>
+#include <sys/syscall.h>
+
+static int read_int_file( const char* path, int fallback )
+{
+	FILE* f = fopen( path, "r" );
+	if (!f) return fallback;
+	int v = fallback;
+	if (fscanf( f, "%d", &v ) != 1) v = fallback;
+	fclose( f );
+	return v;
+}
+
+static int device_numa_node( int device )
+{
+	char bus[32] = "";
+	if (cudaDeviceGetPCIBusId( bus, sizeof( bus ), device ) != cudaSuccess) { cudaGetLastError(); return -1; }
+	for (char* c = bus; *c; c++) if (*c >= 'A' && *c <= 'Z') *c += 'a' - 'A';
+	char path[128];
+	snprintf( path, sizeof( path ), "/sys/bus/pci/devices/%s/numa_node", bus );
+	return read_int_file( path, -1 );
+}
+
+// CPUs of a NUMA node from /sys/devices/system/node/nodeN/cpulist ("0-31,64-95")
+static bool node_cpus( int node, cpu_set_t* set )
+{
+	CPU_ZERO( set );
+	if (node < 0) return false;
+	char path[128], line[1024] = "";
+	snprintf( path, sizeof( path ), "/sys/devices/system/node/node%d/cpulist", node );
+	FILE* f = fopen( path, "r" );
+	if (!f) return false;
+	const bool ok = fgets( line, sizeof( line ), f ) != 0;
+	fclose( f );
+	if (!ok) return false;
+	int any = 0;
+	for (char* p = line; *p && *p != '\n';)
+	{
+		char* e;
+		long lo = strtol( p, &e, 10 ), hi = lo;
+		if (e == p) break;
+		if (*e == '-') { p = e + 1; hi = strtol( p, &e, 10 ); }
+		for (long c = lo; c <= hi && c < CPU_SETSIZE; c++) CPU_SET( (int)c, set ), any = 1;
+		p = *e == ',' ? e + 1 : e;
+	}
+	return any != 0;
+}
+
+// run `fn` with the calling thread restricted to the CPUs of `node` (first-touch and driver allocations then land on that node),
+// then restore the previous affinity.  Without topology information fn just runs.
+template <class F> static auto on_node( int node, F fn ) -> decltype( fn() )
+{
+	cpu_set_t want, old;
+	const bool have = node_cpus( node, &want ) && sched_getaffinity( 0, sizeof( old ), &old ) == 0 && sched_setaffinity( 0, sizeof( want ), &want ) == 0;
+	auto r = fn();
+	if (have) sched_setaffinity( 0, sizeof( old ), &old );
+	return r;
+}
 
 extern "C" {
 
@@ -40,6 +101,19 @@ int tbvh_device_count( void )
 	return n;
 }
 
+int tbvh_device_numa_node( int device ) { return device_numa_node( device ); }
+
+int tbvh_bind_thread_to_device( int device )
+{
+	cpu_set_t want;
+	const int node = device_numa_node( device );
+	if (!node_cpus( node, &want )) { tbvh_set_error( "tbvh_bind_thread_to_device: no NUMA information for device %d", device ); return TBVH_E_UNSUPPORTED; }
+	if (sched_setaffinity( 0, sizeof( want ), &want ) != 0) { tbvh_set_error( "tbvh_bind_thread_to_device: sched_setaffinity failed" ); return TBVH_E_UNSUPPORTED; }
+	return TBVH_OK;
+}
+
+int tbvh_ctx_destroy( tbvh_ctx c );
+
 int tbvh_ctx_create( int device, tbvh_ctx* out )
 {
 	ARG_CHECK( out, "out == NULL" );
@@ -50,19 +124,33 @@ int tbvh_ctx_create( int device, tbvh_ctx* out )
 	tbvh_ctx c = new (std::nothrow) tbvh_ctx_t();
 	ARG_CHECK( c, "out of host memory" );
 	c->device = device;
-	cudaDeviceProp prop;
-	CUDA_TRY( cudaGetDeviceProperties( &prop, device ) );
-	c->sm_count = prop.multiProcessorCount;
-	CUDA_TRY( cudaStreamCreateWithFlags( &c->stream, cudaStreamNonBlocking ) );
-	for (int i = 0; i < 3; i++) CUDA_TRY( cudaStreamCreateWithFlags( &c->copy_streams[i], cudaStreamNonBlocking ) );
-	for (int i = 0; i < 4; i++) CUDA_TRY( cudaStreamCreateWithFlags( &c->aux_streams[i], cudaStreamNonBlocking ) );
-	for (int i = 0; i < 3; i++)
+	c->numa_node = device_numa_node( device );
+	auto body = [&]() -> int
 	{
-		CUDA_TRY( cudaEventCreateWithFlags( &c->ev_done[i], cudaEventDisableTiming ) );
-		for (int p = 0; p < 4; p++) CUDA_TRY( cudaEventCreateWithFlags( &c->ev_part[i][p], cudaEventDisableTiming ) );
-	}
+		cudaDeviceProp prop;
+		CUDA_TRY( cudaGetDeviceProperties( &prop, device ) );
+		c->sm_count = prop.multiProcessorCount;
+		CUDA_TRY( cudaStreamCreateWithFlags( &c->stream, cudaStreamNonBlocking ) );
+		CUDA_TRY( cudaStreamCreateWithFlags( &c->s_in, cudaStreamNonBlocking ) );
+		CUDA_TRY( cudaStreamCreateWithFlags( &c->s_run, cudaStreamNonBlocking ) );
+		CUDA_TRY( cudaStreamCreateWithFlags( &c->s_out, cudaStreamNonBlocking ) );
+		for (int i = 0; i < 3; i++) CUDA_TRY( cudaStreamCreateWithFlags( &c->s_in_part[i], cudaStreamNonBlocking ) );
+		CUDA_TRY( cudaEventCreateWithFlags( &c->ev_fork, cudaEventDisableTiming ) );
+		for (int i = 0; i < TBVH_SLOTS; i++)
+		{
+			CUDA_TRY( cudaEventCreateWithFlags( &c->slot[i].in_done, cudaEventDisableTiming ) );
+			CUDA_TRY( cudaEventCreateWithFlags( &c->slot[i].run_done, cudaEventDisableTiming ) );
+			CUDA_TRY( cudaEventCreateWithFlags( &c->slot[i].out_done, cudaEventDisableTiming ) );
+			for (int p = 0; p < 3; p++) CUDA_TRY( cudaEventCreateWithFlags( &c->ev_part[i][p], cudaEventDisableTiming ) );
+		}
+		CUDA_TRY( cudaMalloc( &c->d_counters, TBVH_COUNTERS * 8 ) );
+		CUDA_TRY( cudaMemset( c->d_counters, 0, TBVH_COUNTERS * 8 ) );
+		return TBVH_OK;
+	};
+	const int rc = body();
+	if (rc != TBVH_OK) { tbvh_ctx_destroy( c ); return rc; }
 	const char* hp = getenv( "TBVH_HOST_PATH" );
-	c->host_path = hp && !strcmp( hp, "zerocopy" ) ? 1 : hp && !strcmp( hp, "packed" ) ? 2 : 0;
+	c->host_path = hp && (!strcmp( hp, "zerocopy" ) || !strcmp( hp, "1" )) ? 1 : 0;
 	const char* tv = getenv( "TBVH_TRACE_VARIANT" );
 	c->trace_variant = tv ? atoi( tv ) : 3; // octant switch: +5 % on camera / shadow rays, -3 % on diffuse (profiles/README.md)
 	const char* st = getenv( "TBVH_SMALL_T" );
@@ -77,16 +165,44 @@ int tbvh_ctx_create( int device, tbvh_ctx* out )
 	c->h2d_split = sp ? atoi( sp ) : 1;
 	if (c->h2d_split < 1) c->h2d_split = 1;
 	if (c->h2d_split > 4) c->h2d_split = 4;
+	const char* cr = getenv( "TBVH_CHUNK_RAYS" );
+	if (cr && atol( cr ) >= 4096) c->chunk_rays = (size_t)atol( cr ) & ~(size_t)31;
 	*out = c;
 	return TBVH_OK;
+}
+
+static void free_slots( tbvh_ctx c )
+{
+	for (int i = 0; i < TBVH_SLOTS; i++)
+	{
+		if (c->slot[i].d_rays) cudaFree( c->slot[i].d_rays );
+		if (c->slot[i].d_hits) cudaFree( c->slot[i].d_hits );
+		if (c->slot[i].d_bits) cudaFree( c->slot[i].d_bits );
+		c->slot[i].d_rays = c->slot[i].d_hits = c->slot[i].d_bits = 0;
+	}
+	c->slot_rays = 0;
 }
 
 int tbvh_ctx_destroy( tbvh_ctx c )
 {
 	if (!c) return TBVH_OK;
 	cudaSetDevice( c->device );
-	for (int i = 0; i < 3; i++) { if (c->d_stage[i]) cudaFree( c->d_stage[i] ); if (c->d_stage_bits[i]) cudaFree( c->d_stage_bits[i] ); cudaStreamDestroy( c->copy_streams[i] ); }
-	cudaStreamDestroy( c->stream );
+	cudaDeviceSynchronize();
+	free_slots( c );
+	for (int i = 0; i < TBVH_SLOTS; i++)
+	{
+		if (c->slot[i].in_done) cudaEventDestroy( c->slot[i].in_done );
+		if (c->slot[i].run_done) cudaEventDestroy( c->slot[i].run_done );
+		if (c->slot[i].out_done) cudaEventDestroy( c->slot[i].out_done );
+		for (int p = 0; p < 3; p++) if (c->ev_part[i][p]) cudaEventDestroy( c->ev_part[i][p] );
+	}
+	if (c->ev_fork) cudaEventDestroy( c->ev_fork );
+	for (int i = 0; i < 3; i++) if (c->s_in_part[i]) cudaStreamDestroy( c->s_in_part[i] );
+	if (c->s_in) cudaStreamDestroy( c->s_in );
+	if (c->s_run) cudaStreamDestroy( c->s_run );
+	if (c->s_out) cudaStreamDestroy( c->s_out );
+	if (c->stream) cudaStreamDestroy( c->stream );
+	if (c->d_counters) cudaFree( c->d_counters );
 	delete c;
 	return TBVH_OK;
 }
@@ -100,17 +216,44 @@ int tbvh_set_option( tbvh_ctx c, const char* key, int value )
 	else if (!strcmp( key, "inst_idx_bits" )) c->inst_idx_bits = value;
 	else if (!strcmp( key, "hq_small" )) c->hq_small = value;
 	else if (!strcmp( key, "hq_cluster" )) c->hq_cluster = value;
-	else if (!strcmp( key, "d2h_mode" )) c->d2h_mode = value;
+	else if (!strcmp( key, "d2h_mode" )) c->d2h_mode = value == 3 ? 3 : 0;
 	else if (!strcmp( key, "h2d_split" )) c->h2d_split = value < 1 ? 1 : value > 4 ? 4 : value;
-	else if (!strcmp( key, "host_path" )) c->host_path = value;
+	else if (!strcmp( key, "host_path" )) c->host_path = value == 1 ? 1 : 0;
+	else if (!strcmp( key, "chunk_rays" ))
+	{
+		ARG_CHECK( value >= 4096, "chunk_rays must be at least 4096" );
+		std::lock_guard<std::mutex> lk( c->host_mutex );
+		CUDA_TRY( cudaSetDevice( c->device ) );
+		CUDA_TRY( cudaDeviceSynchronize() );
+		free_slots( c );
+		c->chunk_rays = (size_t)value & ~(size_t)31;
+	}
 	else { tbvh_set_error( "tbvh_set_option: unknown key '%s'", key ); return TBVH_E_ARG; }
 	return TBVH_OK;
 }
 
-int tbvh_host_alloc( size_t bytes, void** out ) { ARG_CHECK( out, "out == NULL" ); CUDA_TRY( cudaHostAlloc( out, bytes, cudaHostAllocDefault ) ); return TBVH_OK; }
+// Page-locked ray buffers.  The pages are allocated while the calling thread sits on the CPUs of the device's NUMA node, so the
+// DMA engine reads local memory (a dual-socket host serves a remote GPU's reads over the inter-socket link otherwise).
+int tbvh_host_alloc_near( int device, size_t bytes, void** out )
+{
+	ARG_CHECK( out, "out == NULL" );
+	const int node = device_numa_node( device );
+	const cudaError_t e = on_node( node, [&]() { return cudaHostAlloc( out, bytes, cudaHostAllocPortable ); } );
+	if (e != cudaSuccess) { tbvh_set_error( "tbvh_host_alloc: cudaHostAlloc( %zu ) -> %s", bytes, cudaGetErrorString( e ) ); return TBVH_E_CUDA; }
+	return TBVH_OK;
+}
+int tbvh_host_alloc( size_t bytes, void** out )
+{
+	int device = 0;
+	if (cudaGetDevice( &device ) != cudaSuccess) { cudaGetLastError(); device = 0; }
+	return tbvh_host_alloc_near( device, bytes, out );
+}
 int tbvh_host_free( void* p ) { if (p) CUDA_TRY( cudaFreeHost( p ) ); return TBVH_OK; }
-int tbvh_host_register( void* p, size_t bytes ) { CUDA_TRY( cudaHostRegister( p, bytes, cudaHostRegisterDefault ) ); return TBVH_OK; }
+int tbvh_host_register( void* p, size_t bytes ) { CUDA_TRY( cudaHostRegister( p, bytes, cudaHostRegisterPortable ) ); return TBVH_OK; }
 int tbvh_host_unregister( void* p ) { CUDA_TRY( cudaHostUnregister( p ) ); return TBVH_OK; }
+
+static void live_add( tbvh_bvh b );
+static void live_remove( tbvh_bvh b );
 
 int tbvh_bvh_create( tbvh_ctx ctx, tbvh_bvh* out )
 {
@@ -121,6 +264,7 @@ int tbvh_bvh_create( tbvh_ctx ctx, tbvh_bvh* out )
 	CUDA_TRY( cudaSetDevice( ctx->device ) );
 	CUDA_TRY( cudaMalloc( &b->d_stats, 16 ) );
 	CUDA_TRY( cudaMemset( b->d_stats, 0, 16 ) );
+	live_add( b );
 	*out = b;
 	return TBVH_OK;
 }
@@ -128,10 +272,12 @@ int tbvh_bvh_create( tbvh_ctx ctx, tbvh_bvh* out )
 static void free_layouts( tbvh_bvh b )
 {
 	if (b->d_trav && b->d_trav != b->d_nodes) cudaFree( b->d_trav );
-	void* p[] = { b->d_verts, b->d_nodes, b->d_prim_idx, b->d_leaf_tris, b->d_nodes_gpu, b->d_cw_nodes, b->d_cw_tris, b->d_aabbs, b->d_inst, b->d_blas };
+	void* p[] = { b->d_verts, b->d_nodes, b->d_prim_idx, b->d_leaf_tris, b->d_nodes_gpu, b->d_cw_nodes, b->d_cw_tris, b->d_cw_trav, b->d_aabbs, b->d_inst, b->d_blas };
 	for (void* q : p) if (q) cudaFree( q );
-	b->d_verts = 0, b->d_nodes = 0, b->d_prim_idx = 0, b->d_leaf_tris = 0, b->d_nodes_gpu = 0, b->d_cw_nodes = 0, b->d_cw_tris = 0, b->d_trav = 0;
-	b->d_aabbs = 0, b->d_inst = 0, b->d_blas = 0, b->inst_count = 0, b->blas_count = 0;
+	b->d_verts = 0, b->d_nodes = 0, b->d_prim_idx = 0, b->d_leaf_tris = 0, b->d_nodes_gpu = 0, b->d_cw_nodes = 0, b->d_cw_tris = 0, b->d_cw_trav = 0, b->d_trav = 0, b->leaf_tris_count = 0;
+	b->d_aabbs = 0, b->d_inst = 0, b->d_blas = 0, b->inst_count = 0, b->blas_count = 0, b->cw_depth = 0;
+	b->links.clear();
+	b->generation++; // a TLAS built over the old arrays must notice (tlas_check)
 	memset( &b->info, 0, sizeof( b->info ) );
 	b->refittable = true;
 }
@@ -140,6 +286,7 @@ int tbvh_bvh_destroy( tbvh_bvh b )
 {
 	if (!b) return TBVH_OK;
 	cudaSetDevice( b->ctx->device );
+	live_remove( b );
 	free_layouts( b );
 	if (b->d_stats) cudaFree( b->d_stats );
 	delete b;
@@ -334,15 +481,17 @@ int tbvh_upload_cwbvh( tbvh_bvh b, const void* bvh8_data, uint32_t used_blocks, 
 	CUDA_TRY( cudaSetDevice( b->ctx->device ) );
 	cudaStream_t s = b->ctx->stream;
 	const cudaMemcpyKind kind = space == TBVH_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+	ARG_CHECK( used_blocks % 5 == 0, "usedBlocks must be a multiple of 5 (80-byte nodes)" );
 	if (b->d_cw_nodes) cudaFree( b->d_cw_nodes );
 	if (b->d_cw_tris) cudaFree( b->d_cw_tris );
-	b->d_cw_nodes = 0, b->d_cw_tris = 0;
+	if (b->d_cw_trav) cudaFree( b->d_cw_trav );
+	b->d_cw_nodes = 0, b->d_cw_tris = 0, b->d_cw_trav = 0;
 	CUDA_TRY( cudaMalloc( &b->d_cw_nodes, (size_t)used_blocks * 16 ) );
 	CUDA_TRY( cudaMalloc( &b->d_cw_tris, (size_t)tri_count * 48 ) );
 	CUDA_TRY( cudaMemcpyAsync( b->d_cw_nodes, bvh8_data, (size_t)used_blocks * 16, kind, s ) );
 	CUDA_TRY( cudaMemcpyAsync( b->d_cw_tris, bvh8_tris, (size_t)tri_count * 48, kind, s ) );
-	CUDA_TRY( cudaStreamSynchronize( s ) );
 	b->info.used_blocks = used_blocks, b->info.cwbvh_tri_count = tri_count;
+	TRY( cw_make_trav( b, s ) ); // the traversal nodes the kernels read + the wide tree's depth (synchronises the stream)
 	b->info.layouts |= 1u << TBVH_LAYOUT_CWBVH;
 	return TBVH_OK;
 }
@@ -480,6 +629,7 @@ int tbvh_build_tlas( tbvh_bvh t, const void* instances, uint32_t inst_stride, ui
 		ARG_CHECK( b && b != t && b->ctx == t->ctx, "TLAS: a BLAS handle is NULL or lives in another context" );
 		if (!(b->info.layouts & (1u << TBVH_LAYOUT_BVH)) || !b->d_trav || !b->d_leaf_tris || b->d_inst)
 		{ tbvh_set_error( "TLAS: BLAS %u holds no BVH-layout triangle tree (IntersectTLAS walks LAYOUT_BVH BLASses, tiny_bvh.h:3341)", k ); return TBVH_E_STATE; }
+		if (b->info.max_depth + 1 > TBVH_STACK) { tbvh_set_error( "TLAS: BLAS %u has depth %u, the two-level kernel walks a BLAS with a %d-entry stack", k, b->info.max_depth, TBVH_STACK ); return TBVH_E_LIMIT; }
 		refs[k].trav = b->d_trav, refs[k].tris = b->d_leaf_tris, refs[k].root_ref = b->root_ref, refs[k].root_count = b->root_count, refs[k].pad0 = refs[k].pad1 = 0;
 	}
 	for (uint32_t i = 0; i < inst_count; i++)
@@ -505,6 +655,9 @@ int tbvh_build_tlas( tbvh_bvh t, const void* instances, uint32_t inst_stride, ui
 	t->info.prim_count = inst_count, t->inst_count = inst_count, t->blas_count = blas_count;
 	TRY( build_sah_launch( t, c_trav, c_int, TBVH_BUILD_REFERENCE ) ); // "Build(); // or BuildAVX, for large TLAS." :2258
 	t->info.layouts = 1u << TBVH_LAYOUT_BVH, t->refittable = false; // "do not refit a TLAS, use Build(..)" :3060
+	if (t->info.max_depth + 1 > TBVH_STACK) { tbvh_set_error( "TLAS depth %u exceeds the %d-entry stack of IntersectTLAS (tiny_bvh.h:3308)", t->info.max_depth, TBVH_STACK ); return TBVH_E_LIMIT; }
+	// the device table holds raw addresses of the BLAS arrays: remember which generation of each BLAS they belong to
+	for (uint32_t k = 0; k < blas_count; k++) t->links.push_back( BlasLink{ blasses[k], blasses[k]->generation } );
 	return TBVH_OK;
 }
 
@@ -526,6 +679,7 @@ int tbvh_refit( tbvh_bvh b, const void* verts, uint32_t stride, uint32_t prim_co
 	if (b->d_nodes_gpu) cudaFree( b->d_nodes_gpu ), b->d_nodes_gpu = 0;
 	if (b->d_cw_nodes) cudaFree( b->d_cw_nodes ), b->d_cw_nodes = 0;
 	if (b->d_cw_tris) cudaFree( b->d_cw_tris ), b->d_cw_tris = 0;
+	if (b->d_cw_trav) cudaFree( b->d_cw_trav ), b->d_cw_trav = 0;
 	b->info.layouts = 1u << TBVH_LAYOUT_BVH, b->info.used_nodes_gpu = 0, b->info.used_blocks = 0, b->info.cwbvh_tri_count = 0;
 	TRY( make_leaf_tris( b, s ) );
 	CUDA_TRY( cudaStreamSynchronize( s ) );
@@ -594,11 +748,32 @@ int tbvh_download_cwbvh( tbvh_bvh b, void* bvh8_data, void* bvh8_tris, int space
 
 // ---- traversal ------------------------------------------------------------------------------------------------
 
+// live handles (a TLAS remembers its BLAS handles; a destroyed one must be noticed, not dereferenced)
+static std::mutex g_live_mutex;
+static std::vector<tbvh_bvh> g_live;
+static void live_add( tbvh_bvh b ) { std::lock_guard<std::mutex> lk( g_live_mutex ); g_live.push_back( b ); }
+static void live_remove( tbvh_bvh b ) { std::lock_guard<std::mutex> lk( g_live_mutex ); for (size_t i = 0; i < g_live.size(); i++) if (g_live[i] == b) { g_live[i] = g_live.back(); g_live.pop_back(); break; } }
+
+// a TLAS points at the arrays of its BLASses: refuse to walk it once one of them was rebuilt, re-uploaded or destroyed
+static int tlas_check( tbvh_bvh t )
+{
+	std::lock_guard<std::mutex> lk( g_live_mutex );
+	for (const BlasLink& l : t->links)
+	{
+		bool alive = false;
+		for (tbvh_bvh h : g_live) if (h == l.blas) { alive = true; break; }
+		if (!alive || l.blas->generation != l.generation)
+		{ tbvh_set_error( "TLAS is stale: a BLAS it was built over has been %s since (build the TLAS again, tiny_bvh.h:2221)", alive ? "rebuilt or re-uploaded" : "destroyed" ); return TBVH_E_STATE; }
+	}
+	return TBVH_OK;
+}
+
 static int trace_dispatch( tbvh_bvh b, int layout, const void* d_rays, uint32_t stride, void* d_hits, uint32_t hit_stride,
 	uint32_t* d_bits, uint64_t n, bool anyhit, cudaStream_t s )
 {
-	if (layout == TBVH_LAYOUT_BVH || layout == TBVH_LAYOUT_BVH_GPU) return bvh2_trace_launch( b, d_rays, stride, d_hits, hit_stride, d_bits, n, anyhit, s );
-	if (layout == TBVH_LAYOUT_CWBVH) return cwbvh_trace_launch( b, d_rays, stride, d_hits, hit_stride, d_bits, n, anyhit, s );
+	unsigned long long* st = b->stats ? b->d_stats : 0;
+	if (layout == TBVH_LAYOUT_BVH || layout == TBVH_LAYOUT_BVH_GPU) return bvh2_trace_launch( b, d_rays, stride, d_hits, hit_stride, d_bits, n, anyhit, s, st );
+	if (layout == TBVH_LAYOUT_CWBVH) return cwbvh_trace_launch( b, d_rays, stride, d_hits, hit_stride, d_bits, n, anyhit, s, st );
 	tbvh_set_error( "unknown layout %d", layout );
 	return TBVH_E_ARG;
 }
@@ -607,10 +782,12 @@ int tbvh_intersect_device( tbvh_bvh b, int layout, void* d_rays, uint32_t stride
 {
 	ARG_CHECK( b && d_rays && stride >= 64 && (stride & 15) == 0, "bad ray buffer" );
 	CUDA_TRY( cudaSetDevice( b->ctx->device ) );
+	if (b->stats) CUDA_TRY( cudaMemsetAsync( b->d_stats, 0, 16, (cudaStream_t)stream ) );
 	if (b->d_inst)
 	{
 		// TLAS: hits carry the instance (hit.inst, byte 44) and are written into the ray records
 		if (d_hits) { tbvh_set_error( "TLAS hits are written in place (t,u,v,prim at byte 48, inst at byte 44): pass d_hits = NULL" ); return TBVH_E_UNSUPPORTED; }
+		TRY( tlas_check( b ) );
 		return tlas_trace_launch( b, d_rays, stride, 0, n, false, (cudaStream_t)stream );
 	}
 	if (d_hits) return trace_dispatch( b, layout, d_rays, stride, d_hits, 16, 0, n, false, (cudaStream_t)stream );
@@ -621,27 +798,22 @@ int tbvh_occluded_device( tbvh_bvh b, int layout, const void* d_rays, uint32_t s
 {
 	ARG_CHECK( b && d_rays && d_bits && stride >= 64 && (stride & 15) == 0, "bad ray buffer" );
 	CUDA_TRY( cudaSetDevice( b->ctx->device ) );
-	if (b->d_inst) return tlas_trace_launch( b, d_rays, stride, d_bits, n, true, (cudaStream_t)stream );
+	if (b->stats) CUDA_TRY( cudaMemsetAsync( b->d_stats, 0, 16, (cudaStream_t)stream ) );
+	if (b->d_inst) { TRY( tlas_check( b ) ); return tlas_trace_launch( b, d_rays, stride, d_bits, n, true, (cudaStream_t)stream ); }
 	return trace_dispatch( b, layout, d_rays, stride, 0, 0, d_bits, n, true, (cudaStream_t)stream );
 }
 
-static int ensure_stage( tbvh_ctx c )
-{
-	if (c->stage_rays) return TBVH_OK;
-	for (int i = 0; i < 3; i++)
-	{
-		CUDA_TRY( cudaMalloc( &c->d_stage[i], STAGE_RAYS * 64 ) );
-		CUDA_TRY( cudaMalloc( &c->d_stage_bits[i], STAGE_RAYS / 8 ) );
-	}
-	c->stage_rays = STAGE_RAYS;
-	return TBVH_OK;
-}
-
-// Host-buffer path: chunks of 2^20 rays round-robin over three streams so the inbound copy of chunk k+1, the kernel of
-// chunk k and the outbound copy of chunk k-1 overlap.  Only bytes 0..63 of each record cross PCIe inbound and only the
-// 16-byte hit (or 1 bit) outbound.  Page-locked buffers (tbvh_host_alloc / tbvh_host_register) are read and written by
-// copy kernels straight through their device mapping (64 B per ray = one coalesced request per 4 lanes), which beats
-// the copy engine's 2D mode on 64-byte rows; pageable buffers fall back to cudaMemcpy2DAsync.
+// ---- host-buffer path ---------------------------------------------------------------------------------------------
+// tbvh_intersect / tbvh_intersect_packed / tbvh_occluded on HOST ray records.  Only bytes 0..63 of each record cross PCIe inbound
+// and only the 16-byte hit (or one bit) outbound.  The batch is cut into chunks that flow through TBVH_SLOTS stage buffers:
+//
+//     s_in  : chunk k+1   host records --(2D copy of 64-byte rows, or a gather kernel through the pinned mapping)--> slot.d_rays
+//     s_run : chunk k     traversal kernel: slot.d_rays -> slot.d_hits (packed 16-byte hits) / slot.d_bits
+//     s_out : chunk k-1   slot.d_hits --(2D copy of 16-byte rows into Ray.hit, or one contiguous copy for the packed form)--> host
+//
+// Each direction owns a stream, so the inbound copy engine never waits for an outbound copy queued ahead of it; events hand a
+// slot from stage to stage and back (out_done -> the next inbound copy into that slot).  One call at a time per context
+// (host_mutex): concurrent callers on one handle are serialised, as SURVEY 8(b) asks.
 __global__ void __launch_bounds__( 256 ) k_gather_rays( const float4* __restrict__ src, const uint32_t stride_f4, float4* __restrict__ dst, const uint64_t n )
 {
 	const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x, r = t >> 2;
@@ -651,7 +823,7 @@ __global__ void __launch_bounds__( 256 ) k_gather_rays( const float4* __restrict
 __global__ void __launch_bounds__( 256 ) k_scatter_hits( const float4* __restrict__ src, float4* __restrict__ dst, const uint32_t stride_f4, const uint64_t n )
 {
 	const uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-	if (r < n) dst[r * stride_f4 + 3] = src[r * 4 + 3];
+	if (r < n) dst[r * stride_f4 + 3] = src[r];
 }
 
 // device alias of a page-locked host pointer, or NULL when the memory is pageable
@@ -663,164 +835,109 @@ static void* mapped_alias( const void* host )
 	return a.devicePointer;
 }
 
-static int stage_in( tbvh_ctx c, int k, const char* h, const char* h_dev, uint32_t stride, uint64_t cnt, cudaStream_t s )
+static int ensure_slots( tbvh_ctx c )
 {
+	if (c->slot_rays == c->chunk_rays) return TBVH_OK;
+	free_slots( c );
+	for (int i = 0; i < TBVH_SLOTS; i++)
+	{
+		CUDA_TRY( cudaMalloc( &c->slot[i].d_rays, c->chunk_rays * 64 ) );
+		CUDA_TRY( cudaMalloc( &c->slot[i].d_hits, c->chunk_rays * 16 ) );
+		CUDA_TRY( cudaMalloc( &c->slot[i].d_bits, c->chunk_rays / 8 + 4 ) );
+	}
+	c->slot_rays = c->chunk_rays;
+	return TBVH_OK;
+}
+
+// inbound stage of one chunk: on return s_in carries the copy and slot.in_done is recorded behind it
+static int stage_in( tbvh_ctx c, const int k, const uint64_t chunk, const char* h, const char* h_dev, const uint32_t stride, const uint64_t cnt )
+{
+	HostSlot& sl = c->slot[k];
+	if (chunk >= TBVH_SLOTS) CUDA_TRY( cudaStreamWaitEvent( c->s_in, sl.out_done, 0 ) ); // the slot's previous tenant has left the device
 	if (c->host_path == 1 && h_dev && (stride & 15) == 0)
 	{
 		const uint64_t threads = cnt * 4;
-		k_gather_rays<<<(uint32_t)((threads + 255) / 256), 256, 0, s>>>( (const float4*)h_dev, stride / 16, (float4*)c->d_stage[k], cnt );
+		k_gather_rays<<<(uint32_t)((threads + 255) / 256), 256, 0, c->s_in>>>( (const float4*)h_dev, stride / 16, (float4*)sl.d_rays, cnt );
 		LAUNCHED();
-		return TBVH_OK;
 	}
-	if (c->h2d_split > 1 && cnt >= 4096)
+	else if (c->h2d_split > 1 && cnt >= 4096)
 	{
-		// split the rows of this chunk over several streams (copy engines); the chunk's stream waits for all parts, and
-		// the parts wait until the previous user of this staging buffer is done
-		const uint64_t per = (cnt + c->h2d_split - 1) / c->h2d_split;
-		CUDA_TRY( cudaEventRecord( c->ev_done[k], s ) );
-		for (int p = 0; p < c->h2d_split; p++)
+		// rows of the chunk spread over several streams so more than one copy engine pulls them; s_in joins the parts
+		const int parts = c->h2d_split;
+		const uint64_t per = ((cnt + parts - 1) / parts + 31) & ~31ull;
+		CUDA_TRY( cudaEventRecord( c->ev_fork, c->s_in ) );
+		for (int p = 0; p < parts; p++)
 		{
 			const uint64_t a = per * p, e = a + per < cnt ? a + per : cnt;
 			if (a >= e) break;
-			CUDA_TRY( cudaStreamWaitEvent( c->aux_streams[p], c->ev_done[k], 0 ) );
-			CUDA_TRY( cudaMemcpy2DAsync( (char*)c->d_stage[k] + a * 64, 64, h + a * stride, stride, 64, e - a, cudaMemcpyHostToDevice, c->aux_streams[p] ) );
-			CUDA_TRY( cudaEventRecord( c->ev_part[k][p], c->aux_streams[p] ) );
-			CUDA_TRY( cudaStreamWaitEvent( s, c->ev_part[k][p], 0 ) );
+			cudaStream_t ps = p == 0 ? c->s_in : c->s_in_part[p - 1];
+			if (p) CUDA_TRY( cudaStreamWaitEvent( ps, c->ev_fork, 0 ) );
+			CUDA_TRY( cudaMemcpy2DAsync( (char*)sl.d_rays + a * 64, 64, h + a * stride, stride, 64, e - a, cudaMemcpyHostToDevice, ps ) );
+			if (p) { CUDA_TRY( cudaEventRecord( c->ev_part[k][p - 1], ps ) ); CUDA_TRY( cudaStreamWaitEvent( c->s_in, c->ev_part[k][p - 1], 0 ) ); }
 		}
-		return TBVH_OK;
 	}
-	CUDA_TRY( cudaMemcpy2DAsync( c->d_stage[k], 64, h, stride, 64, cnt, cudaMemcpyHostToDevice, s ) );
+	else CUDA_TRY( cudaMemcpy2DAsync( sl.d_rays, 64, h, stride, 64, cnt, cudaMemcpyHostToDevice, c->s_in ) );
+	CUDA_TRY( cudaEventRecord( sl.in_done, c->s_in ) );
+	CUDA_TRY( cudaStreamWaitEvent( c->s_run, sl.in_done, 0 ) );
 	return TBVH_OK;
 }
 
-// host-side scatter of packed 16-byte hits into the strided ray records (d2h_mode 2)
-static void scatter_hits_host( const char* packed, char* rays, uint32_t stride, uint64_t cnt )
+static int drain( tbvh_ctx c )
 {
-	static int env_threads = -1;
-	if (env_threads < 0) { const char* e = getenv( "TBVH_SCATTER_THREADS" ); env_threads = e ? atoi( e ) : 0; }
-	unsigned threads = env_threads > 0 ? (unsigned)env_threads : std::thread::hardware_concurrency() / 4;
-	if (threads < 1) threads = 1;
-	if (threads > 64) threads = 64;
-	if (cnt < 65536) threads = 1;
-	auto work = [=]( uint64_t a, uint64_t e ) { for (uint64_t i = a; i < e; i++) memcpy( rays + i * stride + 48, packed + i * 16, 16 ); };
-	if (threads == 1) { work( 0, cnt ); return; }
-	std::vector<std::thread> pool;
-	const uint64_t per = (cnt + threads - 1) / threads;
-	for (unsigned t = 0; t < threads; t++) { const uint64_t a = per * t, e = a + per < cnt ? a + per : cnt; if (a < e) pool.emplace_back( work, a, e ); }
-	for (auto& t : pool) t.join();
+	CUDA_TRY( cudaStreamSynchronize( c->s_out ) );
+	CUDA_TRY( cudaStreamSynchronize( c->s_run ) );
+	CUDA_TRY( cudaStreamSynchronize( c->s_in ) );
+	return TBVH_OK;
 }
 
-// ---- host_path 2: packed upload ---------------------------------------------------------------------------------
-// The copy engine moves 64-byte rows out of 128-byte records at ~40 GB/s; a contiguous pinned copy runs at the link's ~54 GB/s
-// and needs fewer bytes: the stored rD of a ray built by Ray::Ray is safercp( D ) (tiny_bvh.h:698), which the device can
-// recompute bit for bit (IEEE division).  Host threads therefore pack O, D, mask, t (and u, v, prim for closest hits, so a miss
-// writes back what was there) into 48 / 32 bytes per ray while CHECKING that rD really is safercp( D ); a chunk with any ray
-// whose rD was set by other means falls back to the 64-byte path.  A device kernel expands the packed records into the staged
-// 64-byte layout the traversal kernels read.
-static inline float host_safercp( const float x ) { if (x > 1e-12f || x < -1e-12f) return 1.0f / x; else return x >= 0 ? BVH_FAR : -BVH_FAR; }
-struct PackJob { const char* src; uint32_t stride; uint64_t cnt; char* dst; int rec; };
-static void pack_slice( const PackJob& j, const unsigned t, const unsigned T, std::atomic<int>& bad )
+static int intersect_host( tbvh_bvh b, int layout, void* rays, uint32_t stride, uint64_t n, void* packed_hits )
 {
-	const uint64_t per = (j.cnt + T - 1) / T, a = per * t, e = a + per < j.cnt ? a + per : j.cnt;
-	int mismatch = 0;
-	for (uint64_t i = a; i < e; i++)
+	ARG_CHECK( b && rays && stride >= 64, "bad ray buffer" );
+	tbvh_ctx c = b->ctx;
+	std::lock_guard<std::mutex> lk( c->host_mutex );
+	CUDA_TRY( cudaSetDevice( c->device ) );
+	TRY( ensure_slots( c ) );
+	if (b->stats) CUDA_TRY( cudaMemset( b->d_stats, 0, 16 ) );
+	const bool tlas = b->d_inst != 0;
+	if (tlas)
 	{
-		const float* r = (const float*)(j.src + i * j.stride);
-		float* o = (float*)(j.dst + i * j.rec);
-		const float c0 = host_safercp( r[4] ), c1 = host_safercp( r[5] ), c2 = host_safercp( r[6] );
-		mismatch |= memcmp( &c0, r + 8, 4 ) | memcmp( &c1, r + 9, 4 ) | memcmp( &c2, r + 10, 4 );
-		o[0] = r[0], o[1] = r[1], o[2] = r[2], o[3] = r[12];               // O, hit.t
-		o[4] = r[4], o[5] = r[5], o[6] = r[6], o[7] = r[3];                // D, mask
-		if (j.rec == 48) o[8] = r[13], o[9] = r[14], o[10] = r[15], o[11] = 0; // hit.u, v, prim
+		if (packed_hits) { tbvh_set_error( "tbvh_intersect_packed: TLAS hits carry the instance and are returned in the ray records" ); return TBVH_E_UNSUPPORTED; }
+		TRY( tlas_check( b ) );
 	}
-	if (mismatch) bad = 1;
-}
-class PackPool
-{
-public:
-	explicit PackPool( unsigned threads ) : T( threads ) { for (unsigned t = 0; t < T; t++) th.emplace_back( [this, t]() { worker( t ); } ); }
-	~PackPool() { { std::lock_guard<std::mutex> lk( m ); quit = true; } cv_go.notify_all(); for (auto& t : th) t.join(); }
-	bool run( const PackJob& j ) // true when every ray of the chunk had a canonical rD
+	char* dev_alias = (char*)mapped_alias( rays );
+	const bool scatter = !packed_hits && !tlas && c->d2h_mode == 3 && dev_alias && (stride & 15) == 0;
+	uint64_t chunk = 0;
+	int rc = TBVH_OK;
+	for (uint64_t off = 0; off < n && rc == TBVH_OK; off += c->chunk_rays, chunk++)
 	{
-		{ std::lock_guard<std::mutex> lk( m ); job = j, done = 0, bad = 0, gen++; }
-		cv_go.notify_all();
-		std::unique_lock<std::mutex> lk( m );
-		cv_done.wait( lk, [&]() { return done == T; } );
-		return bad == 0;
-	}
-private:
-	void worker( unsigned t )
-	{
-		uint64_t seen = 0;
-		for (;;)
+		const int k = (int)(chunk % TBVH_SLOTS);
+		HostSlot& sl = c->slot[k];
+		const uint64_t cnt = n - off < c->chunk_rays ? n - off : c->chunk_rays;
+		char* h = (char*)rays + off * stride;
+		char* hd = dev_alias ? dev_alias + off * stride : 0;
+		auto body = [&]() -> int
 		{
-			std::unique_lock<std::mutex> lk( m );
-			cv_go.wait( lk, [&]() { return quit || gen != seen; } );
-			if (quit) return;
-			seen = gen;
-			const PackJob j = job;
-			lk.unlock();
-			pack_slice( j, t, T, bad );
-			lk.lock();
-			if (++done == T) cv_done.notify_one();
-		}
+			TRY( stage_in( c, k, chunk, h, hd, stride, cnt ) );
+			if (tlas) TRY( tlas_trace_launch( b, sl.d_rays, 64, 0, cnt, false, c->s_run ) );  // hit + instance written into the staged records
+			else TRY( trace_dispatch( b, layout, sl.d_rays, 64, sl.d_hits, 16, 0, cnt, false, c->s_run ) );
+			CUDA_TRY( cudaEventRecord( sl.run_done, c->s_run ) );
+			CUDA_TRY( cudaStreamWaitEvent( c->s_out, sl.run_done, 0 ) );
+			if (tlas) CUDA_TRY( cudaMemcpy2DAsync( h + 44, stride, (char*)sl.d_rays + 44, 64, 20, cnt, cudaMemcpyDeviceToHost, c->s_out ) );
+			else if (packed_hits) CUDA_TRY( cudaMemcpyAsync( (char*)packed_hits + off * 16, sl.d_hits, cnt * 16, cudaMemcpyDeviceToHost, c->s_out ) );
+			else if (scatter)
+			{
+				k_scatter_hits<<<(uint32_t)((cnt + 255) / 256), 256, 0, c->s_out>>>( (const float4*)sl.d_hits, (float4*)hd, stride / 16, cnt );
+				LAUNCHED();
+			}
+			else CUDA_TRY( cudaMemcpy2DAsync( h + 48, stride, sl.d_hits, 16, 16, cnt, cudaMemcpyDeviceToHost, c->s_out ) );
+			CUDA_TRY( cudaEventRecord( sl.out_done, c->s_out ) );
+			return TBVH_OK;
+		};
+		rc = body();
 	}
-	unsigned T;
-	std::vector<std::thread> th;
-	std::mutex m;
-	std::condition_variable cv_go, cv_done;
-	uint64_t gen = 0;
-	unsigned done = 0;
-	bool quit = false;
-	PackJob job = {};
-	std::atomic<int> bad{ 0 };
-};
-// packed record -> staged 64-byte ray record: rows (O, mask) (D, 0) (safercp( D ), 0) (t, u, v, prim)
-__global__ void __launch_bounds__( 256 ) k_unpack_rays( const float4* __restrict__ src, const int rows /* 3 or 2 */, float4* __restrict__ dst, const uint64_t n )
-{
-	const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-	if (i >= n) return;
-	const float4 a = src[i * rows], d = src[i * rows + 1];
-	float4 h = make_float4( a.w, 0, 0, 0 );
-	if (rows == 3) { const float4 c = src[i * rows + 2]; h = make_float4( a.w, c.x, c.y, c.z ); }
-	const float rx = (d.x > 1e-12f || d.x < -1e-12f) ? __fdiv_rn( 1.0f, d.x ) : (d.x >= 0 ? BVH_FAR : -BVH_FAR);
-	const float ry = (d.y > 1e-12f || d.y < -1e-12f) ? __fdiv_rn( 1.0f, d.y ) : (d.y >= 0 ? BVH_FAR : -BVH_FAR);
-	const float rz = (d.z > 1e-12f || d.z < -1e-12f) ? __fdiv_rn( 1.0f, d.z ) : (d.z >= 0 ? BVH_FAR : -BVH_FAR);
-	dst[i * 4] = make_float4( a.x, a.y, a.z, d.w ), dst[i * 4 + 1] = make_float4( d.x, d.y, d.z, 0 );
-	dst[i * 4 + 2] = make_float4( rx, ry, rz, 0 ), dst[i * 4 + 3] = h;
+	const int rd = drain( c ); // also after an error: nothing of this call may still be in flight when the mutex is released
+	return rc != TBVH_OK ? rc : rd;
 }
-static int ensure_pack( tbvh_ctx c )
-{
-	if (c->h_pack[0]) return TBVH_OK;
-	for (int i = 0; i < 3; i++)
-	{
-		CUDA_TRY( cudaHostAlloc( &c->h_pack[i], STAGE_RAYS * 48, cudaHostAllocDefault ) );
-		CUDA_TRY( cudaMalloc( &c->d_pack[i], STAGE_RAYS * 48 ) );
-		CUDA_TRY( cudaEventCreateWithFlags( &c->ev_pack[i], cudaEventDisableTiming ) );
-	}
-	return TBVH_OK;
-}
-static unsigned pack_threads()
-{
-	static int env = -1;
-	if (env < 0) { const char* e = getenv( "TBVH_PACK_THREADS" ); env = e ? atoi( e ) : 0; }
-	unsigned t = env > 0 ? (unsigned)env : std::thread::hardware_concurrency() / 8;
-	return t < 1 ? 1 : t > 64 ? 64 : t;
-}
-// one chunk through the packed path; returns 1 when it was taken, 0 when the chunk must use the 64-byte path (non-canonical rD)
-static int stage_in_packed( tbvh_ctx c, PackPool& pool, const int k, const uint64_t chunk, const char* h, const uint32_t stride, const uint64_t cnt, const int rec, cudaStream_t s )
-{
-	if (chunk >= 3) CUDA_TRY( cudaEventSynchronize( c->ev_pack[k] ) ); // the staging buffer's previous copy has left the host
-	const PackJob j = { h, stride, cnt, (char*)c->h_pack[k], rec };
-	if (!pool.run( j )) return 0;
-	CUDA_TRY( cudaMemcpyAsync( c->d_pack[k], c->h_pack[k], cnt * rec, cudaMemcpyHostToDevice, s ) );
-	CUDA_TRY( cudaEventRecord( c->ev_pack[k], s ) );
-	k_unpack_rays<<<(uint32_t)((cnt + 255) / 256), 256, 0, s>>>( (const float4*)c->d_pack[k], rec / 16, (float4*)c->d_stage[k], cnt );
-	LAUNCHED();
-	return 1;
-}
-
-static int intersect_host( tbvh_bvh b, int layout, void* rays, uint32_t stride, uint64_t n, void* packed_hits );
 
 int tbvh_intersect( tbvh_bvh b, int layout, void* rays, uint32_t stride, uint64_t n ) { return intersect_host( b, layout, rays, stride, n, 0 ); }
 
@@ -830,104 +947,39 @@ int tbvh_intersect_packed( tbvh_bvh b, int layout, const void* rays, uint32_t st
 	return intersect_host( b, layout, (void*)rays, stride, n, hits );
 }
 
-static int intersect_host( tbvh_bvh b, int layout, void* rays, uint32_t stride, uint64_t n, void* packed_hits )
-{
-	ARG_CHECK( b && rays && stride >= 64, "bad ray buffer" );
-	CUDA_TRY( cudaSetDevice( b->ctx->device ) );
-	tbvh_ctx c = b->ctx;
-	TRY( ensure_stage( c ) );
-	char* dev_alias = (char*)mapped_alias( rays );
-	if (b->d_inst)
-	{
-		// TLAS: staged 64-byte records, hits written into them by the kernel, bytes 44..63 (inst, t, u, v, prim) copied back
-		if (packed_hits) { tbvh_set_error( "tbvh_intersect_packed: TLAS hits carry the instance and are returned in the ray records" ); return TBVH_E_UNSUPPORTED; }
-		int k = 0;
-		for (uint64_t off = 0; off < n; off += c->stage_rays, k = (k + 1) % 3)
-		{
-			const uint64_t cnt = n - off < c->stage_rays ? n - off : c->stage_rays;
-			cudaStream_t s = c->copy_streams[k];
-			char* h = (char*)rays + off * stride;
-			TRY( stage_in( c, k, h, dev_alias ? dev_alias + off * stride : 0, stride, cnt, s ) );
-			TRY( tlas_trace_launch( b, c->d_stage[k], 64, 0, cnt, false, s ) );
-			CUDA_TRY( cudaMemcpy2DAsync( h + 44, stride, (char*)c->d_stage[k] + 44, 64, 20, cnt, cudaMemcpyDeviceToHost, s ) );
-		}
-		for (int i = 0; i < 3; i++) CUDA_TRY( cudaStreamSynchronize( c->copy_streams[i] ) );
-		return TBVH_OK;
-	}
-	const int mode = packed_hits ? 4 : (c->d2h_mode == 3 && !(dev_alias && (stride & 15) == 0)) ? 0 : c->d2h_mode;
-	if (mode == 2 || mode == 4)
-		for (int i = 0; i < 3; i++) if (!c->d_hits_pack[i]) CUDA_TRY( cudaMalloc( &c->d_hits_pack[i], c->stage_rays * 16 ) );
-	if (mode == 2)
-	{
-		if (c->h_hits_rays < n) { if (c->h_hits) cudaFreeHost( c->h_hits ); c->h_hits = 0; CUDA_TRY( cudaHostAlloc( &c->h_hits, n * 16, cudaHostAllocDefault ) ); c->h_hits_rays = n; }
-	}
-	std::unique_ptr<PackPool> pool;
-	if (c->host_path == 2 && n >= 65536) { TRY( ensure_pack( c ) ); pool.reset( new PackPool( pack_threads() ) ); }
-	int k = 0;
-	uint64_t chunk = 0;
-	for (uint64_t off = 0; off < n; off += c->stage_rays, k = (k + 1) % 3, chunk++)
-	{
-		const uint64_t cnt = n - off < c->stage_rays ? n - off : c->stage_rays;
-		cudaStream_t s = c->copy_streams[k];
-		char* h = (char*)rays + off * stride;
-		char* hd = dev_alias ? dev_alias + off * stride : 0;
-		int took = 0;
-		if (pool) { took = stage_in_packed( c, *pool, k, chunk, h, stride, cnt, 48, s ); if (took < 0) return took; }
-		if (!took) TRY( stage_in( c, k, h, hd, stride, cnt, s ) );
-		if (mode == 2 || mode == 4)
-		{
-			// hits leave the device packed (16 B per ray, one contiguous copy per chunk): into the caller's packed array
-			// (tbvh_intersect_packed) or into pinned staging for the host-side scatter (d2h_mode 2)
-			TRY( trace_dispatch( b, layout, c->d_stage[k], 64, c->d_hits_pack[k], 16, 0, cnt, false, s ) );
-			CUDA_TRY( cudaMemcpyAsync( (char*)(mode == 4 ? packed_hits : c->h_hits) + off * 16, c->d_hits_pack[k], cnt * 16, cudaMemcpyDeviceToHost, s ) );
-			continue;
-		}
-		TRY( trace_dispatch( b, layout, c->d_stage[k], 64, (char*)c->d_stage[k] + 48, 64, 0, cnt, false, s ) );
-		if (mode == 3)
-		{
-			k_scatter_hits<<<(uint32_t)((cnt + 255) / 256), 256, 0, s>>>( (const float4*)c->d_stage[k], (float4*)hd, stride / 16, cnt );
-			LAUNCHED();
-		}
-		else if (mode == 1) CUDA_TRY( cudaMemcpy2DAsync( h, stride, c->d_stage[k], 64, 64, cnt, cudaMemcpyDeviceToHost, s ) );
-		else CUDA_TRY( cudaMemcpy2DAsync( h + 48, stride, (char*)c->d_stage[k] + 48, 64, 16, cnt, cudaMemcpyDeviceToHost, s ) );
-	}
-	if (mode == 2)
-	{
-		// every chunk's packed hits land in h_hits (each chunk has its own slice of it, so nothing is overwritten); wait for
-		// them all, then scatter the 16-byte hits into the strided records with a handful of host threads
-		for (int i = 0; i < 3; i++) CUDA_TRY( cudaStreamSynchronize( c->copy_streams[i] ) );
-		scatter_hits_host( (const char*)c->h_hits, (char*)rays, stride, n );
-		return TBVH_OK;
-	}
-	for (int i = 0; i < 3; i++) CUDA_TRY( cudaStreamSynchronize( c->copy_streams[i] ) );
-	return TBVH_OK;
-}
-
 int tbvh_occluded( tbvh_bvh b, int layout, const void* rays, uint32_t stride, uint64_t n, uint32_t* bits )
 {
 	ARG_CHECK( b && rays && bits && stride >= 64, "bad ray buffer" );
-	CUDA_TRY( cudaSetDevice( b->ctx->device ) );
 	tbvh_ctx c = b->ctx;
-	TRY( ensure_stage( c ) );
+	std::lock_guard<std::mutex> lk( c->host_mutex );
+	CUDA_TRY( cudaSetDevice( c->device ) );
+	TRY( ensure_slots( c ) );
+	if (b->stats) CUDA_TRY( cudaMemset( b->d_stats, 0, 16 ) );
+	if (b->d_inst) TRY( tlas_check( b ) );
 	const char* dev_alias = (const char*)mapped_alias( rays );
-	std::unique_ptr<PackPool> pool;
-	if (c->host_path == 2 && !b->d_inst && n >= 65536) { TRY( ensure_pack( c ) ); pool.reset( new PackPool( pack_threads() ) ); }
-	int k = 0;
 	uint64_t chunk = 0;
-	for (uint64_t off = 0; off < n; off += c->stage_rays, k = (k + 1) % 3, chunk++)
+	int rc = TBVH_OK;
+	for (uint64_t off = 0; off < n && rc == TBVH_OK; off += c->chunk_rays, chunk++)
 	{
-		const uint64_t cnt = n - off < c->stage_rays ? n - off : c->stage_rays;
-		cudaStream_t s = c->copy_streams[k];
+		const int k = (int)(chunk % TBVH_SLOTS);
+		HostSlot& sl = c->slot[k];
+		const uint64_t cnt = n - off < c->chunk_rays ? n - off : c->chunk_rays;
 		const char* h = (const char*)rays + off * stride;
-		int took = 0;
-		if (pool) { took = stage_in_packed( c, *pool, k, chunk, h, stride, cnt, 32, s ); if (took < 0) return took; }
-		if (!took) TRY( stage_in( c, k, h, dev_alias ? dev_alias + off * stride : 0, stride, cnt, s ) );
-		if (b->d_inst) TRY( tlas_trace_launch( b, c->d_stage[k], 64, (uint32_t*)c->d_stage_bits[k], cnt, true, s ) );
-		else TRY( trace_dispatch( b, layout, c->d_stage[k], 64, 0, 0, (uint32_t*)c->d_stage_bits[k], cnt, true, s ) );
-		CUDA_TRY( cudaMemcpyAsync( bits + off / 32, c->d_stage_bits[k], ((cnt + 31) / 32) * 4, cudaMemcpyDeviceToHost, s ) );
+		auto body = [&]() -> int
+		{
+			TRY( stage_in( c, k, chunk, h, dev_alias ? dev_alias + off * stride : 0, stride, cnt ) );
+			if (b->d_inst) TRY( tlas_trace_launch( b, sl.d_rays, 64, (uint32_t*)sl.d_bits, cnt, true, c->s_run ) );
+			else TRY( trace_dispatch( b, layout, sl.d_rays, 64, 0, 0, (uint32_t*)sl.d_bits, cnt, true, c->s_run ) );
+			CUDA_TRY( cudaEventRecord( sl.run_done, c->s_run ) );
+			CUDA_TRY( cudaStreamWaitEvent( c->s_out, sl.run_done, 0 ) );
+			CUDA_TRY( cudaMemcpyAsync( bits + off / 32, sl.d_bits, ((cnt + 31) / 32) * 4, cudaMemcpyDeviceToHost, c->s_out ) ); // chunk_rays is a multiple of 32
+			CUDA_TRY( cudaEventRecord( sl.out_done, c->s_out ) );
+			return TBVH_OK;
+		};
+		rc = body();
 	}
-	for (int i = 0; i < 3; i++) CUDA_TRY( cudaStreamSynchronize( c->copy_streams[i] ) );
-	return TBVH_OK;
+	const int rd = drain( c );
+	return rc != TBVH_OK ? rc : rd;
 }
 
 } // extern "C"

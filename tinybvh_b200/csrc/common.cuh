@@ -3,10 +3,14 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <mutex>
+#include <vector>
+#include <atomic>
 #include "../../include/tinybvh_b200.h"
 
 #define BVH_FAR 1e30f
-#define TBVH_STACK 64          // traversal stack entries per ray (reference: 256 closest / 64 any-hit, tiny_bvh.h:3249,:3409)
+#define TBVH_STACK 64          // traversal stack entries per ray of the default BVH2 kernels; deeper trees run the TBVH_STACK_DEEP instances
+#define TBVH_STACK_DEEP 256    // the reference's own closest-hit stack (tiny_bvh.h:3249; any-hit uses 64, :3409)
 
 // ---- error plumbing -------------------------------------------------------------------------------------
 void tbvh_set_error( const char* fmt, ... );
@@ -15,36 +19,49 @@ extern unsigned long long g_tbvh_launches;
 #define LAUNCHED() do { g_tbvh_launches++; cudaError_t e_ = cudaGetLastError(); if (e_ != cudaSuccess) { tbvh_set_error( "%s:%d launch -> %s", __FILE__, __LINE__, cudaGetErrorString( e_ ) ); return TBVH_E_CUDA; } } while (0)
 
 // ---- handles ----------------------------------------------------------------------------------------------
+// one stage buffer set of the host-buffer pipeline (api.cu "host path")
+struct HostSlot
+{
+	void* d_rays = 0;                // chunk of 64-byte device records
+	void* d_hits = 0;                // packed 16-byte hits of the chunk
+	void* d_bits = 0;                // occlusion words of the chunk
+	cudaEvent_t in_done = 0, run_done = 0, out_done = 0;
+};
+#define TBVH_SLOTS 4
+
 struct tbvh_ctx_t
 {
 	int device = 0;
 	int sm_count = 148;
-	cudaStream_t stream = 0;         // engine stream (builds, uploads, host-path copies)
-	cudaStream_t copy_streams[3] = { 0, 0, 0 }; // host-path pipeline
-	void* d_stage[3] = { 0, 0, 0 };  // staging ray chunks for the host path
-	void* d_stage_bits[3] = { 0, 0, 0 };
-	size_t stage_rays = 0;
-	// host-path tuning (env TBVH_HOST_PATH = copy2d | zerocopy, TBVH_H2D_SPLIT = 1..4): the inbound 2D copy of a chunk
-	// can be split over several streams so more than one copy engine works on it
-	int host_path = 0;               // 0 = copy engine (cudaMemcpy2DAsync), 1 = copy kernels through the pinned mapping
-	int h2d_split = 1;
+	int numa_node = -1;              // host NUMA node the device hangs off (-1 = unknown)
+	cudaStream_t stream = 0;         // engine stream (builds, uploads, conversions)
+	// host-buffer pipeline: inbound copies, traversal and outbound copies each own a stream, so chunk k+1 flows in while chunk k
+	// is traced and the hits of chunk k-1 flow out; the slots are handed round-robin and recycled through events
+	std::mutex host_mutex;           // host batch calls on one context are serialised (thread-safe per handle)
+	cudaStream_t s_in = 0, s_run = 0, s_out = 0;
+	cudaStream_t s_in_part[3] = { 0, 0, 0 }; // extra inbound streams when h2d_split > 1
+	cudaEvent_t ev_part[TBVH_SLOTS][3] = {};
+	cudaEvent_t ev_fork = 0;
+	HostSlot slot[TBVH_SLOTS];
+	size_t chunk_rays = 1u << 19;    // rays per chunk (32 MiB of device records)
+	size_t slot_rays = 0;            // capacity the slots were allocated for
+	int host_path = 0;               // inbound: 0 = copy engine (cudaMemcpy2DAsync of 64-byte rows), 1 = gather kernel through the pinned mapping
+	int h2d_split = 1;               // inbound 2D copy of a chunk split over this many streams (copy engines)
+	int d2h_mode = 0;                // in-place hits: 0 = 2D copy of 16-byte rows, 3 = scatter kernel through the pinned mapping
 	int trace_variant = 3;           // BVH2 traversal kernel: 0 generic, 3 octant switch, 4 persistent warps (see trace_bvh2.cu)
 	int small_mode = 0;              // warp-subtree kernel: bit 0 = fragments staged in shared memory, bit 1 = aggregated bin updates
 	int inst_idx_bits = 32;          // the host program's INST_IDX_BITS (tiny_bvh.h:118): 32 = TLAS hits store hit.inst, 4..31 = top bits of hit.prim
 	int hq_small = 16;               // BuildHQ: nodes of at most this many fragments go to the warp-per-subtree kernel (<= 256)
 	int hq_cluster = 16;             // BuildHQ: largest thread-block cluster a node of the level phase may get (1..16)
 	int small_t = 128;               // builder: subtrees of at most this many primitives go to the warp kernel (<= 256)
-	int d2h_mode = 0;                // hits back to the host: 0 = 2D copy of 16-byte rows, 1 = 2D copy of the whole 64-byte rows,
-	                                 // 2 = packed 1D copy to pinned staging + multi-threaded host scatter, 3 = scatter kernel (zero copy)
-	void* d_hits_pack[3] = { 0, 0, 0 };
-	// host_path 2: rays are packed by host threads into pinned staging (48 or 32 bytes per ray) and cross PCIe as ONE contiguous copy
-	void* h_pack[3] = { 0, 0, 0 }; void* d_pack[3] = { 0, 0, 0 };
-	cudaEvent_t ev_pack[3] = { 0, 0, 0 };
-	void* h_hits = 0; size_t h_hits_rays = 0; // pinned staging for d2h_mode 2
-	cudaStream_t aux_streams[4] = { 0, 0, 0, 0 };
-	cudaEvent_t ev_done[3] = { 0, 0, 0 };
-	cudaEvent_t ev_part[3][4] = {};
+	// ring of 8-byte device counters for kernels that pull work from a counter (one per launch, so launches on different
+	// streams never share one)
+	unsigned long long* d_counters = 0;
+	std::atomic<uint32_t> counter_next{ 0 };
 };
+#define TBVH_COUNTERS 256
+
+struct BlasLink { tbvh_bvh blas; uint32_t generation; }; // host side: what a TLAS was built over
 
 struct tbvh_bvh_t
 {
@@ -61,20 +78,25 @@ struct tbvh_bvh_t
 	// leaf-ordered triangle records for BVH2 traversal: 3 float4 per prim reference
 	//   [0] = (v0.xyz, as_float(primIdx))  [1] = e1 = v1-v0  [2] = e2 = v2-v0
 	float4* d_leaf_tris = 0;
+	uint32_t leaf_tris_count = 0; // records d_leaf_tris was allocated for
 	// LAYOUT_BVH_GPU mirror (only materialised on upload / convert / download)
 	float4* d_nodes_gpu = 0;   // 4 float4 per node
 	// LAYOUT_CWBVH
 	float4* d_cw_nodes = 0;    // 5 float4 per node
 	float4* d_cw_tris = 0;     // 3 float4 per triangle
+	float4* d_cw_trav = 0;     // traversal nodes derived from d_cw_nodes (trace_cwbvh.cu cw_make_trav): 10 float4 per node
+	uint32_t cw_depth = 0;     // depth of the wide tree (root = 0)
+	uint32_t generation = 0;   // bumped whenever the arrays a TLAS may point at are replaced (build, upload, refit, convert)
 	// TLAS (BVH::Build( BLASInstance*, instCount, BVHBase**, blasCount ) :2221): nodes / primIdx over instance boxes + device tables
 	float4* d_aabbs = 0;       // instance boxes the TLAS was built over (2 float4 per instance)
 	void* d_inst = 0;          // TlasInst records (inverse transform, BLAS number, mask)
 	void* d_blas = 0;          // BlasRef records (traversal arrays of every BLAS)
 	uint32_t inst_count = 0, blas_count = 0;
+	std::vector<BlasLink> links; // TLAS only: the BLAS handles it points into, with the generation they had at build time
 	bool refittable = true;    // BVHBase::refittable (:811): false after BuildHQ ("can't refit an SBVH", :3027)
 	// statistics
 	int stats = 0;
-	unsigned long long* d_stats = 0; // [0]=steps [1]=tris
+	unsigned long long* d_stats = 0; // [0]=steps [1]=tris, accumulated over every launch of one API call
 };
 
 // ---- device math in the oracle's exact operation order (oracle/tbvh_oracle.c header lists the pairing) ----
@@ -108,8 +130,11 @@ __device__ __forceinline__ uint32_t f2key( float f ) { uint32_t u = __float_as_u
 __device__ __forceinline__ float key2f( uint32_t k ) { return __uint_as_float( (k & 0x80000000u) ? (k & 0x7fffffffu) : ~k ); }
 
 // ---- internal entry points (one per .cu) -------------------------------------------------------------------
-int bvh2_trace_launch( tbvh_bvh b, const void* d_rays, uint32_t stride, void* d_hits, uint32_t hit_stride, uint32_t* d_bits, uint64_t n, bool anyhit, cudaStream_t s );
-int cwbvh_trace_launch( tbvh_bvh b, const void* d_rays, uint32_t stride, void* d_hits, uint32_t hit_stride, uint32_t* d_bits, uint64_t n, bool anyhit, cudaStream_t s );
+// d_stats: NULL, or two counters the launch ADDS its node visits / triangle tests to (the caller zeroes them once per API call)
+int bvh2_trace_launch( tbvh_bvh b, const void* d_rays, uint32_t stride, void* d_hits, uint32_t hit_stride, uint32_t* d_bits, uint64_t n, bool anyhit, cudaStream_t s, unsigned long long* d_stats );
+int cwbvh_trace_launch( tbvh_bvh b, const void* d_rays, uint32_t stride, void* d_hits, uint32_t hit_stride, uint32_t* d_bits, uint64_t n, bool anyhit, cudaStream_t s, unsigned long long* d_stats );
+int cw_make_trav( tbvh_bvh b, cudaStream_t s, int known_depth = -1 ); // known_depth < 0: measured on the device
+unsigned long long* ctx_next_counter( tbvh_ctx c ); // a zero-on-use 8-byte device counter from the context's ring (persistent-warp ray fetch)
 int build_sah_launch( tbvh_bvh b, float c_trav, float c_int, int flavour );
 int build_hq_launch( tbvh_bvh b, float c_trav, float c_int );
 int refit_launch( tbvh_bvh b, cudaStream_t s );

@@ -21,9 +21,9 @@ __global__ void k_make_leaf_tris( const float4* __restrict__ verts, const uint32
 int make_leaf_tris( tbvh_bvh b, cudaStream_t s )
 {
 	const uint32_t n = b->info.idx_count;
-	if (b->d_leaf_tris) cudaFree( b->d_leaf_tris );
-	b->d_leaf_tris = 0;
-	CUDA_TRY( cudaMalloc( &b->d_leaf_tris, (size_t)n * 48 ) );
+	// a refit keeps the array (same idx_count): a TLAS holding its address stays valid
+	if (b->d_leaf_tris && b->leaf_tris_count != n) { cudaFree( b->d_leaf_tris ); b->d_leaf_tris = 0; }
+	if (!b->d_leaf_tris) { CUDA_TRY( cudaMalloc( &b->d_leaf_tris, (size_t)n * 48 ) ); b->leaf_tris_count = n; b->generation++; }
 	k_make_leaf_tris<<<(n + 255) / 256, 256, 0, s>>>( b->d_verts, b->d_prim_idx, b->d_leaf_tris, n );
 	LAUNCHED();
 	return TBVH_OK;

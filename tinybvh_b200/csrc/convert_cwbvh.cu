@@ -281,7 +281,8 @@ int bvh_to_cwbvh( tbvh_bvh b, cudaStream_t s )
 	#define CW_ALLOC( ptr, bytes ) do { CUDA_TRY( cudaMalloc( (void**)&(ptr), (bytes) ) ); scratch.push_back( (void*)(ptr) ); } while (0)
 	if (b->d_cw_nodes) cudaFree( b->d_cw_nodes );
 	if (b->d_cw_tris) cudaFree( b->d_cw_tris );
-	b->d_cw_nodes = 0, b->d_cw_tris = 0;
+	if (b->d_cw_trav) cudaFree( b->d_cw_trav );
+	b->d_cw_nodes = 0, b->d_cw_tris = 0, b->d_cw_trav = 0;
 	uint32_t* extra = 0, * base = 0, * tile = 0, * lists = 0, * d_count = 0;
 	float4* ext = 0;
 	WideNode* wide = 0;
@@ -345,8 +346,10 @@ int bvh_to_cwbvh( tbvh_bvh b, cudaStream_t s )
 		CUDA_TRY( cudaMalloc( &b->d_cw_nodes, (size_t)wide_count * 80 ) );
 		CUDA_TRY( cudaMalloc( &b->d_cw_tris, (size_t)idx_count * 48 ) );
 		k_encode<<<(wide_count + 127) / 128, 128, 0, s>>>( ext, lists, wide_count, wide, b->d_prim_idx, b->d_verts, b->d_cw_nodes, b->d_cw_tris ); LAUNCHED();
-		CUDA_TRY( cudaStreamSynchronize( s ) );
 		b->info.used_blocks = wide_count * 5, b->info.cwbvh_tri_count = idx_count;
+		// the traversal nodes the kernels read (trace_cwbvh.cu); the wide tree has `levels` levels
+		{ const int r = cw_make_trav( b, s, (int)levels - 1 ); if (r != TBVH_OK) return r; }
+		CUDA_TRY( cudaStreamSynchronize( s ) );
 		return TBVH_OK;
 	};
 	const int rc = body();

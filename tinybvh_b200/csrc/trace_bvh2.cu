@@ -31,7 +31,8 @@
 // OCTSW = 1: when every ray of the warp lies in the same direction octant (the normal case for camera and shadow rays) the
 // slab tests run through an octant-specialised instance picked by a warp-uniform switch, which removes the 12 selects
 // per step; mixed warps use the generic per-lane selects.  Same arithmetic, same order, same results either way.
-template <bool ANYHIT, bool STATS, int MINB, int OCTSW>
+// STACKN = traversal stack entries: TBVH_STACK (64) for trees of depth < 64, TBVH_STACK_DEEP (256, the reference's own stack, :3249) above.
+template <bool ANYHIT, bool STATS, int MINB, int OCTSW, int STACKN>
 __global__ void __launch_bounds__( 128, MINB ) k_trace_bvh2( const float4* __restrict__ nodes, const float4* __restrict__ tris,
 	const char* rays, const uint32_t stride, char* hits, const uint32_t hit_stride, // may alias (in-place hits): plain loads
 	uint32_t* __restrict__ bits, const uint64_t n, const uint32_t root_ref, const uint32_t root_count,
@@ -63,7 +64,7 @@ __global__ void __launch_bounds__( 128, MINB ) k_trace_bvh2( const float4* __res
 		const float nrox = -__fmul_rn( ox, rdx ), nroy = -__fmul_rn( oy, rdy ), nroz = -__fmul_rn( oz, rdz );
 		float tmax = rh4.x, hu = rh4.y, hv = rh4.z;
 		uint32_t hprim = __float_as_uint( rh4.w );
-		uint2 stack[TBVH_STACK];
+		uint2 stack[STACKN];
 		int sp = 0;
 		uint32_t ref = root_ref, cnt = root_count;
 		unsigned long long nsteps = 0, ntris = 0;
@@ -242,24 +243,34 @@ __global__ void __launch_bounds__( 128, 10 ) k_trace_bvh2_persist( const float4*
 	}
 }
 
+unsigned long long* ctx_next_counter( tbvh_ctx c ) { return c->d_counters + (c->counter_next.fetch_add( 1 ) % TBVH_COUNTERS); }
+
 int bvh2_trace_launch( tbvh_bvh b, const void* d_rays, uint32_t stride, void* d_hits, uint32_t hit_stride, uint32_t* d_bits,
-	uint64_t n, bool anyhit, cudaStream_t s )
+	uint64_t n, bool anyhit, cudaStream_t s, unsigned long long* d_stats )
 {
 	if (!b->d_trav || !b->d_leaf_tris) { tbvh_set_error( "BVH2 layout not resident" ); return TBVH_E_STATE; }
 	if (n == 0) return TBVH_OK;
-	if (b->info.max_depth + 1 > TBVH_STACK) { tbvh_set_error( "BVH depth %u exceeds the %d-entry traversal stack", b->info.max_depth, TBVH_STACK ); return TBVH_E_LIMIT; }
+	if (b->info.max_depth + 1 > TBVH_STACK_DEEP) { tbvh_set_error( "BVH depth %u exceeds the %d-entry traversal stack (the reference's own, tiny_bvh.h:3249)", b->info.max_depth, TBVH_STACK_DEEP ); return TBVH_E_LIMIT; }
+	const bool deep = b->info.max_depth + 1 > TBVH_STACK;
 	const uint32_t root_ref = b->root_ref, root_count = b->root_count;
 	const uint32_t block = 128;
 	const uint64_t grid = (n + block - 1) / block;
 	if (grid > 0x7fffffffull) { tbvh_set_error( "ray batch too large for one launch" ); return TBVH_E_ARG; }
-	if (b->stats) CUDA_TRY( cudaMemsetAsync( b->d_stats, 0, 16, s ) );
 	const int variant = b->ctx->trace_variant;
-	#define LAUNCH( A, S, M, O ) k_trace_bvh2<A, S, M, O><<<(uint32_t)grid, block, 0, s>>>( b->d_trav, b->d_leaf_tris, (const char*)d_rays, stride, \
-		(char*)d_hits, hit_stride, d_bits, n, root_ref, root_count, b->d_stats )
-	if (variant == 4 && !b->stats)
+	#define LAUNCH( A, S, M, O, D ) k_trace_bvh2<A, S, M, O, D><<<(uint32_t)grid, block, 0, s>>>( b->d_trav, b->d_leaf_tris, (const char*)d_rays, stride, \
+		(char*)d_hits, hit_stride, d_bits, n, root_ref, root_count, d_stats )
+	if (deep)
 	{
-		// persistent warps: one resident wave (10 CTAs of 128 threads per SM), rays pulled from a counter
-		unsigned long long* next = b->d_stats + 1; // second stats word doubles as the ray counter (stats are off here)
+		// depth 64..255: the same kernel with the reference's 256-entry stack (2 KiB of local memory per ray)
+		if (d_stats) { if (anyhit) LAUNCH( true, true, 10, 0, TBVH_STACK_DEEP ); else LAUNCH( false, true, 10, 0, TBVH_STACK_DEEP ); }
+		else { if (anyhit) LAUNCH( true, false, 10, 1, TBVH_STACK_DEEP ); else LAUNCH( false, false, 10, 1, TBVH_STACK_DEEP ); }
+		LAUNCHED();
+		return TBVH_OK;
+	}
+	if (variant == 4 && !d_stats)
+	{
+		// persistent warps: one resident wave (10 CTAs of 128 threads per SM), rays pulled from a counter that belongs to this launch
+		unsigned long long* next = ctx_next_counter( b->ctx );
 		CUDA_TRY( cudaMemsetAsync( next, 0, 8, s ) );
 		if (anyhit) CUDA_TRY( cudaMemsetAsync( d_bits, 0, ((n + 31) / 32) * 4, s ) );
 		const uint32_t pgrid = (uint32_t)b->ctx->sm_count * 10u;
@@ -268,9 +279,9 @@ int bvh2_trace_launch( tbvh_bvh b, const void* d_rays, uint32_t stride, void* d_
 		LAUNCHED();
 		return TBVH_OK;
 	}
-	if (b->stats) { if (anyhit) LAUNCH( true, true, 10, 0 ); else LAUNCH( false, true, 10, 0 ); }
-	else if (variant == 3) { if (anyhit) LAUNCH( true, false, 10, 1 ); else LAUNCH( false, false, 10, 1 ); }
-	else { if (anyhit) LAUNCH( true, false, 10, 0 ); else LAUNCH( false, false, 10, 0 ); }
+	if (d_stats) { if (anyhit) LAUNCH( true, true, 10, 0, TBVH_STACK ); else LAUNCH( false, true, 10, 0, TBVH_STACK ); }
+	else if (variant == 3) { if (anyhit) LAUNCH( true, false, 10, 1, TBVH_STACK ); else LAUNCH( false, false, 10, 1, TBVH_STACK ); }
+	else { if (anyhit) LAUNCH( true, false, 10, 0, TBVH_STACK ); else LAUNCH( false, false, 10, 0, TBVH_STACK ); }
 	#undef LAUNCH
 	LAUNCHED();
 	return TBVH_OK;

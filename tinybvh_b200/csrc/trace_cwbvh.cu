@@ -1,56 +1,156 @@
-// tinybvh_b200/csrc/trace_cwbvh.cu - compressed wide BVH (CWBVH, Ylitie et al. 2017) closest-hit / any-hit for sm_100a.
+// tinybvh_b200/csrc/trace_cwbvh.cu - closest-hit / any-hit traversal of BVH8_CWBVH data on sm_100a.
 //
-// Replaces the OpenCL kernels traverse_cwbvh / isoccluded_cwbvh (traverse_cwbvh.cl:123,343) and follows the semantics
-// of the reference's own CPU walk of the same data, BVH8_CWBVH::Intersect (tiny_bvh.h:7046-7154): node group
-// (child base, hit bits | imask), triangle group (triangle base, 24 hit bits), children visited in octant order
-// (slot ^ octinv, highest bit first), quantised slabs  t = q * 2^e * rD + (p - O) * rD  with  cmin = max(.., 0),
-// cmax = min(.., tmax),  hit iff cmin <= cmax.
-// Node = 5 x float4 (80 B), triangle = 3 x float4 (48 B: v2-v0, v1-v0, v0|primIdx), byte layout in SURVEY.md 8(a).
-// The triangle test is the oracle's Moeller-Trumbore (common.cuh mt_test), so a ray that ends on the same primitive as
-// BVH::Intersect carries bit-identical t,u,v.
+// Results are those of the reference's own walk of the same data, BVH8_CWBVH::Intersect (tiny_bvh.h:7046-7154), bit for bit:
+// children of a wide node are entered in the order the format defines (inner child in slot s owns bit 24 + (s ^ o) of the
+// node's hit word, o = 7 - ray octant; highest bit first), a leaf child owns `count` consecutive bits from its triangle offset,
+// a child is hit iff  max( tnear_x, tnear_y, tnear_z, 0 ) <= min( tfar_x, tfar_y, tfar_z, t )  with
+// t_plane = fma( q, 2^e * rD, ( p - O ) * rD ),  triangles run through the oracle's Moeller-Trumbore (common.cuh mt_test).
+//
+// What is different from the reference kernels (traverse_cwbvh.cl) is everything the format does not dictate:
+//
+//  * The kernels do not read bvh8Data.  `cw_make_trav` expands every 80-byte node once into a 160-byte TRAVERSAL NODE made for
+//    this GPU (ncu on the byte format: 79 % issue-slot use, ALU pipe 72 % busy, 370 instructions per node visit, of which 96
+//    turn bytes into floats and ~90 test slots that hold no child - the reference's 8-wide collapse fills 4.4 of 8 slots on
+//    Bistro, 36 % of the nodes have two children):
+//        header   32 B   p.xyz | ex ey ez imask | first inner child | first triangle (float4 units) | pairs | -
+//        pair j   32 B   the (2j)-th and (2j+1)-th NON-EMPTY child:  lo.x lo.y lo.z hi.x hi.y hi.z as half2 (child a, child b)
+//                        - 0..255 is exact in fp16 - and one 32-bit hit word per child: a leaf child's triangle bits
+//                        `unary(count) << offset`, an inner child's slot bit `1 << (24 + slot)`
+//    Empty slots are gone, so a node costs ceil(children/2) pair steps, not 8 slot steps.
+//  * A pair step is packed fp32 arithmetic (Blackwell FFMA2, `fma.rn.f32x2`): one instruction evaluates the same plane of both
+//    children, 6 per pair instead of 12 FFMA, exactly rounded per component like the scalar fma.
+//  * The quantised planes reach the registers as halves and are widened by one conversion each (no byte extraction, no
+//    integer-to-float on the quarter-rate unit, no magic-number subtraction).
+//  * Near / far planes are picked per ray by the sign of rD once per pair on the packed words (3 selects for two children).
+//  * Inner-child bits are accumulated in slot order and moved to octant order by one 3-stage bit butterfly per node.
+//
+// Triangles are the reference's 48-byte records (e2, e1, v0 | primIdx) read straight from bvh8Tris.
 #include "common.cuh"
+#include <cuda_fp16.h>
+#include <vector>
 
-#define CW_STACK 48
+#define CW_STACK 128            // node groups a ray can have pending: one per level of the wide tree (the reference's own limit, tiny_bvh.h:7048)
+#define CW_NODE_F4 10           // float4 per traversal node
 
-__device__ __forceinline__ uint32_t sign_extend_s8x4( const uint32_t x )
+// ---- bvh8Data -> traversal nodes ------------------------------------------------------------------------------------
+// One thread per node.  Slot i of the source node: meta byte i (n1.z / n1.w), quantised bounds byte i of the six 8-byte rows at
+// bytes 32..79 (lo.x, lo.y, lo.z, hi.x, hi.y, hi.z) - layout in SURVEY.md 8(a), written by BVH8_CWBVH::ConvertFrom (tiny_bvh.h:5948-6015).
+__global__ void k_cw_expand( const uint4* __restrict__ src, uint4* __restrict__ dst, uint32_t* __restrict__ parent, const uint32_t count )
 {
-	// every byte becomes 0xff when its top bit is set (prmt with the sign-replicate selector)
-	uint32_t v;
-	asm( "prmt.b32 %0, %1, 0x0, 0x0000BA98;" : "=r"( v ) : "r"( x ) );
-	return v;
-}
-
-// (float)byte i of w without the quarter-rate I2F: splice the byte under the mantissa of 2^23 (one PRMT) and subtract 2^23
-// (exact).  The node step converts 48 bytes; with I2F the conversion unit, not the issue slots, bounded the kernel.
-__device__ __forceinline__ float byte_f( const uint32_t w, const int i )
-{
-	return __fsub_rn( __uint_as_float( __byte_perm( w, 0x4b000000u, 0x7650u | (uint32_t)i ) ), 8388608.0f );
-}
-
-// 4 children: quantised bounds words (lo/hi per axis, already swizzled by ray sign) -> hit bits
-__device__ __forceinline__ uint32_t slab4( const uint32_t meta4, const uint32_t octinv4, const uint32_t lox, const uint32_t loy, const uint32_t loz,
-	const uint32_t hix, const uint32_t hiy, const uint32_t hiz, const float ax, const float ay, const float az,
-	const float bx, const float by, const float bz, const float tmax )
-{
-	const uint32_t is_inner4 = (meta4 & (meta4 << 1)) & 0x10101010u;
-	const uint32_t inner_mask4 = sign_extend_s8x4( is_inner4 << 3 );
-	const uint32_t bit_index4 = (meta4 ^ (octinv4 & inner_mask4)) & 0x1f1f1f1fu;
-	const uint32_t child_bits4 = (meta4 >> 5) & 0x07070707u;
-	uint32_t hitmask = 0;
+	const uint32_t x = blockIdx.x * blockDim.x + threadIdx.x;
+	if (x >= count) return;
+	const uint4 n0 = src[(size_t)x * 5], n1 = src[(size_t)x * 5 + 1], n2 = src[(size_t)x * 5 + 2], n3 = src[(size_t)x * 5 + 3], n4 = src[(size_t)x * 5 + 4];
+	const uint32_t row[6][2] = { { n2.x, n2.y }, { n2.z, n2.w }, { n3.x, n3.y }, { n3.z, n3.w }, { n4.x, n4.y }, { n4.z, n4.w } };
+	const uint32_t meta[2] = { n1.z, n1.w };
+	uint32_t word[4][8]; // pair records under construction
 	#pragma unroll
-	for (int i = 0; i < 4; i++)
+	for (int j = 0; j < 4; j++) for (int k = 0; k < 8; k++) word[j][k] = 0;
+	uint32_t kept = 0, inner = 0;
+	#pragma unroll
+	for (int i = 0; i < 8; i++)
 	{
-		const float tminx = __fmaf_rn( byte_f( lox, i ), ax, bx ), tminy = __fmaf_rn( byte_f( loy, i ), ay, by ), tminz = __fmaf_rn( byte_f( loz, i ), az, bz );
-		const float tmaxx = __fmaf_rn( byte_f( hix, i ), ax, bx ), tmaxy = __fmaf_rn( byte_f( hiy, i ), ay, by ), tmaxz = __fmaf_rn( byte_f( hiz, i ), az, bz );
-		const float cmin = fmaxf( fmaxf( fmaxf( tminx, tminy ), tminz ), 0.0f );
-		const float cmax = fminf( fminf( fminf( tmaxx, tmaxy ), tmaxz ), tmax );
-		if (cmin <= cmax) hitmask |= ((child_bits4 >> (8 * i)) & 0xffu) << ((bit_index4 >> (8 * i)) & 0xffu);
+		const uint32_t m = (meta[i >> 2] >> (8 * (i & 3))) & 255u;
+		if (m == 0) continue; // empty slot: contributes no bit whatever its box test says
+		const bool is_inner = (m & 0x18u) == 0x18u; // 0b001sssss with sssss = 24 + slot (tiny_bvh.h:5988); a triangle offset is < 24
+		const uint32_t bits = is_inner ? 1u << (24u + (m & 7u)) : (m >> 5) << (m & 31u);
+		if (is_inner) inner++;
+		const uint32_t j = kept >> 1, side = kept & 1;
+		#pragma unroll
+		for (int r = 0; r < 6; r++)
+		{
+			const uint32_t q = (row[r][i >> 2] >> (8 * (i & 3))) & 255u;
+			const uint32_t h = (uint32_t)__half_as_ushort( __uint2half_rn( q ) );
+			#pragma unroll
+			for (int jj = 0; jj < 4; jj++) if (jj == (int)j) word[jj][r] |= side ? h << 16 : h;
+		}
+		#pragma unroll
+		for (int jj = 0; jj < 4; jj++) if (jj == (int)j) word[jj][6 + side] = bits;
+		kept++;
 	}
-	return hitmask;
+	uint4* o = dst + (size_t)x * CW_NODE_F4;
+	o[0] = n0;
+	o[1] = make_uint4( n1.x, n1.y, (kept + 1) >> 1, kept );
+	#pragma unroll
+	for (int j = 0; j < 4; j++)
+	{
+		o[2 + 2 * j] = make_uint4( word[j][0], word[j][1], word[j][2], word[j][3] );
+		o[3 + 2 * j] = make_uint4( word[j][4], word[j][5], word[j][6], word[j][7] );
+	}
+	// inner children sit at n1.x + 0 .. inner-1 (node units): note their parent for the depth pass
+	if (parent) for (uint32_t c = 0; c < inner; c++) if (n1.x + c < count) parent[n1.x + c] = x;
+}
+
+__global__ void k_cw_depth( const uint32_t* __restrict__ parent, const uint32_t count, uint32_t* __restrict__ max_depth )
+{
+	const uint32_t x = blockIdx.x * blockDim.x + threadIdx.x;
+	if (x >= count) return;
+	uint32_t d = 0, n = x;
+	while (n != 0 && n < count && d < 4096) n = parent[n], d++; // n >= count: a record no node points at (0xffffffff)
+	if (n != 0) return;
+	atomicMax( max_depth, d );
+}
+
+int cw_make_trav( tbvh_bvh b, cudaStream_t s, int known_depth )
+{
+	if (b->d_cw_trav) cudaFree( b->d_cw_trav ), b->d_cw_trav = 0;
+	const uint32_t count = b->info.used_blocks / 5;
+	if (count == 0) { tbvh_set_error( "cw_make_trav: no CWBVH nodes" ); return TBVH_E_STATE; }
+	CUDA_TRY( cudaMalloc( &b->d_cw_trav, (size_t)count * CW_NODE_F4 * 16 ) );
+	if (known_depth >= 0)
+	{
+		k_cw_expand<<<(count + 127) / 128, 128, 0, s>>>( (const uint4*)b->d_cw_nodes, (uint4*)b->d_cw_trav, 0, count ); LAUNCHED();
+		b->cw_depth = (uint32_t)known_depth;
+		return TBVH_OK;
+	}
+	// uploaded data: the depth of the wide tree is not known - every node notes its parent, then walks up to the root
+	uint32_t* d_parent = 0;
+	CUDA_TRY( cudaMalloc( &d_parent, ((size_t)count + 1) * 4 ) );
+	uint32_t depth = 0;
+	auto body = [&]() -> int
+	{
+		CUDA_TRY( cudaMemsetAsync( d_parent, 0xff, (size_t)count * 4, s ) );
+		CUDA_TRY( cudaMemsetAsync( d_parent + count, 0, 4, s ) );
+		k_cw_expand<<<(count + 127) / 128, 128, 0, s>>>( (const uint4*)b->d_cw_nodes, (uint4*)b->d_cw_trav, d_parent, count ); LAUNCHED();
+		k_cw_depth<<<(count + 127) / 128, 128, 0, s>>>( d_parent, count, d_parent + count ); LAUNCHED();
+		CUDA_TRY( cudaMemcpyAsync( &depth, d_parent + count, 4, cudaMemcpyDeviceToHost, s ) );
+		CUDA_TRY( cudaStreamSynchronize( s ) );
+		return TBVH_OK;
+	};
+	const int rc = body();
+	cudaFree( d_parent );
+	b->cw_depth = depth;
+	return rc;
+}
+
+// ---- traversal ------------------------------------------------------------------------------------------------------
+
+struct PairPlanes { float2 nx, ny, nz, fx, fy, fz; };
+
+__device__ __forceinline__ float2 widen( const uint32_t h2 ) { return __half22float2( *(const __half2*)&h2 ); }
+
+// one pair of children against one ray: `near` / `far` words already chosen by the ray's signs
+__device__ __forceinline__ uint32_t pair_hits( const uint32_t wnx, const uint32_t wny, const uint32_t wnz, const uint32_t wfx, const uint32_t wfy, const uint32_t wfz,
+	const uint32_t bits_a, const uint32_t bits_b, const float2 ax, const float2 ay, const float2 az, const float2 bx, const float2 by, const float2 bz, const float t )
+{
+	const float2 tnx = __ffma2_rn( widen( wnx ), ax, bx ), tny = __ffma2_rn( widen( wny ), ay, by ), tnz = __ffma2_rn( widen( wnz ), az, bz );
+	const float2 tfx = __ffma2_rn( widen( wfx ), ax, bx ), tfy = __ffma2_rn( widen( wfy ), ay, by ), tfz = __ffma2_rn( widen( wfz ), az, bz );
+	const float in_a = fmaxf( fmaxf( fmaxf( tnx.x, tny.x ), tnz.x ), 0.0f ), out_a = fminf( fminf( fminf( tfx.x, tfy.x ), tfz.x ), t );
+	const float in_b = fmaxf( fmaxf( fmaxf( tnx.y, tny.y ), tnz.y ), 0.0f ), out_b = fminf( fminf( fminf( tfx.y, tfy.y ), tfz.y ), t );
+	return (in_a <= out_a ? bits_a : 0u) | (in_b <= out_b ? bits_b : 0u);
+}
+
+// bits 24..31 of `w` hold inner-child hits by slot; move slot s to position s ^ o (o = 7 - octant)
+__device__ __forceinline__ uint32_t slots_to_order( const uint32_t w, const uint32_t o )
+{
+	uint32_t top = w >> 24;
+	if (o & 1u) top = ((top & 0x55u) << 1) | ((top >> 1) & 0x55u);
+	if (o & 2u) top = ((top & 0x33u) << 2) | ((top >> 2) & 0x33u);
+	if (o & 4u) top = ((top & 0x0fu) << 4) | (top >> 4);
+	return top << 24;
 }
 
 template <bool ANYHIT, bool STATS>
-__global__ void __launch_bounds__( 128 ) k_trace_cwbvh( const float4* __restrict__ nodes, const float4* __restrict__ tris,
+__global__ void __launch_bounds__( 128 ) k_trace_wide( const float4* __restrict__ nodes, const float4* __restrict__ tris,
 	const char* rays, const uint32_t stride, char* hits, const uint32_t hit_stride, uint32_t* __restrict__ bits, const uint64_t n,
 	unsigned long long* __restrict__ stats )
 {
@@ -62,73 +162,77 @@ __global__ void __launch_bounds__( 128 ) k_trace_cwbvh( const float4* __restrict
 		const float4 ro4 = rp[0], rd4 = rp[1], rr4 = rp[2], rh4 = rp[3];
 		const float ox = ro4.x, oy = ro4.y, oz = ro4.z, dx = rd4.x, dy = rd4.y, dz = rd4.z;
 		const float rdx = rr4.x, rdy = rr4.y, rdz = rr4.z;
-		float tmax = rh4.x, hu = rh4.y, hv = rh4.z;
+		float t = rh4.x, hu = rh4.y, hv = rh4.z;
 		uint32_t hprim = __float_as_uint( rh4.w );
-		const uint32_t octinv4 = (7u - ((dx < 0 ? 4u : 0u) | (dy < 0 ? 2u : 0u) | (dz < 0 ? 1u : 0u))) * 0x01010101u;
-		uint2 stack[CW_STACK];
-		int sp = 0;
-		uint2 ngroup = make_uint2( 0u, 0x80000000u ), tgroup = make_uint2( 0u, 0u );
+		const uint32_t o = 7u - ((dx < 0 ? 4u : 0u) | (dy < 0 ? 2u : 0u) | (dz < 0 ? 1u : 0u)); // octinv of tiny_bvh.h:7053
+		const bool negx = rdx < 0, negy = rdy < 0, negz = rdz < 0;                                // plane swizzle uses rD (:7082)
+		uint2 pending[CW_STACK];
+		int depth = 0;
+		uint32_t base = 0, word = 0x80000000u; // the root as a one-child group: bit 31, no siblings
 		unsigned long long nsteps = 0, ntris = 0;
 		while (true)
 		{
-			if (ngroup.y > 0x00ffffffu)
+			// ---- enter the pending inner child with the highest bit
+			const uint32_t bit = 31u - __clz( word );
+			const uint32_t rest = word & ~(1u << bit);
+			if (rest > 0x00ffffffu) pending[depth++] = make_uint2( base, rest );
+			const uint32_t slot = (bit - 24u) ^ o;
+			const uint32_t nidx = base + __popc( word & ~(0xffffffffu << slot) );
+			const float4* np = nodes + (size_t)nidx * CW_NODE_F4;
+			const float4 h0 = __ldg( np ), h1 = __ldg( np + 1 );
+			if (STATS) nsteps++;
+			const uint32_t ew = __float_as_uint( h0.w ) ^ 0x00808080u; // exponent bytes + 128
+			// scale = 2^e as a float bit pattern, ( e + 127 ) << 23 (:7072-7074)
+			const float scx = __uint_as_float( ((ew & 255u) << 23) - 0x00800000u );
+			const float scy = __uint_as_float( (((ew >> 8) & 255u) << 23) - 0x00800000u );
+			const float scz = __uint_as_float( (((ew >> 16) & 255u) << 23) - 0x00800000u );
+			const float ax1 = __fmul_rn( scx, rdx ), ay1 = __fmul_rn( scy, rdy ), az1 = __fmul_rn( scz, rdz );
+			const float bx1 = __fmul_rn( -__fsub_rn( ox, h0.x ), rdx ), by1 = __fmul_rn( -__fsub_rn( oy, h0.y ), rdy ), bz1 = __fmul_rn( -__fsub_rn( oz, h0.z ), rdz );
+			const float2 ax = make_float2( ax1, ax1 ), ay = make_float2( ay1, ay1 ), az = make_float2( az1, az1 );
+			const float2 bx = make_float2( bx1, bx1 ), by = make_float2( by1, by1 ), bz = make_float2( bz1, bz1 );
+			const uint32_t pairs = __float_as_uint( h1.z );
+			uint32_t got = 0;
+			#pragma unroll
+			for (uint32_t j = 0; j < 4; j++)
 			{
-				const uint32_t hitsm = ngroup.y;
-				const uint32_t bit = 31u - __clz( hitsm );
-				ngroup.y &= ~(1u << bit);
-				if (ngroup.y > 0x00ffffffu) stack[sp++] = ngroup;
-				const uint32_t slot = (bit - 24u) ^ (octinv4 & 255u);
-				const uint32_t rel = __popc( hitsm & ~(0xffffffffu << slot) );
-				const float4* np = nodes + (size_t)(ngroup.x + rel) * 5;
-				const float4 n0 = __ldg( np ), n1 = __ldg( np + 1 ), n2 = __ldg( np + 2 ), n3 = __ldg( np + 3 ), n4 = __ldg( np + 4 );
-				if (STATS) nsteps++;
-				const uint32_t n0w = __float_as_uint( n0.w );
-				// exponents are signed bytes: scale = 2^e as a float bit pattern (tiny_bvh.h:7072-7074)
-				const int ex = (int)(int8_t)(n0w & 0xff), ey = (int)(int8_t)((n0w >> 8) & 0xff), ez = (int)(int8_t)((n0w >> 16) & 0xff);
-				const float ax = __fmul_rn( __uint_as_float( (uint32_t)(ex + 127) << 23 ), rdx );
-				const float ay = __fmul_rn( __uint_as_float( (uint32_t)(ey + 127) << 23 ), rdy );
-				const float az = __fmul_rn( __uint_as_float( (uint32_t)(ez + 127) << 23 ), rdz );
-				const float bx = __fmul_rn( -__fsub_rn( ox, n0.x ), rdx ), by = __fmul_rn( -__fsub_rn( oy, n0.y ), rdy ), bz = __fmul_rn( -__fsub_rn( oz, n0.z ), rdz );
-				const bool nx = rdx < 0, ny = rdy < 0, nz = rdz < 0;
-				// words: n2.x,n2.y = qlox[0..7]; n2.z,n2.w = qloy; n3.x,n3.y = qloz; n3.z,n3.w = qhix; n4.x,n4.y = qhiy; n4.z,n4.w = qhiz
-				const uint32_t qlox0 = __float_as_uint( n2.x ), qlox1 = __float_as_uint( n2.y ), qloy0 = __float_as_uint( n2.z ), qloy1 = __float_as_uint( n2.w );
-				const uint32_t qloz0 = __float_as_uint( n3.x ), qloz1 = __float_as_uint( n3.y ), qhix0 = __float_as_uint( n3.z ), qhix1 = __float_as_uint( n3.w );
-				const uint32_t qhiy0 = __float_as_uint( n4.x ), qhiy1 = __float_as_uint( n4.y ), qhiz0 = __float_as_uint( n4.z ), qhiz1 = __float_as_uint( n4.w );
-				uint32_t hitmask = slab4( __float_as_uint( n1.z ), octinv4, nx ? qhix0 : qlox0, ny ? qhiy0 : qloy0, nz ? qhiz0 : qloz0,
-					nx ? qlox0 : qhix0, ny ? qloy0 : qhiy0, nz ? qloz0 : qhiz0, ax, ay, az, bx, by, bz, tmax );
-				hitmask |= slab4( __float_as_uint( n1.w ), octinv4, nx ? qhix1 : qlox1, ny ? qhiy1 : qloy1, nz ? qhiz1 : qloz1,
-					nx ? qlox1 : qhix1, ny ? qloy1 : qhiy1, nz ? qloz1 : qhiz1, ax, ay, az, bx, by, bz, tmax );
-				ngroup = make_uint2( __float_as_uint( n1.x ), (hitmask & 0xff000000u) | (n0w >> 24) );
-				tgroup = make_uint2( __float_as_uint( n1.y ), hitmask & 0x00ffffffu );
+				if (j < pairs)
+				{
+					const float4 A = __ldg( np + 2 + 2 * j ), B = __ldg( np + 3 + 2 * j );
+					const uint32_t lx = __float_as_uint( A.x ), ly = __float_as_uint( A.y ), lz = __float_as_uint( A.z );
+					const uint32_t hx = __float_as_uint( A.w ), hy = __float_as_uint( B.x ), hz = __float_as_uint( B.y );
+					got |= pair_hits( negx ? hx : lx, negy ? hy : ly, negz ? hz : lz, negx ? lx : hx, negy ? ly : hy, negz ? lz : hz,
+						__float_as_uint( B.z ), __float_as_uint( B.w ), ax, ay, az, bx, by, bz, t );
+				}
 			}
-			else
+			base = __float_as_uint( h1.x );
+			word = slots_to_order( got, o ) | (__float_as_uint( h0.w ) >> 24);
+			// ---- triangles of the leaf children that were hit, highest bit first (:7132-7142)
+			uint32_t tmask = got & 0x00ffffffu;
+			const float4* tbase = tris + __float_as_uint( h1.y );
+			while (tmask)
 			{
-				tgroup = ngroup;
-				ngroup = make_uint2( 0u, 0u );
-			}
-			while (tgroup.y != 0)
-			{
-				const uint32_t ti = 31u - __clz( tgroup.y );
-				tgroup.y -= 1u << ti;
-				const float4* tp = tris + (size_t)tgroup.x + ti * 3;
+				const uint32_t k = 31u - __clz( tmask );
+				tmask &= ~(1u << k);
+				const float4* tp = tbase + k * 3;
 				const float4 e2 = __ldg( tp ), e1 = __ldg( tp + 1 ), v0 = __ldg( tp + 2 );
 				if (STATS) ntris++;
-				float t, u, v;
-				if (mt_test( ox, oy, oz, dx, dy, dz, v0, e1, e2, tmax, t, u, v ))
+				float tt, u, v;
+				if (mt_test( ox, oy, oz, dx, dy, dz, v0, e1, e2, t, tt, u, v ))
 				{
 					if (ANYHIT) { occluded = true; break; }
-					tmax = t, hu = u, hv = v, hprim = __float_as_uint( v0.w );
+					t = tt, hu = u, hv = v, hprim = __float_as_uint( v0.w );
 				}
 			}
 			if (ANYHIT && occluded) break;
-			if (ngroup.y > 0x00ffffffu) continue;
-			if (sp == 0) break;
-			ngroup = stack[--sp];
+			if (word > 0x00ffffffu) continue;
+			if (depth == 0) break;
+			const uint2 e = pending[--depth];
+			base = e.x, word = e.y;
 		}
 		if (!ANYHIT)
 		{
 			float4* hp = (float4*)(hits + i * hit_stride);
-			*hp = make_float4( tmax, hu, hv, __uint_as_float( hprim ) );
+			*hp = make_float4( t, hu, hv, __uint_as_float( hprim ) );
 		}
 		if (STATS) { atomicAdd( &stats[0], nsteps ); atomicAdd( &stats[1], ntris ); }
 	}
@@ -140,18 +244,18 @@ __global__ void __launch_bounds__( 128 ) k_trace_cwbvh( const float4* __restrict
 }
 
 int cwbvh_trace_launch( tbvh_bvh b, const void* d_rays, uint32_t stride, void* d_hits, uint32_t hit_stride, uint32_t* d_bits,
-	uint64_t n, bool anyhit, cudaStream_t s )
+	uint64_t n, bool anyhit, cudaStream_t s, unsigned long long* d_stats )
 {
-	if (!b->d_cw_nodes || !b->d_cw_tris) { tbvh_set_error( "CWBVH layout not resident" ); return TBVH_E_STATE; }
+	if (!b->d_cw_trav || !b->d_cw_tris) { tbvh_set_error( "CWBVH layout not resident" ); return TBVH_E_STATE; }
 	if (n == 0) return TBVH_OK;
+	if (b->cw_depth + 1 > CW_STACK) { tbvh_set_error( "wide-tree depth %u exceeds the %d pending node groups a ray can hold (the reference's own limit)", b->cw_depth, CW_STACK ); return TBVH_E_LIMIT; }
 	const uint32_t block = 128;
 	const uint64_t grid = (n + block - 1) / block;
 	if (grid > 0x7fffffffull) { tbvh_set_error( "ray batch too large for one launch" ); return TBVH_E_ARG; }
-	if (b->stats) CUDA_TRY( cudaMemsetAsync( b->d_stats, 0, 16, s ) );
-	#define LAUNCH( A, S ) k_trace_cwbvh<A, S><<<(uint32_t)grid, block, 0, s>>>( b->d_cw_nodes, b->d_cw_tris, (const char*)d_rays, stride, \
-		(char*)d_hits, hit_stride, d_bits, n, b->d_stats )
-	if (anyhit) { if (b->stats) LAUNCH( true, true ); else LAUNCH( true, false ); }
-	else { if (b->stats) LAUNCH( false, true ); else LAUNCH( false, false ); }
+	#define LAUNCH( A, S ) k_trace_wide<A, S><<<(uint32_t)grid, block, 0, s>>>( b->d_cw_trav, b->d_cw_tris, (const char*)d_rays, stride, \
+		(char*)d_hits, hit_stride, d_bits, n, d_stats )
+	if (anyhit) { if (d_stats) LAUNCH( true, true ); else LAUNCH( true, false ); }
+	else { if (d_stats) LAUNCH( false, true ); else LAUNCH( false, false ); }
 	#undef LAUNCH
 	LAUNCHED();
 	return TBVH_OK;
