@@ -1,15 +1,23 @@
 #!/usr/bin/env python
-"""bench.py - the hot path on N B200s of one node: BVH build once, then per step one pass of primary closest-hit rays
-plus one pass of shadow any-hit rays over the resident BVH (BASELINE.json configs[1]: Crytek Sponza, 16M primary rays;
-the metric is "Mrays/s (primary+shadow)").
+"""bench.py - the hot path on N B200s of one node.
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--scene sponza] [--layout bvh|cwbvh]
+Workload (BASELINE.json configs[2], the configuration the metric "Mrays/s (primary+shadow) on Sponza/Bistro" names for one GPU):
+Bistro exterior (2,837,209 triangles), BVH8_CWBVH layout over the SBVH (BVH8_CWBVH::BuildHQ, built and converted on the GPU),
+one step = one closest-hit pass over 2048 x 2048 x 16 = 67,108,864 camera rays + one any-hit pass over as many shadow rays.
+With --gpus N the ONE ray set is split by ray index over the ranks (strong scaling), the BVH is built on rank 0 and broadcast once.
 
-Prints ONE JSON line (rank 0).  `value` = rays of all ranks / max-over-ranks device time with rays resident in HBM;
-`e2e` = the same passes through the C-ABI host-buffer calls (pinned 128-byte host Ray records in, hits / occlusion
-bits back to host inside the timed region); `roofline` = the closest-hit kernel against measured HBM copy bandwidth;
-`cpu_baseline` = the reference's BVH8_CPU (AVX2) on the host cores (oracle/_ref), the oracle port if that is absent.
---impl reference times that CPU path alone (rank 0; other ranks exit).
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--scene S] [--layout cwbvh|bvh] [--tree hq|sah] [--res R]
+
+Prints ONE JSON line (rank 0).
+  value        rays of all ranks / max-over-ranks device time, ray records resident in HBM when the timed region starts
+  e2e          the same passes through the C-ABI host-buffer calls (tbvh_intersect + tbvh_occluded on page-locked 128-byte host Ray
+               records, hits / occlusion bits back in host memory inside the timed region)
+  roofline     the dominant kernel against measured HBM copy bandwidth (+ roofline_l1: the on-chip roof that actually binds,
+               roofline_build: the builder)
+  parity       the first rays of the timed sets re-traced by the compiled reference (oracle/_ref) outside the timed region
+  cpu_baseline the reference's BVH8_CPU (AVX2) on the host cores, bounded sample (N=1 only)
+--impl reference times the reference's own CPU path (BVH8_CPU::BuildHQ + Intersect / IsOccluded on all host threads) on the same
+workload; rank 0 only, other ranks exit.
 """
 from __future__ import annotations
 
@@ -30,6 +38,7 @@ if REPO not in sys.path:
 from tinybvh_b200 import rays as R, scenes  # noqa: E402
 
 METRIC = "Mrays/s (primary+shadow)"
+ALL_CPUS = sorted(os.sched_getaffinity(0))
 
 
 def log(*a):
@@ -40,14 +49,14 @@ def peaks():
     p = os.path.join(REPO, "MEASURED_PEAKS.json")
     if os.path.isfile(p):
         try:
-            return float(json.load(open(p))["hbm_gbs"]), "measured"
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
         except Exception:
             pass
-    return 6650.0, "fallback"
+    return 6650.0, "fallback (B200_PROFILING.md)"
 
 
 # ---------------------------------------------------------------------------------------------- workload
-def camera_for(scene, verts, k):
+def camera_for(scene, verts, k=0):
     if scene == "sponza":
         return R.SPONZA_EYES[k % 3], R.SPONZA_VIEWS[k % 3]
     lo, hi = scenes.scene_bounds(verts)
@@ -59,6 +68,31 @@ def light_for(scene, verts):
         return np.zeros(3, np.float32)  # tiny_bvh_speedtest.cpp:856
     lo, hi = scenes.scene_bounds(verts)
     return ((lo + hi) * 0.5 + np.array([0, (hi - lo)[1] * 0.45, 0], np.float32)).astype(np.float32)
+
+
+def shadow_eps(verts):
+    lo, hi = scenes.scene_bounds(verts)
+    return float((hi - lo).max() * 5e-7)
+
+
+def data_label(label):
+    if label.startswith("synthetic"):
+        return "synthetic procedural scene of the same triangle count (fixture not found)"
+    if label == "lucy_dragon_x29":
+        return "reference fixtures testdata/lucy.bin + xyzrgb_dragon.bin replicated 29x on a grid (10,145,708 triangles), rays generated synthetically"
+    files = "+".join(scenes.SCENES[label][0])
+    return f"reference fixture testdata/{files} (triangle soup), rays generated synthetically (speedtest camera pattern)"
+
+
+def config_for(args, label, ntris):
+    """The workload, identical for both arms (the driver compares the two `config` objects)."""
+    n = args.res * args.res * 16
+    return {"workload": f"{label}_{'sbvh' if args.tree == 'hq' else 'sah'}_{args.layout}_{args.res}x{args.res}x16_primary+shadow",
+            "scene": label, "scene_tris": int(ntris), "layout": args.layout,
+            "tree": "BVH::BuildHQ (SBVH), as tiny_bvh_speedtest.cpp builds for its traversal runs (:894, 960, 1013, 1099, 1197)" if args.tree == "hq" else "BVH::Build (binned SAH)",
+            "primary_rays": n, "shadow_rays": n, "rays_per_step": 2 * n,
+            "rays": "camera rays of tiny_bvh_speedtest.cpp:497-551 (4x4-pixel tiles, 16 samples per pixel) + one shadow ray per camera ray towards a point light (:853-865)",
+            "l2": "no flush: the per-step inputs (2 x %.2f GB of ray records) exceed the 126 MB L2" % (n * 64 / 1e9)}
 
 
 class ClockSampler:
@@ -101,56 +135,65 @@ class ClockSampler:
             for nm, v in zip(names, f[2:6]):
                 if v.lower().startswith("active"):
                     reasons.add(nm)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+        # median over the samples taken while the GPU was clocked up (the sampler also sees the idle gaps between sections)
+        busy = [x for x in sm if mx and x >= 0.6 * mx] or sm
+        return {"sm_mhz": float(np.median(busy)) if busy else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
 
 
 # ---------------------------------------------------------------------------------------------- reference arm / cpu baseline
-def cpu_reference(scene, verts, prim, shadow, passes, threads=0, hq=True):
-    """The reference's own CPU implementation of the path on the host cores: BVH8_CPU::Build + Intersect / IsOccluded
-    (tiny_bvh.h:7210-7472) from oracle/_ref; the pinned plain-C port of BVH::Intersect when _ref is absent."""
-    from oracle import portpy, refpy
-    n = prim.shape[0]
-    if refpy.available():
-        kind, cores = "reference", refpy.hardware_threads() if threads <= 0 else threads
-        t0 = time.perf_counter()
-        bvh = refpy.RefBVH8CPU(verts, hq=hq)
-        build_s = time.perf_counter() - t0
-        impl = f"BVH8_CPU::{'BuildHQ' if hq else 'Build'} + Intersect/IsOccluded (AVX2), 10k-ray batches off an atomic counter"
-    else:
-        kind, cores = "port", os.cpu_count() if threads <= 0 else threads
-        t0 = time.perf_counter()
-        bvh = portpy.PortBVH(verts)
-        build_s = time.perf_counter() - t0
-        impl = "oracle port of BVH::Build + BVH::Intersect/IsOccluded (scalar C, pthreads)"
-    a, s = prim.copy(), shadow.copy()
-    bvh.intersect(a, threads), bvh.occluded(s, threads)  # warm-up pass (tiny_bvh_speedtest.cpp:185-215)
+def cpu_trace(bvh, prim, shadow, passes, threads=0):
+    """passes x (closest-hit over `prim`, any-hit over `shadow`) on the host cores; -> (primary s, shadow s) means."""
+    bvh.intersect(prim, threads), bvh.occluded(shadow, threads)  # warm-up pass (tiny_bvh_speedtest.cpp:185-215)
     times = []
     for _ in range(passes):
-        R.reset_hits(a)
+        R.reset_hits_fast(prim)
         t0 = time.perf_counter()
-        bvh.intersect(a, threads)
+        bvh.intersect(prim, threads)
         t1 = time.perf_counter()
-        bvh.occluded(s, threads)
+        bvh.occluded(shadow, threads)
         t2 = time.perf_counter()
         times.append((t1 - t0, t2 - t1))
-    tp, ts = float(np.mean([t[0] for t in times])), float(np.mean([t[1] for t in times]))
-    return {"value": 2 * n / (tp + ts) / 1e6, "unit": "Mrays/s", "cores": int(cores), "kind": kind,
-            "sample": f"{n} primary + {n} shadow rays of the workload, {passes} timed passes after 1 warm-up, all host threads",
+    return float(np.mean([t[0] for t in times])), float(np.mean([t[1] for t in times]))
+
+
+def cpu_reference(args, verts, prim, shadow, passes, sample, built=None):
+    """The reference's own CPU implementation of the path on the host cores: BVH8_CPU::Build(HQ) + Intersect / IsOccluded
+    (tiny_bvh.h:7210-7472) from oracle/_ref; the pinned plain-C port of BVH::Intersect when _ref is absent."""
+    from oracle import portpy, refpy
+    os.sched_setaffinity(0, ALL_CPUS)  # the CPU legs use every host thread, whatever the GPU arm bound itself to
+    n, hq = prim.shape[0], args.tree == "hq"
+    t0 = time.perf_counter()
+    if built is not None:
+        kind, cores, bvh = "reference", refpy.hardware_threads(), built[0]
+        impl = f"BVH8_CPU::{'BuildHQ' if hq else 'Build'} + Intersect/IsOccluded (AVX2), 10k-ray batches off an atomic counter (tiny_bvh_speedtest.cpp:392-401)"
+    elif refpy.available():
+        kind, cores = "reference", refpy.hardware_threads()
+        bvh = refpy.RefBVH8CPU(verts, hq=hq)
+        impl = f"BVH8_CPU::{'BuildHQ' if hq else 'Build'} + Intersect/IsOccluded (AVX2), 10k-ray batches off an atomic counter (tiny_bvh_speedtest.cpp:392-401)"
+    else:
+        kind, cores = "port", os.cpu_count()
+        bvh = portpy.PortBVH(verts)
+        impl = "oracle port of BVH::Build + BVH::Intersect/IsOccluded (scalar C, pthreads)"
+    build_s = built[1] if built is not None else time.perf_counter() - t0
+    tp, ts = cpu_trace(bvh, prim, shadow, passes)
+    return {"value": 2 * n / (tp + ts) / 1e6, "unit": "Mrays/s", "cores": int(cores), "kind": kind, "sample": sample,
             "impl": impl, "primary_mrays": n / tp / 1e6, "shadow_mrays": n / ts / 1e6, "build_s": build_s,
             "build_mtris": verts.shape[0] / 3 / build_s / 1e6, "ms_per_step": (tp + ts) * 1e3}
 
 
-def host_primary_and_shadow(scene, verts, label, res, cam_index):
-    """Ray sets on the host: primary rays of one camera, traced once by the CPU reference to derive the shadow rays
-    (tiny_bvh_speedtest.cpp:844-865).  Used by the reference arm only (our arm traces on the GPU)."""
+def host_ray_sets(args, verts, count, tracer=None):
+    """The first `count` camera rays of the workload and their shadow rays, on the host (pageable).  The camera rays are traced by
+    `tracer` (an object with .intersect) to find the shadow-ray origins; default: the reference's BVH::Build + Intersect."""
     from oracle import portpy, refpy
-    eye, view = camera_for(scene, verts, cam_index)
-    prim = R.primary_rays(eye, view, res, res, 16)
-    o = refpy.RefBVH(verts, mode=0, threaded=True) if refpy.available() else portpy.PortBVH(verts)
-    traced = prim.copy()
-    o.intersect(traced, 0)
-    lo, hi = scenes.scene_bounds(verts)
-    sh = R.shadow_rays(traced, light_for(scene, verts), float((hi - lo).max() * 5e-7))
+    eye, view = camera_for(args.scene, verts)
+    prim = np.empty(count, R.RAY_DTYPE)
+    R.primary_rays_into(prim, eye, view, args.res, args.res, 16)
+    if tracer is None:
+        tracer = refpy.RefBVH(verts, mode=0, threaded=True) if refpy.available() else portpy.PortBVH(verts)
+    tracer.intersect(prim, 0)
+    sh = np.empty(count, R.RAY_DTYPE)
+    R.shadow_rays_into(sh, prim, light_for(args.scene, verts), shadow_eps(verts))
+    R.reset_hits_fast(prim)
     return prim, sh
 
 
@@ -158,17 +201,24 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
+    from oracle import refpy
     verts, label = scenes.load_scene(args.scene)
-    res = args.res
-    # bounded sample: the CPU gets a quarter-resolution slice of the workload per step unless --full-reference
-    sres = res if args.full_reference else max(256, res // 2)
-    prim, sh = host_primary_and_shadow(args.scene, verts, label, sres, 0)
-    cb = cpu_reference(args.scene, verts, prim, sh, passes=max(1, args.steps), hq=args.tree == "hq")
+    ntris = verts.shape[0] // 3
+    n = args.res * args.res * 16
+    # the whole workload, traced by the CPU implementation itself (its own closest hits place the shadow rays, as the speedtest does)
+    t0 = time.time()
+    hq = args.tree == "hq"
+    os.sched_setaffinity(0, ALL_CPUS)
+    tb = time.perf_counter()
+    bvh = refpy.RefBVH8CPU(verts, hq=hq) if refpy.available() else None
+    built = (bvh, time.perf_counter() - tb) if bvh is not None else None
+    prim, sh = host_ray_sets(args, verts, n, tracer=bvh)
+    log(f"[bench reference] {label}: {n} camera + {n} shadow rays on the host in {time.time() - t0:.1f}s")
+    cb = cpu_reference(args, verts, prim, sh, passes=max(1, args.steps), built=built,
+                       sample=f"the whole workload: {n} camera + {n} shadow rays per step, {max(1, args.steps)} timed passes after 1 warm-up, all host threads")
     out = {"metric": METRIC, "value": cb["value"], "unit": "Mrays/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-           "ms_per_step": cb["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-           "data": data_label(label), "impl": "reference",
-           "config": {"workload": workload_name(args, label), "rays_per_step": 2 * prim.shape[0], "scene_tris": verts.shape[0] // 3,
-                      "note": "CPU reference on host cores; each step is a bounded sample of the workload (see cpu_baseline.sample)"},
+           "ms_per_step": cb["ms_per_step"], "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+           "data": data_label(label), "impl": "reference", "config": config_for(args, label, ntris),
            "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample", "impl", "primary_mrays", "shadow_mrays", "build_mtris")},
            "e2e": {"value": cb["value"], "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
            "gpu_launches": 0}
@@ -176,28 +226,71 @@ def run_reference(args):
     return 0
 
 
-def data_label(label):
-    if label.startswith("synthetic"):
-        return "synthetic procedural scene of the same triangle count (fixture not found)"
-    if label == "lucy_dragon_x29":
-        return "reference fixtures testdata/lucy.bin + xyzrgb_dragon.bin replicated 29x on a grid (10,145,708 triangles), rays generated synthetically"
-    files = "+".join(scenes.SCENES[label][0])
-    return f"reference fixture testdata/{files} (triangle soup), rays generated synthetically (speedtest camera pattern)"
-
-
-def workload_name(args, label):
-    return f"{label}_{'sbvh' if args.tree == 'hq' else 'sah'}_{args.layout}_{args.res}x{args.res}x16_primary+shadow"
+# ---------------------------------------------------------------------------------------------- parity sample (outside every timed region)
+def parity_sample(args, verts, h_prim, h_shadow, hits, bits, m):
+    """Re-trace the first m rays of the timed sets with the compiled reference and compare with what the engine produced for them.
+    (a) the reference's own walk of the same layout over its own build chain - bit-identical t, u, v, prim expected;
+    (b) the parity oracle BVH::Build + BVH::Intersect / IsOccluded (a different tree): prim mismatches classified by the tie audit
+        of SURVEY 8(c) - tie-equivalent (the engine's primitive re-evaluated with the oracle's Moeller-Trumbore gives the bit-identical
+        t) or real."""
+    from oracle import refpy
+    from tests import util
+    if not refpy.available():
+        return {"unavailable": "oracle/_ref not built"}
+    os.sched_setaffinity(0, ALL_CPUS)
+    t0 = time.time()
+    got = h_prim[:m].copy()
+    got["t"], got["u"], got["v"], got["prim"] = hits[:m, 0], hits[:m, 1], hits[:m, 2], hits[:m, 3].view(np.uint32)
+    occ = np.unpackbits(bits[: (m + 31) // 32].view(np.uint8), bitorder="little")[:m].astype(bool)
+    out = {"sample_rays": int(m)}
+    mode = 1 if args.tree == "hq" else 2   # refpy: 1 = BuildHQ chain, 2 = BVH::Build chain
+    want = h_prim[:m].copy()
+    R.reset_hits_fast(want)
+    if args.layout == "cwbvh":
+        ref = refpy.RefCWBVH(verts, mode=mode)
+        ref.intersect(want, 0)
+        name = "BVH8_CWBVH::BuildHQ + BVH8_CWBVH::Intersect" if mode == 1 else "BVH8_CWBVH::Build + Intersect"
+        sh = h_shadow[:m].copy()
+        d = sh["t"].copy()
+        ref.intersect(sh, 0)
+        occ_ref = sh["t"] < d          # BVH8_CWBVH::IsOccluded is the FALLBACK_SHADOW_QUERY (tiny_bvh.h:312): Intersect, then t < d
+    else:
+        ref = refpy.RefBVH(verts, mode=2 if args.tree == "hq" else 0, threaded=True)
+        ref.intersect(want, 0)
+        name = "BVH::BuildHQ + BVH::Intersect" if args.tree == "hq" else "BVH::Build + BVH::Intersect"
+        occ_ref = np.unpackbits(ref.occluded(h_shadow[:m].copy(), 0).view(np.uint8), bitorder="little")[:m].astype(bool)
+    c = util.compare_hits(got, want)
+    hit = want["t"] < 1e30
+    out["same_layout"] = {"reference": name, "prim_mismatch": c["prim"], "t_bit_mismatch": c["t"],
+                          "uv_bit_mismatch_on_hits": int(((got["u"].view(np.uint32) != want["u"].view(np.uint32)) | (got["v"].view(np.uint32) != want["v"].view(np.uint32)))[hit].sum()),
+                          "occlusion_bit_mismatch": int((occ != occ_ref).sum())}
+    o = refpy.RefBVH(verts, mode=0, threaded=True)
+    w2 = h_prim[:m].copy()
+    R.reset_hits_fast(w2)
+    o.intersect(w2, 0)
+    cls = util.classify_mismatches(got, w2, verts)
+    both = (w2["t"] < 1e30) & (got["t"] < 1e30)
+    rel = np.abs(got["t"][both] - w2["t"][both]) / np.maximum(np.abs(w2["t"][both]), 1e-30)
+    occ_o = np.unpackbits(o.occluded(h_shadow[:m].copy(), 0).view(np.uint8), bitorder="little")[:m].astype(bool)
+    out["oracle"] = {"reference": "BVH::Build + BVH::Intersect / IsOccluded (the parity oracle; another tree than the one traced)",
+                     "prim_mismatch": cls["mismatch"], "tie_equivalent": cls["tie_equivalent"], "real": cls["real"],
+                     "hit_miss_flips": int(((w2["t"] < 1e30) != (got["t"] < 1e30)).sum()), "t_max_rel_err": float(rel.max()) if rel.size else 0.0,
+                     "occlusion_bit_mismatch": int((occ != occ_o).sum())}
+    out["seconds"] = round(time.time() - t0, 1)
+    return out
 
 
 # ---------------------------------------------------------------------------------------------- our arm
 def run_ours(args):
-    import torch
-    import torch.distributed as dist
-    from tinybvh_b200 import api, _lib
-    import ctypes as C
-
     rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    from tinybvh_b200 import api, _lib
+    import ctypes as C
+    # sit on the CPUs of this GPU's NUMA node before anything allocates: page-locked ray buffers, OpenMP ray generation and the host
+    # pipeline's threads then work out of local memory (2 sockets: GPUs 0-3 / 4-7 hang off different nodes)
+    bound = api.bind_to_device(local)
+    import torch
+    import torch.distributed as dist
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
@@ -206,25 +299,24 @@ def run_ours(args):
     L = _lib.lib()
     verts, label = scenes.load_scene(args.scene)
     ntris = verts.shape[0] // 3
+    t_setup = time.time()
 
-    # ---- build on rank 0 (timed separately: build Mtris/s), then ONE broadcast of the BVH over NVLink
+    # ---- build on rank 0 (timed: build Mtris/s), then ONE broadcast of the BVH over NVLink
     bvh = api.BVH(device=local)
-    build_ms, bcast_ms, build_hq = None, None, None
+    build = {}
     if rank == 0:
-        # both builders of the path are timed (second call each: the first pays allocations and first-launch costs); the rays are
-        # traced through the tree --tree names - the SBVH by default, as in the reference's own traversal benchmarks
-        sah = api.BVH(device=local)
-        sah.Build(verts)
-        sah = api.BVH(device=local)
-        sah.Build(verts)
-        build_ms = sah.info().build_ms
-        hq = api.BVH(device=local)
-        hq.BuildHQ(verts)
-        hq = api.BVH(device=local)
-        hq.BuildHQ(verts)
-        build_hq = {"ms": hq.info().build_ms, "mtris_per_s": ntris / hq.info().build_ms / 1e3, "nodes": hq.info().used_nodes, "idx_count": hq.info().idx_count}
-        bvh = hq if args.tree == "hq" else sah
-        del hq, sah
+        # every builder of the path is timed on its second call (the first pays allocations and first-launch costs)
+        for name, fn in (("Build", "Build"), ("BuildHQ", "BuildHQ")):
+            b = api.BVH(device=local)
+            getattr(b, fn)(verts)
+            b = api.BVH(device=local)
+            getattr(b, fn)(verts)
+            i = b.info()
+            build[name] = {"ms": i.build_ms, "mtris_per_s": ntris / i.build_ms / 1e3, "nodes": i.used_nodes, "idx_count": i.idx_count, "depth": i.max_depth}
+            if (name == "BuildHQ") == (args.tree == "hq"):
+                bvh = b
+            del b
+    bcast_ms, bcast_bytes = None, None
     if world > 1:
         from tinybvh_b200 import multi
         arrays = None
@@ -234,50 +326,65 @@ def run_ours(args):
             d_idx = torch.empty(i.idx_count, dtype=torch.int32, device=dev)
             api.check(L.tbvh_download_bvh(bvh.h, C.c_void_p(d_nodes.data_ptr()), C.c_void_p(d_idx.data_ptr()), api.DEVICE))
             arrays = {"nodes": d_nodes, "prim_idx": d_idx, "verts": torch.from_numpy(verts.reshape(-1)).to(dev)}
+            bcast_bytes = int(sum(a.numel() * a.element_size() for a in arrays.values()))
+        warm = torch.zeros(1 << 20, dtype=torch.float32, device=dev)   # communicator set-up is not the broadcast
+        for _ in range(3):
+            dist.all_reduce(warm)
+            dist.broadcast(warm, 0)
         torch.cuda.synchronize()
         dist.barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        got = multi.broadcast_arrays(arrays, 0, dev)   # the ONE exchange step: BVH replica to every GPU over NVLink
+        got = multi.broadcast_arrays(arrays, 0, dev)   # the ONE exchange step: the built BVH to every GPU over NVLink
         e1.record()
         torch.cuda.synchronize()
-        bcast_ms = e0.elapsed_time(e1)
+        t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        bcast_ms = float(t.item())
         if rank != 0:
             api.check(L.tbvh_upload_bvh(bvh.h, C.c_void_p(got["nodes"].data_ptr()), got["nodes"].numel() // 8, C.c_void_p(got["prim_idx"].data_ptr()),
                                         got["prim_idx"].numel(), C.c_void_p(got["verts"].data_ptr()), 16, ntris, api.DEVICE))
-    eng = bvh
+        del got, arrays
+    # derived layout: BVH8_CWBVH::ConvertFrom's chain on every GPU's replica (deterministic; byte-identical to the reference's)
+    convert_ms = None
     if args.layout == "cwbvh":
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
         api.check(L.tbvh_convert(bvh.h, api.LAYOUT_CWBVH))
-        eng.layout = api.LAYOUT_CWBVH  # same handle, traverse its CWBVH layout
+        convert_ms = (time.perf_counter() - t0) * 1e3
+        bvh.layout = api.LAYOUT_CWBVH
+    eng = bvh
     info = bvh.info()
 
-    # ---- this rank's shard of rays (weak scaling: every rank traces res*res*16 primary + as many shadow rays)
-    # every rank traces the same view: per-GPU work is identical, so N-GPU numbers measure the system, not the camera
-    eye, view = camera_for(args.scene, verts, 0)
-    t0 = time.time()
-    prim = R.primary_rays(eye, view, args.res, args.res, 16)
-    n = prim.shape[0]
-    h_prim = api.pinned_empty(n, R.RAY_DTYPE)
-    h_prim[:] = prim
-    del prim
+    # ---- this rank's index range of the ONE ray set (strong scaling)
+    n_total = args.res * args.res * 16
+    first, n = api.shard_range(n_total, rank, world)
+    eye, view = camera_for(args.scene, verts)
+    h_prim = api.pinned_empty(n, R.RAY_DTYPE, device=local)
+    R.primary_rays_into(h_prim, eye, view, args.res, args.res, 16, first=first)
     d_prim = torch.empty((n, 64), dtype=torch.uint8, device=dev)
-    d_prim.copy_(torch.from_numpy(h_prim.view(np.uint8).reshape(n, 128)[:, :64]))
+    api.copy_rays_to_device(h_prim, d_prim)
     d_hits = torch.empty((n, 4), dtype=torch.float32, device=dev)
     eng.Intersect(d_prim, hits=d_hits)
     torch.cuda.synchronize()
     hits = d_hits.cpu().numpy()
-    traced = h_prim.copy()
-    traced["t"], traced["u"], traced["v"], traced["prim"] = hits[:, 0], hits[:, 1], hits[:, 2], hits[:, 3].view(np.uint32)
-    lo, hi = scenes.scene_bounds(verts)
-    h_shadow = api.pinned_empty(n, R.RAY_DTYPE)
-    h_shadow[:] = R.shadow_rays(traced, light_for(args.scene, verts), float((hi - lo).max() * 5e-7))
-    del traced
+    h_shadow = api.pinned_empty(n, R.RAY_DTYPE, device=local)
+    R.shadow_rays_into(h_shadow, h_prim, light_for(args.scene, verts), shadow_eps(verts), hits=hits)
     d_shadow = torch.empty((n, 64), dtype=torch.uint8, device=dev)
-    d_shadow.copy_(torch.from_numpy(h_shadow.view(np.uint8).reshape(n, 128)[:, :64]))
+    api.copy_rays_to_device(h_shadow, d_shadow)
     d_bits = torch.empty((n + 31) // 32, dtype=torch.int32, device=dev)
     h_bits = np.zeros((n + 31) // 32, np.uint32)
     if rank == 0:
-        log(f"[bench] {label}: {ntris} tris, {info.used_nodes} nodes, depth {info.max_depth}, build {build_ms} ms; {n} primary + {n} shadow rays/rank; setup {time.time() - t0:.1f}s")
+        log(f"[bench] {label}: {ntris} tris, {info.used_nodes} nodes, depth {info.max_depth}, builds {build}; rays [{first}, {first + n}) of {n_total} camera + shadow; "
+            f"numa-bound {bound}; setup {time.time() - t_setup:.1f}s")
+
+    # traversal work per ray (kernel counters, one untimed pass each)
+    eng.set_stats(True)
+    eng.Intersect(d_prim, hits=d_hits)
+    st_prim = eng.get_stats()
+    eng.IsOccluded(d_shadow, bits=d_bits)
+    st_shad = eng.get_stats()
+    eng.set_stats(False)
 
     stream = torch.cuda.current_stream(dev)
 
@@ -296,7 +403,8 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(max(3, args.warmup)):
+    W = max(3, args.warmup)
+    for _ in range(W):
         step()
     barrier()
     clocks = ClockSampler(local) if rank == 0 else None
@@ -313,26 +421,36 @@ def run_ours(args):
     total_ms = t_begin.elapsed_time(t_end)
     prim_ms = float(np.mean([e[0].elapsed_time(e[1]) for e in evs]))
     shad_ms = float(np.mean([e[1].elapsed_time(e[2]) for e in evs]))
+    torch.cuda.synchronize()
+    bits_dev = d_bits.cpu().numpy().view(np.uint32)
+    hits = d_hits.cpu().numpy()
 
-    # ---- e2e: the reference-facing C-ABI calls on HOST buffers (pinned), copies inside the timed region
-    for _ in range(2):
-        eng.Intersect(h_prim)
+    # ---- e2e: the reference-facing C-ABI calls on HOST buffers (page-locked), copies inside the timed region
+    def e2e_pass(packed_out=None):
+        if packed_out is None:
+            eng.Intersect(h_prim)
+        else:
+            eng.IntersectPacked(h_prim, hits=packed_out)
         eng.IsOccluded(h_shadow, bits=h_bits)
+
+    for _ in range(2):
+        e2e_pass()
     barrier()
     te0 = time.perf_counter()
     for _ in range(args.steps):
-        eng.Intersect(h_prim)
-        eng.IsOccluded(h_shadow, bits=h_bits)
+        e2e_pass()
     te1 = time.perf_counter()
     e2e_ms = (te1 - te0) * 1e3
+    e2e_ok = bool(np.array_equal(h_prim["t"].view(np.uint32), hits[:, 0].view(np.uint32)) and np.array_equal(h_prim["prim"], hits[:, 3].view(np.uint32))
+                  and np.array_equal(h_bits, bits_dev))
+    R.reset_hits_fast(h_prim)
     # the same with the packed-hits entry point (tbvh_intersect_packed): the return trip is one contiguous copy per chunk
-    h_hits = api.pinned_empty(n, R.HIT_DTYPE)
-    eng.IntersectPacked(h_prim, hits=h_hits)
+    h_hits = api.pinned_empty(n, R.HIT_DTYPE, device=local)
+    e2e_pass(h_hits)
     barrier()
     tp0 = time.perf_counter()
     for _ in range(args.steps):
-        eng.IntersectPacked(h_prim, hits=h_hits)
-        eng.IsOccluded(h_shadow, bits=h_bits)
+        e2e_pass(h_hits)
     tp1 = time.perf_counter()
     e2e_packed_ms = (tp1 - tp0) * 1e3
     clk = clocks.stop() if clocks else None
@@ -341,55 +459,83 @@ def run_ours(args):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     total_ms, e2e_ms, prim_ms, shad_ms, e2e_packed_ms = [float(x) for x in t.cpu()]
+    ok = torch.tensor([1.0 if e2e_ok else 0.0], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+    e2e_ok = bool(ok.item() > 0.5)
 
     if rank == 0:
-        rays_per_step = 2 * n * world
+        rays_per_step = 2 * n_total
         ms_per_step = total_ms / args.steps
         value = rays_per_step / ms_per_step / 1e3
         peak, which = peaks()
         if args.layout == "cwbvh":
-            bvh_bytes = info.used_blocks * 16 + info.cwbvh_tri_count * 48
+            bvh_bytes = (info.used_blocks // 5) * 160 + info.cwbvh_tri_count * 48
+            kernel = "k_trace_wide<closest>"
+            layout_note = "traversal nodes 160 B (derived from the 80-byte bvh8Data nodes) + 48-byte bvh8Tris records"
         else:
             bvh_bytes = info.used_nodes * 32 + info.idx_count * 48
-        alg_bytes = n * 80 + bvh_bytes  # 64 B ray read + 16 B hit write per ray + one pass over the BVH
+            kernel = "k_trace_bvh2<closest>"
+            layout_note = "32-byte Wald nodes (sibling pairs) + 48-byte leaf-ordered triangle records"
+        # 64 B ray record read + 16 B hit written per ray, plus one pass over the BVH per launch; this rank's launch
+        alg_bytes = n * 80 + bvh_bytes
         achieved = alg_bytes / (prim_ms * 1e-3) / 1e9
         traffic = None
         tp = os.path.join(REPO, "profiles", "traffic.json")
         if os.path.isfile(tp):
             try:
-                traffic = json.load(open(tp)).get(f"k_trace_{'cwbvh' if args.layout == 'cwbvh' else 'bvh2'}_closest_{label}" + ("_sbvh" if args.tree == "hq" else ""))
+                traffic = json.load(open(tp)).get(f"{kernel}_{label}_{args.tree}_{args.res}")
             except Exception:
                 traffic = None
+        # the roof that binds: bytes moved from L1 into registers.  Per node visit 32 B of header + 32 B per child pair (CWBVH) or
+        # one 64 B sibling pair (BVH2); per triangle test 48 B; per ray 64 B in.  L1 delivers 128 B / clk / SM.
+        visits, tris, pairs = st_prim[0] / n, st_prim[1] / n, (st_prim[2] / n if len(st_prim) > 2 else 0.0)
+        l1_bytes_ray = (visits * 32 + pairs * 32 if args.layout == "cwbvh" else visits * 64) + tris * 48 + 64
+        sm_count, sm_mhz = torch.cuda.get_device_properties(dev).multi_processor_count, (clk or {}).get("sm_mhz") or 1965.0
+        l1_peak = sm_count * 128 * sm_mhz * 1e6 / 1e9
+        l1_ach = l1_bytes_ray * n / (prim_ms * 1e-3) / 1e9
         out = {
-            "metric": METRIC, "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
-            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-            "data": data_label(label),
-            "config": {"workload": workload_name(args, label), "scene_tris": ntris, "layout": args.layout,
-                       "rays_per_step_per_gpu": 2 * n, "primary_rays_per_gpu": n, "shadow_rays_per_gpu": n,
-                       "parallelism": f"rays sharded by index over {world} GPU(s) (each shard = the same 16.8M-ray view), BVH built on rank 0 and broadcast once (NCCL), no collective during traversal" if world > 1 else "1 GPU",
-                       "l2": "no flush: per-step inputs (2 x %.2f GB ray records) exceed the 126 MB L2" % (n * 64 / 1e9),
-                       "tree": "BVH::BuildHQ (SBVH), as tiny_bvh_speedtest.cpp builds for its traversal runs" if args.tree == "hq" else "BVH::Build (binned SAH)",
-                       "bvh_built_on": "GPU (tbvh_build_flavour)"},
-            "primary_mrays": n * world / prim_ms / 1e3, "shadow_mrays": n * world / shad_ms / 1e3,
-            "build": {"ms": build_ms, "mtris_per_s": (ntris / build_ms / 1e3) if build_ms else None, "bcast_ms": bcast_ms,
-                      "bvh_bytes": bvh_bytes, "build_hq": build_hq},
-            "roofline": {"bound": "hbm", "kernel": "k_trace_cwbvh<closest>" if args.layout == "cwbvh" else "k_trace_bvh2<closest>",
-                         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                         "peak_source": which, "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_ms": prim_ms,
-                         "note": "traversal is latency/issue bound, not HBM bound (SURVEY 8d): see DESIGN.md for the L2-side accounting"},
-            "e2e": {"value": rays_per_step / (e2e_ms / args.steps) / 1e3, "unit": "Mrays/s", "h2d_bytes_per_step": 2 * n * 64,
-                    "d2h_bytes_per_step": n * 16 + ((n + 31) // 32) * 4, "ms_per_step": e2e_ms / args.steps,
-                    "api": "tbvh_intersect + tbvh_occluded on pinned 128-byte host Ray records (hits written in place into Ray.hit)",
+            "metric": METRIC, "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps, "warmup": W,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+            "data": data_label(label), "config": config_for(args, label, ntris),
+            "parallelism": (f"ONE ray set sharded by ray index over {world} GPUs (32-ray-aligned contiguous ranges), BVH built on rank 0 and broadcast once (NCCL over NVLink), "
+                            f"no collective during traversal") if world > 1 else "1 GPU",
+            "primary_mrays": n_total / prim_ms / 1e3, "shadow_mrays": n_total / shad_ms / 1e3,
+            "work_per_ray": {"primary": {"node_visits": visits, "triangle_tests": tris, "pair_steps": pairs},
+                             "shadow": {"node_visits": st_shad[0] / n, "triangle_tests": st_shad[1] / n}},
+            "build": {"Build": build.get("Build"), "BuildHQ": build.get("BuildHQ"), "cwbvh_convert_ms_wall": convert_ms, "bcast_ms": bcast_ms, "bcast_bytes": bcast_bytes,
+                      "bvh_bytes_traversed": bvh_bytes, "built_on": "GPU (tbvh_build_flavour + tbvh_convert)"},
+            "roofline": {"bound": "hbm", "kernel": kernel, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                         "peak_source": which, "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_ms": prim_ms, "layout": layout_note,
+                         "note": "traversal is bound on chip (issue slots / L1), not by HBM: see roofline_l1"},
+            "roofline_l1": {"bound": "l1-to-register bytes", "kernel": kernel, "achieved": l1_ach, "peak": l1_peak, "unit": "GB/s", "frac": l1_ach / l1_peak,
+                            "bytes_per_ray": l1_bytes_ray, "peak_source": f"{sm_count} SMs x 128 B/clk x {sm_mhz:.0f} MHz"},
+            "e2e": {"value": rays_per_step / (e2e_ms / args.steps) / 1e3, "unit": "Mrays/s", "h2d_bytes_per_step": 2 * n_total * 64,
+                    "d2h_bytes_per_step": n_total * 16 + ((n_total + 31) // 32) * 4, "ms_per_step": e2e_ms / args.steps,
+                    "api": "tbvh_intersect + tbvh_occluded on page-locked 128-byte host Ray records (hits written in place into Ray.hit)",
+                    "results_identical_to_device_path": e2e_ok,
                     "packed_hits_value": rays_per_step / (e2e_packed_ms / args.steps) / 1e3,
-                    "packed_hits_api": "tbvh_intersect_packed + tbvh_occluded: same inputs, hits returned as a packed 16-byte array"},
+                    "packed_hits_api": "tbvh_intersect_packed + tbvh_occluded: same inputs, hits returned as a packed 16-byte array",
+                    "numa_bound": bool(bound)},
             "gpu_launches": int(launches),
             "clocks": clk,
         }
+        if build.get("Build"):
+            # reference-algorithm bytes of a binned-SAH build = 48 + 36 + L (2 x 36 + 4) + 64 per triangle, L = mean leaf depth
+            L_mean = {"sponza": 19.9, "bistro": 23.2}.get(label, 18.0)
+            per_tri = 48 + 36 + L_mean * 76 + 64
+            ach = per_tri * ntris / (build["Build"]["ms"] * 1e-3) / 1e9
+            out["roofline_build"] = {"bound": "hbm", "kernel": "tbvh_build (binned SAH, all launches of one build)", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                                     "bytes_per_tri": per_tri, "mtris_per_s": build["Build"]["mtris_per_s"], "traffic": None,
+                                     "note": "reference-algorithm bytes (SURVEY 8d); the GPU builder keeps small subtrees on chip and moves fewer"}
+        if not args.no_parity:
+            out["parity"] = parity_sample(args, verts, h_prim, h_shadow, hits, bits_dev, min(n, args.parity_rays))
         if world == 1 and not args.no_cpu_baseline:
             t0 = time.time()
-            sres = max(256, args.res // 2)
-            p2, s2 = host_primary_and_shadow(args.scene, verts, label, sres, 0)
-            cb = cpu_reference(args.scene, verts, p2, s2, passes=3, hq=args.tree == "hq")
+            m = min(n, args.cpu_sample_rays)
+            p2, s2 = h_prim[:m].copy(), h_shadow[:m].copy()
+            R.reset_hits_fast(p2)
+            cb = cpu_reference(args, verts, p2, s2, passes=3, sample=f"the first {m} camera + {m} shadow rays of the workload, 3 timed passes after 1 warm-up, all host threads")
             out["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample", "impl", "primary_mrays", "shadow_mrays", "build_mtris")}
             log(f"[bench] cpu baseline took {time.time() - t0:.1f}s")
         print(json.dumps(out), flush=True)
@@ -405,13 +551,15 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--scene", default="sponza")
-    ap.add_argument("--layout", default="bvh", choices=["bvh", "cwbvh"])
+    ap.add_argument("--scene", default="bistro")
+    ap.add_argument("--layout", default="cwbvh", choices=["bvh", "cwbvh"])
     ap.add_argument("--tree", default="hq", choices=["hq", "sah"],
                     help="hq: BVH::BuildHQ (SBVH), the tree every traversal benchmark of tiny_bvh_speedtest.cpp builds (:894, 960, 1013, 1099, 1197); sah: BVH::Build")
-    ap.add_argument("--res", type=int, default=1024, help="primary rays = res*res*16 (1024 -> 16,777,216)")
+    ap.add_argument("--res", type=int, default=2048, help="camera rays = res*res*16 (2048 -> 67,108,864)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--full-reference", action="store_true")
+    ap.add_argument("--no-parity", action="store_true")
+    ap.add_argument("--parity-rays", type=int, default=1 << 20)
+    ap.add_argument("--cpu-sample-rays", type=int, default=1 << 23)
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

@@ -189,6 +189,18 @@ int tbvh_occluded_device( tbvh_bvh bvh, int layout, const void* d_rays, uint32_t
  * returns the per-ray cost from Intersect, tiny_bvh.h:3303): steps = nodes visited, tris = triangle tests. */
 int tbvh_set_stats( tbvh_bvh bvh, int enable );
 int tbvh_get_stats( tbvh_bvh bvh, uint64_t* steps, uint64_t* tris );
+/* the same plus the CWBVH kernels' child-pair steps: out = { node visits, triangle tests, pair steps, 0 } */
+int tbvh_get_stats_ex( tbvh_bvh bvh, uint64_t out[4] );
+/* rays[0..n) of a host buffer -> packed 64-byte device records (bytes 0..63 of each record; the speedtest's upload,
+ * tiny_bvh_speedtest.cpp:1110-1115), asynchronous on `stream` */
+int tbvh_copy_rays_to_device( const void* rays, uint32_t stride, uint64_t n, void* d_rays, void* stream );
+/* device memory / synchronisation for host programs that do not link the CUDA runtime themselves (the role tinyocl::Buffer plays
+ * in the reference's GPU section, tiny_bvh_speedtest.cpp:1100-1115): cudaMalloc / cudaFree / cudaDeviceSynchronize / a blocking
+ * device-to-host copy on the context's device */
+int tbvh_device_alloc( tbvh_ctx ctx, size_t bytes, void** out );
+int tbvh_device_free( tbvh_ctx ctx, void* p );
+int tbvh_device_sync( tbvh_ctx ctx );
+int tbvh_copy_from_device( void* host, const void* d_src, size_t bytes );
 
 /* ---- several GPUs in one process (rays shard by index, the BVH is replicated once, no traffic between devices
  * during traversal).  The reference has no counterpart: its GPU path drives one OpenCL device (tiny_bvh_speedtest.cpp:1092-1241).

@@ -83,6 +83,28 @@ public:
 	{
 		TBVH_FATAL_IF( tbvh_occluded( h, layout, rays, (uint32_t)sizeof( RayT ), n, bits ), "IsOccluded" );
 	}
+	// device-resident batches (the reference's GPU section keeps its rays in a tinyocl::Buffer and times the kernel alone,
+	// tiny_bvh_speedtest.cpp:1110-1135): 64-byte records made by UploadRays, hits written in place, asynchronous until Sync()
+	template <class RayT> void* UploadRays( const RayT* rays, uint64_t n ) const
+	{
+		void* d = 0;
+		TBVH_FATAL_IF( tbvh_device_alloc( context(), n * 64, &d ), "UploadRays" );
+		TBVH_FATAL_IF( tbvh_copy_rays_to_device( rays, (uint32_t)sizeof( RayT ), n, d, 0 ), "UploadRays" );
+		Sync();
+		return d;
+	}
+	void IntersectDevice( void* d_rays64, uint64_t n ) const { TBVH_FATAL_IF( tbvh_intersect_device( h, layout, d_rays64, 64, 0, n, 0 ), "IntersectDevice" ); }
+	void IsOccludedDevice( const void* d_rays64, uint64_t n, uint32_t* d_bits ) const { TBVH_FATAL_IF( tbvh_occluded_device( h, layout, d_rays64, 64, d_bits, n, 0 ), "IsOccludedDevice" ); }
+	// t,u,v,prim of n device records back into host Ray records
+	template <class RayT> void DownloadHits( RayT* rays, const void* d_rays64, uint64_t n ) const
+	{
+		char* tmp = (char*)malloc( n * 64 );
+		TBVH_FATAL_IF( tbvh_copy_from_device( tmp, d_rays64, n * 64 ), "DownloadHits" );
+		for (uint64_t i = 0; i < n; i++) memcpy( (char*)&rays[i] + 48, tmp + i * 64 + 48, 16 );
+		free( tmp );
+	}
+	void FreeDevice( void* d ) const { tbvh_device_free( context(), d ); }
+	void Sync() const { TBVH_FATAL_IF( tbvh_device_sync( context() ), "Sync" ); }
 	// per-ray forms with the reference's signatures (correct, but one PCIe round trip each: use the batch forms)
 	template <class RayT> int32_t Intersect( RayT& ray ) const { return Intersect( &ray, 1 ); }
 	template <class RayT> bool IsOccluded( const RayT& ray ) const { uint32_t b = 0; IsOccluded( &ray, 1, &b ); return b & 1; }
@@ -276,3 +298,11 @@ public:
 };
 
 } // namespace tinybvh_b200
+
+// A program that does NOT include tiny_bvh.h can keep writing tinybvh::BVH, tinybvh::BVH8_CWBVH, tinybvh::Ray ...:
+//     #define TINYBVH_B200_AS_TINYBVH
+//     #include "tinybvh_b200.hpp"
+// (next to the real header the two namespaces live side by side, as in harness/speedtest_b200.patch)
+#ifdef TINYBVH_B200_AS_TINYBVH
+namespace tinybvh = tinybvh_b200;
+#endif

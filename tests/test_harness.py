@@ -43,3 +43,41 @@ def test_speedtest_gpu_section_drop_in(gpu):
     print(r.stdout)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
     assert "0 prim mismatches, 0 t-bit mismatches" in r.stdout
+
+
+def test_speedtest_patch_applies_to_the_reference():
+    """harness/speedtest_b200.patch is a patch of the reference's own tiny_bvh_speedtest.cpp (GPU section, :1071): it must apply
+    cleanly to an untouched copy (only where the reference checkout exists - this container, not the GPU box)."""
+    import shutil
+    import tempfile
+    ref = "/root/reference/tiny_bvh_speedtest.cpp"
+    if not os.path.isfile(ref):
+        pytest.skip("reference checkout not present")
+    with tempfile.TemporaryDirectory() as d:
+        shutil.copy(ref, os.path.join(d, "tiny_bvh_speedtest.cpp"))
+        r = subprocess.run(["patch", "-p1", "--dry-run", "-d", d, "-i", os.path.join(REPO, "harness", "speedtest_b200.patch")], capture_output=True, text=True)
+        assert r.returncode == 0, r.stdout + r.stderr
+        subprocess.check_call(["patch", "-s", "-p1", "-d", d, "-i", os.path.join(REPO, "harness", "speedtest_b200.patch")])
+        src = open(os.path.join(d, "tiny_bvh_speedtest.cpp")).read()
+        assert "#ifdef ENABLE_B200" in src and "tinybvh_b200::BVH8_CWBVH" in src
+
+
+@pytest.mark.gpu
+def test_patched_reference_speedtest_runs(gpu):
+    """The literal drop-in: the reference's tiny_bvh_speedtest.cpp + harness/speedtest_b200.patch, built with -DENABLE_B200 (oracle/Makefile
+    speedtest_patched), run as the reference runs it - from a directory holding ./testdata/cryteksponza.bin.  All of its CPU sections
+    run too; no `!! Validation failed` line may appear, and the B200 section must report."""
+    import tempfile
+    exe = os.path.join(REPO, "oracle", "_ref", "tiny_bvh_speedtest_b200")
+    scene = os.path.join(REPO, "data", "scenes", "cryteksponza.bin")
+    if not (os.path.isfile(exe) and os.path.isfile(scene)):
+        pytest.skip("patched speedtest binary or Sponza fixture not present")
+    with tempfile.TemporaryDirectory() as d:
+        os.mkdir(os.path.join(d, "testdata"))
+        os.symlink(scene, os.path.join(d, "testdata", "cryteksponza.bin"))
+        r = subprocess.run([exe], cwd=d, capture_output=True, text=True, timeout=900)
+    print(r.stdout[-6000:])
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+    assert "BVH traversal speed - GPU (B200, tinybvh_b200)" in r.stdout
+    assert "!! Validation" not in r.stdout.split("BVH traversal speed - GPU (B200, tinybvh_b200)")[1].split("BVH traversal speed - CPU multi-core")[0]
+    assert "- BVH8_CWBVH  - primary:" in r.stdout and "(host buffers)" in r.stdout

@@ -64,6 +64,12 @@ SYMBOLS = {
     "tbvh_set_stats": (i32, [vp, i32]),
     "tbvh_get_stats": (i32, [vp, C.POINTER(u64), C.POINTER(u64)]),
     "tbvh_launch_count": (u64, []),
+    "tbvh_get_stats_ex": (i32, [vp, C.POINTER(u64 * 4)]),
+    "tbvh_copy_rays_to_device": (i32, [vp, u32, u64, vp, vp]),
+    "tbvh_device_alloc": (i32, [vp, sz, C.POINTER(vp)]),
+    "tbvh_device_free": (i32, [vp, vp]),
+    "tbvh_device_sync": (i32, [vp]),
+    "tbvh_copy_from_device": (i32, [vp, vp, sz]),
     "tbvh_device_numa_node": (i32, [i32]),
     "tbvh_bind_thread_to_device": (i32, [i32]),
     "tbvh_host_alloc_near": (i32, [i32, sz, C.POINTER(vp)]),

@@ -160,9 +160,10 @@ class _Base:
         check(_lib.lib().tbvh_set_stats(self.h, int(enable)))
 
     def get_stats(self):
-        a, b = C.c_uint64(), C.c_uint64()
-        check(_lib.lib().tbvh_get_stats(self.h, C.byref(a), C.byref(b)))
-        return a.value, b.value
+        """(node visits, triangle tests, CWBVH child-pair steps) of the last traversal call with statistics enabled"""
+        out = (C.c_uint64 * 4)()
+        check(_lib.lib().tbvh_get_stats_ex(self.h, C.byref(out)))
+        return out[0], out[1], out[2]
 
 
 class BVH(_Base):
@@ -327,10 +328,20 @@ def pinned_free(a: np.ndarray):
         check(_lib.lib().tbvh_host_free(p))
 
 
+def copy_rays_to_device(rays: np.ndarray, d_rays, stream=None) -> None:
+    """tbvh_copy_rays_to_device: bytes 0..63 of every host record into a [n, 64]-byte torch CUDA tensor (synchronous here)."""
+    import torch
+    assert rays.dtype.itemsize in (64, 128) and rays.flags.c_contiguous and d_rays.is_cuda and d_rays.is_contiguous()
+    assert d_rays.numel() * d_rays.element_size() >= rays.shape[0] * 64
+    st = torch.cuda.current_stream(d_rays.device)
+    check(_lib.lib().tbvh_copy_rays_to_device(_np_ptr(rays), rays.dtype.itemsize, rays.shape[0], C.c_void_p(d_rays.data_ptr()), C.c_void_p(st.cuda_stream)))
+    st.synchronize()
+
+
 def bind_to_device(device: int = 0) -> bool:
     """Restrict the calling thread (and threads it starts later: OpenMP, the host pipeline) to the CPUs of the NUMA node `device`
     hangs off.  False when the system exposes no topology."""
-    return _lib.lib().tbvh_bind_thread_to_device(device) == OK
+    return _lib.lib().tbvh_bind_thread_to_device(device) == _lib.OK
 
 
 def shard_range(n: int, part: int, parts: int):

@@ -262,8 +262,8 @@ int tbvh_bvh_create( tbvh_ctx ctx, tbvh_bvh* out )
 	ARG_CHECK( b, "out of host memory" );
 	b->ctx = ctx;
 	CUDA_TRY( cudaSetDevice( ctx->device ) );
-	CUDA_TRY( cudaMalloc( &b->d_stats, 16 ) );
-	CUDA_TRY( cudaMemset( b->d_stats, 0, 16 ) );
+	CUDA_TRY( cudaMalloc( &b->d_stats, 32 ) );
+	CUDA_TRY( cudaMemset( b->d_stats, 0, 32 ) );
 	live_add( b );
 	*out = b;
 	return TBVH_OK;
@@ -304,6 +304,14 @@ int tbvh_get_stats( tbvh_bvh b, uint64_t* steps, uint64_t* tris )
 	CUDA_TRY( cudaMemcpy( h, b->d_stats, 16, cudaMemcpyDeviceToHost ) );
 	if (steps) *steps = h[0];
 	if (tris) *tris = h[1];
+	return TBVH_OK;
+}
+int tbvh_get_stats_ex( tbvh_bvh b, uint64_t out[4] )
+{
+	ARG_CHECK( b && out, "NULL argument" );
+	CUDA_TRY( cudaSetDevice( b->ctx->device ) );
+	CUDA_TRY( cudaDeviceSynchronize() );
+	CUDA_TRY( cudaMemcpy( out, b->d_stats, 32, cudaMemcpyDeviceToHost ) );
 	return TBVH_OK;
 }
 
@@ -782,7 +790,7 @@ int tbvh_intersect_device( tbvh_bvh b, int layout, void* d_rays, uint32_t stride
 {
 	ARG_CHECK( b && d_rays && stride >= 64 && (stride & 15) == 0, "bad ray buffer" );
 	CUDA_TRY( cudaSetDevice( b->ctx->device ) );
-	if (b->stats) CUDA_TRY( cudaMemsetAsync( b->d_stats, 0, 16, (cudaStream_t)stream ) );
+	if (b->stats) CUDA_TRY( cudaMemsetAsync( b->d_stats, 0, 32, (cudaStream_t)stream ) );
 	if (b->d_inst)
 	{
 		// TLAS: hits carry the instance (hit.inst, byte 44) and are written into the ray records
@@ -798,9 +806,48 @@ int tbvh_occluded_device( tbvh_bvh b, int layout, const void* d_rays, uint32_t s
 {
 	ARG_CHECK( b && d_rays && d_bits && stride >= 64 && (stride & 15) == 0, "bad ray buffer" );
 	CUDA_TRY( cudaSetDevice( b->ctx->device ) );
-	if (b->stats) CUDA_TRY( cudaMemsetAsync( b->d_stats, 0, 16, (cudaStream_t)stream ) );
+	if (b->stats) CUDA_TRY( cudaMemsetAsync( b->d_stats, 0, 32, (cudaStream_t)stream ) );
 	if (b->d_inst) { TRY( tlas_check( b ) ); return tlas_trace_launch( b, d_rays, stride, d_bits, n, true, (cudaStream_t)stream ); }
 	return trace_dispatch( b, layout, d_rays, stride, 0, 0, d_bits, n, true, (cudaStream_t)stream );
+}
+
+// plain device memory for callers of the *_device entry points that do not link the CUDA runtime themselves
+int tbvh_device_alloc( tbvh_ctx c, size_t bytes, void** out )
+{
+	ARG_CHECK( c && out, "NULL argument" );
+	CUDA_TRY( cudaSetDevice( c->device ) );
+	CUDA_TRY( cudaMalloc( out, bytes ) );
+	return TBVH_OK;
+}
+int tbvh_device_free( tbvh_ctx c, void* p )
+{
+	ARG_CHECK( c, "NULL context" );
+	CUDA_TRY( cudaSetDevice( c->device ) );
+	if (p) CUDA_TRY( cudaFree( p ) );
+	return TBVH_OK;
+}
+int tbvh_device_sync( tbvh_ctx c )
+{
+	ARG_CHECK( c, "NULL context" );
+	CUDA_TRY( cudaSetDevice( c->device ) );
+	CUDA_TRY( cudaDeviceSynchronize() );
+	return TBVH_OK;
+}
+int tbvh_copy_from_device( void* host, const void* d_src, size_t bytes )
+{
+	ARG_CHECK( host && d_src, "NULL argument" );
+	CUDA_TRY( cudaMemcpy( host, d_src, bytes, cudaMemcpyDeviceToHost ) );
+	return TBVH_OK;
+}
+
+// host records -> packed 64-byte device records (bytes 0..63 of each), asynchronous on `stream`: what a caller of the *_device
+// entry points needs to get its batch into HBM (the speedtest's own upload, tiny_bvh_speedtest.cpp:1110-1115)
+int tbvh_copy_rays_to_device( const void* rays, uint32_t stride, uint64_t n, void* d_rays, void* stream )
+{
+	ARG_CHECK( rays && d_rays && stride >= 64, "bad ray buffer" );
+	if (n == 0) return TBVH_OK;
+	CUDA_TRY( cudaMemcpy2DAsync( d_rays, 64, rays, stride, 64, n, cudaMemcpyHostToDevice, (cudaStream_t)stream ) );
+	return TBVH_OK;
 }
 
 // ---- host-buffer path ---------------------------------------------------------------------------------------------
@@ -897,7 +944,7 @@ static int intersect_host( tbvh_bvh b, int layout, void* rays, uint32_t stride, 
 	std::lock_guard<std::mutex> lk( c->host_mutex );
 	CUDA_TRY( cudaSetDevice( c->device ) );
 	TRY( ensure_slots( c ) );
-	if (b->stats) CUDA_TRY( cudaMemset( b->d_stats, 0, 16 ) );
+	if (b->stats) CUDA_TRY( cudaMemset( b->d_stats, 0, 32 ) );
 	const bool tlas = b->d_inst != 0;
 	if (tlas)
 	{
@@ -954,7 +1001,7 @@ int tbvh_occluded( tbvh_bvh b, int layout, const void* rays, uint32_t stride, ui
 	std::lock_guard<std::mutex> lk( c->host_mutex );
 	CUDA_TRY( cudaSetDevice( c->device ) );
 	TRY( ensure_slots( c ) );
-	if (b->stats) CUDA_TRY( cudaMemset( b->d_stats, 0, 16 ) );
+	if (b->stats) CUDA_TRY( cudaMemset( b->d_stats, 0, 32 ) );
 	if (b->d_inst) TRY( tlas_check( b ) );
 	const char* dev_alias = (const char*)mapped_alias( rays );
 	uint64_t chunk = 0;

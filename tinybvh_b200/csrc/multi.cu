@@ -78,8 +78,9 @@ int tbvh_group_create( const int* devices, int count, tbvh_group* out )
 	ARG_CHECK( out, "out == NULL" );
 	int have = 0;
 	CUDA_TRY( cudaGetDeviceCount( &have ) );
-	if (count <= 0) count = have; // all devices
-	ARG_CHECK( count >= 1 && count <= have, "device count out of range" );
+	if (count <= 0) count = have, devices = 0; // all devices
+	ARG_CHECK( count >= 1 && count <= 64, "device count out of range" );
+	for (int i = 0; i < count; i++) ARG_CHECK( (devices ? devices[i] : i) >= 0 && (devices ? devices[i] : i) < have, "no such device" ); // a device may appear twice (two contexts on it)
 	tbvh_group g = new (std::nothrow) tbvh_group_t();
 	ARG_CHECK( g, "out of host memory" );
 	for (int i = 0; i < count; i++)

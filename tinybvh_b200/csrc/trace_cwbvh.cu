@@ -124,8 +124,6 @@ int cw_make_trav( tbvh_bvh b, cudaStream_t s, int known_depth )
 
 // ---- traversal ------------------------------------------------------------------------------------------------------
 
-struct PairPlanes { float2 nx, ny, nz, fx, fy, fz; };
-
 __device__ __forceinline__ float2 widen( const uint32_t h2 ) { return __half22float2( *(const __half2*)&h2 ); }
 
 // one pair of children against one ray: `near` / `far` words already chosen by the ray's signs
@@ -149,27 +147,68 @@ __device__ __forceinline__ uint32_t slots_to_order( const uint32_t w, const uint
 	return top << 24;
 }
 
-template <bool ANYHIT, bool STATS>
+// All child pairs of one node against one ray -> the node's hit word in traversal order (inner children in bits 24..31 by
+// s ^ o, triangles in bits 0..23).  OCT < 0: the ray's own signs (per lane); OCT = 0..7: every ray of the warp has negative
+// x / y / z direction components as bits 2 / 1 / 0 of OCT say - plane choice and bit order are then compile-time.
+template <int OCT> __device__ __forceinline__ uint32_t node_hits( const float4* __restrict__ np, const uint32_t pairs, const bool negx, const bool negy, const bool negz, const uint32_t o,
+	const float ax1, const float ay1, const float az1, const float bx1, const float by1, const float bz1, const float t )
+{
+	const bool nx = OCT < 0 ? negx : (OCT & 4) != 0, ny = OCT < 0 ? negy : (OCT & 2) != 0, nz = OCT < 0 ? negz : (OCT & 1) != 0;
+	const float2 ax = make_float2( ax1, ax1 ), ay = make_float2( ay1, ay1 ), az = make_float2( az1, az1 );
+	const float2 bx = make_float2( bx1, bx1 ), by = make_float2( by1, by1 ), bz = make_float2( bz1, bz1 );
+	uint32_t got = 0;
+	#pragma unroll
+	for (uint32_t j = 0; j < 4; j++)
+	{
+		if (j < pairs)
+		{
+			const float4 A = __ldg( np + 2 + 2 * j ), B = __ldg( np + 3 + 2 * j );
+			const uint32_t lx = __float_as_uint( A.x ), ly = __float_as_uint( A.y ), lz = __float_as_uint( A.z );
+			const uint32_t hx = __float_as_uint( A.w ), hy = __float_as_uint( B.x ), hz = __float_as_uint( B.y );
+			got |= pair_hits( nx ? hx : lx, ny ? hy : ly, nz ? hz : lz, nx ? lx : hx, ny ? ly : hy, nz ? lz : hz,
+				__float_as_uint( B.z ), __float_as_uint( B.w ), ax, ay, az, bx, by, bz, t );
+		}
+	}
+	return slots_to_order( got, OCT < 0 ? o : (uint32_t)(7 - OCT) ) | (got & 0x00ffffffu);
+}
+
+// OCTSW = 1: warps whose rays all point into one direction octant (camera and shadow rays: nearly all of them) run the node step
+// through the instance compiled for that octant, picked by a warp-uniform switch; mixed warps use the per-lane form.
+template <bool ANYHIT, bool STATS, int OCTSW>
 __global__ void __launch_bounds__( 128 ) k_trace_wide( const float4* __restrict__ nodes, const float4* __restrict__ tris,
 	const char* rays, const uint32_t stride, char* hits, const uint32_t hit_stride, uint32_t* __restrict__ bits, const uint64_t n,
 	unsigned long long* __restrict__ stats )
 {
 	const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
 	bool occluded = false;
-	if (i < n)
+	const bool valid = i < n;
+	float4 ro4 = make_float4( 0, 0, 0, 0 ), rd4 = ro4, rr4 = ro4, rh4 = ro4;
+	if (valid)
 	{
 		const float4* rp = (const float4*)(rays + i * stride);
-		const float4 ro4 = rp[0], rd4 = rp[1], rr4 = rp[2], rh4 = rp[3];
-		const float ox = ro4.x, oy = ro4.y, oz = ro4.z, dx = rd4.x, dy = rd4.y, dz = rd4.z;
-		const float rdx = rr4.x, rdy = rr4.y, rdz = rr4.z;
+		ro4 = rp[0], rd4 = rp[1], rr4 = rp[2], rh4 = rp[3];
+	}
+	const float ox = ro4.x, oy = ro4.y, oz = ro4.z, dx = rd4.x, dy = rd4.y, dz = rd4.z;
+	const float rdx = rr4.x, rdy = rr4.y, rdz = rr4.z;
+	const uint32_t o = 7u - ((dx < 0 ? 4u : 0u) | (dy < 0 ? 2u : 0u) | (dz < 0 ? 1u : 0u)); // octinv of tiny_bvh.h:7053 (signs of D)
+	const bool negx = rdx < 0, negy = rdy < 0, negz = rdz < 0;                                // plane swizzle uses rD (:7082)
+	const uint32_t oct = (negx ? 4u : 0u) | (negy ? 2u : 0u) | (negz ? 1u : 0u);
+	bool uni = false;
+	if (OCTSW)
+	{
+		// the compiled-in octant serves both the plane choice (signs of rD) and the visiting order (signs of D): they must agree
+		const uint32_t vm = __ballot_sync( 0xffffffffu, valid );
+		const uint32_t oct0 = __shfl_sync( 0xffffffffu, oct, vm ? __ffs( vm ) - 1 : 0 );
+		uni = __all_sync( 0xffffffffu, !valid || (oct == oct0 && o == 7u - oct) );
+	}
+	if (valid)
+	{
 		float t = rh4.x, hu = rh4.y, hv = rh4.z;
 		uint32_t hprim = __float_as_uint( rh4.w );
-		const uint32_t o = 7u - ((dx < 0 ? 4u : 0u) | (dy < 0 ? 2u : 0u) | (dz < 0 ? 1u : 0u)); // octinv of tiny_bvh.h:7053
-		const bool negx = rdx < 0, negy = rdy < 0, negz = rdz < 0;                                // plane swizzle uses rD (:7082)
 		uint2 pending[CW_STACK];
 		int depth = 0;
 		uint32_t base = 0, word = 0x80000000u; // the root as a one-child group: bit 31, no siblings
-		unsigned long long nsteps = 0, ntris = 0;
+		unsigned long long nsteps = 0, ntris = 0, npairs = 0;
 		while (true)
 		{
 			// ---- enter the pending inner child with the highest bit
@@ -188,24 +227,28 @@ __global__ void __launch_bounds__( 128 ) k_trace_wide( const float4* __restrict_
 			const float scz = __uint_as_float( (((ew >> 16) & 255u) << 23) - 0x00800000u );
 			const float ax1 = __fmul_rn( scx, rdx ), ay1 = __fmul_rn( scy, rdy ), az1 = __fmul_rn( scz, rdz );
 			const float bx1 = __fmul_rn( -__fsub_rn( ox, h0.x ), rdx ), by1 = __fmul_rn( -__fsub_rn( oy, h0.y ), rdy ), bz1 = __fmul_rn( -__fsub_rn( oz, h0.z ), rdz );
-			const float2 ax = make_float2( ax1, ax1 ), ay = make_float2( ay1, ay1 ), az = make_float2( az1, az1 );
-			const float2 bx = make_float2( bx1, bx1 ), by = make_float2( by1, by1 ), bz = make_float2( bz1, bz1 );
 			const uint32_t pairs = __float_as_uint( h1.z );
-			uint32_t got = 0;
-			#pragma unroll
-			for (uint32_t j = 0; j < 4; j++)
+			if (STATS) npairs += pairs;
+			uint32_t got;
+			#define NODE_HITS( O ) got = node_hits<O>( np, pairs, negx, negy, negz, o, ax1, ay1, az1, bx1, by1, bz1, t )
+			if (OCTSW && uni)
 			{
-				if (j < pairs)
+				switch (oct)
 				{
-					const float4 A = __ldg( np + 2 + 2 * j ), B = __ldg( np + 3 + 2 * j );
-					const uint32_t lx = __float_as_uint( A.x ), ly = __float_as_uint( A.y ), lz = __float_as_uint( A.z );
-					const uint32_t hx = __float_as_uint( A.w ), hy = __float_as_uint( B.x ), hz = __float_as_uint( B.y );
-					got |= pair_hits( negx ? hx : lx, negy ? hy : ly, negz ? hz : lz, negx ? lx : hx, negy ? ly : hy, negz ? lz : hz,
-						__float_as_uint( B.z ), __float_as_uint( B.w ), ax, ay, az, bx, by, bz, t );
+				case 0: NODE_HITS( 0 ); break;
+				case 1: NODE_HITS( 1 ); break;
+				case 2: NODE_HITS( 2 ); break;
+				case 3: NODE_HITS( 3 ); break;
+				case 4: NODE_HITS( 4 ); break;
+				case 5: NODE_HITS( 5 ); break;
+				case 6: NODE_HITS( 6 ); break;
+				default: NODE_HITS( 7 ); break;
 				}
 			}
+			else NODE_HITS( -1 );
+			#undef NODE_HITS
 			base = __float_as_uint( h1.x );
-			word = slots_to_order( got, o ) | (__float_as_uint( h0.w ) >> 24);
+			word = (got & 0xff000000u) | (__float_as_uint( h0.w ) >> 24);
 			// ---- triangles of the leaf children that were hit, highest bit first (:7132-7142)
 			uint32_t tmask = got & 0x00ffffffu;
 			const float4* tbase = tris + __float_as_uint( h1.y );
@@ -234,7 +277,7 @@ __global__ void __launch_bounds__( 128 ) k_trace_wide( const float4* __restrict_
 			float4* hp = (float4*)(hits + i * hit_stride);
 			*hp = make_float4( t, hu, hv, __uint_as_float( hprim ) );
 		}
-		if (STATS) { atomicAdd( &stats[0], nsteps ); atomicAdd( &stats[1], ntris ); }
+		if (STATS) { atomicAdd( &stats[0], nsteps ); atomicAdd( &stats[1], ntris ); atomicAdd( &stats[2], npairs ); }
 	}
 	if (ANYHIT)
 	{
@@ -252,10 +295,11 @@ int cwbvh_trace_launch( tbvh_bvh b, const void* d_rays, uint32_t stride, void* d
 	const uint32_t block = 128;
 	const uint64_t grid = (n + block - 1) / block;
 	if (grid > 0x7fffffffull) { tbvh_set_error( "ray batch too large for one launch" ); return TBVH_E_ARG; }
-	#define LAUNCH( A, S ) k_trace_wide<A, S><<<(uint32_t)grid, block, 0, s>>>( b->d_cw_trav, b->d_cw_tris, (const char*)d_rays, stride, \
+	const int sw = b->ctx->trace_variant == 0 ? 0 : 1; // trace_variant 0: the per-lane form only (A/B switch for measurements)
+	#define LAUNCH( A, S, O ) k_trace_wide<A, S, O><<<(uint32_t)grid, block, 0, s>>>( b->d_cw_trav, b->d_cw_tris, (const char*)d_rays, stride, \
 		(char*)d_hits, hit_stride, d_bits, n, d_stats )
-	if (anyhit) { if (d_stats) LAUNCH( true, true ); else LAUNCH( true, false ); }
-	else { if (d_stats) LAUNCH( false, true ); else LAUNCH( false, false ); }
+	if (anyhit) { if (d_stats) LAUNCH( true, true, 0 ); else if (sw) LAUNCH( true, false, 1 ); else LAUNCH( true, false, 0 ); }
+	else { if (d_stats) LAUNCH( false, true, 0 ); else if (sw) LAUNCH( false, false, 1 ); else LAUNCH( false, false, 0 ); }
 	#undef LAUNCH
 	LAUNCHED();
 	return TBVH_OK;

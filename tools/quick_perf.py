@@ -55,7 +55,7 @@ def main():
     hits = torch.empty((n, 4), dtype=torch.float32, device="cuda")
     e.set_stats(True)
     e.Intersect(dprim, hits=hits)
-    steps, tris = e.get_stats()
+    steps, tris = e.get_stats()[:2]
     e.set_stats(False)
     print(f"primary: {n} rays, {steps / n:.1f} steps/ray, {tris / n:.2f} tris/ray")
     best, med = timeit(lambda: e.Intersect(dprim, hits=hits))
@@ -82,7 +82,7 @@ def main():
     ddf = torch.from_numpy(R.gpu_records(df).view(np.uint8).reshape(-1, 64)).cuda()
     e.set_stats(True)
     e.Intersect(ddf, hits=hits)
-    steps, tris = e.get_stats()
+    steps, tris = e.get_stats()[:2]
     e.set_stats(False)
     if layout == "bvh":
         for var in (0, 4):

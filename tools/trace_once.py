@@ -79,7 +79,7 @@ def main():
         if a.stats:
             e.set_stats(True)
             fn()
-            steps, tris = e.get_stats()
+            steps, tris = e.get_stats()[:2]
             e.set_stats(False)
             extra = f"  {steps / n:.2f} node visits/ray {tris / n:.2f} tri tests/ray"
         best, med = timeit(fn, a.reps)
