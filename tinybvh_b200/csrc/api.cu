@@ -10,6 +10,7 @@
 #include <mutex>
 #include <condition_variable>
 #include <memory>
+#include <functional>
 #include <new>
 
 static thread_local char g_err[512] = "";
@@ -89,6 +90,48 @@ template <class F> static auto on_node( int node, F fn ) -> decltype( fn() )
 	return r;
 }
 
+// A few persistent host threads, bound to the CPUs of one NUMA node, that run fn( t, T ) in parallel and block the caller until
+// every slice is done (d2h_mode 2: hits scattered into the caller's strided ray records).
+struct HostPool
+{
+	HostPool( unsigned threads, int node ) : T( threads )
+	{
+		for (unsigned t = 0; t < T; t++) th.emplace_back( [this, t, node]()
+		{
+			cpu_set_t want;
+			if (node_cpus( node, &want )) sched_setaffinity( 0, sizeof( want ), &want );
+			uint64_t seen = 0;
+			for (;;)
+			{
+				std::unique_lock<std::mutex> lk( m );
+				cv_go.wait( lk, [&]() { return quit || gen != seen; } );
+				if (quit) return;
+				seen = gen;
+				lk.unlock();
+				job( t, T );
+				lk.lock();
+				if (++done == T) cv_done.notify_one();
+			}
+		} );
+	}
+	~HostPool() { { std::lock_guard<std::mutex> lk( m ); quit = true; } cv_go.notify_all(); for (auto& t : th) t.join(); }
+	template <class F> void run( F fn )
+	{
+		{ std::lock_guard<std::mutex> lk( m ); job = fn, done = 0, gen++; }
+		cv_go.notify_all();
+		std::unique_lock<std::mutex> lk( m );
+		cv_done.wait( lk, [&]() { return done == T; } );
+	}
+	unsigned T;
+	std::vector<std::thread> th;
+	std::mutex m;
+	std::condition_variable cv_go, cv_done;
+	std::function<void( unsigned, unsigned )> job;
+	uint64_t gen = 0;
+	unsigned done = 0;
+	bool quit = false;
+};
+
 extern "C" {
 
 const char* tbvh_last_error( void ) { return g_err; }
@@ -165,6 +208,8 @@ int tbvh_ctx_create( int device, tbvh_ctx* out )
 	c->h2d_split = sp ? atoi( sp ) : 1;
 	if (c->h2d_split < 1) c->h2d_split = 1;
 	if (c->h2d_split > 4) c->h2d_split = 4;
+	const char* stn = getenv( "TBVH_SCATTER_THREADS" );
+	if (stn && atoi( stn ) >= 1 && atoi( stn ) <= 64) c->scatter_threads = atoi( stn );
 	const char* cr = getenv( "TBVH_CHUNK_RAYS" );
 	if (cr && atol( cr ) >= 4096) c->chunk_rays = (size_t)atol( cr ) & ~(size_t)31;
 	*out = c;
@@ -178,7 +223,8 @@ static void free_slots( tbvh_ctx c )
 		if (c->slot[i].d_rays) cudaFree( c->slot[i].d_rays );
 		if (c->slot[i].d_hits) cudaFree( c->slot[i].d_hits );
 		if (c->slot[i].d_bits) cudaFree( c->slot[i].d_bits );
-		c->slot[i].d_rays = c->slot[i].d_hits = c->slot[i].d_bits = 0;
+		if (c->slot[i].h_hits) cudaFreeHost( c->slot[i].h_hits );
+		c->slot[i].d_rays = c->slot[i].d_hits = c->slot[i].d_bits = c->slot[i].h_hits = 0;
 	}
 	c->slot_rays = 0;
 }
@@ -203,6 +249,7 @@ int tbvh_ctx_destroy( tbvh_ctx c )
 	if (c->s_out) cudaStreamDestroy( c->s_out );
 	if (c->stream) cudaStreamDestroy( c->stream );
 	if (c->d_counters) cudaFree( c->d_counters );
+	delete c->pool;
 	delete c;
 	return TBVH_OK;
 }
@@ -216,7 +263,14 @@ int tbvh_set_option( tbvh_ctx c, const char* key, int value )
 	else if (!strcmp( key, "inst_idx_bits" )) c->inst_idx_bits = value;
 	else if (!strcmp( key, "hq_small" )) c->hq_small = value;
 	else if (!strcmp( key, "hq_cluster" )) c->hq_cluster = value;
-	else if (!strcmp( key, "d2h_mode" )) c->d2h_mode = value == 3 ? 3 : 0;
+	else if (!strcmp( key, "d2h_mode" )) c->d2h_mode = value == 3 ? 3 : value == 2 ? 2 : 0;
+	else if (!strcmp( key, "scatter_threads" ))
+	{
+		ARG_CHECK( value >= 1 && value <= 64, "scatter_threads must be 1..64" );
+		std::lock_guard<std::mutex> lk( c->host_mutex );
+		delete c->pool;
+		c->pool = 0, c->scatter_threads = value;
+	}
 	else if (!strcmp( key, "h2d_split" )) c->h2d_split = value < 1 ? 1 : value > 4 ? 4 : value;
 	else if (!strcmp( key, "host_path" )) c->host_path = value == 1 ? 1 : 0;
 	else if (!strcmp( key, "chunk_rays" ))
@@ -953,6 +1007,33 @@ static int intersect_host( tbvh_bvh b, int layout, void* rays, uint32_t stride, 
 	}
 	char* dev_alias = (char*)mapped_alias( rays );
 	const bool scatter = !packed_hits && !tlas && c->d2h_mode == 3 && dev_alias && (stride & 15) == 0;
+	// d2h_mode 2: the hits leave the device packed (one contiguous copy per chunk) into page-locked staging, and a few host threads on
+	// the device's NUMA node write them into the strided records while later chunks are in flight
+	const bool host_scatter = !packed_hits && !tlas && c->d2h_mode == 2 && n >= 65536;
+	if (host_scatter)
+	{
+		for (int i = 0; i < TBVH_SLOTS; i++) if (!c->slot[i].h_hits)
+		{
+			const cudaError_t e = on_node( c->numa_node, [&]() { return cudaHostAlloc( &c->slot[i].h_hits, c->chunk_rays * 16, cudaHostAllocDefault ); } );
+			if (e != cudaSuccess) { tbvh_set_error( "host staging: %s", cudaGetErrorString( e ) ); return TBVH_E_CUDA; }
+		}
+		if (!c->pool) c->pool = new HostPool( (unsigned)c->scatter_threads, c->numa_node );
+	}
+	// hits of chunk `ch` (already on their way to slot staging) -> the caller's records
+	auto scatter_chunk = [&]( const uint64_t ch ) -> int
+	{
+		HostSlot& sl = c->slot[ch % TBVH_SLOTS];
+		CUDA_TRY( cudaEventSynchronize( sl.out_done ) );
+		const uint64_t off = ch * c->chunk_rays, cnt = n - off < c->chunk_rays ? n - off : c->chunk_rays;
+		char* dst = (char*)rays + off * stride + 48;
+		const char* src = (const char*)sl.h_hits;
+		c->pool->run( [=]( unsigned t, unsigned T )
+		{
+			const uint64_t per = (cnt + T - 1) / T, a = per * t, e = a + per < cnt ? a + per : cnt;
+			for (uint64_t i = a; i < e; i++) memcpy( dst + i * stride, src + i * 16, 16 );
+		} );
+		return TBVH_OK;
+	};
 	uint64_t chunk = 0;
 	int rc = TBVH_OK;
 	for (uint64_t off = 0; off < n && rc == TBVH_OK; off += c->chunk_rays, chunk++)
@@ -964,6 +1045,7 @@ static int intersect_host( tbvh_bvh b, int layout, void* rays, uint32_t stride, 
 		char* hd = dev_alias ? dev_alias + off * stride : 0;
 		auto body = [&]() -> int
 		{
+			if (host_scatter && chunk >= TBVH_SLOTS) TRY( scatter_chunk( chunk - TBVH_SLOTS ) ); // frees this slot's staging
 			TRY( stage_in( c, k, chunk, h, hd, stride, cnt ) );
 			if (tlas) TRY( tlas_trace_launch( b, sl.d_rays, 64, 0, cnt, false, c->s_run ) );  // hit + instance written into the staged records
 			else TRY( trace_dispatch( b, layout, sl.d_rays, 64, sl.d_hits, 16, 0, cnt, false, c->s_run ) );
@@ -971,6 +1053,7 @@ static int intersect_host( tbvh_bvh b, int layout, void* rays, uint32_t stride, 
 			CUDA_TRY( cudaStreamWaitEvent( c->s_out, sl.run_done, 0 ) );
 			if (tlas) CUDA_TRY( cudaMemcpy2DAsync( h + 44, stride, (char*)sl.d_rays + 44, 64, 20, cnt, cudaMemcpyDeviceToHost, c->s_out ) );
 			else if (packed_hits) CUDA_TRY( cudaMemcpyAsync( (char*)packed_hits + off * 16, sl.d_hits, cnt * 16, cudaMemcpyDeviceToHost, c->s_out ) );
+			else if (host_scatter) CUDA_TRY( cudaMemcpyAsync( sl.h_hits, sl.d_hits, cnt * 16, cudaMemcpyDeviceToHost, c->s_out ) );
 			else if (scatter)
 			{
 				k_scatter_hits<<<(uint32_t)((cnt + 255) / 256), 256, 0, c->s_out>>>( (const float4*)sl.d_hits, (float4*)hd, stride / 16, cnt );
@@ -982,6 +1065,8 @@ static int intersect_host( tbvh_bvh b, int layout, void* rays, uint32_t stride, 
 		};
 		rc = body();
 	}
+	if (host_scatter && rc == TBVH_OK)
+		for (uint64_t ch = chunk > TBVH_SLOTS ? chunk - TBVH_SLOTS : 0; ch < chunk && rc == TBVH_OK; ch++) rc = scatter_chunk( ch );
 	const int rd = drain( c ); // also after an error: nothing of this call may still be in flight when the mutex is released
 	return rc != TBVH_OK ? rc : rd;
 }

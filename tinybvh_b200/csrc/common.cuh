@@ -25,6 +25,7 @@ struct HostSlot
 	void* d_rays = 0;                // chunk of 64-byte device records
 	void* d_hits = 0;                // packed 16-byte hits of the chunk
 	void* d_bits = 0;                // occlusion words of the chunk
+	void* h_hits = 0;                // page-locked staging for the chunk's packed hits (d2h_mode 2: scattered into the records by host threads)
 	cudaEvent_t in_done = 0, run_done = 0, out_done = 0;
 };
 #define TBVH_SLOTS 4
@@ -47,7 +48,9 @@ struct tbvh_ctx_t
 	size_t slot_rays = 0;            // capacity the slots were allocated for
 	int host_path = 0;               // inbound: 0 = copy engine (cudaMemcpy2DAsync of 64-byte rows), 1 = gather kernel through the pinned mapping
 	int h2d_split = 1;               // inbound 2D copy of a chunk split over this many streams (copy engines)
-	int d2h_mode = 0;                // in-place hits: 0 = 2D copy of 16-byte rows, 3 = scatter kernel through the pinned mapping
+	int d2h_mode = 0;                // in-place hits: 0 = 2D copy of 16-byte rows, 2 = packed copy + host threads scatter, 3 = scatter kernel through the pinned mapping
+	int scatter_threads = 8;         // d2h_mode 2: host threads (bound to the device's NUMA node) that write the hits into the records
+	struct HostPool* pool = 0;
 	int trace_variant = 3;           // BVH2 traversal kernel: 0 generic, 3 octant switch, 4 persistent warps (see trace_bvh2.cu)
 	int small_mode = 0;              // warp-subtree kernel: bit 0 = fragments staged in shared memory, bit 1 = aggregated bin updates
 	int inst_idx_bits = 32;          // the host program's INST_IDX_BITS (tiny_bvh.h:118): 32 = TLAS hits store hit.inst, 4..31 = top bits of hit.prim

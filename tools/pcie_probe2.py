@@ -66,17 +66,21 @@ h = api.pinned_empty(n, R.RAY_DTYPE, device=0)
 api.bind_to_device(0)
 fill(h)
 run("local pinned buffer", h)
-for key, val in (("chunk_rays", 1 << 18), ("chunk_rays", 1 << 20), ("chunk_rays", 1 << 19)):
-    api.set_option(key, val)
-    run(f"local, {key}={val}", h)
-for sp in (2, 3):
-    api.set_option("h2d_split", sp)
-    run(f"local, h2d_split={sp}", h)
-api.set_option("h2d_split", 1)
-api.set_option("host_path", 1)
-run("local, gather kernel inbound", h)
-api.set_option("host_path", 0)
-api.set_option("d2h_mode", 3)
-run("local, scatter kernel outbound", h)
-api.set_option("host_path", 1)
-run("local, gather + scatter kernels", h)
+for thr in (4, 8, 16, 32):
+    api.set_option("d2h_mode", 2)
+    api.set_option("scatter_threads", thr)
+    run(f"local, host scatter x{thr}", h)
+api.set_option("d2h_mode", 0)
+if "--all" in sys.argv:
+    for key, val in (("chunk_rays", 1 << 18), ("chunk_rays", 1 << 20), ("chunk_rays", 1 << 19)):
+        api.set_option(key, val)
+        run(f"local, {key}={val}", h)
+    for sp in (2, 3):
+        api.set_option("h2d_split", sp)
+        run(f"local, h2d_split={sp}", h)
+    api.set_option("h2d_split", 1)
+    api.set_option("host_path", 1)
+    run("local, gather kernel inbound", h)
+    api.set_option("host_path", 0)
+    api.set_option("d2h_mode", 3)
+    run("local, scatter kernel outbound", h)
