@@ -239,18 +239,23 @@ def parity_sample(args, verts, h_prim, h_shadow, hits, bits, m):
         return {"unavailable": "oracle/_ref not built"}
     os.sched_setaffinity(0, ALL_CPUS)
     t0 = time.time()
-    got = h_prim[:m].copy()
-    got["t"], got["u"], got["v"], got["prim"] = hits[:m, 0], hits[:m, 1], hits[:m, 2], hits[:m, 3].view(np.uint32)
-    occ = np.unpackbits(bits[: (m + 31) // 32].view(np.uint8), bitorder="little")[:m].astype(bool)
-    out = {"sample_rays": int(m)}
+    # m rays spread evenly over this rank's index range (the first rays alone would be one corner of the image)
+    n = h_prim.shape[0]
+    idx = np.unique(np.linspace(0, n - 1, m).astype(np.int64))
+    m = idx.shape[0]
+    sel_prim, sel_shadow = h_prim[idx], h_shadow[idx]
+    got = sel_prim.copy()
+    got["t"], got["u"], got["v"], got["prim"] = hits[idx, 0], hits[idx, 1], hits[idx, 2], hits[idx, 3].view(np.uint32)
+    occ = ((bits[idx >> 5] >> (idx & 31).astype(np.uint32)) & 1).astype(bool)
+    out = {"sample_rays": int(m), "sampling": "every (n/m)-th ray of the timed camera and shadow sets"}
     mode = 1 if args.tree == "hq" else 2   # refpy: 1 = BuildHQ chain, 2 = BVH::Build chain
-    want = h_prim[:m].copy()
+    want = sel_prim.copy()
     R.reset_hits_fast(want)
     if args.layout == "cwbvh":
         ref = refpy.RefCWBVH(verts, mode=mode)
         ref.intersect(want, 0)
         name = "BVH8_CWBVH::BuildHQ + BVH8_CWBVH::Intersect" if mode == 1 else "BVH8_CWBVH::Build + Intersect"
-        sh = h_shadow[:m].copy()
+        sh = sel_shadow.copy()
         d = sh["t"].copy()
         ref.intersect(sh, 0)
         occ_ref = sh["t"] < d          # BVH8_CWBVH::IsOccluded is the FALLBACK_SHADOW_QUERY (tiny_bvh.h:312): Intersect, then t < d
@@ -258,20 +263,20 @@ def parity_sample(args, verts, h_prim, h_shadow, hits, bits, m):
         ref = refpy.RefBVH(verts, mode=2 if args.tree == "hq" else 0, threaded=True)
         ref.intersect(want, 0)
         name = "BVH::BuildHQ + BVH::Intersect" if args.tree == "hq" else "BVH::Build + BVH::Intersect"
-        occ_ref = np.unpackbits(ref.occluded(h_shadow[:m].copy(), 0).view(np.uint8), bitorder="little")[:m].astype(bool)
+        occ_ref = np.unpackbits(ref.occluded(sel_shadow.copy(), 0).view(np.uint8), bitorder="little")[:m].astype(bool)
     c = util.compare_hits(got, want)
     hit = want["t"] < 1e30
     out["same_layout"] = {"reference": name, "prim_mismatch": c["prim"], "t_bit_mismatch": c["t"],
                           "uv_bit_mismatch_on_hits": int(((got["u"].view(np.uint32) != want["u"].view(np.uint32)) | (got["v"].view(np.uint32) != want["v"].view(np.uint32)))[hit].sum()),
                           "occlusion_bit_mismatch": int((occ != occ_ref).sum())}
     o = refpy.RefBVH(verts, mode=0, threaded=True)
-    w2 = h_prim[:m].copy()
+    w2 = sel_prim.copy()
     R.reset_hits_fast(w2)
     o.intersect(w2, 0)
     cls = util.classify_mismatches(got, w2, verts)
     both = (w2["t"] < 1e30) & (got["t"] < 1e30)
     rel = np.abs(got["t"][both] - w2["t"][both]) / np.maximum(np.abs(w2["t"][both]), 1e-30)
-    occ_o = np.unpackbits(o.occluded(h_shadow[:m].copy(), 0).view(np.uint8), bitorder="little")[:m].astype(bool)
+    occ_o = np.unpackbits(o.occluded(sel_shadow.copy(), 0).view(np.uint8), bitorder="little")[:m].astype(bool)
     out["oracle"] = {"reference": "BVH::Build + BVH::Intersect / IsOccluded (the parity oracle; another tree than the one traced)",
                      "prim_mismatch": cls["mismatch"], "tie_equivalent": cls["tie_equivalent"], "real": cls["real"],
                      "hit_miss_flips": int(((w2["t"] < 1e30) != (got["t"] < 1e30)).sum()), "t_max_rel_err": float(rel.max()) if rel.size else 0.0,

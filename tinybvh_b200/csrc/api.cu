@@ -193,7 +193,7 @@ int tbvh_ctx_create( int device, tbvh_ctx* out )
 	const int rc = body();
 	if (rc != TBVH_OK) { tbvh_ctx_destroy( c ); return rc; }
 	const char* hp = getenv( "TBVH_HOST_PATH" );
-	c->host_path = hp && (!strcmp( hp, "zerocopy" ) || !strcmp( hp, "1" )) ? 1 : 0;
+	c->host_path = hp && (!strcmp( hp, "zerocopy" ) || !strcmp( hp, "1" )) ? 1 : hp && !strcmp( hp, "2" ) ? 2 : 0;
 	const char* tv = getenv( "TBVH_TRACE_VARIANT" );
 	c->trace_variant = tv ? atoi( tv ) : 3; // octant switch: +5 % on camera / shadow rays, -3 % on diffuse (profiles/README.md)
 	const char* st = getenv( "TBVH_SMALL_T" );
@@ -226,7 +226,7 @@ static void free_slots( tbvh_ctx c )
 		if (c->slot[i].h_hits) cudaFreeHost( c->slot[i].h_hits );
 		c->slot[i].d_rays = c->slot[i].d_hits = c->slot[i].d_bits = c->slot[i].h_hits = 0;
 	}
-	c->slot_rays = 0;
+	c->slot_rays = 0, c->slot_rec = 0;
 }
 
 int tbvh_ctx_destroy( tbvh_ctx c )
@@ -272,7 +272,11 @@ int tbvh_set_option( tbvh_ctx c, const char* key, int value )
 		c->pool = 0, c->scatter_threads = value;
 	}
 	else if (!strcmp( key, "h2d_split" )) c->h2d_split = value < 1 ? 1 : value > 4 ? 4 : value;
-	else if (!strcmp( key, "host_path" )) c->host_path = value == 1 ? 1 : 0;
+	else if (!strcmp( key, "host_path" ))
+	{
+		std::lock_guard<std::mutex> lk( c->host_mutex );
+		c->host_path = value == 1 ? 1 : value == 2 ? 2 : 0;
+	}
 	else if (!strcmp( key, "chunk_rays" ))
 	{
 		ARG_CHECK( value >= 4096, "chunk_rays must be at least 4096" );
@@ -938,24 +942,33 @@ static void* mapped_alias( const void* host )
 
 static int ensure_slots( tbvh_ctx c )
 {
-	if (c->slot_rays == c->chunk_rays) return TBVH_OK;
+	const size_t rec = c->host_path == 2 ? 128 : 64; // host_path 2 stages whole 128-byte records
+	if (c->slot_rays == c->chunk_rays && c->slot_rec >= rec) return TBVH_OK;
 	free_slots( c );
 	for (int i = 0; i < TBVH_SLOTS; i++)
 	{
-		CUDA_TRY( cudaMalloc( &c->slot[i].d_rays, c->chunk_rays * 64 ) );
+		CUDA_TRY( cudaMalloc( &c->slot[i].d_rays, c->chunk_rays * rec ) );
 		CUDA_TRY( cudaMalloc( &c->slot[i].d_hits, c->chunk_rays * 16 ) );
 		CUDA_TRY( cudaMalloc( &c->slot[i].d_bits, c->chunk_rays / 8 + 4 ) );
 	}
-	c->slot_rays = c->chunk_rays;
+	c->slot_rays = c->chunk_rays, c->slot_rec = rec;
 	return TBVH_OK;
 }
 
 // inbound stage of one chunk: on return s_in carries the copy and slot.in_done is recorded behind it
-static int stage_in( tbvh_ctx c, const int k, const uint64_t chunk, const char* h, const char* h_dev, const uint32_t stride, const uint64_t cnt )
+static int stage_in( tbvh_ctx c, const int k, const uint64_t chunk, const char* h, const char* h_dev, const uint32_t stride, const uint64_t cnt, uint32_t* staged_stride )
 {
 	HostSlot& sl = c->slot[k];
+	*staged_stride = 64;
 	if (chunk >= TBVH_SLOTS) CUDA_TRY( cudaStreamWaitEvent( c->s_in, sl.out_done, 0 ) ); // the slot's previous tenant has left the device
-	if (c->host_path == 1 && h_dev && (stride & 15) == 0)
+	if (c->host_path == 2 && stride == 128 && c->slot_rec >= 128)
+	{
+		// whole records, one contiguous copy: twice the bytes, but large read requests (the 64-byte rows of the 2D copy keep the link
+		// at ~37 GB/s of useful data; a contiguous copy runs at ~54 GB/s, i.e. 27 GB/s useful - profiles/README.md has the numbers)
+		CUDA_TRY( cudaMemcpyAsync( sl.d_rays, h, cnt * 128, cudaMemcpyHostToDevice, c->s_in ) );
+		*staged_stride = 128;
+	}
+	else if (c->host_path == 1 && h_dev && (stride & 15) == 0)
 	{
 		const uint64_t threads = cnt * 4;
 		k_gather_rays<<<(uint32_t)((threads + 255) / 256), 256, 0, c->s_in>>>( (const float4*)h_dev, stride / 16, (float4*)sl.d_rays, cnt );
@@ -1046,12 +1059,13 @@ static int intersect_host( tbvh_bvh b, int layout, void* rays, uint32_t stride, 
 		auto body = [&]() -> int
 		{
 			if (host_scatter && chunk >= TBVH_SLOTS) TRY( scatter_chunk( chunk - TBVH_SLOTS ) ); // frees this slot's staging
-			TRY( stage_in( c, k, chunk, h, hd, stride, cnt ) );
-			if (tlas) TRY( tlas_trace_launch( b, sl.d_rays, 64, 0, cnt, false, c->s_run ) );  // hit + instance written into the staged records
-			else TRY( trace_dispatch( b, layout, sl.d_rays, 64, sl.d_hits, 16, 0, cnt, false, c->s_run ) );
+			uint32_t ss = 64;
+			TRY( stage_in( c, k, chunk, h, hd, stride, cnt, &ss ) );
+			if (tlas) TRY( tlas_trace_launch( b, sl.d_rays, ss, 0, cnt, false, c->s_run ) );  // hit + instance written into the staged records
+			else TRY( trace_dispatch( b, layout, sl.d_rays, ss, sl.d_hits, 16, 0, cnt, false, c->s_run ) );
 			CUDA_TRY( cudaEventRecord( sl.run_done, c->s_run ) );
 			CUDA_TRY( cudaStreamWaitEvent( c->s_out, sl.run_done, 0 ) );
-			if (tlas) CUDA_TRY( cudaMemcpy2DAsync( h + 44, stride, (char*)sl.d_rays + 44, 64, 20, cnt, cudaMemcpyDeviceToHost, c->s_out ) );
+			if (tlas) CUDA_TRY( cudaMemcpy2DAsync( h + 44, stride, (char*)sl.d_rays + 44, ss, 20, cnt, cudaMemcpyDeviceToHost, c->s_out ) );
 			else if (packed_hits) CUDA_TRY( cudaMemcpyAsync( (char*)packed_hits + off * 16, sl.d_hits, cnt * 16, cudaMemcpyDeviceToHost, c->s_out ) );
 			else if (host_scatter) CUDA_TRY( cudaMemcpyAsync( sl.h_hits, sl.d_hits, cnt * 16, cudaMemcpyDeviceToHost, c->s_out ) );
 			else if (scatter)
@@ -1099,9 +1113,10 @@ int tbvh_occluded( tbvh_bvh b, int layout, const void* rays, uint32_t stride, ui
 		const char* h = (const char*)rays + off * stride;
 		auto body = [&]() -> int
 		{
-			TRY( stage_in( c, k, chunk, h, dev_alias ? dev_alias + off * stride : 0, stride, cnt ) );
-			if (b->d_inst) TRY( tlas_trace_launch( b, sl.d_rays, 64, (uint32_t*)sl.d_bits, cnt, true, c->s_run ) );
-			else TRY( trace_dispatch( b, layout, sl.d_rays, 64, 0, 0, (uint32_t*)sl.d_bits, cnt, true, c->s_run ) );
+			uint32_t ss = 64;
+			TRY( stage_in( c, k, chunk, h, dev_alias ? dev_alias + off * stride : 0, stride, cnt, &ss ) );
+			if (b->d_inst) TRY( tlas_trace_launch( b, sl.d_rays, ss, (uint32_t*)sl.d_bits, cnt, true, c->s_run ) );
+			else TRY( trace_dispatch( b, layout, sl.d_rays, ss, 0, 0, (uint32_t*)sl.d_bits, cnt, true, c->s_run ) );
 			CUDA_TRY( cudaEventRecord( sl.run_done, c->s_run ) );
 			CUDA_TRY( cudaStreamWaitEvent( c->s_out, sl.run_done, 0 ) );
 			CUDA_TRY( cudaMemcpyAsync( bits + off / 32, sl.d_bits, ((cnt + 31) / 32) * 4, cudaMemcpyDeviceToHost, c->s_out ) ); // chunk_rays is a multiple of 32

@@ -46,7 +46,8 @@ struct tbvh_ctx_t
 	HostSlot slot[TBVH_SLOTS];
 	size_t chunk_rays = 1u << 19;    // rays per chunk (32 MiB of device records)
 	size_t slot_rays = 0;            // capacity the slots were allocated for
-	int host_path = 0;               // inbound: 0 = copy engine (cudaMemcpy2DAsync of 64-byte rows), 1 = gather kernel through the pinned mapping
+	size_t slot_rec = 0;             // bytes per staged ray record the slots were allocated for (64, or 128 under host_path 2)
+	int host_path = 0;               // inbound: 0 = copy engine (cudaMemcpy2DAsync of 64-byte rows), 1 = gather kernel through the pinned mapping, 2 = whole 128-byte records in one contiguous copy
 	int h2d_split = 1;               // inbound 2D copy of a chunk split over this many streams (copy engines)
 	int d2h_mode = 0;                // in-place hits: 0 = 2D copy of 16-byte rows, 2 = packed copy + host threads scatter, 3 = scatter kernel through the pinned mapping
 	int scatter_threads = 8;         // d2h_mode 2: host threads (bound to the device's NUMA node) that write the hits into the records

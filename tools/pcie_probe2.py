@@ -66,7 +66,14 @@ h = api.pinned_empty(n, R.RAY_DTYPE, device=0)
 api.bind_to_device(0)
 fill(h)
 run("local pinned buffer", h)
-for thr in (4, 8, 16, 32):
+api.set_option("host_path", 2)
+run("local, whole-record inbound", h)
+api.set_option("d2h_mode", 2)
+api.set_option("scatter_threads", 32)
+run("local, whole-record + scatter x32", h)
+api.set_option("d2h_mode", 0)
+api.set_option("host_path", 0)
+for thr in (32,):
     api.set_option("d2h_mode", 2)
     api.set_option("scatter_threads", thr)
     run(f"local, host scatter x{thr}", h)
