@@ -210,6 +210,34 @@ public:
 		sync_info();
 	}
 	void Download( void* bvhNode, uint32_t* primIdx ) const { TBVH_FATAL_IF( tbvh_download_bvh( h, bvhNode, primIdx, TBVH_HOST ), "BVH::Download" ); }
+#ifdef TINY_BVH_H_
+	// BVH::Save / BVH::Load (tiny_bvh.h:1747-1799).  The reference's file is a version word, the triangle count, the C++ object
+	// itself and the node / primIdx arrays, so the format is whatever the tiny_bvh.h the host program was compiled with says it is:
+	// with that header included before this one, a GPU-built tree is handed to a tinybvh::BVH object and written / read by the
+	// reference's own code - files are interchangeable with the reference's in both directions.
+	void ToReference( tinybvh::BVH& out ) const // a CPU-side tinybvh::BVH holding the GPU-built tree (SAHCost, Save, ConvertFrom, Intersect ...)
+	{
+		const tbvh_info i = Info();
+		out.AlignedFree( out.bvhNode ), out.AlignedFree( out.primIdx );
+		out.bvhNode = (tinybvh::BVH::BVHNode*)out.AlignedAlloc( (size_t)i.used_nodes * 32 );
+		out.primIdx = (uint32_t*)out.AlignedAlloc( (size_t)i.idx_count * 4 );
+		Download( out.bvhNode, out.primIdx );
+		out.allocatedNodes = out.usedNodes = i.used_nodes, out.triCount = i.prim_count, out.idxCount = i.idx_count;
+		out.aabbMin = tinybvh::bvhvec3( i.aabb_min[0], i.aabb_min[1], i.aabb_min[2] ), out.aabbMax = tinybvh::bvhvec3( i.aabb_max[0], i.aabb_max[1], i.aabb_max[2] );
+		out.c_trav = c_trav, out.c_int = c_int, out.may_have_holes = false, out.rebuildable = false; // no fragments on the host: not rebuildable
+		out.refittable = i.idx_count == i.prim_count; // an SBVH cannot be refitted (:3027)
+		if (vertsPtr) out.verts = tinybvh::bvhvec4slice{ (const tinybvh::bvhvec4*)vertsPtr, vertsPrims * 3, vertsStride };
+	}
+	void Save( const char* fileName ) const { tinybvh::BVH tmp; ToReference( tmp ); tmp.Save( fileName ); }
+	template <class Vec4> bool Load( const char* fileName, const Vec4* vertices, const uint32_t primCount )
+	{
+		tinybvh::BVH tmp;
+		if (!tmp.Load( fileName, (const tinybvh::bvhvec4*)vertices, primCount )) return false;
+		Upload( tmp.bvhNode, tmp.usedNodes, tmp.primIdx, tmp.idxCount, vertices, primCount );
+		remember( vertices, (uint32_t)sizeof( Vec4 ), 0, primCount );
+		return true;
+	}
+#endif
 private:
 	void remember( const void* v, uint32_t stride, const uint32_t* idx, uint32_t prims ) { vertsPtr = v, vertsStride = stride, vertIdx = idx, vertsPrims = prims; }
 	const void* vertsPtr = 0; const uint32_t* vertIdx = 0; // BVHBase::verts / vertIdx (:806-807): pointers to the caller's arrays, for Refit
@@ -295,6 +323,33 @@ public:
 		usedBlocks = blocks, idxCount = triRecords;
 	}
 	void Download( void* bvh8Data, void* bvh8Tris ) const { TBVH_FATAL_IF( tbvh_download_cwbvh( h, bvh8Data, bvh8Tris, TBVH_HOST ), "BVH8_CWBVH::Download" ); }
+#ifdef TINY_BVH_H_
+	// BVH8_CWBVH::Save / Load (tiny_bvh.h:5786-5820), through the reference's own code (see BVH::Save above): caches written here
+	// load in tools built on the reference (tmpl8/game.cpp:78-81) and the other way round.
+	void ToReference( tinybvh::BVH8_CWBVH& out ) const
+	{
+		const tbvh_info i = Info();
+		out.AlignedFree( out.bvh8Data ), out.AlignedFree( out.bvh8Tris );
+		out.bvh8Data = (tinybvh::bvhvec4*)out.AlignedAlloc( (size_t)i.used_blocks * 16 );
+		out.bvh8Tris = (tinybvh::bvhvec4*)out.AlignedAlloc( (size_t)i.cwbvh_tri_count * 4 * 16 ); // the reference sizes it 4 blocks per triangle (:5895)
+		memset( out.bvh8Tris, 0, (size_t)i.cwbvh_tri_count * 4 * 16 );
+		Download( out.bvh8Data, out.bvh8Tris );
+		out.allocatedBlocks = out.usedBlocks = i.used_blocks;
+		out.triCount = i.prim_count, out.idxCount = i.cwbvh_tri_count, out.usedNodes = i.used_blocks / 5;
+		out.bvh8.triCount = i.prim_count, out.bvh8.idxCount = i.cwbvh_tri_count; // Save sizes the triangle block from bvh8.idxCount (:5796)
+		out.aabbMin = tinybvh::bvhvec3( i.aabb_min[0], i.aabb_min[1], i.aabb_min[2] ), out.aabbMax = tinybvh::bvhvec3( i.aabb_max[0], i.aabb_max[1], i.aabb_max[2] );
+		out.c_trav = c_trav, out.c_int = c_int, out.rebuildable = false, out.refittable = false;
+	}
+	void Save( const char* fileName ) const { tinybvh::BVH8_CWBVH tmp; ToReference( tmp ); tmp.Save( fileName ); }
+	bool Load( const char* fileName, const uint32_t expectedTris )
+	{
+		tinybvh::BVH8_CWBVH tmp;
+		if (!tmp.Load( fileName, expectedTris )) return false;
+		Upload( tmp.bvh8Data, tmp.usedBlocks, tmp.bvh8Tris, tmp.idxCount );
+		triCount = tmp.triCount;
+		return true;
+	}
+#endif
 };
 
 } // namespace tinybvh_b200

@@ -81,3 +81,19 @@ def test_patched_reference_speedtest_runs(gpu):
     assert "BVH traversal speed - GPU (B200, tinybvh_b200)" in r.stdout
     assert "!! Validation" not in r.stdout.split("BVH traversal speed - GPU (B200, tinybvh_b200)")[1].split("BVH traversal speed - CPU multi-core")[0]
     assert "- BVH8_CWBVH  - primary:" in r.stdout and "(host buffers)" in r.stdout
+
+
+@pytest.mark.gpu
+def test_save_load_round_trips_with_the_reference(gpu):
+    """BVH::Save / Load and BVH8_CWBVH::Save / Load (tiny_bvh.h:1747-1799, 5786-5820) between the engine and the compiled reference,
+    both directions (harness/saveload_b200.cpp, built by `make -C oracle saveload` where the reference header exists)."""
+    import tempfile
+    exe = os.path.join(REPO, "oracle", "_ref", "saveload_b200")
+    scene = os.path.join(REPO, "data", "scenes", "bunny.bin")
+    if not (os.path.isfile(exe) and os.path.isfile(scene)):
+        pytest.skip("saveload_b200 binary or bunny fixture not present")
+    with tempfile.TemporaryDirectory() as d:
+        r = subprocess.run([exe, scene, d], capture_output=True, text=True, timeout=600)
+    print(r.stdout)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+    assert "all round trips ok" in r.stdout

@@ -145,3 +145,22 @@ def test_concurrent_host_calls_on_one_handle(gpu):
     [t.start() for t in th]
     [t.join() for t in th]
     assert not errs, errs
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+@pytest.mark.parametrize("ntris,seed", [(90000, 75), (3000, 76), (129, 77)])
+def test_both_large_phase_drivers_build_the_reference_tree(gpu, mode, ntris, seed):
+    """build_mode 0 = the persistent cooperative launch (k_large_phase), 1 = one launch per stage and level: same tree, byte for byte."""
+    v = scenes.procedural_scene(ntris, seed)
+    o = util.oracle_bvh(v)
+    api.set_option("build_mode", mode)
+    try:
+        nodes, idx = api.BVH().Build(v).download()
+        assert np.array_equal(nodes.view(np.uint32), np.ascontiguousarray(o.nodes).view(np.uint32)) and np.array_equal(idx, o.prim_idx)
+        nodes2, _ = api.BVH().BuildAVX(v).download()
+        from oracle import refpy
+        if refpy.available():
+            ra = refpy.RefBVH(v, mode=1, threaded=False)
+            assert np.array_equal(nodes2.view(np.uint32), np.ascontiguousarray(ra.nodes).view(np.uint32))
+    finally:
+        api.set_option("build_mode", 0)

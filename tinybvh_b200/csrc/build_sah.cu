@@ -39,8 +39,10 @@ struct Counters
 	uint32_t small_roots;    // subtree roots for k_build_small
 	uint32_t max_depth;
 	uint32_t total_chunks;   // chunks of the current level list
+	uint32_t cur_num;        // persistent large phase: nodes of the current level
+	uint32_t levels;         // persistent large phase: levels run
 	uint32_t root_key[6];    // root AABB as ordered keys: min xyz, max xyz
-	uint32_t pad;
+	uint32_t pad[3];
 };
 
 struct BuildArgs
@@ -51,8 +53,9 @@ struct BuildArgs
 	uint32_t* idx[2]; uint32_t* idx_final;
 	uint16_t* bin_ids;
 	uint32_t* flags; uint32_t* scan; uint32_t* pos_bl;
+	uint32_t* chunk_pre;     // persistent large phase: exclusive prefix of the per-chunk flag totals (chunks + 1 entries)
 	float4* tmp_nodes; uint32_t* node_first; uint32_t* node_depth;
-	LargeNode* lvl[2]; uint32_t* chunk_start; uint32_t* bins; SplitInfo* split;
+	LargeNode* lvl[2]; uint32_t* chunk_start; uint32_t* chunk_start_next; uint32_t* bins; SplitInfo* split;
 	SmallRoot* small;
 	Counters* ctr;
 	uint32_t n;
@@ -284,7 +287,7 @@ __global__ void __launch_bounds__( 256 ) k_fragments( BuildArgs A )
 __global__ void k_init_counters( BuildArgs A )
 {
 	Counters* c = A.ctr;
-	c->tmp_nodes = 2, c->next_large = 0, c->small_roots = 0, c->max_depth = 0, c->total_chunks = 0;
+	c->tmp_nodes = 2, c->next_large = 0, c->small_roots = 0, c->max_depth = 0, c->total_chunks = 0, c->cur_num = 0, c->levels = 0;
 	for (int k = 0; k < 3; k++) c->root_key[k] = 0xffffffffu, c->root_key[3 + k] = 0;
 }
 
@@ -300,7 +303,7 @@ __global__ void k_init_root( BuildArgs A )
 	{
 		A.lvl[0][0] = LargeNode{ 0, 0, A.n, 0 };
 		A.chunk_start[0] = 0, A.chunk_start[1] = (A.n + CHUNK - 1) / CHUNK;
-		c->total_chunks = (A.n + CHUNK - 1) / CHUNK;
+		c->total_chunks = (A.n + CHUNK - 1) / CHUNK, c->cur_num = 1;
 		for (int k = threadIdx.x; k < BIN_STRIDE; k += blockDim.x) A.bins[k] = bin_init_word( k );
 	}
 	else if (threadIdx.x == 0)
@@ -313,31 +316,35 @@ __global__ void k_init_root( BuildArgs A )
 // ---------------------------------------------------------------------------------------------- large phase
 
 // chunk c of the current level -> (slot j in the node list, first offset inside the node)
-__device__ __forceinline__ uint32_t find_slot( const uint32_t* __restrict__ chunk_start, const uint32_t num, const uint32_t c )
+__device__ __forceinline__ uint32_t find_slot( const uint32_t* chunk_start, const uint32_t num, const uint32_t c )
 {
 	uint32_t lo = 0, hi = num; // largest j with chunk_start[j] <= c
-	while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if (__ldg( chunk_start + mid ) <= c) lo = mid; else hi = mid; }
+	while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if (chunk_start[mid] <= c) lo = mid; else hi = mid; }
 	return lo;
 }
 
-__global__ void __launch_bounds__( CHUNK ) k_bin( BuildArgs A, const LargeNode* __restrict__ cur, const uint32_t num, const uint32_t* __restrict__ idx_in )
+// The per-chunk / per-node bodies of the large phase are device functions over a VIRTUAL block index `vb`: the launch-per-stage
+// path calls them with blockIdx.x, the persistent path (k_large_phase) loops them over the level's chunks between grid-wide
+// barriers.  Inside the persistent kernel the arrays they read were written earlier in the same launch, so none of these loads
+// may take the read-only (.nc) path: LD() is a plain load there.
+#define LD( p ) (*(p))
+__device__ __forceinline__ void bin_chunk( BuildArgs& A, const LargeNode* cur, const uint32_t num, const uint32_t* idx_in, const uint32_t vb, uint32_t* s_bins, uint32_t& s_slot )
 {
 	// binning :2357-2376 for one 256-primitive chunk of one node: shared-memory table, then one flush per CTA
-	__shared__ uint32_t s_bins[BIN_STRIDE];
-	__shared__ uint32_t s_slot;
-	if (threadIdx.x == 0) s_slot = find_slot( A.chunk_start, num, blockIdx.x );
+	__syncthreads(); // the previous user of s_bins / s_slot (an earlier chunk of this CTA) is done
+	if (threadIdx.x == 0) s_slot = find_slot( A.chunk_start, num, vb );
 	for (int k = threadIdx.x; k < BIN_STRIDE; k += CHUNK) s_bins[k] = bin_init_word( k );
 	__syncthreads();
 	const uint32_t j = s_slot;
 	const LargeNode nd = cur[j];
-	const uint32_t off = (blockIdx.x - __ldg( A.chunk_start + j )) * CHUNK + threadIdx.x;
+	const uint32_t off = (vb - LD( A.chunk_start + j )) * CHUNK + threadIdx.x;
 	const bool valid = off < nd.count;
 	uint32_t b3[3] = { 0, 0, 0 }, kmn[3] = { 0xffffffffu, 0xffffffffu, 0xffffffffu }, kmx[3] = { 0, 0, 0 };
 	if (valid)
 	{
-		const float4 nmin = __ldg( A.tmp_nodes + (size_t)nd.tmp * 2 ), nmax = __ldg( A.tmp_nodes + (size_t)nd.tmp * 2 + 1 );
-		const uint32_t p = nd.first + off, fi = __ldg( idx_in + p );
-		const float4 fmn = __ldg( A.frag_min + fi ), fmx = __ldg( A.frag_max + fi );
+		const float4 nmin = LD( A.tmp_nodes + (size_t)nd.tmp * 2 ), nmax = LD( A.tmp_nodes + (size_t)nd.tmp * 2 + 1 );
+		const uint32_t p = nd.first + off, fi = LD( idx_in + p );
+		const float4 fmn = __ldg( A.frag_min + fi ), fmx = __ldg( A.frag_max + fi ); // fragments are written by an earlier launch
 		if (A.flavour)
 		{
 			const float rx = rpd_avx( __fsub_rn( nmax.x, nmin.x ) ), ry = rpd_avx( __fsub_rn( nmax.y, nmin.y ) ), rz = rpd_avx( __fsub_rn( nmax.z, nmin.z ) );
@@ -371,6 +378,12 @@ __global__ void __launch_bounds__( CHUNK ) k_bin( BuildArgs A, const LargeNode* 
 	}
 	else if (threadIdx.x < BIN_STRIDE && A.flavour && s_bins[threadIdx.x] != 0) atomicAdd( A.bins + (size_t)j * BIN_STRIDE + threadIdx.x, s_bins[threadIdx.x] );
 }
+__global__ void __launch_bounds__( CHUNK ) k_bin( BuildArgs A, const LargeNode* cur, const uint32_t num, const uint32_t* idx_in )
+{
+	__shared__ uint32_t s_bins[BIN_STRIDE];
+	__shared__ uint32_t s_slot;
+	bin_chunk( A, cur, num, idx_in, blockIdx.x, s_bins, s_slot );
+}
 
 // append the two children of a split node: bigger than SMALL_T -> next level's list, else -> warp-built subtree
 __device__ __forceinline__ void emit_child( BuildArgs& A, LargeNode* next, const uint32_t tmp, const uint32_t first, const uint32_t count, const uint32_t depth, const uint32_t out_buf )
@@ -379,11 +392,9 @@ __device__ __forceinline__ void emit_child( BuildArgs& A, LargeNode* next, const
 	else A.small[atomicAdd( &A.ctr->small_roots, 1u )] = SmallRoot{ tmp, first, count, depth | (out_buf << 16) };
 }
 
-__global__ void __launch_bounds__( 256 ) k_sweep( BuildArgs A, const LargeNode* __restrict__ cur, LargeNode* next, const uint32_t num,
-	const uint32_t* __restrict__ idx_in, const uint32_t out_buf )
+__device__ __forceinline__ void sweep_one( BuildArgs& A, const LargeNode* cur, LargeNode* next, const uint32_t j, const uint32_t* idx_in, const uint32_t out_buf )
 {
-	const uint32_t j = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-	if (j >= num) return;
+	const uint32_t lane = threadIdx.x & 31;
 	const LargeNode nd = cur[j];
 	const float4 nmin = A.tmp_nodes[(size_t)nd.tmp * 2], nmax = A.tmp_nodes[(size_t)nd.tmp * 2 + 1];
 	const float4 rmin = A.tmp_nodes[0], rmax = A.tmp_nodes[1];
@@ -413,20 +424,30 @@ __global__ void __launch_bounds__( 256 ) k_sweep( BuildArgs A, const LargeNode* 
 		emit_child( A, next, n + 1, nd.first + R.lN, nd.count - R.lN, d, out_buf );
 	}
 }
-
-__global__ void __launch_bounds__( CHUNK ) k_flags( BuildArgs A, const LargeNode* __restrict__ cur, const uint32_t num )
+__global__ void __launch_bounds__( 256 ) k_sweep( BuildArgs A, const LargeNode* cur, LargeNode* next, const uint32_t num, const uint32_t* idx_in, const uint32_t out_buf )
 {
-	__shared__ uint32_t s_slot;
-	if (threadIdx.x == 0) s_slot = find_slot( A.chunk_start, num, blockIdx.x );
+	const uint32_t j = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+	if (j < num) sweep_one( A, cur, next, j, idx_in, out_buf );
+}
+
+__device__ __forceinline__ uint32_t flag_of( BuildArgs& A, const LargeNode* cur, const uint32_t num, const uint32_t vb, uint32_t& s_slot )
+{
+	__syncthreads();
+	if (threadIdx.x == 0) s_slot = find_slot( A.chunk_start, num, vb );
 	__syncthreads();
 	const uint32_t j = s_slot;
 	const LargeNode nd = cur[j];
 	const SplitInfo sp = A.split[j];
-	const uint32_t off = (blockIdx.x - __ldg( A.chunk_start + j )) * CHUNK + threadIdx.x;
+	const uint32_t off = (vb - LD( A.chunk_start + j )) * CHUNK + threadIdx.x;
 	// flags live in CHUNK SPACE (index = chunk * CHUNK + lane): the scan then costs O(active primitives) per level, and a
 	// node's flags stay contiguous because its chunks are; padding lanes of a node's last chunk carry 0
 	const uint32_t p = nd.first + off;
-	A.flags[(size_t)blockIdx.x * CHUNK + threadIdx.x] = (off < nd.count && sp.did && ((((uint32_t)A.bin_ids[p]) >> (3 * sp.axis)) & 7u) <= sp.pos) ? 1u : 0u;
+	return (off < nd.count && sp.did && ((((uint32_t)A.bin_ids[p]) >> (3 * sp.axis)) & 7u) <= sp.pos) ? 1u : 0u;
+}
+__global__ void __launch_bounds__( CHUNK ) k_flags( BuildArgs A, const LargeNode* cur, const uint32_t num )
+{
+	__shared__ uint32_t s_slot;
+	A.flags[(size_t)blockIdx.x * CHUNK + threadIdx.x] = flag_of( A, cur, num, blockIdx.x, s_slot );
 }
 
 // exclusive scan of flags[0..n) into scan[0..n] (scan[n] = total): tile sums, one-block spine, apply
@@ -492,40 +513,55 @@ __global__ void __launch_bounds__( 256 ) k_scan_apply( const uint32_t* __restric
 	if (base < n && base + 8 >= n) out[n] = run; // the thread holding the last element publishes the total
 }
 
-__global__ void __launch_bounds__( CHUNK ) k_posbl( BuildArgs A, const LargeNode* __restrict__ cur, const uint32_t num )
+// exclusive prefix of the flags at chunk-space index i.  PERSIST = false: A.scan holds the global scan (exclusive_scan);
+// PERSIST = true: A.scan holds the prefix inside each chunk and A.chunk_pre the exclusive prefix over chunk totals.
+template <bool PERSIST> __device__ __forceinline__ uint32_t scan_at( const BuildArgs& A, const size_t i )
 {
-	__shared__ uint32_t s_slot;
-	if (threadIdx.x == 0) s_slot = find_slot( A.chunk_start, num, blockIdx.x );
+	return PERSIST ? A.chunk_pre[i / CHUNK] + A.scan[i] : A.scan[i];
+}
+template <bool PERSIST> __device__ __forceinline__ void posbl_chunk( BuildArgs& A, const LargeNode* cur, const uint32_t num, const uint32_t vb, uint32_t& s_slot )
+{
+	__syncthreads();
+	if (threadIdx.x == 0) s_slot = find_slot( A.chunk_start, num, vb );
 	__syncthreads();
 	const uint32_t j = s_slot;
 	const LargeNode nd = cur[j];
 	const SplitInfo sp = A.split[j];
-	const uint32_t off = (blockIdx.x - __ldg( A.chunk_start + j )) * CHUNK + threadIdx.x;
+	const uint32_t off = (vb - LD( A.chunk_start + j )) * CHUNK + threadIdx.x;
 	if (!sp.did || off >= nd.count || off < sp.L) return;
-	const size_t sb = (size_t)__ldg( A.chunk_start + j ) * CHUNK; // this node's base in chunk space
-	if (A.flags[sb + off]) A.pos_bl[nd.first + (A.scan[sb + nd.count] - A.scan[sb + off + 1])] = off; // BL_k, k = lefts behind it
+	const size_t sb = (size_t)LD( A.chunk_start + j ) * CHUNK; // this node's base in chunk space
+	if (A.flags[sb + off]) A.pos_bl[nd.first + (scan_at<PERSIST>( A, sb + nd.count ) - scan_at<PERSIST>( A, sb + off + 1 ))] = off; // BL_k, k = lefts behind it
+}
+__global__ void __launch_bounds__( CHUNK ) k_posbl( BuildArgs A, const LargeNode* cur, const uint32_t num )
+{
+	__shared__ uint32_t s_slot;
+	posbl_chunk<false>( A, cur, num, blockIdx.x, s_slot );
 }
 
-__global__ void __launch_bounds__( CHUNK ) k_scatter( BuildArgs A, const LargeNode* __restrict__ cur, const uint32_t num,
-	const uint32_t* __restrict__ idx_in, uint32_t* __restrict__ idx_out )
+template <bool PERSIST> __device__ __forceinline__ void scatter_chunk( BuildArgs& A, const LargeNode* cur, const uint32_t num, const uint32_t* idx_in, uint32_t* idx_out, const uint32_t vb, uint32_t& s_slot )
 {
-	__shared__ uint32_t s_slot;
-	if (threadIdx.x == 0) s_slot = find_slot( A.chunk_start, num, blockIdx.x );
+	__syncthreads();
+	if (threadIdx.x == 0) s_slot = find_slot( A.chunk_start, num, vb );
 	__syncthreads();
 	const uint32_t j = s_slot;
 	const LargeNode nd = cur[j];
 	const SplitInfo sp = A.split[j];
-	const uint32_t off = (blockIdx.x - __ldg( A.chunk_start + j )) * CHUNK + threadIdx.x;
+	const uint32_t off = (vb - LD( A.chunk_start + j )) * CHUNK + threadIdx.x;
 	if (!sp.did || off >= nd.count) return;
-	const size_t sb = (size_t)__ldg( A.chunk_start + j ) * CHUNK; // this node's base in chunk space
-	const uint32_t p = nd.first + off, s0 = A.scan[sb];
-	const uint32_t lefts_before = A.scan[sb + off] - s0, lefts_in_F = A.scan[sb + sp.L] - s0;
+	const size_t sb = (size_t)LD( A.chunk_start + j ) * CHUNK; // this node's base in chunk space
+	const uint32_t p = nd.first + off, s0 = scan_at<PERSIST>( A, sb );
+	const uint32_t lefts_before = scan_at<PERSIST>( A, sb + off ) - s0, lefts_in_F = scan_at<PERSIST>( A, sb + sp.L ) - s0;
 	const uint32_t m = sp.L - lefts_in_F;
 	const bool extra = sp.L < nd.count && A.flags[sb + sp.L] == 0;
 	uint32_t pull;
 	const uint32_t dest = partition_dest( off, nd.count, sp.L, A.flags[sb + off] != 0, lefts_before, m, extra, A.pos_bl + nd.first, &pull );
 	if (dest != 0xffffffffu) idx_out[nd.first + dest] = idx_in[p];
 	if (pull != 0xffffffffu) idx_out[p] = idx_in[nd.first + pull];
+}
+__global__ void __launch_bounds__( CHUNK ) k_scatter( BuildArgs A, const LargeNode* cur, const uint32_t num, const uint32_t* idx_in, uint32_t* idx_out )
+{
+	__shared__ uint32_t s_slot;
+	scatter_chunk<false>( A, cur, num, idx_in, idx_out, blockIdx.x, s_slot );
 }
 
 // next level: chunk offsets (exclusive scan of ceil(count/CHUNK)) and fresh bin tables, by one block
@@ -564,6 +600,119 @@ __global__ void k_bins_init( uint32_t* bins, const uint32_t words )
 {
 	const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
 	if (k < words) bins[k] = bin_init_word( k % BIN_STRIDE );
+}
+
+// ---------------------------------------------------------------------------------------------- persistent large phase
+// The whole level loop in ONE cooperative launch: every stage of a level is a grid-stride loop over the level's chunks / nodes,
+// stages are separated by grid-wide barriers (cooperative groups), and the level bookkeeping that the launch-per-stage path
+// reads back to the host (how many nodes / chunks the next level has) stays in device memory.  A level costs six barriers
+// instead of eleven launches and a host round trip.
+#include <cooperative_groups.h>
+namespace cg = cooperative_groups;
+
+// block-wide exclusive scan helper for 256 threads: returns the exclusive prefix of v and, in `total`, the block total
+__device__ __forceinline__ uint32_t block_exscan_256( const uint32_t v, uint32_t* s_warp /* 8 */, uint32_t& total )
+{
+	const uint32_t lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+	uint32_t x = v;
+	for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync( 0xffffffffu, x, o ); if (lane >= o) x += y; }
+	__syncthreads();
+	if (lane == 31) s_warp[w] = x;
+	__syncthreads();
+	uint32_t wbase = 0, t = 0;
+	#pragma unroll
+	for (uint32_t k = 0; k < 8; k++) { const uint32_t sw = s_warp[k]; if (k < w) wbase += sw; t += sw; }
+	total = t;
+	return wbase + x - v;
+}
+
+__global__ void __launch_bounds__( CHUNK ) k_large_phase( BuildArgs A )
+{
+	cg::grid_group grid = cg::this_grid();
+	__shared__ uint32_t s_bins[BIN_STRIDE];
+	__shared__ uint32_t s_slot, s_carry;
+	__shared__ uint32_t s_warp[8];
+	Counters* C = A.ctr;
+	const uint32_t warps_per_block = CHUNK / 32, gwarp = blockIdx.x * warps_per_block + (threadIdx.x >> 5), gwarps = gridDim.x * warps_per_block;
+	for (uint32_t level = 0; level < 4096; level++)
+	{
+		const uint32_t num = C->cur_num, chunks = C->total_chunks;
+		if (num == 0) break; // uniform over the grid: the counters were written before the last barrier
+		const LargeNode* cur = A.lvl[level & 1];
+		LargeNode* next = A.lvl[(level + 1) & 1];
+		const uint32_t* idx_in = A.idx[level & 1];
+		uint32_t* idx_out = A.idx[(level + 1) & 1];
+		// ---- 1. bin tables of the level's nodes
+		for (uint32_t c = blockIdx.x; c < chunks; c += gridDim.x) bin_chunk( A, cur, num, idx_in, c, s_bins, s_slot );
+		grid.sync();
+		// ---- 2. one warp per node: sweep, termination, children
+		for (uint32_t j = gwarp; j < num; j += gwarps) sweep_one( A, cur, next, j, idx_in, (level + 1) & 1 );
+		grid.sync();
+		// ---- 3. left / right flags in chunk space + their prefix inside each chunk + the chunk totals
+		for (uint32_t c = blockIdx.x; c < chunks; c += gridDim.x)
+		{
+			const uint32_t f = flag_of( A, cur, num, c, s_slot );
+			uint32_t total;
+			const uint32_t pre = block_exscan_256( f, s_warp, total );
+			A.flags[(size_t)c * CHUNK + threadIdx.x] = f, A.scan[(size_t)c * CHUNK + threadIdx.x] = pre;
+			if (threadIdx.x == 0) A.chunk_pre[c] = total;
+		}
+		grid.sync();
+		// ---- 4. block 0: exclusive prefix over the chunk totals; block 1 (or 0): the next level's chunk offsets; all: fresh bin tables
+		const uint32_t num_next = C->next_large;
+		if (blockIdx.x == 0)
+		{
+			if (threadIdx.x == 0) s_carry = 0;
+			__syncthreads();
+			for (uint32_t base = 0; base < chunks; base += CHUNK)
+			{
+				const uint32_t i = base + threadIdx.x;
+				const uint32_t v = i < chunks ? A.chunk_pre[i] : 0;
+				uint32_t total;
+				const uint32_t pre = block_exscan_256( v, s_warp, total );
+				const uint32_t carry = s_carry;
+				if (i < chunks) A.chunk_pre[i] = carry + pre;
+				__syncthreads();
+				if (threadIdx.x == 0) s_carry = carry + total;
+				__syncthreads();
+			}
+			if (threadIdx.x == 0) A.chunk_pre[chunks] = s_carry, A.scan[(size_t)chunks * CHUNK] = 0; // scan_at( chunks * CHUNK ) = total
+		}
+		if (blockIdx.x == (gridDim.x > 1 ? 1u : 0u))
+		{
+			// chunk offsets of the next level: exclusive scan of ceil( count / CHUNK ) into a second array (the current one is
+			// still needed by stages 5 and 6); swapped in after the last barrier of the level
+			__syncthreads();
+			if (threadIdx.x == 0) s_carry = 0;
+			__syncthreads();
+			for (uint32_t base = 0; base < num_next; base += CHUNK)
+			{
+				const uint32_t i = base + threadIdx.x;
+				const uint32_t v = i < num_next ? (next[i].count + CHUNK - 1) / CHUNK : 0;
+				uint32_t total;
+				const uint32_t pre = block_exscan_256( v, s_warp, total );
+				const uint32_t carry = s_carry;
+				if (i < num_next) A.chunk_start_next[i] = carry + pre;
+				__syncthreads();
+				if (threadIdx.x == 0) s_carry = carry + total;
+				__syncthreads();
+			}
+			if (threadIdx.x == 0) A.chunk_start_next[num_next] = s_carry, C->pad[0] = s_carry; // next level's chunk count, parked
+		}
+		// the bin tables were consumed in stage 2: re-arm them for the next level's nodes
+		for (uint32_t k = blockIdx.x * CHUNK + threadIdx.x; k < num_next * BIN_STRIDE; k += gridDim.x * CHUNK) A.bins[k] = bin_init_word( k % BIN_STRIDE );
+		grid.sync();
+		// ---- 5. positions of the lefts behind the split point
+		for (uint32_t c = blockIdx.x; c < chunks; c += gridDim.x) posbl_chunk<true>( A, cur, num, c, s_slot );
+		grid.sync();
+		// ---- 6. the swap partition as a permutation into the other index buffer
+		for (uint32_t c = blockIdx.x; c < chunks; c += gridDim.x) scatter_chunk<true>( A, cur, num, idx_in, idx_out, c, s_slot );
+		grid.sync();
+		// ---- level hand-over (every block computes the same values; block 0 publishes them after everyone has read the old ones)
+		for (uint32_t k = blockIdx.x * CHUNK + threadIdx.x; k <= num_next; k += gridDim.x * CHUNK) A.chunk_start[k] = A.chunk_start_next[k];
+		if (blockIdx.x == 0 && threadIdx.x == 0) C->cur_num = num_next, C->total_chunks = C->pad[0], C->next_large = 0, C->levels = level + 1;
+		grid.sync();
+	}
 }
 
 // ---------------------------------------------------------------------------------------------- small subtrees
@@ -861,7 +1010,8 @@ int build_sah_launch( tbvh_bvh b, float c_trav, float c_int, int flavour )
 		DEV_ALLOC( A.flags, flag_words * 4 ); DEV_ALLOC( A.scan, flag_words * 4 ); DEV_ALLOC( A.pos_bl, ((size_t)n + 1) * 4 );
 		DEV_ALLOC( A.tmp_nodes, max_nodes * 32 ); DEV_ALLOC( A.node_first, max_nodes * 4 ); DEV_ALLOC( A.node_depth, max_nodes * 4 );
 		DEV_ALLOC( A.lvl[0], max_large * sizeof( LargeNode ) ); DEV_ALLOC( A.lvl[1], max_large * sizeof( LargeNode ) );
-		DEV_ALLOC( A.chunk_start, (max_large + 1) * 4 ); DEV_ALLOC( A.bins, max_large * BIN_STRIDE * 4 ); DEV_ALLOC( A.split, max_large * sizeof( SplitInfo ) );
+		DEV_ALLOC( A.chunk_start, (max_large + 1) * 4 ); DEV_ALLOC( A.chunk_start_next, (max_large + 1) * 4 ); DEV_ALLOC( A.bins, max_large * BIN_STRIDE * 4 ); DEV_ALLOC( A.split, max_large * sizeof( SplitInfo ) );
+		DEV_ALLOC( A.chunk_pre, (flag_words / CHUNK + 2) * 4 );
 		DEV_ALLOC( A.small, ((size_t)n + 1) * sizeof( SmallRoot ) );
 		DEV_ALLOC( A.ctr, sizeof( Counters ) );
 		DEV_ALLOC( tile_sum, (flag_words / SCAN_TILE + 2) * 4 );
@@ -872,6 +1022,21 @@ int build_sah_launch( tbvh_bvh b, float c_trav, float c_int, int flavour )
 		k_fragments<<<(n + 255) / 256, 256, 0, s>>>( A ); LAUNCHED();
 		k_init_root<<<1, 256, 0, s>>>( A ); LAUNCHED();
 		uint32_t num = n > A.small_t ? 1 : 0, chunks = (n + CHUNK - 1) / CHUNK, level = 0;
+		if (num && b->ctx->build_mode == 0)
+		{
+			// persistent large phase: one cooperative launch walks every level (k_large_phase); grid = what the device can hold
+			int per_sm = 0;
+			CUDA_TRY( cudaOccupancyMaxActiveBlocksPerMultiprocessor( &per_sm, k_large_phase, CHUNK, 0 ) );
+			if (per_sm > 4) per_sm = 4; // more resident CTAs only make the barriers slower
+			if (per_sm >= 1)
+			{
+				const uint32_t grid = (uint32_t)(per_sm * b->ctx->sm_count);
+				void* params[] = { (void*)&A };
+				CUDA_TRY( cudaLaunchCooperativeKernel( (const void*)k_large_phase, dim3( grid ), dim3( CHUNK ), params, 0, s ) );
+				g_tbvh_launches++;
+				num = 0; // the level loop below is skipped
+			}
+		}
 		while (num)
 		{
 			const LargeNode* cur = A.lvl[level & 1];

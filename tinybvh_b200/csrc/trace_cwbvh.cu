@@ -13,14 +13,14 @@
 //    turn bytes into floats and ~90 test slots that hold no child - the reference's 8-wide collapse fills 4.4 of 8 slots on
 //    Bistro, 36 % of the nodes have two children):
 //        header   32 B   p.xyz | ex ey ez imask | first inner child | first triangle (float4 units) | pairs | -
-//        pair j   32 B   the (2j)-th and (2j+1)-th NON-EMPTY child:  lo.x lo.y lo.z hi.x hi.y hi.z as half2 (child a, child b)
-//                        - 0..255 is exact in fp16 - and one 32-bit hit word per child: a leaf child's triangle bits
+//        pair j   32 B   the (2j)-th and (2j+1)-th NON-EMPTY child:  lo.x lo.y lo.z hi.x hi.y hi.z as 16-bit float pairs (child a,
+//                        child b) - 0..255 is exact in bfloat16 and in fp16 - and one 32-bit hit word per child: a leaf child's triangle bits
 //                        `unary(count) << offset`, an inner child's slot bit `1 << (24 + slot)`
 //    Empty slots are gone, so a node costs ceil(children/2) pair steps, not 8 slot steps.
 //  * A pair step is packed fp32 arithmetic (Blackwell FFMA2, `fma.rn.f32x2`): one instruction evaluates the same plane of both
 //    children, 6 per pair instead of 12 FFMA, exactly rounded per component like the scalar fma.
-//  * The quantised planes reach the registers as halves and are widened by one conversion each (no byte extraction, no
-//    integer-to-float on the quarter-rate unit, no magic-number subtraction).
+//  * The quantised planes reach the registers as 16-bit floats and are widened by one instruction each (a shift or a mask for
+//    bfloat16; no byte extraction, no integer-to-float on the quarter-rate unit, no magic-number subtraction).
 //  * Near / far planes are picked per ray by the sign of rD once per pair on the packed words (3 selects for two children).
 //  * Inner-child bits are accumulated in slot order and moved to octant order by one 3-stage bit butterfly per node.
 //
@@ -31,6 +31,12 @@
 
 #define CW_STACK 128            // node groups a ray can have pending: one per level of the wide tree (the reference's own limit, tiny_bvh.h:7048)
 #define CW_NODE_F4 10           // float4 per traversal node
+// Quantised planes in the traversal nodes: 1 = bfloat16 pairs (0..255 is exact in 8 significant bits; widening is one shift for
+// the low half - an IMAD on the FMA pipe - and one mask for the high half), 0 = half pairs (two HADD2.F32, which ncu shows on
+// the ALU pipe next to the min / max / select work that already saturates it).
+#ifndef CW_PLANES_BF16
+#define CW_PLANES_BF16 1
+#endif
 
 // ---- bvh8Data -> traversal nodes ------------------------------------------------------------------------------------
 // One thread per node.  Slot i of the source node: meta byte i (n1.z / n1.w), quantised bounds byte i of the six 8-byte rows at
@@ -59,7 +65,7 @@ __global__ void k_cw_expand( const uint4* __restrict__ src, uint4* __restrict__ 
 		for (int r = 0; r < 6; r++)
 		{
 			const uint32_t q = (row[r][i >> 2] >> (8 * (i & 3))) & 255u;
-			const uint32_t h = (uint32_t)__half_as_ushort( __uint2half_rn( q ) );
+			const uint32_t h = CW_PLANES_BF16 ? __float_as_uint( (float)q ) >> 16 : (uint32_t)__half_as_ushort( __uint2half_rn( q ) );
 			#pragma unroll
 			for (int jj = 0; jj < 4; jj++) if (jj == (int)j) word[jj][r] |= side ? h << 16 : h;
 		}
@@ -124,7 +130,14 @@ int cw_make_trav( tbvh_bvh b, cudaStream_t s, int known_depth )
 
 // ---- traversal ------------------------------------------------------------------------------------------------------
 
-__device__ __forceinline__ float2 widen( const uint32_t h2 ) { return __half22float2( *(const __half2*)&h2 ); }
+__device__ __forceinline__ float2 widen( const uint32_t h2 )
+{
+#if CW_PLANES_BF16
+	return make_float2( __uint_as_float( h2 * 65536u ), __uint_as_float( h2 & 0xffff0000u ) );
+#else
+	return __half22float2( *(const __half2*)&h2 );
+#endif
+}
 
 // one pair of children against one ray: `near` / `far` words already chosen by the ray's signs
 __device__ __forceinline__ uint32_t pair_hits( const uint32_t wnx, const uint32_t wny, const uint32_t wnz, const uint32_t wfx, const uint32_t wfy, const uint32_t wfz,
