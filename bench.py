@@ -430,6 +430,31 @@ def run_ours(args):
     bits_dev = d_bits.cpu().numpy().view(np.uint32)
     hits = d_hits.cpu().numpy()
 
+    # ---- extra: incoherent rays - one diffuse bounce off every camera hit (tiny_bvh_speedtest.cpp:564-587 with a
+    # per-ray xorshift seeded by the global ray index), same index shard, device resident; reported beside the headline, not in it
+    incoherent = None
+    if not args.no_extra:
+        h_diff = h_shadow  # the shadow records are regenerated from h_prim + hits on demand; reuse the buffer for the bounce rays
+        R.diffuse_rays_into(h_diff, h_prim, verts, hits=hits, first=first)
+        d_diff = torch.empty((n, 64), dtype=torch.uint8, device=dev)
+        api.copy_rays_to_device(h_diff, d_diff)
+        d_hits2 = torch.empty((n, 4), dtype=torch.float32, device=dev)
+        eng.set_stats(True)
+        eng.Intersect(d_diff, hits=d_hits2)
+        st_diff = eng.get_stats()
+        eng.set_stats(False)
+        eng.Intersect(d_diff, hits=d_hits2)
+        barrier()
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a0.record(stream)
+        for _ in range(3):
+            eng.Intersect(d_diff, hits=d_hits2)
+        a1.record(stream)
+        barrier()
+        incoherent = {"ms": a0.elapsed_time(a1) / 3, "node_visits": st_diff[0] / n, "triangle_tests": st_diff[1] / n}
+        del d_diff, d_hits2
+        R.shadow_rays_into(h_shadow, h_prim, light_for(args.scene, verts), shadow_eps(verts), hits=hits)  # restore for the e2e passes
+
     # ---- e2e: the reference-facing C-ABI calls on HOST buffers (page-locked), copies inside the timed region
     def e2e_pass(packed_out=None):
         if packed_out is None:
@@ -460,10 +485,10 @@ def run_ours(args):
     e2e_packed_ms = (tp1 - tp0) * 1e3
     clk = clocks.stop() if clocks else None
 
-    t = torch.tensor([total_ms, e2e_ms, prim_ms, shad_ms, e2e_packed_ms], dtype=torch.float64, device=dev)
+    t = torch.tensor([total_ms, e2e_ms, prim_ms, shad_ms, e2e_packed_ms, incoherent["ms"] if incoherent else 0.0], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    total_ms, e2e_ms, prim_ms, shad_ms, e2e_packed_ms = [float(x) for x in t.cpu()]
+    total_ms, e2e_ms, prim_ms, shad_ms, e2e_packed_ms, inc_ms = [float(x) for x in t.cpu()]
     ok = torch.tensor([1.0 if e2e_ok else 0.0], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(ok, op=dist.ReduceOp.MIN)
@@ -525,6 +550,9 @@ def run_ours(args):
             "gpu_launches": int(launches),
             "clocks": clk,
         }
+        if incoherent:
+            out["incoherent"] = {"rays": n_total, "mrays": n_total / inc_ms / 1e3, "ms": inc_ms, "node_visits_per_ray": incoherent["node_visits"], "triangle_tests_per_ray": incoherent["triangle_tests"],
+                                 "what": "closest hit of one diffuse bounce ray per camera hit (SURVEY 8(d) config 4 generator), same layout, device resident, sharded like the headline set"}
         if build.get("Build"):
             # reference-algorithm bytes of a binned-SAH build = 48 + 36 + L (2 x 36 + 4) + 64 per triangle, L = mean leaf depth
             L_mean = {"sponza": 19.9, "bistro": 23.2}.get(label, 18.0)
@@ -563,6 +591,7 @@ def main():
     ap.add_argument("--res", type=int, default=2048, help="camera rays = res*res*16 (2048 -> 67,108,864)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-parity", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the incoherent-ray section")
     ap.add_argument("--parity-rays", type=int, default=1 << 20)
     ap.add_argument("--cpu-sample-rays", type=int, default=1 << 23)
     args = ap.parse_args()

@@ -196,6 +196,8 @@ int tbvh_ctx_create( int device, tbvh_ctx* out )
 	c->host_path = hp && (!strcmp( hp, "zerocopy" ) || !strcmp( hp, "1" )) ? 1 : hp && !strcmp( hp, "2" ) ? 2 : 0;
 	const char* tv = getenv( "TBVH_TRACE_VARIANT" );
 	c->trace_variant = tv ? atoi( tv ) : 3; // octant switch: +5 % on camera / shadow rays, -3 % on diffuse (profiles/README.md)
+	const char* bc = getenv( "TBVH_BUILD_CTAS" );
+	if (bc) c->build_ctas = atoi( bc );
 	const char* bm = getenv( "TBVH_BUILD_MODE" );
 	if (bm) c->build_mode = atoi( bm ) ? 1 : 0;
 	const char* st = getenv( "TBVH_SMALL_T" );
@@ -263,6 +265,7 @@ int tbvh_set_option( tbvh_ctx c, const char* key, int value )
 	else if (!strcmp( key, "small_t" )) c->small_t = value;
 	else if (!strcmp( key, "small_mode" )) c->small_mode = value & 3;
 	else if (!strcmp( key, "build_mode" )) c->build_mode = value ? 1 : 0;
+	else if (!strcmp( key, "build_ctas" )) c->build_ctas = value < 0 ? 0 : value > 16 ? 16 : value;
 	else if (!strcmp( key, "inst_idx_bits" )) c->inst_idx_bits = value;
 	else if (!strcmp( key, "hq_small" )) c->hq_small = value;
 	else if (!strcmp( key, "hq_cluster" )) c->hq_cluster = value;

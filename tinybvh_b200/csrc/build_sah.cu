@@ -39,10 +39,11 @@ struct Counters
 	uint32_t small_roots;    // subtree roots for k_build_small
 	uint32_t max_depth;
 	uint32_t total_chunks;   // chunks of the current level list
-	uint32_t cur_num;        // persistent large phase: nodes of the current level
+	uint32_t lvl_num[2];     // persistent large phase: nodes / chunks of the level with parity 0 / 1
+	uint32_t lvl_chunks[2];
 	uint32_t levels;         // persistent large phase: levels run
 	uint32_t root_key[6];    // root AABB as ordered keys: min xyz, max xyz
-	uint32_t pad[3];
+	uint32_t pad[4];
 };
 
 struct BuildArgs
@@ -287,7 +288,7 @@ __global__ void __launch_bounds__( 256 ) k_fragments( BuildArgs A )
 __global__ void k_init_counters( BuildArgs A )
 {
 	Counters* c = A.ctr;
-	c->tmp_nodes = 2, c->next_large = 0, c->small_roots = 0, c->max_depth = 0, c->total_chunks = 0, c->cur_num = 0, c->levels = 0;
+	c->tmp_nodes = 2, c->next_large = 0, c->small_roots = 0, c->max_depth = 0, c->total_chunks = 0, c->lvl_num[0] = c->lvl_num[1] = 0, c->lvl_chunks[0] = c->lvl_chunks[1] = 0, c->levels = 0;
 	for (int k = 0; k < 3; k++) c->root_key[k] = 0xffffffffu, c->root_key[3 + k] = 0;
 }
 
@@ -303,7 +304,7 @@ __global__ void k_init_root( BuildArgs A )
 	{
 		A.lvl[0][0] = LargeNode{ 0, 0, A.n, 0 };
 		A.chunk_start[0] = 0, A.chunk_start[1] = (A.n + CHUNK - 1) / CHUNK;
-		c->total_chunks = (A.n + CHUNK - 1) / CHUNK, c->cur_num = 1;
+		c->total_chunks = (A.n + CHUNK - 1) / CHUNK, c->lvl_num[0] = 1, c->lvl_chunks[0] = (A.n + CHUNK - 1) / CHUNK;
 		for (int k = threadIdx.x; k < BIN_STRIDE; k += blockDim.x) A.bins[k] = bin_init_word( k );
 	}
 	else if (threadIdx.x == 0)
@@ -328,16 +329,16 @@ __device__ __forceinline__ uint32_t find_slot( const uint32_t* chunk_start, cons
 // barriers.  Inside the persistent kernel the arrays they read were written earlier in the same launch, so none of these loads
 // may take the read-only (.nc) path: LD() is a plain load there.
 #define LD( p ) (*(p))
-__device__ __forceinline__ void bin_chunk( BuildArgs& A, const LargeNode* cur, const uint32_t num, const uint32_t* idx_in, const uint32_t vb, uint32_t* s_bins, uint32_t& s_slot )
+__device__ __forceinline__ void bin_chunk( const BuildArgs& A, const uint32_t* cs, const LargeNode* cur, const uint32_t num, const uint32_t* idx_in, const uint32_t vb, uint32_t* s_bins, uint32_t& s_slot )
 {
 	// binning :2357-2376 for one 256-primitive chunk of one node: shared-memory table, then one flush per CTA
 	__syncthreads(); // the previous user of s_bins / s_slot (an earlier chunk of this CTA) is done
-	if (threadIdx.x == 0) s_slot = find_slot( A.chunk_start, num, vb );
+	if (threadIdx.x == 0) s_slot = find_slot( cs, num, vb );
 	for (int k = threadIdx.x; k < BIN_STRIDE; k += CHUNK) s_bins[k] = bin_init_word( k );
 	__syncthreads();
 	const uint32_t j = s_slot;
 	const LargeNode nd = cur[j];
-	const uint32_t off = (vb - LD( A.chunk_start + j )) * CHUNK + threadIdx.x;
+	const uint32_t off = (vb - LD( cs + j )) * CHUNK + threadIdx.x;
 	const bool valid = off < nd.count;
 	uint32_t b3[3] = { 0, 0, 0 }, kmn[3] = { 0xffffffffu, 0xffffffffu, 0xffffffffu }, kmx[3] = { 0, 0, 0 };
 	if (valid)
@@ -382,17 +383,17 @@ __global__ void __launch_bounds__( CHUNK ) k_bin( BuildArgs A, const LargeNode* 
 {
 	__shared__ uint32_t s_bins[BIN_STRIDE];
 	__shared__ uint32_t s_slot;
-	bin_chunk( A, cur, num, idx_in, blockIdx.x, s_bins, s_slot );
+	bin_chunk( A, A.chunk_start, cur, num, idx_in, blockIdx.x, s_bins, s_slot );
 }
 
 // append the two children of a split node: bigger than SMALL_T -> next level's list, else -> warp-built subtree
-__device__ __forceinline__ void emit_child( BuildArgs& A, LargeNode* next, const uint32_t tmp, const uint32_t first, const uint32_t count, const uint32_t depth, const uint32_t out_buf )
+__device__ __forceinline__ void emit_child( const BuildArgs& A, LargeNode* next, const uint32_t tmp, const uint32_t first, const uint32_t count, const uint32_t depth, const uint32_t out_buf )
 {
 	if (count > A.small_t) next[atomicAdd( &A.ctr->next_large, 1u )] = LargeNode{ tmp, first, count, depth };
 	else A.small[atomicAdd( &A.ctr->small_roots, 1u )] = SmallRoot{ tmp, first, count, depth | (out_buf << 16) };
 }
 
-__device__ __forceinline__ void sweep_one( BuildArgs& A, const LargeNode* cur, LargeNode* next, const uint32_t j, const uint32_t* idx_in, const uint32_t out_buf )
+__device__ __forceinline__ void sweep_one( const BuildArgs& A, const LargeNode* cur, LargeNode* next, const uint32_t j, const uint32_t* idx_in, const uint32_t out_buf )
 {
 	const uint32_t lane = threadIdx.x & 31;
 	const LargeNode nd = cur[j];
@@ -430,15 +431,15 @@ __global__ void __launch_bounds__( 256 ) k_sweep( BuildArgs A, const LargeNode* 
 	if (j < num) sweep_one( A, cur, next, j, idx_in, out_buf );
 }
 
-__device__ __forceinline__ uint32_t flag_of( BuildArgs& A, const LargeNode* cur, const uint32_t num, const uint32_t vb, uint32_t& s_slot )
+__device__ __forceinline__ uint32_t flag_of( const BuildArgs& A, const uint32_t* cs, const LargeNode* cur, const uint32_t num, const uint32_t vb, uint32_t& s_slot )
 {
 	__syncthreads();
-	if (threadIdx.x == 0) s_slot = find_slot( A.chunk_start, num, vb );
+	if (threadIdx.x == 0) s_slot = find_slot( cs, num, vb );
 	__syncthreads();
 	const uint32_t j = s_slot;
 	const LargeNode nd = cur[j];
 	const SplitInfo sp = A.split[j];
-	const uint32_t off = (vb - LD( A.chunk_start + j )) * CHUNK + threadIdx.x;
+	const uint32_t off = (vb - LD( cs + j )) * CHUNK + threadIdx.x;
 	// flags live in CHUNK SPACE (index = chunk * CHUNK + lane): the scan then costs O(active primitives) per level, and a
 	// node's flags stay contiguous because its chunks are; padding lanes of a node's last chunk carry 0
 	const uint32_t p = nd.first + off;
@@ -447,7 +448,7 @@ __device__ __forceinline__ uint32_t flag_of( BuildArgs& A, const LargeNode* cur,
 __global__ void __launch_bounds__( CHUNK ) k_flags( BuildArgs A, const LargeNode* cur, const uint32_t num )
 {
 	__shared__ uint32_t s_slot;
-	A.flags[(size_t)blockIdx.x * CHUNK + threadIdx.x] = flag_of( A, cur, num, blockIdx.x, s_slot );
+	A.flags[(size_t)blockIdx.x * CHUNK + threadIdx.x] = flag_of( A, A.chunk_start, cur, num, blockIdx.x, s_slot );
 }
 
 // exclusive scan of flags[0..n) into scan[0..n] (scan[n] = total): tile sums, one-block spine, apply
@@ -519,36 +520,36 @@ template <bool PERSIST> __device__ __forceinline__ uint32_t scan_at( const Build
 {
 	return PERSIST ? A.chunk_pre[i / CHUNK] + A.scan[i] : A.scan[i];
 }
-template <bool PERSIST> __device__ __forceinline__ void posbl_chunk( BuildArgs& A, const LargeNode* cur, const uint32_t num, const uint32_t vb, uint32_t& s_slot )
+template <bool PERSIST> __device__ __forceinline__ void posbl_chunk( const BuildArgs& A, const uint32_t* cs, const LargeNode* cur, const uint32_t num, const uint32_t vb, uint32_t& s_slot )
 {
 	__syncthreads();
-	if (threadIdx.x == 0) s_slot = find_slot( A.chunk_start, num, vb );
+	if (threadIdx.x == 0) s_slot = find_slot( cs, num, vb );
 	__syncthreads();
 	const uint32_t j = s_slot;
 	const LargeNode nd = cur[j];
 	const SplitInfo sp = A.split[j];
-	const uint32_t off = (vb - LD( A.chunk_start + j )) * CHUNK + threadIdx.x;
+	const uint32_t off = (vb - LD( cs + j )) * CHUNK + threadIdx.x;
 	if (!sp.did || off >= nd.count || off < sp.L) return;
-	const size_t sb = (size_t)LD( A.chunk_start + j ) * CHUNK; // this node's base in chunk space
+	const size_t sb = (size_t)LD( cs + j ) * CHUNK; // this node's base in chunk space
 	if (A.flags[sb + off]) A.pos_bl[nd.first + (scan_at<PERSIST>( A, sb + nd.count ) - scan_at<PERSIST>( A, sb + off + 1 ))] = off; // BL_k, k = lefts behind it
 }
 __global__ void __launch_bounds__( CHUNK ) k_posbl( BuildArgs A, const LargeNode* cur, const uint32_t num )
 {
 	__shared__ uint32_t s_slot;
-	posbl_chunk<false>( A, cur, num, blockIdx.x, s_slot );
+	posbl_chunk<false>( A, A.chunk_start, cur, num, blockIdx.x, s_slot );
 }
 
-template <bool PERSIST> __device__ __forceinline__ void scatter_chunk( BuildArgs& A, const LargeNode* cur, const uint32_t num, const uint32_t* idx_in, uint32_t* idx_out, const uint32_t vb, uint32_t& s_slot )
+template <bool PERSIST> __device__ __forceinline__ void scatter_chunk( const BuildArgs& A, const uint32_t* cs, const LargeNode* cur, const uint32_t num, const uint32_t* idx_in, uint32_t* idx_out, const uint32_t vb, uint32_t& s_slot )
 {
 	__syncthreads();
-	if (threadIdx.x == 0) s_slot = find_slot( A.chunk_start, num, vb );
+	if (threadIdx.x == 0) s_slot = find_slot( cs, num, vb );
 	__syncthreads();
 	const uint32_t j = s_slot;
 	const LargeNode nd = cur[j];
 	const SplitInfo sp = A.split[j];
-	const uint32_t off = (vb - LD( A.chunk_start + j )) * CHUNK + threadIdx.x;
+	const uint32_t off = (vb - LD( cs + j )) * CHUNK + threadIdx.x;
 	if (!sp.did || off >= nd.count) return;
-	const size_t sb = (size_t)LD( A.chunk_start + j ) * CHUNK; // this node's base in chunk space
+	const size_t sb = (size_t)LD( cs + j ) * CHUNK; // this node's base in chunk space
 	const uint32_t p = nd.first + off, s0 = scan_at<PERSIST>( A, sb );
 	const uint32_t lefts_before = scan_at<PERSIST>( A, sb + off ) - s0, lefts_in_F = scan_at<PERSIST>( A, sb + sp.L ) - s0;
 	const uint32_t m = sp.L - lefts_in_F;
@@ -561,7 +562,7 @@ template <bool PERSIST> __device__ __forceinline__ void scatter_chunk( BuildArgs
 __global__ void __launch_bounds__( CHUNK ) k_scatter( BuildArgs A, const LargeNode* cur, const uint32_t num, const uint32_t* idx_in, uint32_t* idx_out )
 {
 	__shared__ uint32_t s_slot;
-	scatter_chunk<false>( A, cur, num, idx_in, idx_out, blockIdx.x, s_slot );
+	scatter_chunk<false>( A, A.chunk_start, cur, num, idx_in, idx_out, blockIdx.x, s_slot );
 }
 
 // next level: chunk offsets (exclusive scan of ceil(count/CHUNK)) and fresh bin tables, by one block
@@ -633,17 +634,22 @@ __global__ void __launch_bounds__( CHUNK ) k_large_phase( BuildArgs A )
 	__shared__ uint32_t s_slot, s_carry;
 	__shared__ uint32_t s_warp[8];
 	Counters* C = A.ctr;
+	uint32_t* const chunk_start0 = A.chunk_start;
 	const uint32_t warps_per_block = CHUNK / 32, gwarp = blockIdx.x * warps_per_block + (threadIdx.x >> 5), gwarps = gridDim.x * warps_per_block;
 	for (uint32_t level = 0; level < 4096; level++)
 	{
-		const uint32_t num = C->cur_num, chunks = C->total_chunks;
-		if (num == 0) break; // uniform over the grid: the counters were written before the last barrier
+		// level state is kept per parity (this level reads [level & 1], stage 4 writes [(level + 1) & 1]): no hand-over stage
+		const uint32_t par = level & 1;
+		const uint32_t num = C->lvl_num[par], chunks = C->lvl_chunks[par];
+		if (num == 0) break; // uniform over the grid: written before the last barrier
+		const uint32_t* const cs = par ? A.chunk_start_next : chunk_start0;
+		uint32_t* const chunk_start_out = par ? chunk_start0 : A.chunk_start_next;
 		const LargeNode* cur = A.lvl[level & 1];
 		LargeNode* next = A.lvl[(level + 1) & 1];
 		const uint32_t* idx_in = A.idx[level & 1];
 		uint32_t* idx_out = A.idx[(level + 1) & 1];
 		// ---- 1. bin tables of the level's nodes
-		for (uint32_t c = blockIdx.x; c < chunks; c += gridDim.x) bin_chunk( A, cur, num, idx_in, c, s_bins, s_slot );
+		for (uint32_t c = blockIdx.x; c < chunks; c += gridDim.x) bin_chunk( A, cs, cur, num, idx_in, c, s_bins, s_slot );
 		grid.sync();
 		// ---- 2. one warp per node: sweep, termination, children
 		for (uint32_t j = gwarp; j < num; j += gwarps) sweep_one( A, cur, next, j, idx_in, (level + 1) & 1 );
@@ -651,7 +657,7 @@ __global__ void __launch_bounds__( CHUNK ) k_large_phase( BuildArgs A )
 		// ---- 3. left / right flags in chunk space + their prefix inside each chunk + the chunk totals
 		for (uint32_t c = blockIdx.x; c < chunks; c += gridDim.x)
 		{
-			const uint32_t f = flag_of( A, cur, num, c, s_slot );
+			const uint32_t f = flag_of( A, cs, cur, num, c, s_slot );
 			uint32_t total;
 			const uint32_t pre = block_exscan_256( f, s_warp, total );
 			A.flags[(size_t)c * CHUNK + threadIdx.x] = f, A.scan[(size_t)c * CHUNK + threadIdx.x] = pre;
@@ -692,25 +698,22 @@ __global__ void __launch_bounds__( CHUNK ) k_large_phase( BuildArgs A )
 				uint32_t total;
 				const uint32_t pre = block_exscan_256( v, s_warp, total );
 				const uint32_t carry = s_carry;
-				if (i < num_next) A.chunk_start_next[i] = carry + pre;
+				if (i < num_next) chunk_start_out[i] = carry + pre;
 				__syncthreads();
 				if (threadIdx.x == 0) s_carry = carry + total;
 				__syncthreads();
 			}
-			if (threadIdx.x == 0) A.chunk_start_next[num_next] = s_carry, C->pad[0] = s_carry; // next level's chunk count, parked
+			if (threadIdx.x == 0) chunk_start_out[num_next] = s_carry, C->lvl_num[par ^ 1] = num_next, C->lvl_chunks[par ^ 1] = s_carry, C->levels = level + 1;
 		}
 		// the bin tables were consumed in stage 2: re-arm them for the next level's nodes
 		for (uint32_t k = blockIdx.x * CHUNK + threadIdx.x; k < num_next * BIN_STRIDE; k += gridDim.x * CHUNK) A.bins[k] = bin_init_word( k % BIN_STRIDE );
 		grid.sync();
-		// ---- 5. positions of the lefts behind the split point
-		for (uint32_t c = blockIdx.x; c < chunks; c += gridDim.x) posbl_chunk<true>( A, cur, num, c, s_slot );
+		// ---- 5. positions of the lefts behind the split point (every block has read next_large by now: re-arm it for the next level's sweep)
+		if (blockIdx.x == 0 && threadIdx.x == 0) C->next_large = 0;
+		for (uint32_t c = blockIdx.x; c < chunks; c += gridDim.x) posbl_chunk<true>( A, cs, cur, num, c, s_slot );
 		grid.sync();
 		// ---- 6. the swap partition as a permutation into the other index buffer
-		for (uint32_t c = blockIdx.x; c < chunks; c += gridDim.x) scatter_chunk<true>( A, cur, num, idx_in, idx_out, c, s_slot );
-		grid.sync();
-		// ---- level hand-over (every block computes the same values; block 0 publishes them after everyone has read the old ones)
-		for (uint32_t k = blockIdx.x * CHUNK + threadIdx.x; k <= num_next; k += gridDim.x * CHUNK) A.chunk_start[k] = A.chunk_start_next[k];
-		if (blockIdx.x == 0 && threadIdx.x == 0) C->cur_num = num_next, C->total_chunks = C->pad[0], C->next_large = 0, C->levels = level + 1;
+		for (uint32_t c = blockIdx.x; c < chunks; c += gridDim.x) scatter_chunk<true>( A, cs, cur, num, idx_in, idx_out, c, s_slot );
 		grid.sync();
 	}
 }
@@ -1027,7 +1030,8 @@ int build_sah_launch( tbvh_bvh b, float c_trav, float c_int, int flavour )
 			// persistent large phase: one cooperative launch walks every level (k_large_phase); grid = what the device can hold
 			int per_sm = 0;
 			CUDA_TRY( cudaOccupancyMaxActiveBlocksPerMultiprocessor( &per_sm, k_large_phase, CHUNK, 0 ) );
-			if (per_sm > 4) per_sm = 4; // more resident CTAs only make the barriers slower
+			const int want = b->ctx->build_ctas > 0 ? b->ctx->build_ctas : (n > 1500000 ? 8 : 2); // small scenes: barrier cost dominates; large ones want the CTAs
+			if (per_sm > want) per_sm = want;
 			if (per_sm >= 1)
 			{
 				const uint32_t grid = (uint32_t)(per_sm * b->ctx->sm_count);

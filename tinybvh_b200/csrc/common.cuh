@@ -58,6 +58,7 @@ struct tbvh_ctx_t
 	int hq_small = 16;               // BuildHQ: nodes of at most this many fragments go to the warp-per-subtree kernel (<= 256)
 	int hq_cluster = 16;             // BuildHQ: largest thread-block cluster a node of the level phase may get (1..16)
 	int small_t = 128;               // builder: subtrees of at most this many primitives go to the warp kernel (<= 256)
+	int build_ctas = 0;              // persistent large phase: CTAs per SM (0 = by scene size)
 	int build_mode = 0;              // BVH::Build large phase: 0 = one persistent cooperative launch (k_large_phase), 1 = one launch per stage and level
 	// ring of 8-byte device counters for kernels that pull work from a counter (one per launch, so launches on different
 	// streams never share one)

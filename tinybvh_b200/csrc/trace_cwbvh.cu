@@ -13,14 +13,14 @@
 //    turn bytes into floats and ~90 test slots that hold no child - the reference's 8-wide collapse fills 4.4 of 8 slots on
 //    Bistro, 36 % of the nodes have two children):
 //        header   32 B   p.xyz | ex ey ez imask | first inner child | first triangle (float4 units) | pairs | -
-//        pair j   32 B   the (2j)-th and (2j+1)-th NON-EMPTY child:  lo.x lo.y lo.z hi.x hi.y hi.z as 16-bit float pairs (child a,
-//                        child b) - 0..255 is exact in bfloat16 and in fp16 - and one 32-bit hit word per child: a leaf child's triangle bits
+//        pair j   32 B   the (2j)-th and (2j+1)-th NON-EMPTY child:  lo.x lo.y lo.z hi.x hi.y hi.z as half2 (child a, child b)
+//                        - 0..255 is exact in fp16 - and one 32-bit hit word per child: a leaf child's triangle bits
 //                        `unary(count) << offset`, an inner child's slot bit `1 << (24 + slot)`
 //    Empty slots are gone, so a node costs ceil(children/2) pair steps, not 8 slot steps.
 //  * A pair step is packed fp32 arithmetic (Blackwell FFMA2, `fma.rn.f32x2`): one instruction evaluates the same plane of both
 //    children, 6 per pair instead of 12 FFMA, exactly rounded per component like the scalar fma.
-//  * The quantised planes reach the registers as 16-bit floats and are widened by one instruction each (a shift or a mask for
-//    bfloat16; no byte extraction, no integer-to-float on the quarter-rate unit, no magic-number subtraction).
+//  * The quantised planes reach the registers as halves and are widened by one conversion each (no byte extraction, no
+//    integer-to-float on the quarter-rate unit, no magic-number subtraction).
 //  * Near / far planes are picked per ray by the sign of rD once per pair on the packed words (3 selects for two children).
 //  * Inner-child bits are accumulated in slot order and moved to octant order by one 3-stage bit butterfly per node.
 //
@@ -31,11 +31,11 @@
 
 #define CW_STACK 128            // node groups a ray can have pending: one per level of the wide tree (the reference's own limit, tiny_bvh.h:7048)
 #define CW_NODE_F4 10           // float4 per traversal node
-// Quantised planes in the traversal nodes: 1 = bfloat16 pairs (0..255 is exact in 8 significant bits; widening is one shift for
-// the low half - an IMAD on the FMA pipe - and one mask for the high half), 0 = half pairs (two HADD2.F32, which ncu shows on
-// the ALU pipe next to the min / max / select work that already saturates it).
+// Quantised planes in the traversal nodes: 0 = half pairs (widened by two HADD2.F32), 1 = bfloat16 pairs (0..255 is exact in 8
+// significant bits; widening is one IMAD shift for the low half and one mask for the high half).  Measured on Bistro, 16.8 M rays:
+// half 5.13 / 12.55 / 0.92 Grays/s (camera / shadow / bounce), bfloat16 4.87 / 11.91 / 0.90 - the half form stays.
 #ifndef CW_PLANES_BF16
-#define CW_PLANES_BF16 1
+#define CW_PLANES_BF16 0
 #endif
 
 // ---- bvh8Data -> traversal nodes ------------------------------------------------------------------------------------
