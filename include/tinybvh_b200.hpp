@@ -68,11 +68,20 @@ public:
 	tbvh_bvh handle() const { return h; }
 	tbvh_info Info() const { tbvh_info i; TBVH_FATAL_IF( tbvh_bvh_info( h, &i ), "Info" ); return i; }
 	// batch traversal: the calls the patched harness makes instead of its per-ray loops
-	template <class RayT> int32_t Intersect( RayT* rays, uint64_t n ) const
+	// Return value: 0, or - with collectCost set - the sum over the batch of what the reference's per-ray Intersect returns,
+	// (int32_t)( c_trav * nodes visited + c_int * triangles tested ) (tiny_bvh.h:3303; the speedtest adds these up into rayCost,
+	// tiny_bvh_speedtest.cpp:197-214).  Exact for integral c_trav / c_int (the defaults); the counting kernels are slower.
+	bool collectCost = false;
+	template <class RayT> int64_t Intersect( RayT* rays, uint64_t n ) const
 	{
 		static_assert( sizeof( RayT ) == 64 || sizeof( RayT ) == 128, "ray record must be the 64- or 128-byte layout" );
+		if (collectCost) TBVH_FATAL_IF( tbvh_set_stats( h, 1 ), "Intersect" );
 		TBVH_FATAL_IF( tbvh_intersect( h, layout, rays, (uint32_t)sizeof( RayT ), n ), "Intersect" );
-		return 0;
+		if (!collectCost) return 0;
+		uint64_t steps = 0, tris = 0;
+		TBVH_FATAL_IF( tbvh_get_stats( h, &steps, &tris ), "Intersect" );
+		TBVH_FATAL_IF( tbvh_set_stats( h, 0 ), "Intersect" );
+		return (int64_t)(c_trav * (double)steps + c_int * (double)tris);
 	}
 	// batch traversal with packed results: hits[i] = { t, u, v, prim } (16 bytes), rays untouched - the fast return path
 	template <class RayT> void Intersect( const RayT* rays, uint64_t n, void* hits16 ) const
@@ -106,7 +115,7 @@ public:
 	void FreeDevice( void* d ) const { tbvh_device_free( context(), d ); }
 	void Sync() const { TBVH_FATAL_IF( tbvh_device_sync( context() ), "Sync" ); }
 	// per-ray forms with the reference's signatures (correct, but one PCIe round trip each: use the batch forms)
-	template <class RayT> int32_t Intersect( RayT& ray ) const { return Intersect( &ray, 1 ); }
+	template <class RayT> int32_t Intersect( RayT& ray ) const { return (int32_t)Intersect( &ray, 1 ); }
 	template <class RayT> bool IsOccluded( const RayT& ray ) const { uint32_t b = 0; IsOccluded( &ray, 1, &b ); return b & 1; }
 protected:
 	BVHBase( int l ) : layout( l ) { TBVH_FATAL_IF( tbvh_bvh_create( context(), &h ), "BVHBase" ); }

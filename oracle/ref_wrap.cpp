@@ -108,6 +108,16 @@ void ref_bvh_intersect( void* h, void* rays, uint64_t n, int threads )
 	const BVH* b = (BVH*)h; Ray* r = (Ray*)rays;
 	parallel_rays( n, threads, [=]( uint64_t s, uint64_t e ) { for (uint64_t i = s; i < e; i++) b->Intersect( r[i] ); } );
 }
+// the sum of the values BVH::Intersect returns - (int32_t)( c_trav * nodes visited + c_int * triangles tested ) per ray (:3303), which
+// the speedtest accumulates into rayCost (tiny_bvh_speedtest.cpp:197-214)
+uint64_t ref_bvh_intersect_cost( void* h, void* rays, uint64_t n, int threads )
+{
+	const BVH* b = (BVH*)h; Ray* r = (Ray*)rays;
+	std::atomic<uint64_t> total( 0 );
+	std::atomic<uint64_t>* tp = &total;
+	parallel_rays( n, threads, [=]( uint64_t s, uint64_t e ) { uint64_t c = 0; for (uint64_t i = s; i < e; i++) c += (uint64_t)b->Intersect( r[i] ); *tp += c; } );
+	return total.load();
+}
 // bits: one bit per ray, bit (i&31) of word i>>5; caller zero-initialises.  Batches are 10,000 rays, not
 // word-aligned, so occlusion is first written as bytes and packed afterwards.
 void ref_bvh_occluded( void* h, const void* rays, uint64_t n, uint32_t* bits, int threads )

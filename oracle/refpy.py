@@ -41,6 +41,7 @@ def lib():
             "ref_bvh_compact": (None, [vp]), "ref_bvh_refit": (None, [vp]), "ref_bvh_split_leafs": (None, [vp, u32]),
             "ref_bvh_from_arrays": (vp, [vp, u32, vp, u32, vp, u32]),
             "ref_bvh_intersect": (None, [vp, vp, u64, i32]),
+            "ref_bvh_intersect_cost": (u64, [vp, vp, u64, i32]),
             "ref_bvh_occluded": (None, [vp, vp, u64, vp, i32]),
             "ref_clip_frag": (i32, [vp, vp, vp, vp, vp, vp, u32]),
             "ref_split_frag": (None, [vp, vp, vp, vp, vp, u32, C.c_float, vp, vp]),
@@ -96,6 +97,11 @@ class _Traceable:
 class RefBVH(_Traceable):
     """BVH::Build / BuildAVX / BuildHQ + BVH::Intersect / IsOccluded - THE parity oracle (mode 0)."""
     _intersect, _occluded = "ref_bvh_intersect", "ref_bvh_occluded"
+
+    def intersect_cost(self, rays: np.ndarray, threads: int = 0) -> int:
+        """trace and return the sum of BVH::Intersect's return values (traversal cost, tiny_bvh.h:3303)"""
+        assert rays.dtype.itemsize == 128 and rays.flags.c_contiguous
+        return int(lib().ref_bvh_intersect_cost(self.h, _ptr(rays), rays.shape[0], threads))
 
     def __init__(self, verts: np.ndarray = None, mode: int = 0, threaded: bool = False, _handle=None, _owner=None, indices=None, costs=None):
         self._owner = _owner

@@ -108,3 +108,22 @@ def test_reference_fixtures_full_parity(gpu, scene):
         a, b = d["diffuse"].copy(), d["diffuse"].copy()
         o.intersect(a), e.Intersect(b)
         assert util.compare_hits(b, a) == ZERO, label
+
+
+def test_traversal_cost_equals_the_sum_of_the_references_return_values(gpu):
+    """BVH::Intersect returns (int32_t)( c_trav * nodes visited + c_int * triangles tested ) (tiny_bvh.h:3303); the speedtest sums it
+    into rayCost.  The engine's counters (tbvh_get_stats) over a batch are that sum exactly (c_trav = c_int = 1)."""
+    from oracle import refpy
+    if not refpy.available():
+        pytest.skip("needs oracle/_ref")
+    v = scenes.procedural_scene(20000, 41)
+    o = refpy.RefBVH(v, mode=0, threaded=False)
+    e = api.BVH().upload(o.nodes, o.prim_idx, v)
+    sets, bounds = util.ray_sets(v, res=128)
+    rays = sets["primary"]
+    want = o.intersect_cost(rays.copy())
+    e.set_stats(True)
+    e.Intersect(rays.copy())
+    steps, tris = e.get_stats()[:2]
+    e.set_stats(False)
+    assert steps + tris == want, (steps, tris, want)

@@ -62,6 +62,7 @@ struct BuildArgs
 	uint32_t n;
 	uint32_t flavour;        // 0 = BVH::Build (scalar reference builder), 1 = BVH::BuildAVX (what BuildDefault runs on x86)
 	uint32_t small_t;        // runtime switch point large phase -> warp subtrees (<= SMALL_T; env TBVH_SMALL_T for tuning)
+	uint32_t level0;         // persistent large phase: the level it starts at (the launch-per-stage path may have run the first ones)
 	float c_trav, c_int;
 };
 
@@ -644,15 +645,16 @@ __global__ void __launch_bounds__( CHUNK ) k_large_phase( BuildArgs A )
 		if (num == 0) break; // uniform over the grid: written before the last barrier
 		const uint32_t* const cs = par ? A.chunk_start_next : chunk_start0;
 		uint32_t* const chunk_start_out = par ? chunk_start0 : A.chunk_start_next;
-		const LargeNode* cur = A.lvl[level & 1];
-		LargeNode* next = A.lvl[(level + 1) & 1];
-		const uint32_t* idx_in = A.idx[level & 1];
-		uint32_t* idx_out = A.idx[(level + 1) & 1];
+		const uint32_t lp = (A.level0 + level) & 1; // parity of the ping-pong node lists / index buffers (absolute level)
+		const LargeNode* cur = A.lvl[lp];
+		LargeNode* next = A.lvl[lp ^ 1];
+		const uint32_t* idx_in = A.idx[lp];
+		uint32_t* idx_out = A.idx[lp ^ 1];
 		// ---- 1. bin tables of the level's nodes
 		for (uint32_t c = blockIdx.x; c < chunks; c += gridDim.x) bin_chunk( A, cs, cur, num, idx_in, c, s_bins, s_slot );
 		grid.sync();
 		// ---- 2. one warp per node: sweep, termination, children
-		for (uint32_t j = gwarp; j < num; j += gwarps) sweep_one( A, cur, next, j, idx_in, (level + 1) & 1 );
+		for (uint32_t j = gwarp; j < num; j += gwarps) sweep_one( A, cur, next, j, idx_in, lp ^ 1 );
 		grid.sync();
 		// ---- 3. left / right flags in chunk space + their prefix inside each chunk + the chunk totals
 		for (uint32_t c = blockIdx.x; c < chunks; c += gridDim.x)
@@ -1025,24 +1027,33 @@ int build_sah_launch( tbvh_bvh b, float c_trav, float c_int, int flavour )
 		k_fragments<<<(n + 255) / 256, 256, 0, s>>>( A ); LAUNCHED();
 		k_init_root<<<1, 256, 0, s>>>( A ); LAUNCHED();
 		uint32_t num = n > A.small_t ? 1 : 0, chunks = (n + CHUNK - 1) / CHUNK, level = 0;
+		// Large phase.  The first levels of a big scene are bandwidth work over all primitives: one launch per stage, every CTA the
+		// device can hold.  Once a level is down to a few chunks per SM the stages are launch-latency sized, and the rest of the
+		// phase runs inside ONE persistent cooperative launch (k_large_phase) without further host round trips.
+		int per_sm = 0;
+		uint32_t pgrid = 0;
 		if (num && b->ctx->build_mode == 0)
 		{
-			// persistent large phase: one cooperative launch walks every level (k_large_phase); grid = what the device can hold
-			int per_sm = 0;
 			CUDA_TRY( cudaOccupancyMaxActiveBlocksPerMultiprocessor( &per_sm, k_large_phase, CHUNK, 0 ) );
-			const int want = b->ctx->build_ctas > 0 ? b->ctx->build_ctas : (n > 1500000 ? 8 : 2); // small scenes: barrier cost dominates; large ones want the CTAs
+			const int want = b->ctx->build_ctas > 0 ? b->ctx->build_ctas : 4;
 			if (per_sm > want) per_sm = want;
-			if (per_sm >= 1)
-			{
-				const uint32_t grid = (uint32_t)(per_sm * b->ctx->sm_count);
-				void* params[] = { (void*)&A };
-				CUDA_TRY( cudaLaunchCooperativeKernel( (const void*)k_large_phase, dim3( grid ), dim3( CHUNK ), params, 0, s ) );
-				g_tbvh_launches++;
-				num = 0; // the level loop below is skipped
-			}
+			pgrid = (uint32_t)(per_sm > 0 ? per_sm * b->ctx->sm_count : 0);
 		}
+		const uint32_t persist_chunks = pgrid * 3;
 		while (num)
 		{
+			if (pgrid && chunks <= persist_chunks)
+			{
+				const uint32_t state[2] = { num, chunks };
+				CUDA_TRY( cudaMemcpyAsync( &A.ctr->lvl_num[0], &state[0], 4, cudaMemcpyHostToDevice, s ) );
+				CUDA_TRY( cudaMemcpyAsync( &A.ctr->lvl_chunks[0], &state[1], 4, cudaMemcpyHostToDevice, s ) );
+				A.level0 = level;
+				void* params[] = { (void*)&A };
+				CUDA_TRY( cudaLaunchCooperativeKernel( (const void*)k_large_phase, dim3( pgrid ), dim3( CHUNK ), params, 0, s ) );
+				g_tbvh_launches++;
+				CUDA_TRY( cudaStreamSynchronize( s ) ); // `state` is on this frame
+				break;
+			}
 			const LargeNode* cur = A.lvl[level & 1];
 			LargeNode* next = A.lvl[(level + 1) & 1];
 			const uint32_t* idx_in = A.idx[level & 1];

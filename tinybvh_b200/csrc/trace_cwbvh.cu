@@ -12,7 +12,7 @@
 //    this GPU (ncu on the byte format: 79 % issue-slot use, ALU pipe 72 % busy, 370 instructions per node visit, of which 96
 //    turn bytes into floats and ~90 test slots that hold no child - the reference's 8-wide collapse fills 4.4 of 8 slots on
 //    Bistro, 36 % of the nodes have two children):
-//        header   32 B   p.xyz | ex ey ez imask | first inner child | first triangle (float4 units) | pairs | -
+//        header   32 B   p.xyz | 2^ex 2^ey as float top halves | first inner child | first triangle (float4 units) | 2^ez, imask, pairs | children
 //        pair j   32 B   the (2j)-th and (2j+1)-th NON-EMPTY child:  lo.x lo.y lo.z hi.x hi.y hi.z as half2 (child a, child b)
 //                        - 0..255 is exact in fp16 - and one 32-bit hit word per child: a leaf child's triangle bits
 //                        `unary(count) << offset`, an inner child's slot bit `1 << (24 + slot)`
@@ -74,8 +74,12 @@ __global__ void k_cw_expand( const uint4* __restrict__ src, uint4* __restrict__ 
 		kept++;
 	}
 	uint4* o = dst + (size_t)x * CW_NODE_F4;
-	o[0] = n0;
-	o[1] = make_uint4( n1.x, n1.y, (kept + 1) >> 1, kept );
+	// 2^e per axis as the top half of its float bit pattern, ( e + 127 ) << 7 for the signed exponent byte e - including the
+	// reference's own wrap for e = -128, ( -1 ) << 23 = 0xff800000 (tiny_bvh.h:7072-7074)
+	const uint32_t sx = (uint32_t)(((int)(int8_t)(n0.w & 255u) + 127) * 128) & 0xffffu, sy = (uint32_t)(((int)(int8_t)((n0.w >> 8) & 255u) + 127) * 128) & 0xffffu;
+	const uint32_t sz = (uint32_t)(((int)(int8_t)((n0.w >> 16) & 255u) + 127) * 128) & 0xffffu;
+	o[0] = make_uint4( n0.x, n0.y, n0.z, sx | (sy << 16) );
+	o[1] = make_uint4( n1.x, n1.y, sz | ((n0.w >> 24) << 16) | (((kept + 1) >> 1) << 24), kept );
 	#pragma unroll
 	for (int j = 0; j < 4; j++)
 	{
@@ -169,18 +173,21 @@ template <int OCT> __device__ __forceinline__ uint32_t node_hits( const float4* 
 	const bool nx = OCT < 0 ? negx : (OCT & 4) != 0, ny = OCT < 0 ? negy : (OCT & 2) != 0, nz = OCT < 0 ? negz : (OCT & 1) != 0;
 	const float2 ax = make_float2( ax1, ax1 ), ay = make_float2( ay1, ay1 ), az = make_float2( az1, az1 );
 	const float2 bx = make_float2( bx1, bx1 ), by = make_float2( by1, by1 ), bz = make_float2( bz1, bz1 );
+	// All four pair records, unconditionally: a node visited on the way to a hit is almost always full (3.83 of 4 pair steps per visited
+	// node on Bistro camera rays), the records behind `pairs` are zero (no bits, so whatever their planes say contributes nothing), and
+	// without the four branch regions the eight loads leave together.
+	(void)pairs;
+	float4 A[4], B[4];
+	#pragma unroll
+	for (int j = 0; j < 4; j++) A[j] = __ldg( np + 2 + 2 * j ), B[j] = __ldg( np + 3 + 2 * j );
 	uint32_t got = 0;
 	#pragma unroll
-	for (uint32_t j = 0; j < 4; j++)
+	for (int j = 0; j < 4; j++)
 	{
-		if (j < pairs)
-		{
-			const float4 A = __ldg( np + 2 + 2 * j ), B = __ldg( np + 3 + 2 * j );
-			const uint32_t lx = __float_as_uint( A.x ), ly = __float_as_uint( A.y ), lz = __float_as_uint( A.z );
-			const uint32_t hx = __float_as_uint( A.w ), hy = __float_as_uint( B.x ), hz = __float_as_uint( B.y );
-			got |= pair_hits( nx ? hx : lx, ny ? hy : ly, nz ? hz : lz, nx ? lx : hx, ny ? ly : hy, nz ? lz : hz,
-				__float_as_uint( B.z ), __float_as_uint( B.w ), ax, ay, az, bx, by, bz, t );
-		}
+		const uint32_t lx = __float_as_uint( A[j].x ), ly = __float_as_uint( A[j].y ), lz = __float_as_uint( A[j].z );
+		const uint32_t hx = __float_as_uint( A[j].w ), hy = __float_as_uint( B[j].x ), hz = __float_as_uint( B[j].y );
+		got |= pair_hits( nx ? hx : lx, ny ? hy : ly, nz ? hz : lz, nx ? lx : hx, ny ? ly : hy, nz ? lz : hz,
+			__float_as_uint( B[j].z ), __float_as_uint( B[j].w ), ax, ay, az, bx, by, bz, t );
 	}
 	return slots_to_order( got, OCT < 0 ? o : (uint32_t)(7 - OCT) ) | (got & 0x00ffffffu);
 }
@@ -233,14 +240,12 @@ __global__ void __launch_bounds__( 128 ) k_trace_wide( const float4* __restrict_
 			const float4* np = nodes + (size_t)nidx * CW_NODE_F4;
 			const float4 h0 = __ldg( np ), h1 = __ldg( np + 1 );
 			if (STATS) nsteps++;
-			const uint32_t ew = __float_as_uint( h0.w ) ^ 0x00808080u; // exponent bytes + 128
-			// scale = 2^e as a float bit pattern, ( e + 127 ) << 23 (:7072-7074)
-			const float scx = __uint_as_float( ((ew & 255u) << 23) - 0x00800000u );
-			const float scy = __uint_as_float( (((ew >> 8) & 255u) << 23) - 0x00800000u );
-			const float scz = __uint_as_float( (((ew >> 16) & 255u) << 23) - 0x00800000u );
+			// scale = 2^e as a float bit pattern, ( e + 127 ) << 23 (:7072-7074), stored by cw_make_trav as top halves
+			const uint32_t sxy = __float_as_uint( h0.w ), szm = __float_as_uint( h1.z );
+			const float scx = __uint_as_float( sxy << 16 ), scy = __uint_as_float( sxy & 0xffff0000u ), scz = __uint_as_float( szm << 16 );
 			const float ax1 = __fmul_rn( scx, rdx ), ay1 = __fmul_rn( scy, rdy ), az1 = __fmul_rn( scz, rdz );
 			const float bx1 = __fmul_rn( -__fsub_rn( ox, h0.x ), rdx ), by1 = __fmul_rn( -__fsub_rn( oy, h0.y ), rdy ), bz1 = __fmul_rn( -__fsub_rn( oz, h0.z ), rdz );
-			const uint32_t pairs = __float_as_uint( h1.z );
+			const uint32_t pairs = szm >> 24;
 			if (STATS) npairs += pairs;
 			uint32_t got;
 			#define NODE_HITS( O ) got = node_hits<O>( np, pairs, negx, negy, negz, o, ax1, ay1, az1, bx1, by1, bz1, t )
@@ -261,7 +266,7 @@ __global__ void __launch_bounds__( 128 ) k_trace_wide( const float4* __restrict_
 			else NODE_HITS( -1 );
 			#undef NODE_HITS
 			base = __float_as_uint( h1.x );
-			word = (got & 0xff000000u) | (__float_as_uint( h0.w ) >> 24);
+			word = (got & 0xff000000u) | ((szm >> 16) & 255u);
 			// ---- triangles of the leaf children that were hit, highest bit first (:7132-7142)
 			uint32_t tmask = got & 0x00ffffffu;
 			const float4* tbase = tris + __float_as_uint( h1.y );
