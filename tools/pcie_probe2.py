@@ -66,6 +66,8 @@ h = api.pinned_empty(n, R.RAY_DTYPE, device=0)
 api.bind_to_device(0)
 fill(h)
 run("local pinned buffer", h)
+if "--short" in sys.argv:
+    sys.exit(0)
 api.set_option("host_path", 2)
 run("local, whole-record inbound", h)
 api.set_option("d2h_mode", 2)
