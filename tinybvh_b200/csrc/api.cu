@@ -307,7 +307,7 @@ int tbvh_host_alloc_near( int device, size_t bytes, void** out )
 	ARG_CHECK( out, "out == NULL" );
 	const int node = device_numa_node( device );
 	static int huge = -1;
-	if (huge < 0) { const char* e = getenv( "TBVH_HOST_HUGE" ); huge = e ? atoi( e ) : 0; }
+	if (huge < 0) { const char* e = getenv( "TBVH_HOST_HUGE" ); huge = e ? atoi( e ) : 1; } // default on: +5..9 % on the host path where the IOMMU translates DMA addresses (profiles/README.md)
 	if (huge && bytes >= (8u << 20))
 	{
 		// anonymous memory advised into transparent huge pages, first touched on the device's node, then page-locked: 2 MiB pages
