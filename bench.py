@@ -205,6 +205,7 @@ def run_reference(args):
     verts, label = scenes.load_scene(args.scene)
     ntris = verts.shape[0] // 3
     n = args.res * args.res * 16
+    R.set_generator_threads(len(ALL_CPUS))
     # the whole workload, traced by the CPU implementation itself (its own closest hits place the shadow rays, as the speedtest does)
     t0 = time.time()
     hq = args.tree == "hq"
@@ -299,6 +300,7 @@ def run_ours(args):
     # sit on the CPUs of this GPU's NUMA node before anything allocates: page-locked ray buffers, OpenMP ray generation and the host
     # pipeline's threads then work out of local memory (2 sockets: GPUs 0-3 / 4-7 hang off different nodes)
     bound = api.bind_to_device(local)
+    R.set_generator_threads(max(1, len(os.sched_getaffinity(0)) // max(1, min(world, 4))))  # the ranks of one socket share its cores
     import torch
     import torch.distributed as dist
     if world > 1:

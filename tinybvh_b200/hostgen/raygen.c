@@ -8,6 +8,10 @@
 #include <math.h>
 #include <stdint.h>
 #include <string.h>
+#include <omp.h>
+
+/* launchers such as torchrun export OMP_NUM_THREADS=1; the generators are told explicitly how many threads they may use */
+void tbvh_gen_set_threads( const int n ) { if (n > 0) omp_set_num_threads( n ); }
 
 #define BVH_FAR 1e30f
 

@@ -187,10 +187,18 @@ def _genlib():
         L.tbvh_gen_diffuse.argtypes = [vp, vp, vp, u64, u64, vp, u32]
         L.tbvh_gen_reset_hits.argtypes = [vp, u64, f]
         L.tbvh_gen_store_hits.argtypes = [vp, vp, u64]
-        for fn in (L.tbvh_gen_primary, L.tbvh_gen_shadow, L.tbvh_gen_diffuse, L.tbvh_gen_reset_hits, L.tbvh_gen_store_hits):
+        L.tbvh_gen_set_threads.argtypes = [C.c_int]
+        for fn in (L.tbvh_gen_primary, L.tbvh_gen_shadow, L.tbvh_gen_diffuse, L.tbvh_gen_reset_hits, L.tbvh_gen_store_hits, L.tbvh_gen_set_threads):
             fn.restype = None
         _gen = L
     return _gen or None
+
+
+def set_generator_threads(n: int) -> None:
+    """Threads the C generators may use (launchers such as torchrun export OMP_NUM_THREADS=1)."""
+    L = _genlib()
+    if L is not None:
+        L.tbvh_gen_set_threads(int(n))
 
 
 def _p(a):
