@@ -28,7 +28,7 @@ def line(src, dst):
 
 names = {"bench_n1.json": f"{tag}_bench_bistro_cwbvh_n1.json", "bench_ref.json": f"{tag}_bench_reference_arm.json", "bench_n1_bvh.json": f"{tag}_bench_bistro_bvh_n1.json",
          "bench_sponza_bvh.json": f"{tag}_bench_sponza_bvh_n1.json", "bench_sponza_cwbvh.json": f"{tag}_bench_sponza_cwbvh_n1.json", "bench_config5.json": f"{tag}_bench_config5_lucy_dragon_x29_n1.json",
-         "bench_n2.json": f"{tag}_bench_bistro_cwbvh_n2.json", "bench_n8.json": f"{tag}_bench_bistro_cwbvh_n8.json", "bench_config4_n8.json": f"{tag}_bench_config4_bistro_537M_n8.json"}
+         "bench_n2.json": f"{tag}_bench_bistro_cwbvh_n2.json", "bench_n4.json": f"{tag}_bench_bistro_cwbvh_n4.json", "bench_n8.json": f"{tag}_bench_bistro_cwbvh_n8.json", "bench_config4_n8.json": f"{tag}_bench_config4_bistro_537M_n8.json"}
 for src, dst in names.items():
     d = line(src, dst)
     if d:
@@ -39,13 +39,17 @@ traffic = {}
 tp = os.path.join(P, "traffic.json")
 if os.path.isfile(tp):
     traffic = json.load(open(tp))
-for name, rep in (("cw_primary", f"{tag}_cw_primary.ncu-rep"), ("cw_shadow", f"{tag}_cw_shadow.ncu-rep"), ("large_phase", f"{tag}_large_phase.ncu-rep")):
+for name, rep in (("cw_primary", f"{tag}_cw_primary.ncu-rep"), ("cw_shadow", f"{tag}_cw_shadow.ncu-rep"), ("large_phase", f"{tag}_large_phase.ncu-rep"),
+                  ("cw_primary_2048", f"{tag}_cw_primary_2048.ncu-rep")):
     p = os.path.join(G, rep)
     if os.path.isfile(p):
         t = sp.report(tag, name, p)
         for k, v in t.items():
             traffic[f"{tag}:{name}:{k}"] = v[0]
-        if name != "large_phase":
+        if name == "cw_primary_2048":
+            for v in t.values():
+                traffic["k_trace_wide<closest>_bistro_hq_2048"] = v[0]   # what bench.py's default line looks up
+        elif name != "large_phase":
             subprocess.run([sys.executable, os.path.join(REPO, "tools", "ncu_opmix.py"), p, "16777216", os.path.join(P, f"{tag}_{name}_opmix.txt")], stdout=subprocess.DEVNULL)
 # bench.py looks the dominant kernel's DRAM bytes up by "<kernel>_<scene>_<tree>_<res>"; the capture is the 1024^2 x 16 camera set
 k = f"{tag}:cw_primary:k_trace_wide<0, 0, 1>"

@@ -1,4 +1,4 @@
-# One gpurun call that refreshes every measured artefact under profiles/ (about 8 GPU-minutes on one B200):
+# One gpurun call that refreshes every measured artefact under profiles/ (about 10 GPU-minutes on one B200):
 #   /usr/local/graft/bin/gpurun --timeout 3000 -- 'bash tools/gpu_session_full.sh'
 # then here:  python tools/collect_profiles.py r2
 set -x
@@ -16,6 +16,7 @@ timeout 1200 python bench.py --scene lucy_dragon_x29 --layout bvh --tree sah --r
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches.csv python bench.py --res 1024 --steps 2 --warmup 1 --no-cpu-baseline --no-parity --no-extra > /dev/null 2>&1
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_trace_wide -s 2 -c 1 -o gpurun_out/r2_cw_primary python tools/trace_once.py bistro 1024 cwbvh --reps 1 --sets primary > /dev/null 2>&1
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_trace_wide -s 3 -c 1 -o gpurun_out/r2_cw_shadow python tools/trace_once.py bistro 1024 cwbvh --reps 1 --sets primary,shadow > /dev/null 2>&1
+timeout 900 ncu --set full --clock-control none -k regex:k_trace_wide -c 1 -o gpurun_out/r2_cw_primary_2048 python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-parity --no-extra > /dev/null 2>&1
 timeout 600 ncu --set full --clock-control none -k regex:k_large_phase -c 1 -o gpurun_out/r2_large_phase python tools/quick_build.py sponza > /dev/null 2>&1
 timeout 300 python tools/quick_build.py sponza bunny bistro lucy_dragon_x29 > gpurun_out/build.log 2>&1; tail -4 gpurun_out/build.log
 timeout 300 python tools/quick_hq.py bunny sponza bistro > gpurun_out/hq.log 2>&1; tail -3 gpurun_out/hq.log
