@@ -380,7 +380,11 @@ def run_ours(args):
     n = sum(c for _, c in blocks)
     first = blocks[0][0] if blocks else 0
     eye, view = camera_for(args.scene, verts)
-    h_prim = api.pinned_empty(n, R.RAY_DTYPE, device=local)
+    # TBVH_BENCH_NUMA_SPREAD=1 (experiment): every second rank keeps its ray buffers on the OTHER socket's memory
+    spread = os.environ.get("TBVH_BENCH_NUMA_SPREAD") == "1" and (local & 1) == 1
+    buf_node = (1 - max(0, L.tbvh_device_numa_node(local))) if spread else None
+    palloc = (lambda cnt, dt: api.pinned_empty(cnt, dt, node=buf_node)) if spread else (lambda cnt, dt: api.pinned_empty(cnt, dt, device=local))
+    h_prim = palloc(n, R.RAY_DTYPE)
     off = 0
     for b0, bc in blocks:
         R.primary_rays_into(h_prim[off:off + bc], eye, view, args.res, args.res, 16, first=b0)
@@ -391,7 +395,7 @@ def run_ours(args):
     eng.Intersect(d_prim, hits=d_hits)
     torch.cuda.synchronize()
     hits = d_hits.cpu().numpy()
-    h_shadow = api.pinned_empty(n, R.RAY_DTYPE, device=local)
+    h_shadow = palloc(n, R.RAY_DTYPE)
     R.shadow_rays_into(h_shadow, h_prim, light_for(args.scene, verts), shadow_eps(verts), hits=hits)
     d_shadow = torch.empty((n, 64), dtype=torch.uint8, device=dev)
     api.copy_rays_to_device(h_shadow, d_shadow)
@@ -496,7 +500,7 @@ def run_ours(args):
                   and np.array_equal(h_bits, bits_dev))
     R.reset_hits_fast(h_prim)
     # the same with the packed-hits entry point (tbvh_intersect_packed): the return trip is one contiguous copy per chunk
-    h_hits = api.pinned_empty(n, R.HIT_DTYPE, device=local)
+    h_hits = palloc(n, R.HIT_DTYPE)
     e2e_pass(h_hits)
     barrier()
     tp0 = time.perf_counter()

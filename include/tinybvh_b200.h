@@ -77,7 +77,8 @@ int tbvh_bind_thread_to_device( int device );
 /* tuning knobs (no reference counterpart; defaults are the measured best): "trace_variant" 0 = generic BVH2 kernel,
  * 3 = octant-switch, 4 = persistent warps; "small_t" builder switch point (8..256); "d2h_mode" / "h2d_split" / "host_path"
  * select how the host-buffer path moves ray records and hits across PCIe ("host_path" 0 = copy engine 2D copies, the default;
- * 1 = gather kernel over the pinned mapping; "d2h_mode" 0 = 2D copy of the 16-byte hits into the records, 3 = scatter kernel over
+ * 1 = gather kernel over the pinned mapping; "d2h_mode" 0 = 2D copy of the 16-byte hits into the records, 1 = bytes 0..63 of every record return (full cache lines), 2 = packed copy + host
+ * threads scatter, 3 = scatter kernel over
  * the pinned mapping; "h2d_split" 1..4 inbound streams per chunk; "chunk_rays" rays per pipeline chunk, default 524288).
  * Environment variables TBVH_<KEY> set the defaults at context creation.  BuildHQ: "hq_small" (fragments below which a subtree goes to the warp kernel, default 16),
  * "hq_cluster" (largest thread-block cluster per node, 1..16).  "inst_idx_bits": the host program's INST_IDX_BITS (see
@@ -89,6 +90,7 @@ int tbvh_set_option( tbvh_ctx ctx, const char* key, int value );
  * translating the DMA engine's addresses, 2 MiB pages are worth 5-9 % on the host-buffer path. */
 int tbvh_host_alloc( size_t bytes, void** out );
 int tbvh_host_alloc_near( int device, size_t bytes, void** out );
+int tbvh_host_alloc_node( int numa_node, size_t bytes, void** out );
 int tbvh_host_free( void* p );
 int tbvh_host_register( void* p, size_t bytes );
 int tbvh_host_unregister( void* p );

@@ -32,7 +32,9 @@ def check(e, cw, o, rays_in, verts, label):
     assert np.array_equal(ref_dis, eng_dis)
     cls = util.classify_mismatches(got, want_o, verts)
     cls["reference_layout_disagreement"] = int(ref_dis.sum())
-    assert ref_dis.mean() < 1e-2, f"{label}: {cls}"
+    # pinned: the engine differs from the oracle on EXACTLY the rays on which the reference's own walk of this layout differs (above);
+    # the rate itself is a property of the reference (ties, t = -0.0 on a surface) and stays far below this sanity bound
+    assert ref_dis.mean() < 2e-3, f"{label}: {cls}"
     same = ~eng_dis
     rel = np.abs(got["t"] - want_o["t"]) / np.maximum(np.abs(want_o["t"]), 1e-30)
     assert (rel[same & (want_o["t"] < 1e30)] == 0).all()

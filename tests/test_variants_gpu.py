@@ -50,7 +50,7 @@ def test_trace_variants_are_bit_exact(gpu, world, variant):
         api.set_option("trace_variant", 3)
 
 
-@pytest.mark.parametrize("mode", [0, 2, 3])
+@pytest.mark.parametrize("mode", [0, 1, 2, 3])
 def test_host_path_modes_return_the_same_hits(gpu, world, mode):
     v, primary, d, want = world
     api.set_option("d2h_mode", mode)

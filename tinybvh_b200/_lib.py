@@ -73,6 +73,7 @@ SYMBOLS = {
     "tbvh_device_numa_node": (i32, [i32]),
     "tbvh_bind_thread_to_device": (i32, [i32]),
     "tbvh_host_alloc_near": (i32, [i32, sz, C.POINTER(vp)]),
+    "tbvh_host_alloc_node": (i32, [i32, sz, C.POINTER(vp)]),
     "tbvh_group_create": (i32, [vp, i32, C.POINTER(vp)]),
     "tbvh_group_destroy": (i32, [vp]),
     "tbvh_group_size": (i32, [vp]),

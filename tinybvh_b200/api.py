@@ -303,12 +303,14 @@ class BVH8_CWBVH(_Base):
         return d, t
 
 
-def pinned_empty(n: int, dtype, device: int = None) -> np.ndarray:
+def pinned_empty(n: int, dtype, device: int = None, node: int = None) -> np.ndarray:
     """numpy array in page-locked host memory on the NUMA node of `device` (default: the current CUDA device): full-speed DMA
     for the host path (tbvh_host_alloc / tbvh_host_alloc_near)."""
     dtype = np.dtype(dtype)
     p = C.c_void_p()
-    if device is None:
+    if node is not None:
+        check(_lib.lib().tbvh_host_alloc_node(node, n * dtype.itemsize, C.byref(p)))
+    elif device is None:
         check(_lib.lib().tbvh_host_alloc(n * dtype.itemsize, C.byref(p)))
     else:
         check(_lib.lib().tbvh_host_alloc_near(device, n * dtype.itemsize, C.byref(p)))

@@ -269,7 +269,7 @@ int tbvh_set_option( tbvh_ctx c, const char* key, int value )
 	else if (!strcmp( key, "inst_idx_bits" )) c->inst_idx_bits = value;
 	else if (!strcmp( key, "hq_small" )) c->hq_small = value;
 	else if (!strcmp( key, "hq_cluster" )) c->hq_cluster = value;
-	else if (!strcmp( key, "d2h_mode" )) c->d2h_mode = value == 3 ? 3 : value == 2 ? 2 : 0;
+	else if (!strcmp( key, "d2h_mode" )) c->d2h_mode = value >= 0 && value <= 3 ? value : 0;
 	else if (!strcmp( key, "scatter_threads" ))
 	{
 		ARG_CHECK( value >= 1 && value <= 64, "scatter_threads must be 1..64" );
@@ -302,10 +302,12 @@ int tbvh_set_option( tbvh_ctx c, const char* key, int value )
 static std::mutex g_huge_mutex;
 static std::vector<std::pair<void*, size_t>> g_huge;
 
-int tbvh_host_alloc_near( int device, size_t bytes, void** out )
+static int host_alloc_on_node( int node, size_t bytes, void** out );
+int tbvh_host_alloc_near( int device, size_t bytes, void** out ) { return host_alloc_on_node( device_numa_node( device ), bytes, out ); }
+int tbvh_host_alloc_node( int node, size_t bytes, void** out ) { return host_alloc_on_node( node, bytes, out ); }
+static int host_alloc_on_node( int node, size_t bytes, void** out )
 {
 	ARG_CHECK( out, "out == NULL" );
-	const int node = device_numa_node( device );
 	static int huge = -1;
 	if (huge < 0) { const char* e = getenv( "TBVH_HOST_HUGE" ); huge = e ? atoi( e ) : 1; } // default on: +5..9 % on the host path where the IOMMU translates DMA addresses (profiles/README.md)
 	if (huge && bytes >= (8u << 20))
@@ -1062,6 +1064,9 @@ static int intersect_host( tbvh_bvh b, int layout, void* rays, uint32_t stride, 
 	}
 	char* dev_alias = (char*)mapped_alias( rays );
 	const bool scatter = !packed_hits && !tlas && c->d2h_mode == 3 && dev_alias && (stride & 15) == 0;
+	// d2h_mode 1: the kernel writes the hit into the staged record and bytes 0..63 of every record - exactly its first cache line - travel
+	// back, so the host receives FULL-line writes (no read-for-ownership of a partially written line); bytes 0..47 return unchanged
+	const bool full_line = !packed_hits && !tlas && c->d2h_mode == 1 && stride >= 64;
 	// d2h_mode 2: the hits leave the device packed (one contiguous copy per chunk) into page-locked staging, and a few host threads on
 	// the device's NUMA node write them into the strided records while later chunks are in flight
 	const bool host_scatter = !packed_hits && !tlas && c->d2h_mode == 2 && n >= 65536;
@@ -1104,12 +1109,14 @@ static int intersect_host( tbvh_bvh b, int layout, void* rays, uint32_t stride, 
 			uint32_t ss = 64;
 			TRY( stage_in( c, k, chunk, h, hd, stride, cnt, &ss ) );
 			if (tlas) TRY( tlas_trace_launch( b, sl.d_rays, ss, 0, cnt, false, c->s_run ) );  // hit + instance written into the staged records
+			else if (full_line) TRY( trace_dispatch( b, layout, sl.d_rays, ss, (char*)sl.d_rays + 48, ss, 0, cnt, false, c->s_run ) );
 			else TRY( trace_dispatch( b, layout, sl.d_rays, ss, sl.d_hits, 16, 0, cnt, false, c->s_run ) );
 			CUDA_TRY( cudaEventRecord( sl.run_done, c->s_run ) );
 			CUDA_TRY( cudaStreamWaitEvent( c->s_out, sl.run_done, 0 ) );
 			if (tlas) CUDA_TRY( cudaMemcpy2DAsync( h + 44, stride, (char*)sl.d_rays + 44, ss, 20, cnt, cudaMemcpyDeviceToHost, c->s_out ) );
 			else if (packed_hits) CUDA_TRY( cudaMemcpyAsync( (char*)packed_hits + off * 16, sl.d_hits, cnt * 16, cudaMemcpyDeviceToHost, c->s_out ) );
 			else if (host_scatter) CUDA_TRY( cudaMemcpyAsync( sl.h_hits, sl.d_hits, cnt * 16, cudaMemcpyDeviceToHost, c->s_out ) );
+			else if (full_line) CUDA_TRY( cudaMemcpy2DAsync( h, stride, sl.d_rays, ss, 64, cnt, cudaMemcpyDeviceToHost, c->s_out ) );
 			else if (scatter)
 			{
 				k_scatter_hits<<<(uint32_t)((cnt + 255) / 256), 256, 0, c->s_out>>>( (const float4*)sl.d_hits, (float4*)hd, stride / 16, cnt );
