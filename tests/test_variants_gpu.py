@@ -68,7 +68,7 @@ def test_host_path_modes_return_the_same_hits(gpu, world, mode):
         assert np.array_equal(hits["t"].view(np.uint32), want["primary"]["t"].view(np.uint32)) and np.array_equal(hits["prim"], want["primary"]["prim"])
         api.pinned_free(pinned)
     finally:
-        api.set_option("d2h_mode", 0)
+        api.set_option("d2h_mode", 1)
 
 
 @pytest.mark.parametrize("small_t", [8, 64, 256])

@@ -49,7 +49,8 @@ struct tbvh_ctx_t
 	size_t slot_rec = 0;             // bytes per staged ray record the slots were allocated for (64, or 128 under host_path 2)
 	int host_path = 0;               // inbound: 0 = copy engine (cudaMemcpy2DAsync of 64-byte rows), 1 = gather kernel through the pinned mapping, 2 = whole 128-byte records in one contiguous copy
 	int h2d_split = 1;               // inbound 2D copy of a chunk split over this many streams (copy engines)
-	int d2h_mode = 0;                // in-place hits: 0 = 2D copy of 16-byte rows, 2 = packed copy + host threads scatter, 3 = scatter kernel through the pinned mapping
+	int d2h_mode = 1;                // in-place hits: 1 = bytes 0..63 of every record return (full cache lines, the default), 0 = 2D copy of 16-byte rows,
+	                                 // 2 = packed copy + host threads scatter, 3 = scatter kernel through the pinned mapping
 	int scatter_threads = 8;         // d2h_mode 2: host threads (bound to the device's NUMA node) that write the hits into the records
 	struct HostPool* pool = 0;
 	int trace_variant = 3;           // BVH2 traversal kernel: 0 generic, 3 octant switch, 4 persistent warps (see trace_bvh2.cu)

@@ -66,6 +66,9 @@ h = api.pinned_empty(n, R.RAY_DTYPE, device=0)
 api.bind_to_device(0)
 fill(h)
 run("local pinned buffer", h)
+api.set_option("d2h_mode", 0)
+run("local, 16-byte rows back (d2h 0)", h)
+api.set_option("d2h_mode", 1)
 if "--short" in sys.argv:
     sys.exit(0)
 api.set_option("host_path", 2)
