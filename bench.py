@@ -373,10 +373,8 @@ def run_ours(args):
     # Sharding by ray index, block-cyclic: the set is cut into blocks of 2^20 consecutive rays (4x4-pixel tiles stay together, warps stay
     # coherent) and block b belongs to rank b % world - a rank's rays come from all over the image, so no rank owns "the expensive
     # corner" (contiguous eighths of the Bistro view differ by 30 % in traversal work).  Every rank generates its own blocks.
-    BLOCK = 1 << 20
-    blocks = [(b * BLOCK, min(BLOCK, n_total - b * BLOCK)) for b in range((n_total + BLOCK - 1) // BLOCK) if b % world == rank]
-    if world == 1:
-        blocks = [(0, n_total)]
+    from tinybvh_b200 import multi as M
+    blocks = M.block_cyclic(n_total, rank, world)
     n = sum(c for _, c in blocks)
     first = blocks[0][0] if blocks else 0
     eye, view = camera_for(args.scene, verts)

@@ -75,3 +75,24 @@ def test_world_size_2_gloo_broadcast_and_shard(tmp_path):
     r = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "MULTI_OK 2" in r.stdout
+
+
+def test_block_cyclic_partition_covers_the_set_once():
+    """bench.py --gpus N deals the one ray set out in 2^20-ray blocks, block b to rank b % N."""
+    from tinybvh_b200 import multi
+    for n in (0, 5, 1 << 20, (1 << 20) + 1, 67108864, 67108864 + 12345):
+        for world in (1, 2, 3, 4, 8):
+            seen = []
+            for r in range(world):
+                blocks = multi.block_cyclic(n, r, world)
+                assert all(c > 0 and a % 32 == 0 for a, c in blocks)
+                seen += blocks
+            seen.sort()
+            pos = 0
+            for a, c in seen:
+                assert a == pos
+                pos += c
+            assert pos == n
+            if world > 1 and n >= world << 20:
+                sizes = [sum(c for _, c in multi.block_cyclic(n, r, world)) for r in range(world)]
+                assert max(sizes) - min(sizes) <= 1 << 20

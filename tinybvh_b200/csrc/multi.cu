@@ -19,8 +19,8 @@
 struct tbvh_group_t
 {
 	std::vector<tbvh_ctx> ctx;        // one per device
-	std::vector<tbvh_bvh> replica;    // replica[g] lives on ctx[g]; replica[0] may be the caller's source handle
-	bool owns_first = true;
+	std::vector<tbvh_bvh> replica;    // replica[g] lives on ctx[g]
+	std::vector<char> owned;          // 0 where replica[g] IS the caller's source handle (its context belongs to the group)
 	std::vector<std::pair<void*, size_t>> host_blocks; // tbvh_group_host_alloc results (mmap + cudaHostRegister)
 };
 
@@ -29,8 +29,8 @@ struct tbvh_group_t
 
 static void release_replicas( tbvh_group g )
 {
-	for (size_t i = 0; i < g->replica.size(); i++) if (g->replica[i] && !(i == 0 && !g->owns_first)) tbvh_bvh_destroy( g->replica[i] );
-	g->replica.clear();
+	for (size_t i = 0; i < g->replica.size(); i++) if (g->replica[i] && g->owned[i]) tbvh_bvh_destroy( g->replica[i] );
+	g->replica.clear(), g->owned.clear();
 }
 
 // device-to-device copy of `bytes` from (src_dev) to a fresh allocation on (dst_dev)
@@ -131,16 +131,15 @@ int tbvh_group_replicate( tbvh_group g, tbvh_bvh src, double* ms_out )
 	CUDA_TRY( cudaEventCreate( &e0 ) );
 	CUDA_TRY( cudaEventCreate( &e1 ) );
 	CUDA_TRY( cudaEventRecord( e0, src->ctx->stream ) );
-	g->owns_first = g->ctx[0] != src->ctx;
 	int rc = TBVH_OK;
 	for (size_t i = 0; i < g->ctx.size() && rc == TBVH_OK; i++)
 	{
 		tbvh_ctx c = g->ctx[i];
-		if (c == src->ctx) { g->replica.push_back( src ); continue; }
+		if (c == src->ctx) { g->replica.push_back( src ), g->owned.push_back( 0 ); continue; }
 		tbvh_bvh r = 0;
 		rc = tbvh_bvh_create( c, &r );
 		if (rc != TBVH_OK) break;
-		g->replica.push_back( r );
+		g->replica.push_back( r ), g->owned.push_back( 1 );
 		auto body = [&]() -> int
 		{
 			CUDA_TRY( cudaSetDevice( c->device ) );
