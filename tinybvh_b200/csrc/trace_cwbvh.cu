@@ -16,13 +16,20 @@
 //        pair j   32 B   the (2j)-th and (2j+1)-th NON-EMPTY child:  lo.x lo.y lo.z hi.x hi.y hi.z as half2 (child a, child b)
 //                        - 0..255 is exact in fp16 - and one 32-bit hit word per child: a leaf child's triangle bits
 //                        `unary(count) << offset`, an inner child's slot bit `1 << (24 + slot)`
-//    Empty slots are gone, so a node costs ceil(children/2) pair steps, not 8 slot steps.
+//    Empty slots are gone: a node holds ceil(children/2) pair records (the rest of the four are zero and contribute no bit), and a
+//    visited node is nearly always full (3.83 of 4 on Bistro camera rays), so the kernel runs all four pair steps without branching -
+//    four pair steps instead of eight slot steps, and the eight loads leave together.
 //  * A pair step is packed fp32 arithmetic (Blackwell FFMA2, `fma.rn.f32x2`): one instruction evaluates the same plane of both
 //    children, 6 per pair instead of 12 FFMA, exactly rounded per component like the scalar fma.
 //  * The quantised planes reach the registers as halves and are widened by one conversion each (no byte extraction, no
 //    integer-to-float on the quarter-rate unit, no magic-number subtraction).
-//  * Near / far planes are picked per ray by the sign of rD once per pair on the packed words (3 selects for two children).
-//  * Inner-child bits are accumulated in slot order and moved to octant order by one 3-stage bit butterfly per node.
+//  * Near / far planes are picked by the sign of rD once per pair on the packed words, inner-child bits are accumulated in slot order
+//    and moved to octant order by one 3-stage bit butterfly per node - and when every ray of a warp points into the same direction
+//    octant (camera and shadow rays), a warp-uniform switch runs the node step through the instance compiled for that octant, where
+//    both are compile-time (node_hits<OCT>).
+//  * The per-axis scales 2^e are stored as the top halves of their float patterns: one shift or mask each instead of a byte decode.
+//
+// Executed-instruction mix, ncu extracts and the history of the variants: profiles/README.md ("The CWBVH kernel ...").
 //
 // Triangles are the reference's 48-byte records (e2, e1, v0 | primIdx) read straight from bvh8Tris.
 #include "common.cuh"
