@@ -236,6 +236,25 @@ int main( int argc, char** argv )
 		tlasSame = diff == 0 && gpu_tlas.usedNodes == ref_tlas.usedNodes && updSame;
 		printf( "TLAS of %d instances: reference IntersectTLAS %.2f ms (%u threads), tinybvh_b200 %.2f ms incl. PCIe; %zu of %zu rays hit, %zu differ (t,u,v,prim,inst)\n",
 			N, refT * 1000, std::thread::hardware_concurrency(), gpuT * 1000, hits, M, diff );
+		// the same instances over a BVH8_CWBVH BLAS (tiny_bvh_gpu2.cpp's arrangement; the reference's CPU IntersectTLAS does not take one):
+		// reported, not part of the verdict - two layouts of the same triangles agree up to exact-distance ties
+		{
+			tinybvh_b200::BVH8_CWBVH gpu_wide;
+			gpu_wide.Build( triangles, verts / 3 );
+			tinybvh_b200::BVHBase* wideList[1] = { &gpu_wide };
+			tinybvh_b200::BVH gpu_tlas_wide;
+			gpu_tlas_wide.Build( inst2, N, wideList, 1 );
+			for (size_t k = 0; k < M; k++) b[k].hit = Ray( eye, view ).hit;
+			gpu_tlas_wide.Intersect( b, M );
+			for (size_t k = 0; k < M; k++) b[k].hit = Ray( eye, view ).hit;
+			t.reset();
+			gpu_tlas_wide.Intersect( b, M );
+			const float wideT = t.elapsed();
+			size_t wdiff = 0;
+			for (size_t k = 0; k < M; k++) wdiff += memcmp( &a[k].hit.t, &b[k].hit.t, 16 ) != 0 || (a[k].hit.t < 1e30f && a[k].hit.inst != b[k].hit.inst);
+			printf( "TLAS over a BVH8_CWBVH BLAS (layout %d): tinybvh_b200 %.2f ms incl. PCIe; %zu of %zu rays differ from the reference's IntersectTLAS over the BVH BLAS\n",
+				gpu_tlas_wide.Layout(), wideT * 1000, wdiff, M );
+		}
 	}
 	return ok && primDiff == 0 && tDiff == 0 && hqSame && refitSame && tlasSame ? 0 : 1;
 }

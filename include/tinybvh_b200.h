@@ -133,7 +133,12 @@ int tbvh_build_indexed( tbvh_bvh bvh, const void* verts, uint32_t stride, uint32
  * record, so closest hits are always returned in place (tbvh_intersect_packed / a separate d_hits array: TBVH_E_UNSUPPORTED).
  * A host program compiled with another INST_IDX_BITS (4..31) sets tbvh_set_option( ctx, "inst_idx_bits", bits ): hits then
  * carry the instance in the top bits of hit.prim (prim = triIdx + (inst << (32 - bits)), :8527) and byte 44 is left alone.
- * Pass layout TBVH_LAYOUT_BVH to the traversal calls. */
+ * The `layout` argument of the traversal calls on a TLAS names the layout the BLASses are walked in: TBVH_LAYOUT_BVH (what the
+ * reference's CPU IntersectTLAS does, :3341), or TBVH_LAYOUT_CWBVH - the arrangement of the reference's GPU path (traverse_tlas.cl:13-107:
+ * BVH2 TLAS, per-instance ray transform, CWBVH BLASses, a BLAS hit kept when it is closer, the instance attached), semantics of
+ * BVH8_CWBVH::Intersect (:7046) per BLAS.  A BLAS may hold either layout or both (CWBVH: tbvh_convert / tbvh_upload_cwbvh BEFORE
+ * tbvh_build_tlas - the TLAS records the arrays each BLAS holds at that moment); walking a layout some BLAS did not hold is
+ * TBVH_E_STATE, and so is walking a TLAS after one of its BLASses was rebuilt, re-converted, re-uploaded or destroyed. */
 /* BVH::SAHCost( 0 ) tiny_bvh.h:1889-1897: the tree's SAH cost, host recursion over the (downloaded) 32-byte node array in the
  * reference's own order and rounding - the number the speedtest prints after every build.  _nodes works on a host array. */
 int tbvh_sah_cost( tbvh_bvh bvh, float c_trav, float c_int, float* out );

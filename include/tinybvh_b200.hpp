@@ -66,6 +66,7 @@ public:
 	float aabbMin[3] = { 0, 0, 0 }, aabbMax[3] = { 0, 0, 0 };
 	double buildMs = 0;            // device time of the last Build
 	tbvh_bvh handle() const { return h; }
+	int Layout() const { return layout; }  // TBVH_LAYOUT_*: the layout Intersect / IsOccluded walk (BVHBase::layout, tiny_bvh.h:795-805)
 	tbvh_info Info() const { tbvh_info i; TBVH_FATAL_IF( tbvh_bvh_info( h, &i ), "Info" ); return i; }
 	// batch traversal: the calls the patched harness makes instead of its per-ray loops
 	// Return value: 0, or - with collectCost set - the sum over the batch of what the reference's per-ray Intersect returns,
@@ -187,6 +188,8 @@ public:
 	// reference's 192-byte tinybvh::BLASInstance.  As in the reference (:2245-2250) every instance is Update()d first - inverse
 	// transform and world box, computed on the host bit-identically to BLASInstance::Update (:8386) - and written back.
 	// Intersect / IsOccluded on the TLAS are then IntersectTLAS / IsOccludedTLAS; a hit carries hit.inst (INST_IDX_BITS == 32).
+	// When EVERY BLAS is a BVH8_CWBVH object the BLASses are walked in that layout (the arrangement of the reference's GPU path,
+	// traverse_tlas.cl:60-67 "GPU_STATIC"); otherwise in the BVH layout, which every BLAS built by this shim holds as well.
 	template <class Inst> void Build( Inst* instances, const uint32_t instCount, BVHBase** blasses, const uint32_t blasCount )
 	{
 		static_assert( sizeof( Inst ) == 192, "tinybvh::BLASInstance is 192 bytes (tiny_bvh.h:1443)" );
@@ -194,7 +197,9 @@ public:
 		TBVH_FATAL_IF( tbvh_set_option( context(), "inst_idx_bits", INST_IDX_BITS ), "inst_idx_bits" ); // where a hit stores its instance (:114-119)
 #endif
 		tbvh_bvh* hs = (tbvh_bvh*)malloc( sizeof( tbvh_bvh ) * (blasCount ? blasCount : 1) );
-		for (uint32_t k = 0; k < blasCount; k++) hs[k] = blasses[k]->handle();
+		bool allWide = blasCount > 0;
+		for (uint32_t k = 0; k < blasCount; k++) hs[k] = blasses[k]->handle(), allWide = allWide && blasses[k]->Layout() == TBVH_LAYOUT_CWBVH;
+		layout = allWide ? TBVH_LAYOUT_CWBVH : TBVH_LAYOUT_BVH;
 		for (uint32_t i = 0; i < instCount; i++) // instList[i].Update( blas ) :2247-2249, bit-identical to the reference's
 		{
 			uint32_t blasIdx;

@@ -43,6 +43,8 @@ def lib():
         L.orc_intersect_tlas.restype, L.orc_intersect_tlas.argtypes = None, [vp, vp, vp, vp, vp, u64]
         L.orc_occluded_tlas.restype, L.orc_occluded_tlas.argtypes = None, [vp, vp, vp, vp, vp, u64, vp]
         L.orc_instance_update.restype, L.orc_instance_update.argtypes = None, [vp, vp, vp]
+        L.orc_intersect_tlas_cw.restype, L.orc_intersect_tlas_cw.argtypes = None, [vp, vp, vp, vp, vp, u64]
+        L.orc_occluded_tlas_cw.restype, L.orc_occluded_tlas_cw.argtypes = None, [vp, vp, vp, vp, vp, u64, vp]
         L.orc_cwbvh_from_bvh.restype, L.orc_cwbvh_from_bvh.argtypes = u32, [vp, u32, vp, u32, vp, u32, vp, vp]
         L.orc_cwbvh_intersect.restype, L.orc_cwbvh_intersect.argtypes = None, [vp, vp, vp, u64]
         L.orc_refit.restype, L.orc_refit.argtypes = None, [vp, u32, vp, vp]
@@ -146,6 +148,33 @@ class PortCWBVH:
         assert rays.dtype.itemsize == 128 and rays.flags.c_contiguous
         lib().orc_cwbvh_intersect(_ptr(self.nodes), _ptr(self.tris), _ptr(rays), rays.shape[0])
         return rays
+
+
+class PortTLASCW:
+    """orc_intersect_tlas_cw / orc_occluded_tlas_cw: the TLAS walk of IntersectTLAS with BVH8_CWBVH::Intersect as the per-instance BLAS step
+    (a composition of two pinned restatements - the reference's CPU TLAS does not take CWBVH BLASses; see tbvh_oracle.h).
+    blasses: PortCWBVH objects (or anything with .nodes / .tris float4 arrays)."""
+
+    def __init__(self, nodes, prim_idx, instances, blasses):
+        self.nodes = np.ascontiguousarray(nodes).view(NODE32).reshape(-1)
+        self.prim_idx = np.ascontiguousarray(prim_idx, np.uint32)
+        self.instances = np.ascontiguousarray(instances)
+        assert self.instances.dtype.itemsize == 192
+        self.blasses = [(np.ascontiguousarray(b.nodes, np.float32), np.ascontiguousarray(b.tris, np.float32)) for b in blasses]
+        class _B(C.Structure):
+            _fields_ = [("data", C.c_void_p), ("tris", C.c_void_p)]
+        self._table = (_B * len(self.blasses))(*[_B(d.ctypes.data, t.ctypes.data) for d, t in self.blasses])
+
+    def intersect(self, rays):
+        assert rays.dtype.itemsize == 128 and rays.flags.c_contiguous
+        lib().orc_intersect_tlas_cw(_ptr(self.nodes), _ptr(self.prim_idx), _ptr(self.instances), C.cast(self._table, C.c_void_p), _ptr(rays), rays.shape[0])
+        return rays
+
+    def occluded(self, rays):
+        assert rays.dtype.itemsize == 128 and rays.flags.c_contiguous
+        bits = np.zeros((rays.shape[0] + 31) // 32, np.uint32)
+        lib().orc_occluded_tlas_cw(_ptr(self.nodes), _ptr(self.prim_idx), _ptr(self.instances), C.cast(self._table, C.c_void_p), _ptr(rays), rays.shape[0], _ptr(bits))
+        return bits
 
 
 def instance_update(instances, bmin, bmax):

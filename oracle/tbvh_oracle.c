@@ -383,8 +383,16 @@ static void transform_ray( const float* T, const orc_ray* ray, orc_ray* temp )
 		temp->rD[k] = safercp( temp->D[k] );
 	}
 }
-static int intersect_tlas1( const orc_node* nodes, const uint32_t* primIdx, const orc_instance* inst, const orc_blas* blas, orc_ray* ray, int anyhit )
+/* the BLAS step of one TLAS-leaf instance: walks `temp` (the transformed ray, hit copied from the world-space ray) through BLAS
+ * blasIdx and leaves the updated hit in it; returns 1 when an any-hit query found an occluder */
+static int walk_bvh_blas( const void* user, uint32_t blasIdx, void* temp, int anyhit )
 {
+	const orc_blas* b = (const orc_blas*)user + blasIdx;
+	return intersect1( b->nodes, b->primIdx, b->verts, (orc_ray*)temp, anyhit );
+}
+int orc_tlas_walk1( const orc_node* nodes, const uint32_t* primIdx, const orc_instance* inst, void* ray_, int anyhit, orc_blas_walk walk, const void* user )
+{
+	orc_ray* ray = (orc_ray*)ray_;
 	const orc_node* node = &nodes[0], * stack[64];
 	uint32_t stackPtr = 0;
 	const int pos[3] = { ray->D[0] >= 0, ray->D[1] >= 0, ray->D[2] >= 0 };
@@ -398,14 +406,13 @@ static int intersect_tlas1( const orc_node* nodes, const uint32_t* primIdx, cons
 				const uint32_t instIdx = primIdx[node->leftFirst + i];
 				const orc_instance* in = &inst[instIdx];
 				if (!(in->mask & ray->mask)) continue;
-				const orc_blas* b = &blas[in->blasIdx];
 				orc_ray temp;
 				memset( &temp, 0, sizeof( temp ) );
 				temp.mask = 0xFFFF; /* Ray() = default: mask = RAY_MASK_INTERSECT_ALL */
 				transform_ray( in->invTransform, ray, &temp );
 				temp.instIdx = instIdx; /* << (32 - INST_IDX_BITS) = << 0 */
 				temp.pad = ray->pad, temp.t = ray->t, temp.u = ray->u, temp.v = ray->v, temp.prim = ray->prim; /* temp.hit = ray.hit */
-				if (intersect1( b->nodes, b->primIdx, b->verts, &temp, anyhit )) return 1;
+				if (walk( user, in->blasIdx, &temp, anyhit )) return 1;
 				if (!anyhit) ray->pad = temp.pad, ray->t = temp.t, ray->u = temp.u, ray->v = temp.v, ray->prim = temp.prim; /* ray.hit = temp.hit */
 			}
 			if (stackPtr == 0) break; else node = stack[--stackPtr];
@@ -418,6 +425,10 @@ static int intersect_tlas1( const orc_node* nodes, const uint32_t* primIdx, cons
 		else { node = child1; if (dist2 != BVH_FAR) stack[stackPtr++] = child2; }
 	}
 	return 0;
+}
+static int intersect_tlas1( const orc_node* nodes, const uint32_t* primIdx, const orc_instance* inst, const orc_blas* blas, orc_ray* ray, int anyhit )
+{
+	return orc_tlas_walk1( nodes, primIdx, inst, ray, anyhit, walk_bvh_blas, blas );
 }
 void orc_intersect_tlas( const orc_node* nodes, const uint32_t* primIdx, const orc_instance* inst, const orc_blas* blas, void* rays, uint64_t n )
 {

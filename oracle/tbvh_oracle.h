@@ -49,6 +49,11 @@ typedef struct { const orc_node* nodes; const uint32_t* primIdx; const float* ve
 void orc_instance_update( orc_instance* inst, const float* bmin, const float* bmax );
 void orc_intersect_tlas( const orc_node* nodes, const uint32_t* primIdx, const orc_instance* inst, const orc_blas* blas, void* rays, uint64_t n );
 void orc_occluded_tlas( const orc_node* nodes, const uint32_t* primIdx, const orc_instance* inst, const orc_blas* blas, const void* rays, uint64_t n, uint32_t* bits );
+/* the TLAS walk of IntersectTLAS / IsOccludedTLAS for ONE ray with the per-instance BLAS step supplied by the caller: walk( user, blasIdx,
+ * temp, anyhit ) receives the transformed ray (hit = the world-space ray's current hit, instIdx set) and leaves the updated hit in it;
+ * a non-zero return ends an any-hit query */
+typedef int (*orc_blas_walk)( const void* user, uint32_t blasIdx, void* temp_ray, int anyhit );
+int orc_tlas_walk1( const orc_node* nodes, const uint32_t* primIdx, const orc_instance* inst, void* ray, int anyhit, orc_blas_walk walk, const void* user );
 
 /* One Moeller-Trumbore test in the oracle's arithmetic (MOLLER_TRUMBORE_TEST :1644-1656).
  * Returns 1 and writes t,u,v when the triangle is accepted for a ray with the given tmax. */
@@ -66,6 +71,14 @@ void orc_refit( orc_node* nodes, uint32_t usedNodes, const uint32_t* primIdx, co
 uint32_t orc_cwbvh_from_bvh( const orc_node* nodes, uint32_t usedNodes, const uint32_t* primIdx, uint32_t idxCount, const float* verts, uint32_t triCount, float* data, float* tris );
 /* BVH8_CWBVH::Intersect (:7046-7154), the reference's CPU walk of the compressed layout, over 128-byte Ray records in place */
 void orc_cwbvh_intersect( const float* bvh8Data, const float* bvh8Tris, void* rays, uint64_t n );
+/* A TLAS over BVH8_CWBVH BLASses - the arrangement of the reference's GPU path (traverse_tlas.cl:13-107: BVH2 TLAS, per-instance ray
+ * transform, traverse_cwbvh per BLAS, `if (blasHit.x < hit.x) hit = blasHit` with the instance attached); the reference's CPU
+ * IntersectTLAS does not accept LAYOUT_CWBVH BLASses (:3339), so this is a COMPOSITION of two pinned pieces, not a pinned function:
+ * orc_tlas_walk1 (IntersectTLAS :3306, transform and safercp as on the CPU) with BVH8_CWBVH::Intersect (:7046) as the BLAS step; a
+ * BLAS that finds nothing closer leaves the hit as it was; occlusion = a BLAS walk that ends below the ray's t (FALLBACK_SHADOW_QUERY). */
+typedef struct { const float* bvh8Data; const float* bvh8Tris; } orc_cwblas;
+void orc_intersect_tlas_cw( const orc_node* nodes, const uint32_t* primIdx, const orc_instance* inst, const orc_cwblas* blas, void* rays, uint64_t n );
+void orc_occluded_tlas_cw( const orc_node* nodes, const uint32_t* primIdx, const orc_instance* inst, const orc_cwblas* blas, const void* rays, uint64_t n, uint32_t* bits );
 
 /* BVH::SAHCost (:1889) */
 float orc_sah_cost( const orc_node* nodes, uint32_t nodeIdx, float c_trav, float c_int );

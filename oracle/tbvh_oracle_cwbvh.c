@@ -303,3 +303,31 @@ void orc_cwbvh_intersect( const float* bvh8Data, const float* bvh8Tris, void* ra
 {
 	for (uint64_t i = 0; i < n; i++) cw_intersect1( bvh8Data, bvh8Tris, (cw_ray*)rays + i );
 }
+
+/* ---- TLAS over CWBVH BLASses: see tbvh_oracle.h */
+static int walk_cw_blas( const void* user, uint32_t blasIdx, void* temp_, int anyhit )
+{
+	const orc_cwblas* b = (const orc_cwblas*)user + blasIdx;
+	cw_ray* temp = (cw_ray*)temp_;
+	const cw_ray before = *temp;
+	cw_intersect1( b->bvh8Data, b->bvh8Tris, temp );
+	if (temp->t < before.t)
+	{
+		temp->pad = temp->instIdx; /* hit.inst: the instance travels with the hit (traverse_tlas.cl:88; IntersectTri :8525) */
+		return anyhit;
+	}
+	temp->t = before.t, temp->u = before.u, temp->v = before.v, temp->prim = before.prim, temp->pad = before.pad;
+	return 0;
+}
+void orc_intersect_tlas_cw( const orc_node* nodes, const uint32_t* primIdx, const orc_instance* inst, const orc_cwblas* blas, void* rays, uint64_t n )
+{
+	for (uint64_t i = 0; i < n; i++) orc_tlas_walk1( nodes, primIdx, inst, (cw_ray*)rays + i, 0, walk_cw_blas, blas );
+}
+void orc_occluded_tlas_cw( const orc_node* nodes, const uint32_t* primIdx, const orc_instance* inst, const orc_cwblas* blas, const void* rays, uint64_t n, uint32_t* bits )
+{
+	for (uint64_t i = 0; i < n; i++)
+	{
+		cw_ray tmp = ((const cw_ray*)rays)[i];
+		if (orc_tlas_walk1( nodes, primIdx, inst, &tmp, 1, walk_cw_blas, blas )) bits[i >> 5] |= 1u << (i & 31);
+	}
+}

@@ -33,8 +33,9 @@ def check(e, cw, o, rays_in, verts, label):
     cls = util.classify_mismatches(got, want_o, verts)
     cls["reference_layout_disagreement"] = int(ref_dis.sum())
     # pinned: the engine differs from the oracle on EXACTLY the rays on which the reference's own walk of this layout differs (above);
-    # the rate itself is a property of the reference (ties, t = -0.0 on a surface) and stays far below this sanity bound
-    assert ref_dis.mean() < 2e-3, f"{label}: {cls}"
+    # the rate itself is a property of the reference (ties, t = -0.0 on a surface, rays with a zero direction component whose quantised
+    # plane distances overflow: 69 of 32,768 = 2.1e-3 on the 900-triangle seeded scene, reproducible with the reference alone on the CPU)
+    assert ref_dis.mean() < 5e-3, f"{label}: {cls}"
     same = ~eng_dis
     rel = np.abs(got["t"] - want_o["t"]) / np.maximum(np.abs(want_o["t"]), 1e-30)
     assert (rel[same & (want_o["t"] < 1e30)] == 0).all()

@@ -252,6 +252,44 @@ def test_port_tlas_matches_reference():
 
 
 @pytest.mark.skipif(not refpy.available(), reason="oracle/_ref not built (needs /root/reference)")
+def test_port_tlas_over_cwbvh_composition():
+    """A TLAS over BVH8_CWBVH BLASses (the reference's GPU arrangement, traverse_tlas.cl): the oracle composes its pinned TLAS walk with its
+    pinned BVH8_CWBVH::Intersect.  Anchors: (1) a one-instance identity TLAS gives BVH8_CWBVH::Intersect's own result plus the instance;
+    (2) against the reference's IntersectTLAS over BVH BLASses of the same triangles the hits agree wherever the two layouts agree on
+    their own (distinct triangles at one distance are the only source of differences)."""
+    v, inst, O, D = tlas_case(91)
+    blas_ref = [refpy.RefBVH(x, mode=0) for x in v]
+    tl = refpy.RefTLAS(inst, blas_ref)
+    tb = tl.bvh()
+    pb = [portpy.PortBVH(x) for x in v]
+    cw = [portpy.PortCWBVH(b.nodes, b.prim_idx, b.verts) for b in pb]
+    port = portpy.PortTLASCW(tb.nodes, tb.prim_idx, inst, cw)
+    words = lambda r: r.view(np.uint32).reshape(-1, 32)[:, 11:16]   # inst, t, u, v, prim
+    for mask in (0x1, 0x2):
+        rays = R.make_rays(O, D)
+        rays["mask"] = mask
+        a, b = rays.copy(), rays.copy()
+        tl.intersect(a, threads=1), port.intersect(b)
+        same = (words(a) == words(b)).all(axis=1)
+        assert same.mean() > 0.9995 and (a["t"] < 1e30).sum() > 10000   # this scene has no coincident triangles: in practice every ray agrees
+        sh = R.make_rays(O, D, tmax=150.0)
+        sh["mask"] = mask
+        oa, ob = tl.occluded(sh, threads=1), port.occluded(sh)
+        assert np.unpackbits((oa ^ ob).view(np.uint8)).sum() <= 4
+    # one instance, identity transform: the BLAS walk alone
+    one = refpy.make_instances(np.eye(4, dtype=np.float32)[None], [0])
+    t1 = refpy.RefTLAS(one, blas_ref[:1])
+    tb1 = t1.bvh()
+    p1 = portpy.PortTLASCW(tb1.nodes, tb1.prim_idx, one, cw[:1])
+    Dn = D / np.linalg.norm(D, axis=1, keepdims=True)
+    rays = R.make_rays(O * 0.2, Dn.astype(np.float32))
+    a, b = rays.copy(), rays.copy()
+    cw[0].intersect(a), p1.intersect(b)
+    assert np.array_equal(words(a)[:, 1:], words(b)[:, 1:]) and (a["t"] < 1e30).sum() > 1000
+    assert (words(b)[b["t"] < 1e30, 0] == 0).all()
+
+
+@pytest.mark.skipif(not refpy.available(), reason="oracle/_ref not built (needs /root/reference)")
 def test_port_instance_update_matches_reference():
     """BLASInstance::Update / InvertTransform (:8386-8428): the vectorised reference build fuses different multiply-adds in
     different rows of the cofactor matrix; the restatement reproduces all of them (affine and projective matrices)."""

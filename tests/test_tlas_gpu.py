@@ -87,3 +87,70 @@ def test_tlas_instance_bits_in_prim(gpu):
     assert np.array_equal(g[:, 1:4], w[:, 1:4])           # t, u, v
     assert np.array_equal(g[hit, 4], w[hit, 4] + (w[hit, 0] << 22)) and np.array_equal(g[~hit, 4], w[~hit, 4])
     assert np.array_equal(g[:, 0], words(rays)[:, 0])     # byte 44 untouched
+
+
+class _CW:
+    def __init__(self, blas):
+        self.nodes, self.tris = blas.download()          # bvh8Data / bvh8Tris, byte-identical to the reference's converter (tests/test_convert_gpu.py)
+
+
+@pytest.mark.parametrize("n_inst,builder", [(40, "Build"), (1, "Build"), (200, "BuildHQ")])
+def test_tlas_over_cwbvh_blasses(gpu, n_inst, builder):
+    """The BLASses walked in their BVH8_CWBVH layout (the reference's GPU arrangement, traverse_tlas.cl): bit-identical to the oracle's
+    composition of IntersectTLAS's walk with BVH8_CWBVH::Intersect per instance (oracle/tbvh_oracle.h, orc_intersect_tlas_cw)."""
+    from oracle import portpy
+    v, inst, O, D = tlas_case(97, n_inst)
+    blas = [getattr(api.BVH8_CWBVH(), builder)(x) for x in v]
+    t = api.TLAS().Build(inst, blas, blas_layout=api.LAYOUT_CWBVH)
+    nodes, idx = t.download()
+    port = portpy.PortTLASCW(nodes, idx, inst, [_CW(b) for b in blas])
+    t_bvh = api.TLAS().Build(inst.copy(), blas)           # the same instances, BLASses walked through their BVH layout
+    for mask in (0x1, 0x2):
+        rays = R.make_rays(O, D)
+        rays["mask"] = mask
+        want, got, other = rays.copy(), rays.copy(), rays.copy()
+        port.intersect(want), t.Intersect(got), t_bvh.Intersect(other)
+        assert np.array_equal(words(got), words(want)), f"closest hits differ (ray mask {mask:#x})"
+        assert (want["t"] < 1e30).sum() > 1000
+        assert (words(got) == words(other)).all(axis=1).mean() > 0.999   # two layouts of the same triangles: ties aside, the same hits
+        sh = R.make_rays(O, D, tmax=150.0)
+        sh["mask"] = mask
+        assert np.array_equal(t.IsOccluded(sh), port.occluded(sh))
+    # device-resident rays
+    import torch
+    rays = R.make_rays(O, D)
+    want = rays.copy()
+    port.intersect(want)
+    d = torch.from_numpy(rays.view(np.uint8).reshape(-1, 128)).cuda()
+    t.Intersect(d)
+    assert np.array_equal(words(d.cpu().numpy().view(R.RAY_DTYPE).reshape(-1)), words(want))
+    bits = t.IsOccluded(torch.from_numpy(R.make_rays(O, D, tmax=150.0).view(np.uint8).reshape(-1, 128)).cuda())
+    assert np.array_equal(bits.cpu().numpy().view(np.uint32), port.occluded(R.make_rays(O, D, tmax=150.0)))
+
+
+def test_tlas_over_cwbvh_uploaded_and_errors(gpu):
+    """BLASses that hold ONLY the CWBVH arrays (uploaded bvh8Data / bvh8Tris); layout / staleness errors."""
+    from oracle import portpy
+    v, inst, O, D = tlas_case(99, 30)
+    built = [api.BVH8_CWBVH().Build(x) for x in v]
+    t0 = api.TLAS().Build(inst, built, blas_layout=api.LAYOUT_CWBVH)    # Update()s inst
+    cws = [_CW(b) for b in built]
+    only_cw = [api.BVH8_CWBVH().upload(c.nodes, c.tris) for c in cws]
+    t = api.TLAS().Build(inst, only_cw, update=False, blas_layout=api.LAYOUT_CWBVH)
+    nodes, idx = t.download()
+    port = portpy.PortTLASCW(nodes, idx, inst, cws)
+    rays = R.make_rays(O, D)
+    want, got = rays.copy(), rays.copy()
+    port.intersect(want), t.Intersect(got)
+    assert np.array_equal(words(got), words(want)) and (want["t"] < 1e30).sum() > 1000
+    t.layout = api.LAYOUT_BVH
+    with pytest.raises(api.TbvhError):
+        t.Intersect(rays.copy())                          # these BLASses hold no BVH-layout tree
+    plain = [api.BVH().Build(x) for x in v]
+    tb = api.TLAS().Build(inst.copy(), plain)
+    tb.layout = api.LAYOUT_CWBVH
+    with pytest.raises(api.TbvhError):
+        tb.Intersect(rays.copy())                         # ... and these no CWBVH
+    built[0].Build(v[0])                                  # the BLAS was rebuilt and re-converted: its arrays moved
+    with pytest.raises(api.TbvhError):
+        t0.Intersect(rays.copy())

@@ -225,10 +225,13 @@ class TLAS(BVH):
     it are IntersectTLAS / IsOccludedTLAS.  `instances`: BLAS_INSTANCE records already Update()d by the caller (inverse transform
     and world box, as BLASInstance::Update :8386 computes them); `blasses`: BVH objects of this module, kept alive by this one."""
 
-    def Build(self, instances, blasses, update: bool = True):
+    def Build(self, instances, blasses, update: bool = True, blas_layout: int = LAYOUT_BVH):
         """update=True: BLASInstance::Update (:8386) is applied to every record first - in place, as the reference's Build does when it
-        is handed the BLAS list (:2245-2250); update=False: the records already carry inverse transform and world box."""
+        is handed the BLAS list (:2245-2250); update=False: the records already carry inverse transform and world box.
+        blas_layout=LAYOUT_CWBVH: Intersect / IsOccluded walk every BLAS in its BVH8_CWBVH layout (the arrangement of the reference's GPU
+        path, traverse_tlas.cl); the BLASses must hold that layout when the TLAS is built (BVH8_CWBVH objects, or tbvh_convert)."""
         inst = instances
+        self.layout = blas_layout
         assert inst.dtype.itemsize == 192 and inst.flags.c_contiguous
         self.blasses = list(blasses)
         if update:

@@ -378,7 +378,7 @@ static void free_layouts( tbvh_bvh b )
 	void* p[] = { b->d_verts, b->d_nodes, b->d_prim_idx, b->d_leaf_tris, b->d_nodes_gpu, b->d_cw_nodes, b->d_cw_tris, b->d_cw_trav, b->d_aabbs, b->d_inst, b->d_blas };
 	for (void* q : p) if (q) cudaFree( q );
 	b->d_verts = 0, b->d_nodes = 0, b->d_prim_idx = 0, b->d_leaf_tris = 0, b->d_nodes_gpu = 0, b->d_cw_nodes = 0, b->d_cw_tris = 0, b->d_cw_trav = 0, b->d_trav = 0, b->leaf_tris_count = 0;
-	b->d_aabbs = 0, b->d_inst = 0, b->d_blas = 0, b->inst_count = 0, b->blas_count = 0, b->cw_depth = 0;
+	b->d_aabbs = 0, b->d_inst = 0, b->d_blas = 0, b->inst_count = 0, b->blas_count = 0, b->cw_depth = 0, b->tlas_blas_layouts = 0;
 	b->links.clear();
 	b->generation++; // a TLAS built over the old arrays must notice (tlas_check)
 	memset( &b->info, 0, sizeof( b->info ) );
@@ -593,6 +593,7 @@ int tbvh_upload_cwbvh( tbvh_bvh b, const void* bvh8_data, uint32_t used_blocks, 
 	cudaStream_t s = b->ctx->stream;
 	const cudaMemcpyKind kind = space == TBVH_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
 	ARG_CHECK( used_blocks % 5 == 0, "usedBlocks must be a multiple of 5 (80-byte nodes)" );
+	if (b->d_cw_trav || b->d_cw_tris) b->generation++; // a TLAS may hold these addresses (tlas_check)
 	if (b->d_cw_nodes) cudaFree( b->d_cw_nodes );
 	if (b->d_cw_tris) cudaFree( b->d_cw_tris );
 	if (b->d_cw_trav) cudaFree( b->d_cw_trav );
@@ -734,14 +735,19 @@ int tbvh_build_tlas( tbvh_bvh t, const void* instances, uint32_t inst_stride, ui
 	std::vector<float4> boxes( (size_t)inst_count * 2 );
 	std::vector<TlasInst> inst( inst_count );
 	std::vector<BlasRef> refs( blas_count );
+	uint32_t blas_layouts = (1u << TBVH_LAYOUT_BVH) | (1u << TBVH_LAYOUT_CWBVH);
 	for (uint32_t k = 0; k < blas_count; k++)
 	{
 		const tbvh_bvh b = blasses[k];
 		ARG_CHECK( b && b != t && b->ctx == t->ctx, "TLAS: a BLAS handle is NULL or lives in another context" );
-		if (!(b->info.layouts & (1u << TBVH_LAYOUT_BVH)) || !b->d_trav || !b->d_leaf_tris || b->d_inst)
-		{ tbvh_set_error( "TLAS: BLAS %u holds no BVH-layout triangle tree (IntersectTLAS walks LAYOUT_BVH BLASses, tiny_bvh.h:3341)", k ); return TBVH_E_STATE; }
-		if (b->info.max_depth + 1 > TBVH_STACK) { tbvh_set_error( "TLAS: BLAS %u has depth %u, the two-level kernel walks a BLAS with a %d-entry stack", k, b->info.max_depth, TBVH_STACK ); return TBVH_E_LIMIT; }
-		refs[k].trav = b->d_trav, refs[k].tris = b->d_leaf_tris, refs[k].root_ref = b->root_ref, refs[k].root_count = b->root_count, refs[k].pad0 = refs[k].pad1 = 0;
+		const bool has_bvh = (b->info.layouts & (1u << TBVH_LAYOUT_BVH)) && b->d_trav && b->d_leaf_tris, has_cw = b->d_cw_trav && b->d_cw_tris;
+		if (b->d_inst || (!has_bvh && !has_cw))
+		{ tbvh_set_error( "TLAS: BLAS %u holds no triangle tree (IntersectTLAS walks LAYOUT_BVH BLASses, tiny_bvh.h:3341; traverse_tlas.cl CWBVH ones)", k ); return TBVH_E_STATE; }
+		if (has_bvh && b->info.max_depth + 1 > TBVH_STACK) { tbvh_set_error( "TLAS: BLAS %u has depth %u, the two-level kernel walks a BLAS with a %d-entry stack", k, b->info.max_depth, TBVH_STACK ); return TBVH_E_LIMIT; }
+		if (has_cw && b->cw_depth + 1 > 128) { tbvh_set_error( "TLAS: the wide tree of BLAS %u has depth %u (128 pending node groups per ray, tiny_bvh.h:7048)", k, b->cw_depth ); return TBVH_E_LIMIT; }
+		refs[k].trav = has_bvh ? b->d_trav : 0, refs[k].tris = has_bvh ? b->d_leaf_tris : 0, refs[k].root_ref = b->root_ref, refs[k].root_count = b->root_count, refs[k].pad0 = refs[k].pad1 = 0;
+		refs[k].cw_nodes = has_cw ? b->d_cw_trav : 0, refs[k].cw_tris = has_cw ? b->d_cw_tris : 0;
+		blas_layouts &= (has_bvh ? 1u << TBVH_LAYOUT_BVH : 0u) | (has_cw ? 1u << TBVH_LAYOUT_CWBVH : 0u);
 	}
 	for (uint32_t i = 0; i < inst_count; i++)
 	{
@@ -763,7 +769,7 @@ int tbvh_build_tlas( tbvh_bvh t, const void* instances, uint32_t inst_stride, ui
 	CUDA_TRY( cudaMemcpyAsync( t->d_inst, inst.data(), inst.size() * sizeof( TlasInst ), cudaMemcpyHostToDevice, s ) );
 	CUDA_TRY( cudaMemcpyAsync( t->d_blas, refs.data(), refs.size() * sizeof( BlasRef ), cudaMemcpyHostToDevice, s ) );
 	CUDA_TRY( cudaStreamSynchronize( s ) ); // the host vectors go out of scope
-	t->info.prim_count = inst_count, t->inst_count = inst_count, t->blas_count = blas_count;
+	t->info.prim_count = inst_count, t->inst_count = inst_count, t->blas_count = blas_count, t->tlas_blas_layouts = blas_layouts;
 	TRY( build_sah_launch( t, c_trav, c_int, TBVH_BUILD_REFERENCE ) ); // "Build(); // or BuildAVX, for large TLAS." :2258
 	t->info.layouts = 1u << TBVH_LAYOUT_BVH, t->refittable = false; // "do not refit a TLAS, use Build(..)" :3060
 	if (t->info.max_depth + 1 > TBVH_STACK) { tbvh_set_error( "TLAS depth %u exceeds the %d-entry stack of IntersectTLAS (tiny_bvh.h:3308)", t->info.max_depth, TBVH_STACK ); return TBVH_E_LIMIT; }
@@ -788,6 +794,7 @@ int tbvh_refit( tbvh_bvh b, const void* verts, uint32_t stride, uint32_t prim_co
 	TRY( refit_launch( b, s ) );
 	// derived layouts describe the old boxes: drop them (the reference's BVH_GPU / BVH8_CWBVH are re-converted after a refit too)
 	if (b->d_nodes_gpu) cudaFree( b->d_nodes_gpu ), b->d_nodes_gpu = 0;
+	if (b->d_cw_trav || b->d_cw_tris) b->generation++; // a TLAS may hold these addresses (tlas_check)
 	if (b->d_cw_nodes) cudaFree( b->d_cw_nodes ), b->d_cw_nodes = 0;
 	if (b->d_cw_tris) cudaFree( b->d_cw_tris ), b->d_cw_tris = 0;
 	if (b->d_cw_trav) cudaFree( b->d_cw_trav ), b->d_cw_trav = 0;
@@ -899,7 +906,7 @@ int tbvh_intersect_device( tbvh_bvh b, int layout, void* d_rays, uint32_t stride
 		// TLAS: hits carry the instance (hit.inst, byte 44) and are written into the ray records
 		if (d_hits) { tbvh_set_error( "TLAS hits are written in place (t,u,v,prim at byte 48, inst at byte 44): pass d_hits = NULL" ); return TBVH_E_UNSUPPORTED; }
 		TRY( tlas_check( b ) );
-		return tlas_trace_launch( b, d_rays, stride, 0, n, false, (cudaStream_t)stream );
+		return tlas_trace_launch( b, layout, d_rays, stride, 0, n, false, (cudaStream_t)stream );
 	}
 	if (d_hits) return trace_dispatch( b, layout, d_rays, stride, d_hits, 16, 0, n, false, (cudaStream_t)stream );
 	return trace_dispatch( b, layout, d_rays, stride, (char*)d_rays + 48, stride, 0, n, false, (cudaStream_t)stream );
@@ -910,7 +917,7 @@ int tbvh_occluded_device( tbvh_bvh b, int layout, const void* d_rays, uint32_t s
 	ARG_CHECK( b && d_rays && d_bits && stride >= 64 && (stride & 15) == 0, "bad ray buffer" );
 	CUDA_TRY( cudaSetDevice( b->ctx->device ) );
 	if (b->stats) CUDA_TRY( cudaMemsetAsync( b->d_stats, 0, 32, (cudaStream_t)stream ) );
-	if (b->d_inst) { TRY( tlas_check( b ) ); return tlas_trace_launch( b, d_rays, stride, d_bits, n, true, (cudaStream_t)stream ); }
+	if (b->d_inst) { TRY( tlas_check( b ) ); return tlas_trace_launch( b, layout, d_rays, stride, d_bits, n, true, (cudaStream_t)stream ); }
 	return trace_dispatch( b, layout, d_rays, stride, 0, 0, d_bits, n, true, (cudaStream_t)stream );
 }
 
@@ -1109,7 +1116,7 @@ static int intersect_host( tbvh_bvh b, int layout, void* rays, uint32_t stride, 
 			if (host_scatter && chunk >= TBVH_SLOTS) TRY( scatter_chunk( chunk - TBVH_SLOTS ) ); // frees this slot's staging
 			uint32_t ss = 64;
 			TRY( stage_in( c, k, chunk, h, hd, stride, cnt, &ss ) );
-			if (tlas) TRY( tlas_trace_launch( b, sl.d_rays, ss, 0, cnt, false, c->s_run ) );  // hit + instance written into the staged records
+			if (tlas) TRY( tlas_trace_launch( b, layout, sl.d_rays, ss, 0, cnt, false, c->s_run ) );  // hit + instance written into the staged records
 			else if (full_line) TRY( trace_dispatch( b, layout, sl.d_rays, ss, (char*)sl.d_rays + 48, ss, 0, cnt, false, c->s_run ) );
 			else TRY( trace_dispatch( b, layout, sl.d_rays, ss, sl.d_hits, 16, 0, cnt, false, c->s_run ) );
 			CUDA_TRY( cudaEventRecord( sl.run_done, c->s_run ) );
@@ -1165,7 +1172,7 @@ int tbvh_occluded( tbvh_bvh b, int layout, const void* rays, uint32_t stride, ui
 		{
 			uint32_t ss = 64;
 			TRY( stage_in( c, k, chunk, h, dev_alias ? dev_alias + off * stride : 0, stride, cnt, &ss ) );
-			if (b->d_inst) TRY( tlas_trace_launch( b, sl.d_rays, ss, (uint32_t*)sl.d_bits, cnt, true, c->s_run ) );
+			if (b->d_inst) TRY( tlas_trace_launch( b, layout, sl.d_rays, ss, (uint32_t*)sl.d_bits, cnt, true, c->s_run ) );
 			else TRY( trace_dispatch( b, layout, sl.d_rays, ss, 0, 0, (uint32_t*)sl.d_bits, cnt, true, c->s_run ) );
 			CUDA_TRY( cudaEventRecord( sl.run_done, c->s_run ) );
 			CUDA_TRY( cudaStreamWaitEvent( c->s_out, sl.run_done, 0 ) );

@@ -99,6 +99,7 @@ struct tbvh_bvh_t
 	void* d_inst = 0;          // TlasInst records (inverse transform, BLAS number, mask)
 	void* d_blas = 0;          // BlasRef records (traversal arrays of every BLAS)
 	uint32_t inst_count = 0, blas_count = 0;
+	uint32_t tlas_blas_layouts = 0; // TLAS only: layouts EVERY BLAS held at build time (bit TBVH_LAYOUT_BVH / TBVH_LAYOUT_CWBVH)
 	std::vector<BlasLink> links; // TLAS only: the BLAS handles it points into, with the generation they had at build time
 	bool refittable = true;    // BVHBase::refittable (:811): false after BuildHQ ("can't refit an SBVH", :3027)
 	// statistics
@@ -145,9 +146,9 @@ unsigned long long* ctx_next_counter( tbvh_ctx c ); // a zero-on-use 8-byte devi
 int build_sah_launch( tbvh_bvh b, float c_trav, float c_int, int flavour );
 int build_hq_launch( tbvh_bvh b, float c_trav, float c_int );
 int refit_launch( tbvh_bvh b, cudaStream_t s );
-int tlas_trace_launch( tbvh_bvh b, const void* d_rays, uint32_t stride, uint32_t* d_bits, uint64_t n, bool anyhit, cudaStream_t s );
+int tlas_trace_launch( tbvh_bvh b, int layout, const void* d_rays, uint32_t stride, uint32_t* d_bits, uint64_t n, bool anyhit, cudaStream_t s );
 struct TlasInst { float inv[16]; uint32_t blasIdx, mask, pad0, pad1; };                                  // 80 bytes
-struct BlasRef { const float4* trav; const float4* tris; uint32_t root_ref, root_count, pad0, pad1; };   // 32 bytes
+struct BlasRef { const float4* trav; const float4* tris; uint32_t root_ref, root_count, pad0, pad1; const float4* cw_nodes; const float4* cw_tris; }; // 48 bytes: BVH-layout arrays, CWBVH traversal nodes + bvh8Tris (0 when absent)
 int make_leaf_tris( tbvh_bvh b, cudaStream_t s );
 int bvh_gpu_to_bvh( tbvh_bvh b, uint32_t used_nodes_gpu, cudaStream_t s );
 int bvh_to_bvh_gpu( tbvh_bvh b, cudaStream_t s );

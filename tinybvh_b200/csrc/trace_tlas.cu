@@ -8,7 +8,13 @@
 // row, the point divided by w only when w != 1); rD' = safercp( D' ) (:442); then the BLAS is walked exactly as
 // k_trace_bvh2 walks it, with the running hit distance, and a hit records the instance.  Results are bit-identical to the
 // oracle's (tests/test_tlas_gpu.py): t, u, v, prim, inst, occlusion bits.
-#include "common.cuh"
+//
+// CW = true: the BLASses are walked in their BVH8_CWBVH layout instead - the arrangement of the reference's GPU path (traverse_tlas.cl:
+// BVH2 TLAS, per-instance transform, CWBVH per BLAS, the hit kept when it is closer, the instance attached to it).  The reference's CPU
+// IntersectTLAS refuses LAYOUT_CWBVH BLASses (:3339), so the oracle here is the composition of its two pinned pieces (oracle/tbvh_oracle.h,
+// orc_intersect_tlas_cw): this file's TLAS walk and transform with BVH8_CWBVH::Intersect (:7046-7154) as the BLAS step - the per-lane form
+// of the node step in cw_walk.cuh, since transformed rays of one warp share no octant.
+#include "cw_walk.cuh"
 
 #define TLAS_STACK 64   // the reference's IntersectTLAS stack (:3308)
 
@@ -76,7 +82,60 @@ template <bool ANYHIT> __device__ bool trace_blas( const BlasRef B, const float 
 	return false;
 }
 
-template <bool ANYHIT> __global__ void __launch_bounds__( 128 ) k_trace_tlas( const float4* __restrict__ nodes, const uint32_t* __restrict__ prim_idx,
+// one BLAS in its CWBVH layout, walked as k_trace_wide walks it (trace_cwbvh.cu) in the per-lane form.  BVH8_CWBVH::Intersect starts from
+// the running hit distance and the two-level walk keeps its result only when it ends BELOW that distance (`blasHit.x < hit.x`): a
+// triangle met at exactly the running distance changes nothing.
+template <bool ANYHIT> __device__ bool trace_blas_cw( const float4* __restrict__ nodes, const float4* __restrict__ tris, const float ox, const float oy, const float oz,
+	const float dx, const float dy, const float dz, const float rdx, const float rdy, const float rdz, float& tmax, float& hu, float& hv, uint32_t& hprim, bool& hit, uint2* pending )
+{
+	const uint32_t o = 7u - ((dx < 0 ? 4u : 0u) | (dy < 0 ? 2u : 0u) | (dz < 0 ? 1u : 0u)); // octinv (:7053, signs of D)
+	const bool negx = rdx < 0, negy = rdy < 0, negz = rdz < 0;                                // plane choice (:7082, signs of rD)
+	const float t_in = tmax;
+	float t = tmax, lu = 0, lv = 0;
+	uint32_t lprim = 0;
+	int depth = 0;
+	uint32_t base = 0, word = 0x80000000u;
+	while (true)
+	{
+		const uint32_t bit = 31u - __clz( word );
+		const uint32_t rest = word & ~(1u << bit);
+		if (rest > 0x00ffffffu) pending[depth++] = make_uint2( base, rest );
+		const uint32_t slot = (bit - 24u) ^ o;
+		const uint32_t nidx = base + __popc( word & ~(0xffffffffu << slot) );
+		const float4* np = nodes + (size_t)nidx * CW_NODE_F4;
+		const float4 h0 = __ldg( np ), h1 = __ldg( np + 1 );
+		const uint32_t sxy = __float_as_uint( h0.w ), szm = __float_as_uint( h1.z );
+		const float scx = __uint_as_float( sxy << 16 ), scy = __uint_as_float( sxy & 0xffff0000u ), scz = __uint_as_float( szm << 16 );
+		const float ax1 = __fmul_rn( scx, rdx ), ay1 = __fmul_rn( scy, rdy ), az1 = __fmul_rn( scz, rdz );
+		const float bx1 = __fmul_rn( -__fsub_rn( ox, h0.x ), rdx ), by1 = __fmul_rn( -__fsub_rn( oy, h0.y ), rdy ), bz1 = __fmul_rn( -__fsub_rn( oz, h0.z ), rdz );
+		const uint32_t got = node_hits<-1>( np, szm >> 24, negx, negy, negz, o, ax1, ay1, az1, bx1, by1, bz1, t );
+		base = __float_as_uint( h1.x );
+		word = (got & 0xff000000u) | ((szm >> 16) & 255u);
+		uint32_t tmask = got & 0x00ffffffu;
+		const float4* tbase = tris + __float_as_uint( h1.y );
+		while (tmask)
+		{
+			const uint32_t k = 31u - __clz( tmask );
+			tmask &= ~(1u << k);
+			const float4* tp = tbase + k * 3;
+			const float4 e2 = __ldg( tp ), e1 = __ldg( tp + 1 ), v0 = __ldg( tp + 2 );
+			float tt, u, v;
+			if (mt_test( ox, oy, oz, dx, dy, dz, v0, e1, e2, t, tt, u, v ))
+			{
+				if (ANYHIT) { if (tt < t_in) return true; }
+				else t = tt, lu = u, lv = v, lprim = __float_as_uint( v0.w );
+			}
+		}
+		if (word > 0x00ffffffu) continue;
+		if (depth == 0) break;
+		const uint2 e = pending[--depth];
+		base = e.x, word = e.y;
+	}
+	if (!ANYHIT && t < t_in) tmax = t, hu = lu, hv = lv, hprim = lprim, hit = true;
+	return false;
+}
+
+template <bool ANYHIT, bool CW> __global__ void __launch_bounds__( 128 ) k_trace_tlas( const float4* __restrict__ nodes, const uint32_t* __restrict__ prim_idx,
 	const TlasInst* __restrict__ inst, const BlasRef* __restrict__ blas, char* rays, const uint32_t stride, uint32_t* __restrict__ bits, const uint64_t n,
 	const uint32_t root_ref, const uint32_t root_count, const uint32_t inst_shift /* 32 - INST_IDX_BITS; 0 = separate hit.inst field */ )
 {
@@ -92,7 +151,7 @@ template <bool ANYHIT> __global__ void __launch_bounds__( 128 ) k_trace_tlas( co
 		const float nrox = -__fmul_rn( ox, rdx ), nroy = -__fmul_rn( oy, rdy ), nroz = -__fmul_rn( oz, rdz );
 		float tmax = rh4.x, hu = rh4.y, hv = rh4.z;
 		uint32_t hprim = __float_as_uint( rh4.w ), hinst = __float_as_uint( rr4.w ); // hit.inst sits in the w lane of the rD row (byte 44)
-		uint2 stack[TLAS_STACK], bstack[TBVH_STACK];
+		uint2 stack[TLAS_STACK], bstack[CW ? CW_STACK : TBVH_STACK];
 		int sp = 0;
 		uint32_t ref = root_ref, cnt = root_count;
 		while (true)
@@ -133,7 +192,10 @@ template <bool ANYHIT> __global__ void __launch_bounds__( 128 ) k_trace_tlas( co
 					const float tdy = __fmaf_rn( r1.z, dz, __fmaf_rn( r1.x, dx, __fmul_rn( r1.y, dy ) ) );
 					const float tdz = __fmaf_rn( r2.z, dz, __fmaf_rn( r2.x, dx, __fmul_rn( r2.y, dy ) ) );
 					bool hit = false;
-					if (trace_blas<ANYHIT>( blas[__float_as_uint( meta.x )], tox, toy, toz, tdx, tdy, tdz, safercp( tdx ), safercp( tdy ), safercp( tdz ), tmax, hu, hv, hprim, hit, bstack ))
+					const BlasRef B = blas[__float_as_uint( meta.x )];
+					const bool occ = CW ? trace_blas_cw<ANYHIT>( B.cw_nodes, B.cw_tris, tox, toy, toz, tdx, tdy, tdz, safercp( tdx ), safercp( tdy ), safercp( tdz ), tmax, hu, hv, hprim, hit, bstack )
+						: trace_blas<ANYHIT>( B, tox, toy, toz, tdx, tdy, tdz, safercp( tdx ), safercp( tdy ), safercp( tdz ), tmax, hu, hv, hprim, hit, bstack );
+					if (occ)
 					{
 						occluded = true;
 						break;
@@ -165,16 +227,25 @@ template <bool ANYHIT> __global__ void __launch_bounds__( 128 ) k_trace_tlas( co
 }
 } // namespace
 
-int tlas_trace_launch( tbvh_bvh b, const void* d_rays, uint32_t stride, uint32_t* d_bits, uint64_t n, bool anyhit, cudaStream_t s )
+int tlas_trace_launch( tbvh_bvh b, int layout, const void* d_rays, uint32_t stride, uint32_t* d_bits, uint64_t n, bool anyhit, cudaStream_t s )
 {
 	if (!b->d_inst || !b->d_blas || !b->d_nodes) { tbvh_set_error( "TLAS not resident" ); return TBVH_E_STATE; }
+	const bool cw = layout == TBVH_LAYOUT_CWBVH;
+	if (!cw && layout != TBVH_LAYOUT_BVH && layout != TBVH_LAYOUT_BVH_GPU) { tbvh_set_error( "unknown layout %d", layout ); return TBVH_E_ARG; }
+	if (cw && !(b->tlas_blas_layouts & (1u << TBVH_LAYOUT_CWBVH)))
+	{ tbvh_set_error( "TLAS: not every BLAS held its CWBVH layout when the TLAS was built (tbvh_convert the BLASses, then tbvh_build_tlas)" ); return TBVH_E_STATE; }
+	if (!cw && !(b->tlas_blas_layouts & (1u << TBVH_LAYOUT_BVH)))
+	{ tbvh_set_error( "TLAS: not every BLAS holds a BVH-layout tree; walk it with TBVH_LAYOUT_CWBVH" ); return TBVH_E_STATE; }
 	if (n == 0) return TBVH_OK;
 	const uint64_t grid = (n + 127) / 128;
 	if (grid > 0x7fffffffull) { tbvh_set_error( "ray batch too large for one launch" ); return TBVH_E_ARG; }
 	const int bits_opt = b->ctx->inst_idx_bits;
 	const uint32_t shift = bits_opt >= 4 && bits_opt < 32 ? (uint32_t)(32 - bits_opt) : 0u;
-	if (anyhit) k_trace_tlas<true><<<(uint32_t)grid, 128, 0, s>>>( b->d_nodes, b->d_prim_idx, (const TlasInst*)b->d_inst, (const BlasRef*)b->d_blas, (char*)d_rays, stride, d_bits, n, b->root_ref, b->root_count, shift );
-	else k_trace_tlas<false><<<(uint32_t)grid, 128, 0, s>>>( b->d_nodes, b->d_prim_idx, (const TlasInst*)b->d_inst, (const BlasRef*)b->d_blas, (char*)d_rays, stride, d_bits, n, b->root_ref, b->root_count, shift );
+	#define LAUNCH( A, C ) k_trace_tlas<A, C><<<(uint32_t)grid, 128, 0, s>>>( b->d_nodes, b->d_prim_idx, (const TlasInst*)b->d_inst, (const BlasRef*)b->d_blas, \
+		(char*)d_rays, stride, d_bits, n, b->root_ref, b->root_count, shift )
+	if (anyhit) { if (cw) LAUNCH( true, true ); else LAUNCH( true, false ); }
+	else { if (cw) LAUNCH( false, true ); else LAUNCH( false, false ); }
+	#undef LAUNCH
 	LAUNCHED();
 	return TBVH_OK;
 }

@@ -56,6 +56,19 @@ def main():
     bits = torch.empty((n + 31) // 32, dtype=torch.int32, device="cuda")
     best, _ = timeit(lambda: tl.IsOccluded(dsh, bits=bits))
     print(f"IsOccludedTLAS on the GPU: {best:.3f} ms = {n / best / 1e3:.1f} Mrays/s")
+    # the same instances over the BVH8_CWBVH layout of the BLAS (the reference's GPU arrangement, traverse_tlas.cl)
+    wide = api.BVH8_CWBVH().Build(v)
+    tw = api.TLAS().Build(inst.copy(), [wide], blas_layout=api.LAYOUT_CWBVH)
+    dw = fresh.clone()
+    def run_wide():
+        dw.copy_(fresh)
+        tw.Intersect(dw)
+    best, _ = timeit(run_wide)
+    gw = dw.cpu().numpy().view(R.RAY_DTYPE).reshape(-1)
+    ww = lambda r: r.view(np.uint32).reshape(-1, 32)[:, 11:16]
+    print(f"TLAS over the CWBVH BLAS: {best - tcopy:.3f} ms = {n / (best - tcopy) / 1e3:.1f} Mrays/s; {int((ww(gw) != ww(got)).any(axis=1).sum())} of {n} rays differ from the BVH-BLAS walk (ties)")
+    best, _ = timeit(lambda: tw.IsOccluded(dsh, bits=bits))
+    print(f"... any-hit: {best:.3f} ms = {n / best / 1e3:.1f} Mrays/s")
     smp = prim[: 1 << 20].copy()
     t0 = time.time(); ref.intersect(smp, threads=0); dt = time.time() - t0
     print(f"reference IntersectTLAS, {refpy.hardware_threads()} host threads: {smp.shape[0] / dt / 1e6:.1f} Mrays/s")
