@@ -873,8 +873,13 @@ static void live_add( tbvh_bvh b ) { std::lock_guard<std::mutex> lk( g_live_mute
 static void live_remove( tbvh_bvh b ) { std::lock_guard<std::mutex> lk( g_live_mutex ); for (size_t i = 0; i < g_live.size(); i++) if (g_live[i] == b) { g_live[i] = g_live.back(); g_live.pop_back(); break; } }
 
 // a TLAS points at the arrays of its BLASses: refuse to walk it once one of them was rebuilt, re-uploaded or destroyed
-static int tlas_check( tbvh_bvh t )
+static int tlas_check( tbvh_bvh t, int layout )
 {
+	// the layout argument of a traversal call on a TLAS names the layout the BLASses are walked in (trace_tlas.cu)
+	const uint32_t want = layout == TBVH_LAYOUT_CWBVH ? 1u << TBVH_LAYOUT_CWBVH : 1u << TBVH_LAYOUT_BVH;
+	if (layout != TBVH_LAYOUT_CWBVH && layout != TBVH_LAYOUT_BVH && layout != TBVH_LAYOUT_BVH_GPU) { tbvh_set_error( "unknown layout %d", layout ); return TBVH_E_ARG; }
+	if (!(t->tlas_blas_layouts & want))
+	{ tbvh_set_error( "TLAS: not every BLAS held its %s layout when the TLAS was built", layout == TBVH_LAYOUT_CWBVH ? "CWBVH" : "BVH" ); return TBVH_E_STATE; }
 	std::lock_guard<std::mutex> lk( g_live_mutex );
 	for (const BlasLink& l : t->links)
 	{
@@ -905,7 +910,7 @@ int tbvh_intersect_device( tbvh_bvh b, int layout, void* d_rays, uint32_t stride
 	{
 		// TLAS: hits carry the instance (hit.inst, byte 44) and are written into the ray records
 		if (d_hits) { tbvh_set_error( "TLAS hits are written in place (t,u,v,prim at byte 48, inst at byte 44): pass d_hits = NULL" ); return TBVH_E_UNSUPPORTED; }
-		TRY( tlas_check( b ) );
+		TRY( tlas_check( b, layout ) );
 		return tlas_trace_launch( b, layout, d_rays, stride, 0, n, false, (cudaStream_t)stream );
 	}
 	if (d_hits) return trace_dispatch( b, layout, d_rays, stride, d_hits, 16, 0, n, false, (cudaStream_t)stream );
@@ -917,7 +922,7 @@ int tbvh_occluded_device( tbvh_bvh b, int layout, const void* d_rays, uint32_t s
 	ARG_CHECK( b && d_rays && d_bits && stride >= 64 && (stride & 15) == 0, "bad ray buffer" );
 	CUDA_TRY( cudaSetDevice( b->ctx->device ) );
 	if (b->stats) CUDA_TRY( cudaMemsetAsync( b->d_stats, 0, 32, (cudaStream_t)stream ) );
-	if (b->d_inst) { TRY( tlas_check( b ) ); return tlas_trace_launch( b, layout, d_rays, stride, d_bits, n, true, (cudaStream_t)stream ); }
+	if (b->d_inst) { TRY( tlas_check( b, layout ) ); return tlas_trace_launch( b, layout, d_rays, stride, d_bits, n, true, (cudaStream_t)stream ); }
 	return trace_dispatch( b, layout, d_rays, stride, 0, 0, d_bits, n, true, (cudaStream_t)stream );
 }
 
@@ -1068,7 +1073,7 @@ static int intersect_host( tbvh_bvh b, int layout, void* rays, uint32_t stride, 
 	if (tlas)
 	{
 		if (packed_hits) { tbvh_set_error( "tbvh_intersect_packed: TLAS hits carry the instance and are returned in the ray records" ); return TBVH_E_UNSUPPORTED; }
-		TRY( tlas_check( b ) );
+		TRY( tlas_check( b, layout ) );
 	}
 	char* dev_alias = (char*)mapped_alias( rays );
 	const bool scatter = !packed_hits && !tlas && c->d2h_mode == 3 && dev_alias && (stride & 15) == 0;
@@ -1158,7 +1163,7 @@ int tbvh_occluded( tbvh_bvh b, int layout, const void* rays, uint32_t stride, ui
 	CUDA_TRY( cudaSetDevice( c->device ) );
 	TRY( ensure_slots( c ) );
 	if (b->stats) CUDA_TRY( cudaMemset( b->d_stats, 0, 32 ) );
-	if (b->d_inst) TRY( tlas_check( b ) );
+	if (b->d_inst) TRY( tlas_check( b, layout ) );
 	const char* dev_alias = (const char*)mapped_alias( rays );
 	uint64_t chunk = 0;
 	int rc = TBVH_OK;
