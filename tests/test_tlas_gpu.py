@@ -111,7 +111,7 @@ def test_tlas_over_cwbvh_blasses(gpu, n_inst, builder):
         want, got, other = rays.copy(), rays.copy(), rays.copy()
         port.intersect(want), t.Intersect(got), t_bvh.Intersect(other)
         assert np.array_equal(words(got), words(want)), f"closest hits differ (ray mask {mask:#x})"
-        assert (want["t"] < 1e30).sum() > 1000
+        assert n_inst == 1 or (want["t"] < 1e30).sum() > 1000   # (the single instance of the n_inst = 1 case carries mask 0x2 only)
         assert (words(got) == words(other)).all(axis=1).mean() > 0.999   # two layouts of the same triangles: ties aside, the same hits
         sh = R.make_rays(O, D, tmax=150.0)
         sh["mask"] = mask
