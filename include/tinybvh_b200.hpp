@@ -182,7 +182,7 @@ public:
 	template <class Vec4> void BuildHQ( const Vec4* vertices, const uint32_t primCount )
 	{
 		TBVH_FATAL_IF( tbvh_build_flavour( h, vertices, (uint32_t)sizeof( Vec4 ), primCount, TBVH_HOST, c_trav, c_int, TBVH_BUILD_HQ ), "BVH::BuildHQ" );
-		sync_info();
+		remember( vertices, (uint32_t)sizeof( Vec4 ), 0, primCount ), sync_info();
 	}
 	// TLAS: BVH::Build( BLASInstance* instances, instCount, BVHBase** blasses, blasCount ) tiny_bvh.h:2221.  Inst is the
 	// reference's 192-byte tinybvh::BLASInstance.  As in the reference (:2245-2250) every instance is Update()d first - inverse
@@ -229,18 +229,40 @@ public:
 	// itself and the node / primIdx arrays, so the format is whatever the tiny_bvh.h the host program was compiled with says it is:
 	// with that header included before this one, a GPU-built tree is handed to a tinybvh::BVH object and written / read by the
 	// reference's own code - files are interchangeable with the reference's in both directions.
-	void ToReference( tinybvh::BVH& out ) const // a CPU-side tinybvh::BVH holding the GPU-built tree (SAHCost, Save, ConvertFrom, Intersect ...)
+	// the arrays and counters of a tree in the reference's BVH layout -> a tinybvh::BVH object (no device involved: usable on its own)
+	static void FillReference( tinybvh::BVH& out, const tbvh_info& i, const void* nodes32, const uint32_t* primIdx, const float c_trav, const float c_int,
+		const void* vertsPtr, const uint32_t vertsPrims, const uint32_t vertsStride )
 	{
-		const tbvh_info i = Info();
 		out.AlignedFree( out.bvhNode ), out.AlignedFree( out.primIdx );
 		out.bvhNode = (tinybvh::BVH::BVHNode*)out.AlignedAlloc( (size_t)i.used_nodes * 32 );
 		out.primIdx = (uint32_t*)out.AlignedAlloc( (size_t)i.idx_count * 4 );
-		Download( out.bvhNode, out.primIdx );
+		memcpy( out.bvhNode, nodes32, (size_t)i.used_nodes * 32 ), memcpy( out.primIdx, primIdx, (size_t)i.idx_count * 4 );
 		out.allocatedNodes = out.usedNodes = i.used_nodes, out.triCount = i.prim_count, out.idxCount = i.idx_count;
 		out.aabbMin = tinybvh::bvhvec3( i.aabb_min[0], i.aabb_min[1], i.aabb_min[2] ), out.aabbMax = tinybvh::bvhvec3( i.aabb_max[0], i.aabb_max[1], i.aabb_max[2] );
 		out.c_trav = c_trav, out.c_int = c_int, out.may_have_holes = false, out.rebuildable = false; // no fragments on the host: not rebuildable
 		out.refittable = i.idx_count == i.prim_count; // an SBVH cannot be refitted (:3027)
 		if (vertsPtr) out.verts = tinybvh::bvhvec4slice{ (const tinybvh::bvhvec4*)vertsPtr, vertsPrims * 3, vertsStride };
+	}
+	void ToReference( tinybvh::BVH& out ) const // a CPU-side tinybvh::BVH holding the GPU-built tree (SAHCost, Save, ConvertFrom, Intersect ...)
+	{
+		const tbvh_info i = Info();
+		void* nodes = malloc( (size_t)i.used_nodes * 32 );
+		uint32_t* idx = (uint32_t*)malloc( (size_t)i.idx_count * 4 + 4 );
+		Download( nodes, idx );
+		FillReference( out, i, nodes, idx, c_trav, c_int, vertsPtr, vertsPrims, vertsStride );
+		free( nodes ), free( idx );
+	}
+	// BVH::Optimize( iterations, extreme, stochastic ) tiny_bvh.h:3043 - the insertion-based optimiser (BVH_Verbose::Optimize :4338) is
+	// sequential host code in the reference and stays exactly that: the GPU-built tree is handed to a tinybvh::BVH, the reference's own
+	// Optimize runs on it, and the result is uploaded (derived layouts are dropped: ConvertFrom again, as in the reference).
+	void Optimize( const uint32_t iterations = 25, bool extreme = false, bool stochastic = false )
+	{
+		if (!vertsPtr || vertIdx) { fprintf( stderr, "Fatal error in tinybvh_b200 BVH::Optimize: needs a tree built from a (non-indexed) host vertex array.\n" ); exit( 1 ); }
+		tinybvh::BVH tmp;
+		ToReference( tmp );
+		tmp.Optimize( iterations, extreme, stochastic );
+		TBVH_FATAL_IF( tbvh_upload_bvh( h, tmp.bvhNode, tmp.usedNodes, tmp.primIdx, tmp.idxCount, vertsPtr, vertsStride, vertsPrims, TBVH_HOST ), "BVH::Optimize" );
+		sync_info();
 	}
 	void Save( const char* fileName ) const { tinybvh::BVH tmp; ToReference( tmp ); tmp.Save( fileName ); }
 	template <class Vec4> bool Load( const char* fileName, const Vec4* vertices, const uint32_t primCount )

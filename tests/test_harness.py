@@ -97,3 +97,16 @@ def test_save_load_round_trips_with_the_reference(gpu):
     print(r.stdout)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
     assert "all round trips ok" in r.stdout
+
+
+def test_optimize_host_half_matches_the_reference_objects():
+    """tinybvh_b200::BVH::Optimize = download -> FillReference -> the reference's own BVH::Optimize (tiny_bvh.h:3043) -> upload.  The part between the
+    two transfers runs without a GPU: a tinybvh::BVH filled from plain arrays must behave under Optimize exactly like the object the reference's
+    builder made (harness/optimize_host_check.cpp, built by `make -C oracle optimize_check` where the reference header exists)."""
+    exe = os.path.join(REPO, "oracle", "_ref", "optimize_host_check")
+    scene = os.path.join(REPO, "data", "scenes", "bunny.bin")
+    if not (os.path.isfile(exe) and os.path.isfile(scene)):
+        pytest.skip("optimize_host_check binary or bunny fixture not present")
+    r = subprocess.run([exe, scene, "3"], capture_output=True, text=True, timeout=600)
+    print(r.stdout)
+    assert r.returncode == 0 and "host half of Optimize ok" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
