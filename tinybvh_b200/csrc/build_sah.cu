@@ -1049,7 +1049,15 @@ int build_sah_launch( tbvh_bvh b, float c_trav, float c_int, int flavour )
 				CUDA_TRY( cudaMemcpyAsync( &A.ctr->lvl_chunks[0], &state[1], 4, cudaMemcpyHostToDevice, s ) );
 				A.level0 = level;
 				void* params[] = { (void*)&A };
-				CUDA_TRY( cudaLaunchCooperativeKernel( (const void*)k_large_phase, dim3( pgrid ), dim3( CHUNK ), params, 0, s ) );
+				const cudaError_t ce = cudaLaunchCooperativeKernel( (const void*)k_large_phase, dim3( pgrid ), dim3( CHUNK ), params, 0, s );
+				if (ce == cudaErrorCooperativeLaunchTooLarge || ce == cudaErrorNotSupported || ce == cudaErrorLaunchOutOfResources)
+				{
+					// this device (or partition of it) cannot keep the persistent grid resident: the launch-per-stage path serves every level
+					cudaGetLastError();
+					pgrid = 0;
+					continue;
+				}
+				CUDA_TRY( ce );
 				g_tbvh_launches++;
 				CUDA_TRY( cudaStreamSynchronize( s ) ); // `state` is on this frame
 				break;
