@@ -364,9 +364,15 @@ int tbvh_bvh_create( tbvh_ctx ctx, tbvh_bvh* out )
 	tbvh_bvh b = new (std::nothrow) tbvh_bvh_t();
 	ARG_CHECK( b, "out of host memory" );
 	b->ctx = ctx;
-	CUDA_TRY( cudaSetDevice( ctx->device ) );
-	CUDA_TRY( cudaMalloc( &b->d_stats, 32 ) );
-	CUDA_TRY( cudaMemset( b->d_stats, 0, 32 ) );
+	const cudaError_t ce = cudaSetDevice( ctx->device ) != cudaSuccess ? cudaGetLastError() : cudaMalloc( &b->d_stats, 32 );
+	if (ce != cudaSuccess || cudaMemset( b->d_stats, 0, 32 ) != cudaSuccess)
+	{
+		tbvh_set_error( "tbvh_bvh_create: %s", cudaGetErrorString( ce != cudaSuccess ? ce : cudaGetLastError() ) );
+		if (b->d_stats) cudaFree( b->d_stats );
+		delete b;
+		return TBVH_E_CUDA;
+	}
+	b->generation = tbvh_next_generation();
 	live_add( b );
 	*out = b;
 	return TBVH_OK;
@@ -380,7 +386,7 @@ static void free_layouts( tbvh_bvh b )
 	b->d_verts = 0, b->d_nodes = 0, b->d_prim_idx = 0, b->d_leaf_tris = 0, b->d_nodes_gpu = 0, b->d_cw_nodes = 0, b->d_cw_tris = 0, b->d_cw_trav = 0, b->d_trav = 0, b->leaf_tris_count = 0;
 	b->d_aabbs = 0, b->d_inst = 0, b->d_blas = 0, b->inst_count = 0, b->blas_count = 0, b->cw_depth = 0, b->tlas_blas_layouts = 0;
 	b->links.clear();
-	b->generation++; // a TLAS built over the old arrays must notice (tlas_check)
+	b->generation = tbvh_next_generation(); // a TLAS built over the old arrays must notice (tlas_check)
 	memset( &b->info, 0, sizeof( b->info ) );
 	b->refittable = true;
 }
@@ -593,7 +599,7 @@ int tbvh_upload_cwbvh( tbvh_bvh b, const void* bvh8_data, uint32_t used_blocks, 
 	cudaStream_t s = b->ctx->stream;
 	const cudaMemcpyKind kind = space == TBVH_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
 	ARG_CHECK( used_blocks % 5 == 0, "usedBlocks must be a multiple of 5 (80-byte nodes)" );
-	if (b->d_cw_trav || b->d_cw_tris) b->generation++; // a TLAS may hold these addresses (tlas_check)
+	if (b->d_cw_trav || b->d_cw_tris) b->generation = tbvh_next_generation(); // a TLAS may hold these addresses (tlas_check)
 	if (b->d_cw_nodes) cudaFree( b->d_cw_nodes );
 	if (b->d_cw_tris) cudaFree( b->d_cw_tris );
 	if (b->d_cw_trav) cudaFree( b->d_cw_trav );
@@ -794,7 +800,7 @@ int tbvh_refit( tbvh_bvh b, const void* verts, uint32_t stride, uint32_t prim_co
 	TRY( refit_launch( b, s ) );
 	// derived layouts describe the old boxes: drop them (the reference's BVH_GPU / BVH8_CWBVH are re-converted after a refit too)
 	if (b->d_nodes_gpu) cudaFree( b->d_nodes_gpu ), b->d_nodes_gpu = 0;
-	if (b->d_cw_trav || b->d_cw_tris) b->generation++; // a TLAS may hold these addresses (tlas_check)
+	if (b->d_cw_trav || b->d_cw_tris) b->generation = tbvh_next_generation(); // a TLAS may hold these addresses (tlas_check)
 	if (b->d_cw_nodes) cudaFree( b->d_cw_nodes ), b->d_cw_nodes = 0;
 	if (b->d_cw_tris) cudaFree( b->d_cw_tris ), b->d_cw_tris = 0;
 	if (b->d_cw_trav) cudaFree( b->d_cw_trav ), b->d_cw_trav = 0;

@@ -68,6 +68,7 @@ struct tbvh_ctx_t
 };
 #define TBVH_COUNTERS 256
 
+uint32_t tbvh_next_generation(); // process-wide: a value no handle has carried before (a recycled handle address cannot revalidate a stale TLAS)
 struct BlasLink { tbvh_bvh blas; uint32_t generation; }; // host side: what a TLAS was built over
 
 struct tbvh_bvh_t
@@ -93,7 +94,7 @@ struct tbvh_bvh_t
 	float4* d_cw_tris = 0;     // 3 float4 per triangle
 	float4* d_cw_trav = 0;     // traversal nodes derived from d_cw_nodes (trace_cwbvh.cu cw_make_trav): 10 float4 per node
 	uint32_t cw_depth = 0;     // depth of the wide tree (root = 0)
-	uint32_t generation = 0;   // bumped whenever the arrays a TLAS may point at are replaced (build, upload, refit, convert)
+	uint32_t generation = 0;   // renewed (tbvh_next_generation) whenever the arrays a TLAS may point at are replaced (build, upload, refit, convert)
 	// TLAS (BVH::Build( BLASInstance*, instCount, BVHBase**, blasCount ) :2221): nodes / primIdx over instance boxes + device tables
 	float4* d_aabbs = 0;       // instance boxes the TLAS was built over (2 float4 per instance)
 	void* d_inst = 0;          // TlasInst records (inverse transform, BLAS number, mask)

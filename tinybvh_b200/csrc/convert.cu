@@ -5,6 +5,13 @@
 //   bvh_to_cwbvh     : BVH8_CWBVH::Build's conversion chain (tiny_bvh.h:5827-5834)
 #include "common.cuh"
 
+// TLAS staleness (api.cu tlas_check): every change of the arrays a TLAS may point at gives the handle a generation no handle has had before
+uint32_t tbvh_next_generation()
+{
+	static std::atomic<uint32_t> counter{ 0 };
+	return ++counter;
+}
+
 // one thread per primitive reference: 4 B index read, 3 x 16 B gathered vertex reads, 3 x 16 B coalesced writes
 __global__ void k_make_leaf_tris( const float4* __restrict__ verts, const uint32_t* __restrict__ prim_idx, float4* __restrict__ out, const uint32_t idx_count )
 {
@@ -23,7 +30,7 @@ int make_leaf_tris( tbvh_bvh b, cudaStream_t s )
 	const uint32_t n = b->info.idx_count;
 	// a refit keeps the array (same idx_count): a TLAS holding its address stays valid
 	if (b->d_leaf_tris && b->leaf_tris_count != n) { cudaFree( b->d_leaf_tris ); b->d_leaf_tris = 0; }
-	if (!b->d_leaf_tris) { CUDA_TRY( cudaMalloc( &b->d_leaf_tris, (size_t)n * 48 ) ); b->leaf_tris_count = n; b->generation++; }
+	if (!b->d_leaf_tris) { CUDA_TRY( cudaMalloc( &b->d_leaf_tris, (size_t)n * 48 ) ); b->leaf_tris_count = n; b->generation = tbvh_next_generation(); }
 	k_make_leaf_tris<<<(n + 255) / 256, 256, 0, s>>>( b->d_verts, b->d_prim_idx, b->d_leaf_tris, n );
 	LAUNCHED();
 	return TBVH_OK;

@@ -279,7 +279,7 @@ int bvh_to_cwbvh( tbvh_bvh b, cudaStream_t s )
 	const uint32_t used = b->info.used_nodes, idx_count = b->info.idx_count;
 	std::vector<void*> scratch;
 	#define CW_ALLOC( ptr, bytes ) do { CUDA_TRY( cudaMalloc( (void**)&(ptr), (bytes) ) ); scratch.push_back( (void*)(ptr) ); } while (0)
-	if (b->d_cw_trav || b->d_cw_tris) b->generation++; // a TLAS may hold these addresses (api.cu tlas_check)
+	if (b->d_cw_trav || b->d_cw_tris) b->generation = tbvh_next_generation(); // a TLAS may hold these addresses (api.cu tlas_check)
 	if (b->d_cw_nodes) cudaFree( b->d_cw_nodes );
 	if (b->d_cw_tris) cudaFree( b->d_cw_tris );
 	if (b->d_cw_trav) cudaFree( b->d_cw_trav );
